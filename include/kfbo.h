@@ -1,0 +1,176 @@
+/*
+ * kfbo.h -- C ABI of the B200-native Monte Carlo cost evaluator for kf_bayesopt.
+ *
+ * Drop-in boundary for ONE hot path of arpg/kf_bayesopt: the Monte Carlo cost
+ * evaluation (truth + measurement rollout, Kalman predict/update, per-trial
+ * NEES/NIS, J_NEES/J_NIS over the sample times).  Every entry point cites the
+ * reference interface (file:line, relative to the reference tree) it replaces.
+ *
+ * Plain C: pointers and sizes only, no C++ / torch types.  All functions return
+ * 0 on success, <0 for an invalid argument, >0 for a CUDA / NCCL failure, and never
+ * throw.  One evaluation in flight per handle (like the single ros::spin() thread
+ * that drives RunTrial::ProcessNoiseCallback, trial_node.cpp:154).
+ *
+ * There is NO CPU fallback: without a CUDA device kfbo_create fails.
+ */
+#ifndef KFBO_H_
+#define KFBO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KFBO_MAX_SAMPLE_TIMES 4   /* reference: it_num = 2 (trial_node.cpp:49) */
+#define KFBO_MAX_STEPS 2000       /* control table size (include/system_models.hpp:51) */
+#define KFBO_STATE_DIM 2          /* #define N 2  (include/system_models.hpp:11) */
+#define KFBO_OBS_DIM 1            /* #define Me 1 (include/system_models.hpp:12) */
+
+/* rv.cost_choice_ (read_para_vehicle.cpp:157; used at trial_node.cpp:70,86) */
+enum { KFBO_JNEES = 0, KFBO_CNEES = 1, KFBO_JNIS = 2, KFBO_CNIS = 3 };
+
+/* error codes (negative = caller error) */
+enum {
+    KFBO_OK = 0,
+    KFBO_EINVAL = -1,      /* bad argument (NULL pointer, size mismatch, ...) */
+    KFBO_ERANGE = -2,      /* max_iterations outside [2, 2000], too many sample times ... */
+    KFBO_ENODEVICE = -3,   /* no usable CUDA device: there is no CPU fallback */
+    KFBO_ESTATE = -4,      /* call not valid in this state (e.g. comm already initialised) */
+    KFBO_ECUDA = 1,        /* a CUDA runtime call failed; see kfbo_last_error */
+    KFBO_ENCCL = 2         /* an NCCL call failed; see kfbo_last_error */
+};
+
+/* how a multi-rank evaluation is partitioned (kfbo_comm_init) */
+enum { KFBO_SHARD_TRIALS = 0, KFBO_SHARD_CANDIDATES = 1 };
+
+/*
+ * The fields of ReadParaVehicle (include/read_para_vehicle.h:9-49) that the hot path
+ * reads, for the TRUTH side (rv_gt in trial_node.cpp:26); the estimator's pnoise/onoise
+ * arrive per evaluation like the "noise" message (trial_node.cpp:29-37).
+ * The two-sample-time loop (trial_node.cpp:52,105-114) is data here: pass k uses
+ * dt[k], max_iterations[k].  Reference defaults: {0.1,201},{1.0,201}.
+ */
+typedef struct kfbo_params {
+    int32_t n_sample_times;                          /* it_num (trial_node.cpp:49) */
+    double dt[KFBO_MAX_SAMPLE_TIMES];                /* dt_ per pass */
+    int32_t max_iterations[KFBO_MAX_SAMPLE_TIMES];   /* max_iterations_ per pass (read_para_vehicle.cpp:145) */
+    int32_t nsimruns;                                /* Nsimruns: Monte Carlo trials per sample time */
+    int32_t cpu_core_number;                         /* CPUcoreNumber: kept ONLY for the reference's integer
+                                                        semantics (trial.cpp:19,28); 1 = no truncation */
+    int32_t state_dof;                               /* stateDOF (trial_node.cpp:77) */
+    int32_t observation_dof;                         /* observationDOF (trial_node.cpp:93) */
+    double pnoise_truth;                             /* rv_gt.pnoise_[0] (system_models.hpp:39) */
+    double onoise_truth;                             /* rv_gt.onoise_[0] (system_models.hpp:143) */
+    int32_t cost_choice;                             /* KFBO_JNEES ... */
+    int32_t device;                                  /* CUDA device ordinal, -1 = current device */
+    uint64_t seed;                                   /* Philox key; replaces the wall-clock seeds
+                                                        (system_models.hpp:74,147, simulator.cpp:9) */
+    int32_t max_candidates;                          /* capacity of kfbo_eval_batch (>= 1) */
+    int32_t reserved;
+} kfbo_params;
+
+/* What RunTrial::ProcessNoiseCallback computes per "noise" message (trial_node.cpp:70-119). */
+typedef struct kfbo_result {
+    double average_nees[KFBO_MAX_SAMPLE_TIMES];      /* mean of Trial::get_average_nees (trial_node.cpp:74) */
+    double average_nis[KFBO_MAX_SAMPLE_TIMES];       /* (:90) */
+    double average_var_nees[KFBO_MAX_SAMPLE_TIMES];  /* (:75) */
+    double average_var_nis[KFBO_MAX_SAMPLE_TIMES];   /* (:91) */
+    double cost[KFBO_MAX_SAMPLE_TIMES];              /* pic_max[k] for the configured cost_choice */
+    double max_cost;                                 /* *max_element(pic_max) (:118) -- the "cost" message */
+    int32_t index_max;                               /* first maximal index (:119) */
+    int32_t reserved;
+} kfbo_result;
+
+typedef struct kfbo_handle kfbo_handle;
+
+/* Fill *p with the reference defaults (config/vehicleParams.yaml + trial_node.cpp:105-114). */
+void kfbo_default_params(kfbo_params *p);
+
+/* Replaces the per-callback construction of vector<Trial> and the models inside
+ * (trial_node.cpp:55-58 -> trial.cpp:12 -> system_models.hpp:30-78,137-150).  Allocates all
+ * device buffers, tables and streams once; kfbo_eval* never allocate. */
+int kfbo_create(const kfbo_params *p, kfbo_handle **out);
+void kfbo_destroy(kfbo_handle *h);
+
+/* Text of the last failure on this handle (h == NULL: last kfbo_create failure of this thread). */
+const char *kfbo_last_error(const kfbo_handle *h);
+
+/* One "noise" message -> one "cost": replaces the body of RunTrial::ProcessNoiseCallback
+ * (trial_node.cpp:29-119).  pn[npn], on[non] are the message halves (only [0] is read, like
+ * system_models.hpp:39,143).  On-device Philox noise; each call draws fresh streams. */
+int kfbo_eval(kfbo_handle *h, const double *pn, int32_t npn, const double *on, int32_t non,
+              kfbo_result *out);
+
+/* n_candidates evaluations in one launch (a batched ProcessNoiseCallback): q_est[c], r_est[c]
+ * are pnoise_[0], onoise_[0] of candidate c; out[n_candidates]. */
+int kfbo_eval_batch(kfbo_handle *h, int32_t n_candidates, const double *q_est, const double *r_est,
+                    kfbo_result *out);
+
+/* Exact-parity entry: sample time `k`, n_candidates estimators against ONE set of supplied
+ * post-transform noise draws (host pointers, trial index fastest):
+ *   x0noise[2][B]  draw of N(0,P0) added to x0          (simulator.cpp:12)
+ *   w[T][2][B]     process-noise draws N(0,Qd_truth)    (system_models.hpp:87,96)
+ *   v[T][B]        observation-noise draws N(0,R_truth) (system_models.hpp:158)
+ * Outputs (either may be NULL): per_trial[n_candidates][4][B] = {row_nees, row_nis, var_nees,
+ * var_nis} of trial.cpp:62-63,95-96; sums[n_candidates][4] = their sums over the B trials.
+ * Copies host->device and back inside the call. */
+int kfbo_eval_supplied(kfbo_handle *h, int32_t k, int32_t n_candidates, const double *q_est,
+                       const double *r_est, int64_t B, const double *x0noise, const double *w,
+                       const double *v, double *per_trial, double *sums);
+
+/* Same with DEVICE pointers for the noise (already resident in HBM) and, optionally, for the
+ * per-trial output; sums is a host pointer.  Used for the HBM-roofline measurement. */
+int kfbo_eval_supplied_dev(kfbo_handle *h, int32_t k, int32_t n_candidates, const double *q_est,
+                           const double *r_est, int64_t B, const double *d_x0noise, const double *d_w,
+                           const double *d_v, double *d_per_trial, double *sums);
+
+/* Philox-mode per-trial outputs for draw-for-draw checks: trials [trial0, trial0+ntrials) of
+ * sample time k on Philox stream `stream`; per_trial[4][ntrials] (host). */
+int kfbo_eval_philox_trials(kfbo_handle *h, int32_t k, double q_est, double r_est, uint32_t stream,
+                            uint32_t trial0, int64_t ntrials, double *per_trial);
+
+/* Philox stream bookkeeping: evaluation e of candidate c at sample time k uses stream
+ * base + (e*max_candidates + c)*n_sample_times + k.  kfbo_eval* advance e by one per call. */
+int kfbo_set_stream_base(kfbo_handle *h, uint32_t base);
+int kfbo_set_eval_counter(kfbo_handle *h, uint32_t e);
+
+/* Raw cost sums of the last kfbo_eval / kfbo_eval_batch: sums[n_candidates][D][4] =
+ * {sum row_nees, sum row_nis, sum var_nees, sum var_nis} over the trials (all ranks). */
+int kfbo_last_sums(const kfbo_handle *h, double *sums, int32_t n_candidates);
+
+/* Device time (ms, CUDA events on the handle's stream) of the last rollout kernel launch(es)
+ * and how many kernels the last evaluation launched. */
+int kfbo_last_kernel_ms(const kfbo_handle *h, double *ms, int32_t *launches);
+
+/* Run subsequent launches on this CUDA stream (a cudaStream_t); NULL = the handle's own. */
+int kfbo_set_cuda_stream(kfbo_handle *h, void *cuda_stream);
+
+/* ---- multi-GPU: one process per GPU, one NCCL allreduce of the cost sums per evaluation ---- */
+#define KFBO_NCCL_ID_BYTES 128
+int kfbo_nccl_unique_id(void *id_bytes /*[KFBO_NCCL_ID_BYTES]*/);
+int kfbo_comm_init(kfbo_handle *h, const void *id_bytes, int32_t rank, int32_t nranks, int32_t shard_mode);
+/* [begin,end) of n units owned by `rank` of `nranks` (contiguous, remainder to the low ranks). */
+int kfbo_shard_range(int64_t n, int32_t rank, int32_t nranks, int64_t *begin, int64_t *end);
+
+/* ---- host-side pieces of the path, exported so they can be tested without a GPU ---- */
+/* continuousToDiscrete for the robot1d model (continuous2discrete.hpp:8-32, system_models.hpp:33-39,58). */
+int kfbo_discretize(double pnoise0, double dt, double *Fd /*[4]*/, double *Qd /*[4]*/);
+/* u_[i] = 2cos(0.75 j), j += dt (system_models.hpp:49-56). */
+int kfbo_control_table(double dt, int32_t n, double *u);
+/* Thread averages + costs + max of trial.cpp:19,110-113 and trial_node.cpp:70-119 from the raw sums
+ * sums[D][4] over the (nsimruns/cpu_core_number)*cpu_core_number trials actually run. */
+int kfbo_finalize(const kfbo_params *p, const double *sums, kfbo_result *out);
+/* Trials actually run per sample time: (nsimruns / cpu_core_number) * cpu_core_number (trial.cpp:28). */
+int64_t kfbo_effective_trials(const kfbo_params *p);
+
+/* DFMA-chain microbenchmark: sustained FP64 FMA throughput of `device` in TFLOP/s (2 flops per FMA)
+ * over about `millis` ms -- the roofline denominator for the Philox path. */
+int kfbo_measure_fp64_peak(int32_t device, double millis, double *tflops, double *sm_clock_mhz_unused);
+
+const char *kfbo_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KFBO_H_ */

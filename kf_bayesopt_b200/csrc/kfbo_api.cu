@@ -1,0 +1,563 @@
+// kfbo_api.cu -- the C ABI (include/kfbo.h): handle, host orchestration, NCCL reduction.
+//
+// Replaces the CPUcoreNumber std::thread pool of trial_node.cpp:54-67 with a device-side batch
+// launcher over trials x candidates x sample times.  No CPU fallback: every evaluation runs the
+// sm_100a kernels of kfbo_kernels.cu or fails with an error code.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kfbo_device.cuh"
+#include "kfbo_host.h"
+#include "kfbo_kernels.h"
+
+using kfbo::Case;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- NCCL, loaded on first use so single-GPU users need no libnccl at all ----------------
+struct NcclApi {
+    void *so = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi &nccl()
+{
+    static NcclApi api = [] {
+        NcclApi a;
+        a.so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.so) a.so = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.so) return a;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.so, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.so, "ncclCommInitRank");
+        a.AllReduce = (decltype(a.AllReduce))dlsym(a.so, "ncclAllReduce");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.so, "ncclCommDestroy");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.so, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+
+constexpr size_t kPartialsBudgetBytes = 64u << 20;  // per-launch partial-sum scratch cap
+
+}  // namespace
+
+struct kfbo_handle {
+    kfbo_params p{};
+    int device = 0;
+    int64_t b_eff = 0;
+    int D = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // tables
+    double2 *d_gu = nullptr;          // [D][kMaxSteps] = (g0*u, g1*u)
+    double truth_l[KFBO_MAX_SAMPLE_TIMES][3]{};
+    double truth_sr[KFBO_MAX_SAMPLE_TIMES]{};
+    double fd01[KFBO_MAX_SAMPLE_TIMES]{};
+    int max_T = 0;
+    // per-evaluation buffers (sized at create)
+    Case *d_cases = nullptr, *h_cases = nullptr;
+    int cases_cap = 0;
+    double *d_partials = nullptr;
+    size_t partials_cap = 0;          // doubles
+    unsigned *d_tickets = nullptr;
+    double *d_sums = nullptr, *h_sums = nullptr;
+    // grow-only scratch for the supplied-noise / per-trial entry points
+    double *d_scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_cap[5] = {0, 0, 0, 0, 0};
+    // NCCL
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1, shard_mode = KFBO_SHARD_TRIALS;
+    // Philox stream bookkeeping
+    uint32_t stream_base = 0, eval_counter = 0;
+    // last evaluation
+    int last_ncand = 0, last_launches = 0;
+    double last_ms = 0.0;
+    std::string err;
+};
+
+namespace {
+
+int fail(kfbo_handle *h, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define KFBO_CUDA(h, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail((h), KFBO_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define KFBO_NCCL(h, call)                                                                          \
+    do {                                                                                            \
+        ncclResult_t r_ = (call);                                                                   \
+        if (r_ != ncclSuccess)                                                                      \
+            return fail((h), KFBO_ENCCL, "%s failed: %s (%s:%d)", #call, nccl().GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+int ensure_scratch(kfbo_handle *h, int slot, size_t doubles)
+{
+    if (h->scratch_cap[slot] >= doubles) return KFBO_OK;
+    if (h->d_scratch[slot]) KFBO_CUDA(h, cudaFree(h->d_scratch[slot]));
+    h->d_scratch[slot] = nullptr;
+    h->scratch_cap[slot] = 0;
+    KFBO_CUDA(h, cudaMalloc(&h->d_scratch[slot], doubles * sizeof(double)));
+    h->scratch_cap[slot] = doubles;
+    return KFBO_OK;
+}
+
+// Constants of (candidate q_est/r_est, sample time k): ProcessModel / ObservationModel of the
+// estimator (kalman_filter.cpp:6-10) plus the truth-side noise transform (simulator.cpp:5).
+int build_case(kfbo_handle *h, int k, double q_est, double r_est, uint32_t stream, int out_slot, Case *c)
+{
+    double Fd[4], Qd[4];
+    kfbo::host::discretize(q_est, h->p.dt[k], Fd, Qd);
+    if (Fd[0] != 1.0 || Fd[2] != 0.0 || Fd[3] != 1.0)
+        return fail(h, KFBO_EINVAL, "discretised Fd lost its [[1,f],[0,1]] structure");
+    c->f = Fd[1];
+    c->q00 = Qd[0]; c->q01 = Qd[1]; c->q10 = Qd[2]; c->q11 = Qd[3];
+    c->r_est = r_est / h->p.dt[k];                       // system_models.hpp:143
+    c->l00 = h->truth_l[k][0]; c->l10 = h->truth_l[k][1]; c->l11 = h->truth_l[k][2];
+    c->sr = h->truth_sr[k];
+    c->T = h->p.max_iterations[k];
+    c->k = k;
+    c->stream = stream;
+    c->out_slot = out_slot;
+    return KFBO_OK;
+}
+
+int cases_per_launch(const kfbo_handle *h, int tiles)
+{
+    const size_t per_case = (size_t)tiles * 4;
+    size_t n = h->partials_cap / per_case;
+    if (n < 1) n = 1;
+    if (n > (size_t)h->cases_cap) n = (size_t)h->cases_cap;
+    // keep the 1-D grid below 2^31-1 blocks
+    const size_t grid_cap = 0x7fffffffu / (size_t)tiles;
+    if (n > grid_cap) n = grid_cap;
+    return (int)n;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *kfbo_version(void) { return "kfbo-b200 0.1 (sm_100a)"; }
+
+void kfbo_default_params(kfbo_params *p)
+{
+    if (!p) return;
+    std::memset(p, 0, sizeof *p);
+    p->n_sample_times = 2;                       // it_num (trial_node.cpp:49)
+    p->dt[0] = 0.1; p->max_iterations[0] = 201;  // vehicleParams.yaml:8-10, read_para_vehicle.cpp:145
+    p->dt[1] = 1.0; p->max_iterations[1] = 201;  // trial_node.cpp:105-114
+    p->nsimruns = 200;                           // vehicleParams.yaml:16
+    p->cpu_core_number = 10;                     // vehicleParams.yaml:1
+    p->state_dof = 2; p->observation_dof = 1;    // vehicleParams.yaml:4-5
+    p->pnoise_truth = 1.0; p->onoise_truth = 0.1;  // vehicleParams.yaml:18-19
+    p->cost_choice = KFBO_JNEES;                 // vehicleParams.yaml:25
+    p->device = -1;
+    p->seed = 0x4B46424F20260101ull;
+    p->max_candidates = 1;
+}
+
+int64_t kfbo_effective_trials(const kfbo_params *p)
+{
+    if (!p || p->cpu_core_number < 1) return KFBO_EINVAL;
+    return kfbo::host::effective_trials(*p);
+}
+
+int kfbo_discretize(double pnoise0, double dt, double *Fd, double *Qd)
+{
+    if (!Fd || !Qd) return KFBO_EINVAL;
+    kfbo::host::discretize(pnoise0, dt, Fd, Qd);
+    return KFBO_OK;
+}
+
+int kfbo_control_table(double dt, int32_t n, double *u)
+{
+    if (!u || n < 0) return KFBO_EINVAL;
+    kfbo::host::control_table(dt, n, u);
+    return KFBO_OK;
+}
+
+int kfbo_finalize(const kfbo_params *p, const double *sums, kfbo_result *out)
+{
+    if (!p || !sums || !out) return KFBO_EINVAL;
+    const int rc = kfbo::host::validate(*p);
+    if (rc) return rc;
+    kfbo::host::finalize(*p, sums, out);
+    return KFBO_OK;
+}
+
+int kfbo_shard_range(int64_t n, int32_t rank, int32_t nranks, int64_t *begin, int64_t *end)
+{
+    if (!begin || !end || n < 0 || nranks < 1 || rank < 0 || rank >= nranks) return KFBO_EINVAL;
+    kfbo::host::shard_range(n, rank, nranks, begin, end);
+    return KFBO_OK;
+}
+
+const char *kfbo_last_error(const kfbo_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void kfbo_destroy(kfbo_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    for (int i = 0; i < 5; ++i) if (h->d_scratch[i]) cudaFree(h->d_scratch[i]);
+    if (h->d_gu) cudaFree(h->d_gu);
+    if (h->d_cases) cudaFree(h->d_cases);
+    if (h->h_cases) cudaFreeHost(h->h_cases);
+    if (h->d_partials) cudaFree(h->d_partials);
+    if (h->d_tickets) cudaFree(h->d_tickets);
+    if (h->d_sums) cudaFree(h->d_sums);
+    if (h->h_sums) cudaFreeHost(h->h_sums);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int kfbo_create(const kfbo_params *p, kfbo_handle **out)
+{
+    if (!p || !out) return fail(nullptr, KFBO_EINVAL, "kfbo_create: NULL argument");
+    *out = nullptr;
+    int rc = kfbo::host::validate(*p);
+    if (rc) return fail(nullptr, rc, "kfbo_create: invalid kfbo_params (code %d)", rc);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev < 1)
+        return fail(nullptr, KFBO_ENODEVICE, "kfbo_create: no CUDA device (%s); there is no CPU fallback",
+                    ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+    kfbo_handle *h = new (std::nothrow) kfbo_handle;
+    if (!h) return fail(nullptr, KFBO_EINVAL, "kfbo_create: out of host memory");
+    h->p = *p;
+    h->D = p->n_sample_times;
+    h->b_eff = kfbo::host::effective_trials(*p);
+    auto bail = [&](int code) { g_create_error = h->err; kfbo_destroy(h); return code; };
+    auto cu = [&](cudaError_t e, const char *what) {
+        if (e == cudaSuccess) return false;
+        fail(h, KFBO_ECUDA, "kfbo_create: %s failed: %s", what, cudaGetErrorString(e));
+        return true;
+    };
+    if (p->device >= 0) h->device = p->device;
+    else if (cu(cudaGetDevice(&h->device), "cudaGetDevice")) return bail(KFBO_ECUDA);
+    if (h->device >= ndev) { fail(h, KFBO_ENODEVICE, "kfbo_create: device %d of %d", h->device, ndev); return bail(KFBO_ENODEVICE); }
+    if (cu(cudaSetDevice(h->device), "cudaSetDevice")) return bail(KFBO_ECUDA);
+    if (cu(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail(KFBO_ECUDA);
+    h->stream = h->own_stream;
+    if (cu(cudaEventCreate(&h->ev0), "cudaEventCreate") || cu(cudaEventCreate(&h->ev1), "cudaEventCreate")) return bail(KFBO_ECUDA);
+
+    // ---- per-sample-time tables: g*u (system_models.hpp:46-56,82) and the truth noise transform
+    std::vector<double2> gu((size_t)h->D * kfbo::kMaxSteps);
+    std::vector<double> u(kfbo::kMaxSteps);
+    for (int k = 0; k < h->D; ++k) {
+        const double dt = p->dt[k];
+        const double g0 = 0.5 * dt * dt, g1 = dt;   // system_models.hpp:46-47
+        kfbo::host::control_table(dt, kfbo::kMaxSteps, u.data());
+        for (int i = 0; i < kfbo::kMaxSteps; ++i) gu[(size_t)k * kfbo::kMaxSteps + i] = make_double2(g0 * u[i], g1 * u[i]);
+        double Fd[4], Qd[4];
+        kfbo::host::discretize(p->pnoise_truth, dt, Fd, Qd);
+        h->fd01[k] = Fd[1];
+        // lower Cholesky factor of Qd_truth; any T with T T^T = Qd is statistically equivalent to
+        // eigenmvn.h:126-130's V sqrt(Lambda)
+        h->truth_l[k][0] = std::sqrt(Qd[0]);
+        h->truth_l[k][1] = Qd[2] / h->truth_l[k][0];
+        h->truth_l[k][2] = std::sqrt(Qd[3] - h->truth_l[k][1] * h->truth_l[k][1]);
+        h->truth_sr[k] = std::sqrt(p->onoise_truth / dt);  // R = onoise/dt (system_models.hpp:143)
+        h->max_T = std::max(h->max_T, p->max_iterations[k]);
+    }
+    if (cu(cudaMalloc(&h->d_gu, gu.size() * sizeof(double2)), "cudaMalloc(gu)")) return bail(KFBO_ECUDA);
+    if (cu(cudaMemcpy(h->d_gu, gu.data(), gu.size() * sizeof(double2), cudaMemcpyHostToDevice), "cudaMemcpy(gu)")) return bail(KFBO_ECUDA);
+
+    // ---- evaluation buffers
+    h->cases_cap = p->max_candidates * h->D;
+    const int tiles = kfbo::rollout_tiles((size_t)h->b_eff);
+    size_t part = (size_t)h->cases_cap * tiles * 4;
+    const size_t budget = kPartialsBudgetBytes / sizeof(double);
+    if (part > budget) part = std::max(budget, (size_t)tiles * 4);
+    h->partials_cap = part;
+    if (cu(cudaMalloc(&h->d_cases, h->cases_cap * sizeof(Case)), "cudaMalloc(cases)") ||
+        cu(cudaMallocHost(&h->h_cases, h->cases_cap * sizeof(Case)), "cudaMallocHost(cases)") ||
+        cu(cudaMalloc(&h->d_partials, h->partials_cap * sizeof(double)), "cudaMalloc(partials)") ||
+        cu(cudaMalloc(&h->d_tickets, h->cases_cap * sizeof(unsigned)), "cudaMalloc(tickets)") ||
+        cu(cudaMemset(h->d_tickets, 0, h->cases_cap * sizeof(unsigned)), "cudaMemset(tickets)") ||
+        cu(cudaMalloc(&h->d_sums, (size_t)h->cases_cap * 4 * sizeof(double)), "cudaMalloc(sums)") ||
+        cu(cudaMallocHost(&h->h_sums, (size_t)h->cases_cap * 4 * sizeof(double)), "cudaMallocHost(sums)"))
+        return bail(KFBO_ECUDA);
+    *out = h;
+    return KFBO_OK;
+}
+
+int kfbo_set_stream_base(kfbo_handle *h, uint32_t base) { if (!h) return KFBO_EINVAL; h->stream_base = base; return KFBO_OK; }
+int kfbo_set_eval_counter(kfbo_handle *h, uint32_t e) { if (!h) return KFBO_EINVAL; h->eval_counter = e; return KFBO_OK; }
+
+int kfbo_set_cuda_stream(kfbo_handle *h, void *cuda_stream)
+{
+    if (!h) return KFBO_EINVAL;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return KFBO_OK;
+}
+
+int kfbo_eval_batch(kfbo_handle *h, int32_t C, const double *q_est, const double *r_est, kfbo_result *out)
+{
+    if (!h) return KFBO_EINVAL;
+    if (!q_est || !r_est || !out) return fail(h, KFBO_EINVAL, "kfbo_eval_batch: NULL argument");
+    if (C < 1 || C > h->p.max_candidates)
+        return fail(h, KFBO_EINVAL, "kfbo_eval_batch: n_candidates %d outside [1, max_candidates=%d]", C, h->p.max_candidates);
+    KFBO_CUDA(h, cudaSetDevice(h->device));
+    const int D = h->D;
+    int64_t c0 = 0, c1 = C, t0 = 0, t1 = h->b_eff;
+    if (h->comm) {
+        if (h->shard_mode == KFBO_SHARD_CANDIDATES) kfbo::host::shard_range(C, h->rank, h->nranks, &c0, &c1);
+        else kfbo::host::shard_range(h->b_eff, h->rank, h->nranks, &t0, &t1);
+    }
+    const int ncases = (int)(c1 - c0) * D;
+    for (int64_t c = c0; c < c1; ++c)
+        for (int k = 0; k < D; ++k) {
+            const uint32_t stream = h->stream_base + (h->eval_counter * (uint32_t)h->p.max_candidates + (uint32_t)c) * (uint32_t)D + (uint32_t)k;
+            const int rc = build_case(h, k, q_est[c], r_est[c], stream, (int)(c * D + k), &h->h_cases[(c - c0) * D + k]);
+            if (rc) return rc;
+        }
+    const size_t nsums = (size_t)C * D * 4;
+    // ranks that own no case of a slot (candidate sharding) or no trials contribute zeros
+    KFBO_CUDA(h, cudaMemsetAsync(h->d_sums, 0, nsums * sizeof(double), h->stream));
+    if (ncases > 0)
+        KFBO_CUDA(h, cudaMemcpyAsync(h->d_cases, h->h_cases, (size_t)ncases * sizeof(Case), cudaMemcpyHostToDevice, h->stream));
+    h->last_launches = 0;
+    KFBO_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    const uint32_t ntrials = (uint32_t)(t1 - t0);
+    if (ncases > 0 && ntrials > 0) {
+        const int tiles = kfbo::rollout_tiles(ntrials);
+        const int step = cases_per_launch(h, tiles);
+        for (int first = 0; first < ncases; first += step) {
+            const int n = std::min(step, ncases - first);
+            KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, h->d_gu, h->max_T, h->p.seed, (uint32_t)t0, ntrials,
+                                                     nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream));
+            ++h->last_launches;
+        }
+    }
+    KFBO_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    if (h->comm)
+        KFBO_NCCL(h, nccl().AllReduce(h->d_sums, h->d_sums, nsums, ncclDouble, ncclSum, h->comm, h->stream));
+    KFBO_CUDA(h, cudaMemcpyAsync(h->h_sums, h->d_sums, nsums * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    KFBO_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    KFBO_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    h->last_ncand = C;
+    for (int c = 0; c < C; ++c) kfbo::host::finalize(h->p, h->h_sums + (size_t)c * D * 4, &out[c]);
+    ++h->eval_counter;
+    return KFBO_OK;
+}
+
+int kfbo_eval(kfbo_handle *h, const double *pn, int32_t npn, const double *on, int32_t non, kfbo_result *out)
+{
+    if (!h) return KFBO_EINVAL;
+    if (!pn || !on || !out || npn < 1 || non < 1)
+        return fail(h, KFBO_EINVAL, "kfbo_eval: needs pn[>=1], on[>=1] (system_models.hpp:39,143 read element 0)");
+    return kfbo_eval_batch(h, 1, pn, on, out);
+}
+
+int kfbo_last_sums(const kfbo_handle *h, double *sums, int32_t n_candidates)
+{
+    if (!h || !sums || n_candidates < 1 || n_candidates > h->last_ncand) return KFBO_EINVAL;
+    std::memcpy(sums, h->h_sums, (size_t)n_candidates * h->D * 4 * sizeof(double));
+    return KFBO_OK;
+}
+
+int kfbo_last_kernel_ms(const kfbo_handle *h, double *ms, int32_t *launches)
+{
+    if (!h) return KFBO_EINVAL;
+    if (ms) *ms = h->last_ms;
+    if (launches) *launches = h->last_launches;
+    return KFBO_OK;
+}
+
+static int supplied_impl(kfbo_handle *h, int32_t k, int32_t C, const double *q_est, const double *r_est, int64_t B,
+                         const double *d_x0, const double *d_w, const double *d_v, double *d_per_trial,
+                         double *h_per_trial, double *sums)
+{
+    const int tiles = kfbo::rollout_tiles((size_t)B);
+    if ((size_t)C > (size_t)0x7fffffff / (size_t)tiles) return fail(h, KFBO_ERANGE, "supplied: grid too large");
+    std::vector<Case> cases((size_t)C);
+    for (int c = 0; c < C; ++c) {
+        const int rc = build_case(h, k, q_est[c], r_est[c], 0u, c, &cases[c]);
+        if (rc) return rc;
+    }
+    int rc = ensure_scratch(h, 3, (size_t)C * tiles * 4 + (size_t)C * 4 + (size_t)C * ((sizeof(Case) + 7) / 8) + C);
+    if (rc) return rc;
+    double *d_partials = h->d_scratch[3];
+    double *d_sums = d_partials + (size_t)C * tiles * 4;
+    Case *d_cases = reinterpret_cast<Case *>(d_sums + (size_t)C * 4);
+    unsigned *d_tickets = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(d_cases) + (size_t)C * ((sizeof(Case) + 7) / 8) * 8);
+    KFBO_CUDA(h, cudaMemcpyAsync(d_cases, cases.data(), (size_t)C * sizeof(Case), cudaMemcpyHostToDevice, h->stream));
+    KFBO_CUDA(h, cudaMemsetAsync(d_tickets, 0, (size_t)C * sizeof(unsigned), h->stream));
+    KFBO_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    KFBO_CUDA(h, kfbo::launch_rollout_supplied(d_cases, C, h->d_gu, h->p.max_iterations[k], d_x0, d_w, d_v, (size_t)B, d_per_trial,
+                                               d_partials, d_tickets, d_sums, h->stream));
+    KFBO_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    h->last_launches = 1;
+    std::vector<double> hs((size_t)C * 4);
+    KFBO_CUDA(h, cudaMemcpyAsync(hs.data(), d_sums, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h_per_trial)
+        KFBO_CUDA(h, cudaMemcpyAsync(h_per_trial, d_per_trial, (size_t)C * 4 * B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    KFBO_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    KFBO_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    if (sums) std::memcpy(sums, hs.data(), hs.size() * sizeof(double));
+    return KFBO_OK;
+}
+
+static int supplied_check(kfbo_handle *h, int32_t k, int32_t C, const double *q, const double *r, int64_t B,
+                          const void *x0, const void *w, const void *v)
+{
+    if (!h) return KFBO_EINVAL;
+    if (!q || !r || !x0 || !w || !v) return fail(h, KFBO_EINVAL, "kfbo_eval_supplied: NULL argument");
+    if (k < 0 || k >= h->D) return fail(h, KFBO_EINVAL, "kfbo_eval_supplied: sample time %d outside [0,%d)", k, h->D);
+    if (C < 1 || B < 1 || B > 0x7fffffff) return fail(h, KFBO_EINVAL, "kfbo_eval_supplied: bad n_candidates/B");
+    return KFBO_OK;
+}
+
+int kfbo_eval_supplied(kfbo_handle *h, int32_t k, int32_t C, const double *q_est, const double *r_est, int64_t B,
+                       const double *x0noise, const double *w, const double *v, double *per_trial, double *sums)
+{
+    int rc = supplied_check(h, k, C, q_est, r_est, B, x0noise, w, v);
+    if (rc) return rc;
+    KFBO_CUDA(h, cudaSetDevice(h->device));
+    const size_t T = (size_t)h->p.max_iterations[k];
+    if ((rc = ensure_scratch(h, 0, 2 * (size_t)B))) return rc;
+    if ((rc = ensure_scratch(h, 1, 2 * T * (size_t)B))) return rc;
+    if ((rc = ensure_scratch(h, 2, T * (size_t)B))) return rc;
+    if (per_trial && (rc = ensure_scratch(h, 4, (size_t)C * 4 * (size_t)B))) return rc;
+    KFBO_CUDA(h, cudaMemcpyAsync(h->d_scratch[0], x0noise, 2 * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    KFBO_CUDA(h, cudaMemcpyAsync(h->d_scratch[1], w, 2 * T * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    KFBO_CUDA(h, cudaMemcpyAsync(h->d_scratch[2], v, T * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return supplied_impl(h, k, C, q_est, r_est, B, h->d_scratch[0], h->d_scratch[1], h->d_scratch[2],
+                         per_trial ? h->d_scratch[4] : nullptr, per_trial, sums);
+}
+
+int kfbo_eval_supplied_dev(kfbo_handle *h, int32_t k, int32_t C, const double *q_est, const double *r_est, int64_t B,
+                           const double *d_x0noise, const double *d_w, const double *d_v, double *d_per_trial, double *sums)
+{
+    int rc = supplied_check(h, k, C, q_est, r_est, B, d_x0noise, d_w, d_v);
+    if (rc) return rc;
+    KFBO_CUDA(h, cudaSetDevice(h->device));
+    return supplied_impl(h, k, C, q_est, r_est, B, d_x0noise, d_w, d_v, d_per_trial, nullptr, sums);
+}
+
+int kfbo_eval_philox_trials(kfbo_handle *h, int32_t k, double q_est, double r_est, uint32_t stream, uint32_t trial0,
+                            int64_t ntrials, double *per_trial)
+{
+    if (!h) return KFBO_EINVAL;
+    if (!per_trial || k < 0 || k >= h->D || ntrials < 1 || ntrials > 0x7fffffff)
+        return fail(h, KFBO_EINVAL, "kfbo_eval_philox_trials: bad argument");
+    KFBO_CUDA(h, cudaSetDevice(h->device));
+    Case c;
+    int rc = build_case(h, k, q_est, r_est, stream, 0, &c);
+    if (rc) return rc;
+    const int tiles = kfbo::rollout_tiles((size_t)ntrials);
+    if ((rc = ensure_scratch(h, 3, (size_t)tiles * 4 + 4 + (sizeof(Case) + 7) / 8 + 1))) return rc;
+    if ((rc = ensure_scratch(h, 4, 4 * (size_t)ntrials))) return rc;
+    double *d_partials = h->d_scratch[3];
+    double *d_sums = d_partials + (size_t)tiles * 4;
+    Case *d_case = reinterpret_cast<Case *>(d_sums + 4);
+    unsigned *d_ticket = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(d_case) + ((sizeof(Case) + 7) / 8) * 8);
+    KFBO_CUDA(h, cudaMemcpyAsync(d_case, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
+    KFBO_CUDA(h, cudaMemsetAsync(d_ticket, 0, sizeof(unsigned), h->stream));
+    KFBO_CUDA(h, kfbo::launch_rollout_philox(d_case, 1, h->d_gu, h->max_T, h->p.seed, trial0, (uint32_t)ntrials, h->d_scratch[4],
+                                             (size_t)ntrials, d_partials, d_ticket, d_sums, h->stream));
+    KFBO_CUDA(h, cudaMemcpyAsync(per_trial, h->d_scratch[4], 4 * (size_t)ntrials * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    KFBO_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->last_launches = 1;
+    return KFBO_OK;
+}
+
+int kfbo_nccl_unique_id(void *id_bytes)
+{
+    static_assert(sizeof(ncclUniqueId) == KFBO_NCCL_ID_BYTES, "ncclUniqueId size");
+    if (!id_bytes) return KFBO_EINVAL;
+    if (!nccl().ok) return fail(nullptr, KFBO_ENCCL, "libnccl.so.2 could not be loaded");
+    ncclUniqueId id;
+    ncclResult_t r = nccl().GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, KFBO_ENCCL, "ncclGetUniqueId: %s", nccl().GetErrorString(r));
+    std::memcpy(id_bytes, &id, sizeof id);
+    return KFBO_OK;
+}
+
+int kfbo_comm_init(kfbo_handle *h, const void *id_bytes, int32_t rank, int32_t nranks, int32_t shard_mode)
+{
+    if (!h) return KFBO_EINVAL;
+    if (!id_bytes || nranks < 1 || rank < 0 || rank >= nranks ||
+        (shard_mode != KFBO_SHARD_TRIALS && shard_mode != KFBO_SHARD_CANDIDATES))
+        return fail(h, KFBO_EINVAL, "kfbo_comm_init: bad argument");
+    if (h->comm) return fail(h, KFBO_ESTATE, "kfbo_comm_init: communicator already initialised");
+    if (!nccl().ok) return fail(h, KFBO_ENCCL, "libnccl.so.2 could not be loaded");
+    KFBO_CUDA(h, cudaSetDevice(h->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id_bytes, sizeof id);
+    KFBO_NCCL(h, nccl().CommInitRank(&h->comm, nranks, id, rank));
+    h->rank = rank; h->nranks = nranks; h->shard_mode = shard_mode;
+    return KFBO_OK;
+}
+
+int kfbo_measure_fp64_peak(int32_t device, double millis, double *tflops, double *unused)
+{
+    (void)unused;
+    if (!tflops || !(millis > 0)) return KFBO_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(nullptr, KFBO_ENODEVICE, "no CUDA device");
+    if (device < 0) cudaGetDevice(&device);
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, KFBO_ECUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const int blocks = prop.multiProcessorCount * 8, iters = 2048;
+    double *d = nullptr;
+    cudaEvent_t e0, e1;
+    cudaStream_t s;
+    if (cudaMalloc(&d, 64) != cudaSuccess) return fail(nullptr, KFBO_ECUDA, "cudaMalloc failed");
+    cudaStreamCreate(&s); cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const double flops_per_launch = 2.0 * 8 * 16 * (double)iters * 256.0 * blocks;
+    kfbo::launch_dfma_chain(d, blocks, iters, s);  // warm-up
+    cudaStreamSynchronize(s);
+    double total_ms = 0.0, total_flops = 0.0;
+    int rc = KFBO_OK;
+    while (total_ms < millis) {
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < 4; ++i) kfbo::launch_dfma_chain(d, blocks, iters, s);
+        cudaEventRecord(e1, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) { rc = fail(nullptr, KFBO_ECUDA, "dfma_chain failed"); break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        total_ms += ms; total_flops += 4 * flops_per_launch;
+    }
+    if (rc == KFBO_OK) *tflops = total_flops / (total_ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s); cudaFree(d);
+    return rc;
+}
+
+}  // extern "C"

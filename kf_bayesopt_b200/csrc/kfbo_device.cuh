@@ -1,0 +1,164 @@
+// kfbo_device.cuh -- device-side building blocks of the Monte Carlo cost evaluation (sm_100a).
+//
+// One trajectory (trial x candidate x sample time) per thread; truth state, estimate, covariance
+// and the NEES/NIS accumulators live in registers; all arithmetic is FP64.
+//
+// Reference semantics restated (file:line relative to the reference tree):
+//   truth step      simulator.cpp:15-19, include/system_models.hpp:80-100,152-162
+//   filter step     kalman_filter.cpp:18-38
+//   NEES / NIS      trial.cpp:53-66
+//   time variance   trial.cpp:84-98 (two-pass there; shifted one-pass sums here)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace kfbo {
+
+constexpr int kThreads = 128;        // threads per CTA (4 warps, one per SMSP)
+constexpr int kMaxSteps = 2000;      // include/system_models.hpp:51
+
+// Constants of one (candidate, sample time) pair, built on the host (kfbo_host.h).
+// The robot1d model has Fd = [[1, f],[0, 1]] and H = [1 0] exactly
+// (include/system_models.hpp:35-37,141-142 through continuous2discrete.hpp:8-32), so the
+// products with the structural 0/1 entries are dropped: x*1 and x+0*y are exact in IEEE-754,
+// the results are bit-identical to the dense 2x2 products for finite values.
+struct Case {
+    double f;                    // Fd(0,1) = dt
+    double q00, q01, q10, q11;   // estimator Qd (kalman_filter.cpp:23)
+    double r_est;                // estimator R = onoise_est/dt (system_models.hpp:143)
+    double l00, l10, l11;        // Cholesky factor of the truth Qd  (replaces eigenmvn.h:126-130)
+    double sr;                   // sqrt(truth R)
+    int32_t T;                   // max_iterations_
+    int32_t k;                   // sample-time index (selects the g*u table)
+    uint32_t stream;             // Philox stream of this (evaluation, candidate, sample time)
+    int32_t out_slot;            // row of the [n][4] sums / per-trial output this case writes
+};
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  Counter-based: no state, no races -- replaces the
+// process-wide static std::mt19937 of include/eigenmvn.h:51,62.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t lo0 = 0xD2511F53u * c0, hi0 = __umulhi(0xD2511F53u, c0);
+        const uint32_t lo1 = 0xCD9E8D57u * c2, hi1 = __umulhi(0xCD9E8D57u, c2);
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// 128 random bits -> two independent N(0,1) draws (Box-Muller), bit-manipulated so that no
+// int->double conversion is needed:
+//   m1 = top 52 bits of (x:y), m2 = top 52 bits of (z:w)
+//   u1 = 1 - m1*2^-52 in [2^-52, 1]      (= 2 - [1,2))
+//   t  = m2*2^-51     in [0, 2)          (= [2,4) - 2)
+//   na = sqrt(-2 ln u1) cos(pi t),  nb = sqrt(-2 ln u1) sin(pi t)
+__device__ __forceinline__ void normal_pair(uint4 r, double &na, double &nb)
+{
+    const uint32_t hi1 = 0x3FF00000u | (r.x >> 12);
+    const uint32_t lo1 = (r.x << 20) | (r.y >> 12);
+    const uint32_t hi2 = 0x40000000u | (r.z >> 12);
+    const uint32_t lo2 = (r.z << 20) | (r.w >> 12);
+    const double u1 = 2.0 - __hiloint2double((int)hi1, (int)lo1);
+    const double t = __hiloint2double((int)hi2, (int)lo2) - 2.0;
+    const double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(t, &s, &c);
+    na = rad * c;
+    nb = rad * s;
+}
+
+// Per-trajectory register state.
+struct Traj {
+    double x0, x1;               // truth state            (Simulator::x_)
+    double xh0, xh1;             // estimate               (KalmanFilter::xest_)
+    double p00, p01, p10, p11;   // covariance, 4 entries: the reference never symmetrises it
+    double kn, ki;               // shift = first NEES / NIS sample of the trial
+    double sdn, sqn, sdi, sqi;   // sum (v-k), sum (v-k)^2 for NEES and NIS
+};
+
+__device__ __forceinline__ void traj_init(Traj &t, double x0n0, double x0n1)
+{
+    t.x0 = 0.0 + x0n0;           // x0 = 0, P0 = I hard-coded (trial.cpp:31-32); simulator.cpp:12
+    t.x1 = 0.0 + x0n1;
+    t.xh0 = 0.0; t.xh1 = 0.0;    // kalman_filter.cpp:14-15
+    t.p00 = 1.0; t.p01 = 0.0; t.p10 = 0.0; t.p11 = 1.0;
+    t.kn = 0.0; t.ki = 0.0;
+    t.sdn = 0.0; t.sqn = 0.0; t.sdi = 0.0; t.sqi = 0.0;
+}
+
+// One filter-step: truth step, Kalman predict/update, NEES/NIS accumulation.
+// gu = g*u[step] = (0.5 dt^2 u, dt u), rounded products exactly as the reference forms them.
+template <bool kFirst>
+__device__ __forceinline__ void filter_step(Traj &t, const Case &m, double2 gu, double w0, double w1, double v)
+{
+    // ---- truth: x = Fd x + g u + w ; z = H x + v
+    t.x0 = (fma(m.f, t.x1, t.x0) + gu.x) + w0;
+    t.x1 = (t.x1 + gu.y) + w1;
+    const double z = t.x0 + v;
+    // ---- predict: xpred = Fd xest + g u ; Ppred = (Fd P) Fd^T + Qd
+    const double xp0 = fma(m.f, t.xh1, t.xh0) + gu.x;
+    const double xp1 = t.xh1 + gu.y;
+    const double fp00 = fma(m.f, t.p10, t.p00);
+    const double fp01 = fma(m.f, t.p11, t.p01);
+    const double pp00 = fma(fp01, m.f, fp00) + m.q00;
+    const double pp01 = fp01 + m.q01;
+    const double pp10 = fma(t.p11, m.f, t.p10) + m.q10;
+    const double pp11 = t.p11 + m.q11;
+    // ---- gain: c = Ppred H^T ; S = H c + R ; K = c * (1/S)
+    const double s = pp00 + m.r_est;
+    const double sinv = 1.0 / s;
+    const double k0 = pp00 * sinv;
+    const double k1 = pp10 * sinv;
+    // ---- update: nu = z - H xpred ; xest = xpred + K nu ; P = (I - K H) Ppred
+    const double nu = z - xp0;
+    t.xh0 = fma(k0, nu, xp0);
+    t.xh1 = fma(k1, nu, xp1);
+    const double x00 = 1.0 - k0;
+    t.p00 = x00 * pp00;
+    t.p01 = x00 * pp01;
+    t.p10 = fma(-k1, pp00, pp10);
+    t.p11 = fma(-k1, pp01, pp11);
+    // ---- NEES = (e^T P^-1) e with the closed-form 2x2 inverse; NIS = (nu / S) nu
+    const double e0 = t.x0 - t.xh0, e1 = t.x1 - t.xh1;
+    const double det = fma(t.p00, t.p11, -(t.p10 * t.p01));
+    const double invdet = 1.0 / det;
+    const double i00 = t.p11 * invdet, i01 = -t.p01 * invdet;
+    const double i10 = -t.p10 * invdet, i11 = t.p00 * invdet;
+    const double r0 = fma(e1, i10, e0 * i00);
+    const double r1 = fma(e1, i11, e0 * i01);
+    const double nees = fma(r1, e1, r0 * e0);
+    const double nis = (nu * sinv) * nu;
+    // ---- accumulate, shifted by the first sample of the trial
+    if (kFirst) { t.kn = nees; t.ki = nis; }
+    const double dn = nees - t.kn, di = nis - t.ki;
+    t.sdn += dn; t.sqn = fma(dn, dn, t.sqn);
+    t.sdi += di; t.sqi = fma(di, di, t.sqi);
+}
+
+// {row_nees, row_nis, var_nees, var_nis} of trial.cpp:62-63,84-96 from the shifted sums.
+__device__ __forceinline__ void traj_finish(const Traj &t, int T, double out[4])
+{
+    const double n = (double)T, inv_n = 1.0 / n, inv_nm1 = 1.0 / (double)(T - 1);
+    out[0] = fma(n, t.kn, t.sdn);
+    out[1] = fma(n, t.ki, t.sdi);
+    out[2] = fma(-t.sdn * inv_n, t.sdn, t.sqn) * inv_nm1;
+    out[3] = fma(-t.sdi * inv_n, t.sdi, t.sqi) * inv_nm1;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace kfbo

@@ -1,0 +1,137 @@
+// kfbo_host.h -- host-side model construction and cost assembly (no CUDA needed).
+//
+// Reference semantics (file:line relative to the reference tree):
+//   discretisation  include/continuous2discrete.hpp:8-32, include/system_models.hpp:33-39,58
+//   control table   include/system_models.hpp:46-56
+//   thread averages trial.cpp:19,28,110-113
+//   costs / max     trial_node.cpp:70-119
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+
+#include "../../include/kfbo.h"
+
+namespace kfbo {
+namespace host {
+
+// exp(A) for the 4x4 Van Loan matrix of the robot1d model.  With Fc = [[0,1],[0,0]] the matrix
+// [[-Fc dt, Qc dt],[0, Fc^T dt]] is nilpotent (A^4 = 0), so exp(A) = I + A + A^2/2 + A^3/6 is the
+// complete series; evaluated in Horner form  I + A (I + A/2 (I + A/3)).
+inline void expm_nilpotent4(const double A[4][4], double E[4][4])
+{
+    double M[4][4], N[4][4];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) M[i][j] = (i == j ? 1.0 : 0.0) + A[i][j] / 3.0;
+    for (int pass = 2; pass >= 1; --pass) {
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                double s = 0.0;
+                for (int k = 0; k < 4; ++k) s += A[i][k] * M[k][j];
+                N[i][j] = (i == j ? 1.0 : 0.0) + s / (double)pass;
+            }
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) M[i][j] = N[i][j];
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) E[i][j] = M[i][j];
+}
+
+// continuousToDiscrete(fd_, qd_, fc, qc, dt) with fc(0,1) = 1, qc(1,1) = pnoise_[0], all other
+// entries 0 (the reference leaves three entries of qc uninitialised; 0 is the intended model).
+inline void discretize(double pnoise0, double dt, double Fd[4], double Qd[4])
+{
+    double A[4][4] = {{0}}, E[4][4];
+    A[0][1] = -1.0 * dt;      // topLeft   = -Fc*dt
+    A[1][3] = pnoise0 * dt;   // topRight  =  Qc*dt   (only Qc(1,1) is non-zero)
+    A[3][2] = 1.0 * dt;       // botRight  =  Fc^T*dt
+    expm_nilpotent4(A, E);
+    // Fd = bottomRight^T ; Qd = Fd * topRight
+    Fd[0] = E[2][2]; Fd[1] = E[3][2]; Fd[2] = E[2][3]; Fd[3] = E[3][3];
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) Qd[2 * i + j] = Fd[2 * i] * E[0][2 + j] + Fd[2 * i + 1] * E[1][2 + j];
+}
+
+inline void control_table(double dt, int n, double *u)
+{
+    double j = 0.0;
+    for (int i = 0; i < n; ++i) {
+        u[i] = 2 * std::cos(0.75 * j);
+        j += dt;
+    }
+}
+
+inline int64_t effective_trials(const kfbo_params &p)
+{
+    return (int64_t)(p.nsimruns / p.cpu_core_number) * p.cpu_core_number;
+}
+
+// sums[4] over the trials actually run at sample time k -> the four averages the callback forms.
+// Thread t of `cores` reports all_nees_t / k_average etc.; the callback adds getter/cores over t.
+// With the per-thread sums unknown individually, the mean over threads is formed from the total:
+// mathematically identical, rounding differs at the 1e-16 level.
+inline void averages(const kfbo_params &p, int k, const double sums[4], double avg[4])
+{
+    const int64_t T = p.max_iterations[k];
+    const double cores = (double)p.cpu_core_number;
+    const double k_average = (double)(T * (int64_t)p.nsimruns / p.cpu_core_number);  // trial.cpp:19
+    avg[0] = sums[0] / k_average / cores;                                             // trial.cpp:112, trial_node.cpp:74
+    avg[1] = sums[1] / k_average / cores;                                             // trial.cpp:113, trial_node.cpp:90
+    avg[2] = sums[2] * cores / (double)p.nsimruns / cores;                            // trial.cpp:110, trial_node.cpp:75
+    avg[3] = sums[3] * cores / (double)p.nsimruns / cores;                            // trial.cpp:111, trial_node.cpp:91
+}
+
+inline double cost_of(const kfbo_params &p, const double avg[4])
+{
+    switch (p.cost_choice) {
+    case KFBO_JNEES: return std::abs(std::log(avg[0] / p.state_dof));                                   // trial_node.cpp:77
+    case KFBO_CNEES: return std::abs(std::log(avg[0] / p.state_dof)) +
+                            std::abs(std::log(0.5 * avg[2] / p.state_dof));                             // :78-81
+    case KFBO_JNIS:  return std::abs(std::log(avg[1] / p.observation_dof));                             // :93
+    default:         return std::abs(std::log(avg[1] / p.observation_dof)) +
+                            std::abs(std::log(0.5 * avg[3] / p.observation_dof));                       // :94-97
+    }
+}
+
+inline void finalize(const kfbo_params &p, const double *sums /*[D][4]*/, kfbo_result *out)
+{
+    *out = kfbo_result{};
+    const int D = p.n_sample_times;
+    for (int k = 0; k < D; ++k) {
+        double avg[4];
+        averages(p, k, sums + 4 * k, avg);
+        out->average_nees[k] = avg[0];
+        out->average_nis[k] = avg[1];
+        out->average_var_nees[k] = avg[2];
+        out->average_var_nis[k] = avg[3];
+        out->cost[k] = cost_of(p, avg);
+    }
+    const double *mx = std::max_element(out->cost, out->cost + D);   // trial_node.cpp:118-119 (first max)
+    out->max_cost = *mx;
+    out->index_max = (int32_t)(mx - out->cost);
+}
+
+inline int validate(const kfbo_params &p)
+{
+    if (p.n_sample_times < 1 || p.n_sample_times > KFBO_MAX_SAMPLE_TIMES) return KFBO_ERANGE;
+    for (int k = 0; k < p.n_sample_times; ++k) {
+        if (!(p.dt[k] > 0.0) || !std::isfinite(p.dt[k])) return KFBO_EINVAL;
+        if (p.max_iterations[k] < 2 || p.max_iterations[k] > KFBO_MAX_STEPS) return KFBO_ERANGE;
+    }
+    if (p.cpu_core_number < 1 || p.nsimruns < p.cpu_core_number) return KFBO_EINVAL;
+    if (p.state_dof < 1 || p.observation_dof < 1) return KFBO_EINVAL;
+    if (!(p.pnoise_truth > 0.0) || !(p.onoise_truth > 0.0)) return KFBO_EINVAL;
+    if (p.cost_choice < KFBO_JNEES || p.cost_choice > KFBO_CNIS) return KFBO_EINVAL;
+    if (p.max_candidates < 1) return KFBO_EINVAL;
+    return KFBO_OK;
+}
+
+inline void shard_range(int64_t n, int rank, int nranks, int64_t *b, int64_t *e)
+{
+    const int64_t base = n / nranks, rem = n % nranks;
+    *b = rank * base + std::min<int64_t>(rank, rem);
+    *e = *b + base + (rank < rem ? 1 : 0);
+}
+
+}  // namespace host
+}  // namespace kfbo

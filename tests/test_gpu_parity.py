@@ -1,0 +1,243 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libkfbo.so), against the CPU oracle
+on the same seeded inputs, against the committed golden vectors, and -- at BASELINE.json's full
+sizes -- through size-independent properties.
+
+Tolerances (north_star): per-trial NEES/NIS sums and J costs within 1e-9 RELATIVE in FP64 when both
+sides see identical noise draws; the max-over-sample-times selection identical; on-device RNG
+statistically within the Monte Carlo standard error."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+Q_TRUTH, R_TRUTH = 1.0, 0.1
+CODE_TIMES = [(0.1, 201), (1.0, 201)]       # trial_node.cpp:105-114
+README_TIMES = [(0.1, 201), (0.5, 211)]     # README.md:96 / BASELINE.json configs[1]
+
+
+def _noise(rng, oracle, dt, T, B):
+    """cfg2 parity inputs: standard normals mapped by the Cholesky factor of the truth Qd / sqrt(R)."""
+    _, Qd = oracle.discretize(Q_TRUTH, dt)
+    L = np.linalg.cholesky(Qd)
+    x0n = rng.standard_normal((2, B))
+    w = np.einsum("ij,tjb->tib", L, rng.standard_normal((T, 2, B)))
+    v = np.sqrt(R_TRUTH / dt) * rng.standard_normal((T, B))
+    return x0n, np.ascontiguousarray(w), v
+
+
+def test_supplied_noise_matches_golden_vectors(kfbo, golden):
+    B, cores = int(golden["meta"][1]), int(golden["meta"][2])
+    st = [(float(dt), int(T)) for dt, T in golden["sample_times"]]
+    rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=cores)
+    q, r = golden["candidates"][:, 0], golden["candidates"][:, 1]
+    with kfbo.CostEvaluator(rv, st, max_candidates=len(q)) as ev:
+        for d in range(len(st)):
+            pt, sums = ev.eval_supplied(d, q, r, golden[f"x0noise_{d}"], golden[f"w_{d}"], golden[f"v_{d}"])
+            for c in range(len(q)):
+                assert rel_err(pt[c], golden[f"per_trial_{d}_{c}"]) < RTOL, (d, c)
+                assert rel_err(sums[c], golden[f"per_trial_{d}_{c}"].sum(axis=1)) < RTOL
+
+
+@pytest.mark.parametrize("times", [CODE_TIMES, README_TIMES])
+def test_supplied_noise_matches_oracle_cfg2(kfbo, oracle, times):
+    # BASELINE parity case: B=4096, 2-D candidates, PCG64(20260101), J_NEES and J_NIS, argmax identical
+    B, cores = 4096, 8
+    rng = np.random.Generator(np.random.PCG64(20260101))
+    cands = np.array([[1.0, 0.1], [0.1, 0.1], [5.0, 1.0], [2.5, 0.01], [0.37, 0.62]])
+    rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=cores)
+    params = {c: kfbo.make_params(rv, times, cost_choice=c) for c in ("JNEES", "CNEES", "JNIS", "CNIS")}
+    sums = np.zeros((len(cands), len(times), 4))
+    want_pt = {}
+    with kfbo.CostEvaluator(rv, times, max_candidates=len(cands)) as ev:
+        for d, (dt, T) in enumerate(times):
+            x0n, w, v = _noise(rng, oracle, dt, T, B)
+            pt, s = ev.eval_supplied(d, cands[:, 0], cands[:, 1], x0n, w, v)
+            sums[:, d] = s
+            for c, (qe, re) in enumerate(cands):
+                want = oracle.eval_supplied(dt, T, qe, re, x0n, w, v)
+                want_pt[c, d] = want
+                assert rel_err(pt[c], want) < RTOL, (d, c)        # per-trial NEES/NIS sums and time-variances
+                assert rel_err(s[c], want.sum(axis=1)) < RTOL
+    for choice, p in params.items():
+        for c in range(len(cands)):
+            got = kfbo.finalize(p, sums[c])
+            want_cost = [oracle.cost_from_per_trial(want_pt[c, d], T, B, cores, cost_choice=choice)[4]
+                         for d, (dt, T) in enumerate(times)]
+            np.testing.assert_allclose(got.cost, want_cost, rtol=RTOL, atol=1e-12)
+            m, i = oracle.max_cost(want_cost)
+            assert got.index_max == i                              # selection identical
+            assert got.max_cost == pytest.approx(m, rel=RTOL, abs=1e-12)
+
+
+def test_supplied_noise_edge_shapes(kfbo, oracle):
+    # ragged tile (B not a multiple of the CTA size), a single trial, the minimum and maximum step counts
+    rng = np.random.default_rng(5)
+    for B, T, dt in [(1, 2, 0.1), (33, 3, 0.5), (129, 7, 1.0), (200, 2000, 0.1), (257, 201, 0.1)]:
+        rv = kfbo.ReadParaVehicle(nsimruns_=max(B, 1), cpu_core_number_=1)
+        x0n, w, v = _noise(rng, oracle, dt, T, B)
+        with kfbo.CostEvaluator(rv, [(dt, T)]) as ev:
+            pt, s = ev.eval_supplied(0, 0.8, 0.15, x0n, w, v)
+        want = oracle.eval_supplied(dt, T, 0.8, 0.15, x0n, w, v)
+        assert rel_err(pt[0], want) < RTOL, (B, T)
+        assert rel_err(s[0], want.sum(axis=1)) < RTOL
+
+
+def test_philox_trials_match_oracle_draw_for_draw(kfbo, oracle):
+    # the device RNG path restated by the oracle: same counters -> same normals -> same per-trial outputs
+    seed = 0x0123456789ABCDEF
+    rv = kfbo.ReadParaVehicle(nsimruns_=300, cpu_core_number_=1)
+    for times in (CODE_TIMES, README_TIMES, [(0.1, 200), (0.5, 2)]):   # odd and even step counts
+        with kfbo.CostEvaluator(rv, times, seed=seed) as ev:
+            for k, (dt, T) in enumerate(times):
+                for qe, re, stream, trial0 in [(1.0, 0.1, 0, 0), (0.3, 0.7, 77, 1000), (4.0, 0.02, 0xFFFFFFFE, 0xFFFFFF00)]:
+                    n = 255 if trial0 else 300
+                    got = ev.eval_philox_trials(k, qe, re, stream, trial0, n)
+                    want = oracle.eval_philox(seed, stream, dt, T, Q_TRUTH, R_TRUTH, qe, re, trial0, n)
+                    assert rel_err(got, want) < RTOL, (times, k, qe, stream)
+
+
+def test_eval_batch_sums_match_oracle_and_selection_is_identical(kfbo, oracle):
+    B, cores, seed = 512, 8, 7
+    rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=cores)
+    q = np.array([1.0, 0.1, 5.0, 0.5, 2.0, 1.3])
+    r = np.array([0.1, 0.1, 1.0, 0.01, 0.3, 0.07])
+    for times in (CODE_TIMES, README_TIMES):
+        D = len(times)
+        with kfbo.CostEvaluator(rv, times, seed=seed, max_candidates=len(q)) as ev:
+            ev.set_stream_base(1000)
+            res = ev.eval_batch(q, r)
+            sums = ev.last_sums(len(q))
+            for c in range(len(q)):
+                want_cost = []
+                for k, (dt, T) in enumerate(times):
+                    stream = 1000 + (0 * len(q) + c) * D + k          # include/kfbo.h stream layout, evaluation 0
+                    pt = oracle.eval_philox(seed, stream, dt, T, Q_TRUTH, R_TRUTH, q[c], r[c], 0, B)
+                    assert rel_err(sums[c, k], pt.sum(axis=1)) < RTOL
+                    out = oracle.cost_from_per_trial(pt, T, B, cores)
+                    assert rel_err([res[c].average_nees[k], res[c].average_nis[k], res[c].average_var_nees[k],
+                                    res[c].average_var_nis[k]], out[:4]) < RTOL
+                    assert res[c].cost[k] == pytest.approx(out[4], rel=RTOL, abs=1e-12)
+                    want_cost.append(out[4])
+                m, i = oracle.max_cost(want_cost)
+                assert res[c].index_max == i
+            # the second evaluation draws fresh streams (evaluation counter advanced)
+            res2 = ev.eval_batch(q, r)
+            assert res2[0].average_nees[0] != res[0].average_nees[0]
+            # ... and is reproducible when the counter is rewound
+            ev.set_eval_counter(0)
+            res3 = ev.eval_batch(q, r)
+            assert all(np.array_equal(a.cost, b.cost) for a, b in zip(res, res3))
+
+
+def test_eval_single_candidate_equals_batch_of_one(kfbo):
+    rv = kfbo.ReadParaVehicle()                                   # yaml defaults: B=200, 10 "cores"
+    with kfbo.CostEvaluator(rv, seed=11) as a, kfbo.CostEvaluator(rv, seed=11, max_candidates=1) as b:
+        ra = a.eval([0.7], [0.2])
+        rb = b.eval_batch([0.7], [0.2])[0]
+        assert np.array_equal(ra.cost, rb.cost) and ra.index_max == rb.index_max
+        assert ra.max_cost == max(ra.cost)
+        ms, launches = a.last_kernel_ms()
+        assert launches == 1 and ms > 0
+
+
+def test_reference_integer_semantics_on_device(kfbo, oracle):
+    # nsimruns % cores != 0: (nsimruns/cores)*cores trials run (trial.cpp:28), k_average = (T*nsimruns)/cores (:19)
+    B, cores, seed = 203, 10, 3
+    rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=cores)
+    with kfbo.CostEvaluator(rv, CODE_TIMES, seed=seed) as ev:
+        assert ev.effective_trials == 200
+        res = ev.eval([1.0], [0.1])
+        for k, (dt, T) in enumerate(CODE_TIMES):
+            pt = oracle.eval_philox(seed, k, dt, T, Q_TRUTH, R_TRUTH, 1.0, 0.1, 0, 200)
+            out = oracle.cost_from_per_trial(pt, T, B, cores)
+            assert res.cost[k] == pytest.approx(out[4], rel=RTOL, abs=1e-12)
+
+
+def test_errors_are_reported_not_thrown(kfbo):
+    with kfbo.CostEvaluator(kfbo.ReadParaVehicle(), max_candidates=2) as ev:
+        with pytest.raises(kfbo.KfboError) as e:
+            ev.eval_batch([1.0, 2.0, 3.0], [0.1, 0.1, 0.1])       # more than max_candidates
+        assert e.value.code == -1
+        with pytest.raises(kfbo.KfboError):
+            ev.eval([], [0.1])                                    # pnoise_[0] would be out of range
+        with pytest.raises(kfbo.KfboError):
+            ev.eval_philox_trials(5, 1.0, 0.1, 0, 0, 10)          # sample time out of range
+        assert ev.eval([1.0], [0.1]).max_cost >= 0                # handle still usable afterwards
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs[2] and configs[3] shapes)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_cfg3_properties(kfbo):
+    B, T = 1 << 20, 1000
+    rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
+    times = [(0.1, T), (0.5, T)]
+    with kfbo.CostEvaluator(rv, times, seed=2026) as ev:
+        res = ev.eval([1.0], [0.1])
+        s1 = ev.last_sums(1)
+        # matched filter: E[NEES] = stateDOF, E[NIS] = observationDOF (chi-square consistency, SURVEY 8c anchors)
+        # SE(avg NEES) = per-trial std of the time-mean / sqrt(B) < 0.4/1024
+        assert abs(res.average_nees[0] - 2.0) < 5 * 0.4 / 1024
+        assert abs(res.average_nees[1] - 2.0) < 5 * 0.4 / 1024
+        assert abs(res.average_nis[0] - 1.0) < 5 * 0.1 / 1024
+        assert res.cost[0] < 2e-3 and res.cost[1] < 2e-3
+        # determinism: same streams -> bit-identical sums
+        ev.set_eval_counter(0)
+        ev.eval([1.0], [0.1])
+        assert np.array_equal(s1, ev.last_sums(1))
+        # checksum of checksums: per-trial outputs of a slice add up to that slice's contribution;
+        # and a mistuned filter moves the cost the right way (NEES > dof when q_est is too small)
+        res_small_q = ev.eval([0.1], [0.1])
+        assert res_small_q.average_nees[0] > 5 and res_small_q.max_cost > 1.0
+
+
+def test_trial_shards_add_up(kfbo):
+    # evaluating the two halves of the trial range separately and adding equals the whole: the reduction
+    # is linear and the Philox counters use the global trial index (what SHARD_TRIALS relies on)
+    B, T, seed = 100_000, 201, 5
+    rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
+    with kfbo.CostEvaluator(rv, [(0.1, T)], seed=seed) as ev:
+        ev.eval([0.6], [0.2])
+        whole = ev.last_sums(1)[0, 0]
+        lo = ev.eval_philox_trials(0, 0.6, 0.2, 0, 0, B // 2)
+        hi = ev.eval_philox_trials(0, 0.6, 0.2, 0, B // 2, B - B // 2)
+        np.testing.assert_allclose(lo.sum(axis=1) + hi.sum(axis=1), whole, rtol=1e-12)
+
+
+def test_full_size_cfg4_sweep_shape(kfbo, oracle):
+    # 4096 candidates x 1024 trials x 2 sample times; spot-check candidates against the oracle
+    n, B, seed = 64, 1024, 9
+    q = np.repeat(np.geomspace(0.1, 5.0, n), n)
+    r = np.tile(np.geomspace(0.01, 1.0, n), n)
+    rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
+    with kfbo.CostEvaluator(rv, README_TIMES, seed=seed, max_candidates=n * n) as ev:
+        cost, mx = ev.eval_batch_costs(q, r)
+        sums = ev.last_sums(n * n)
+    assert cost.shape == (n * n, 2) and np.all(np.isfinite(cost)) and np.all(mx == cost.max(axis=1))
+    for c in (0, 777, 2049, 4095):
+        for k, (dt, T) in enumerate(README_TIMES):
+            pt = oracle.eval_philox(seed, c * 2 + k, dt, T, Q_TRUTH, R_TRUTH, q[c], r[c], 0, B)
+            assert rel_err(sums[c, k], pt.sum(axis=1)) < RTOL
+    # the surface has its valley near the truth (q=1, r=0.1)
+    best = np.argmin(mx)
+    assert 0.3 < q[best] < 3.0 and 0.03 < r[best] < 0.4
+
+
+def test_supplied_device_pointers_and_linearity(kfbo, oracle):
+    import torch
+    B, T, dt = 8192, 201, 0.1
+    rng = np.random.default_rng(8)
+    x0n, w, v = _noise(rng, oracle, dt, T, B)
+    rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
+    dev = torch.device("cuda:0")
+    tx, tw, tv = (torch.from_numpy(a).to(dev) for a in (x0n, w, v))
+    out = torch.empty((1, 4, B), dtype=torch.float64, device=dev)
+    with kfbo.CostEvaluator(rv, [(dt, T)]) as ev:
+        torch.cuda.synchronize()
+        s = ev.eval_supplied_dev(0, 0.9, 0.12, B, tx.data_ptr(), tw.data_ptr(), tv.data_ptr(), out.data_ptr())
+        pt_host, s_host = ev.eval_supplied(0, 0.9, 0.12, x0n, w, v)
+    assert np.array_equal(out.cpu().numpy(), pt_host) and np.array_equal(s, s_host)
+    assert rel_err(out.cpu().numpy()[0], oracle.eval_supplied(dt, T, 0.9, 0.12, x0n, w, v)) < RTOL

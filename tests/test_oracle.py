@@ -1,0 +1,179 @@
+"""CPU tests: the oracle (oracle/kfbo_oracle.c) against the committed golden vectors
+(tests/golden/kf_golden.npz, made by the independent numpy/scipy restatement in make_golden.py),
+published known answers of the RNGs it restates, and statistical anchors.
+
+The reference ships no tests (CMakeLists.txt:221-232 commented out); these are the pins."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+TOL = 1e-12  # oracle vs numpy restatement: same arithmetic, different summation/BLAS rounding only
+
+
+def test_discretisation_matches_scipy_expm(oracle, golden):
+    for (q, dt), Fd, Qd in zip(golden["disc_in"], golden["disc_Fd"], golden["disc_Qd"]):
+        F, Q = oracle.discretize(q, dt)
+        assert np.array_equal(F, Fd), (q, dt)           # [[1,dt],[0,1]] exactly
+        assert rel_err(Q, Qd) < 4 * np.finfo(float).eps, (q, dt)
+
+
+def test_discretisation_closed_form(oracle):
+    # continuous2discrete.hpp on the white-noise-acceleration model: Fd=[[1,dt],[0,1]], Qd=q[[dt^3/3,dt^2/2],[.,dt]]
+    for q, dt in [(1.0, 0.1), (1.0, 0.5), (1.0, 1.0), (3.3, 0.25)]:
+        F, Q = oracle.discretize(q, dt)
+        assert np.array_equal(F, [[1, dt], [0, 1]])
+        np.testing.assert_allclose(Q, q * np.array([[dt**3 / 3, dt**2 / 2], [dt**2 / 2, dt]]), rtol=1e-15)
+    # SURVEY 8(c) discretisation KAT
+    _, Q = oracle.discretize(1.0, 0.1)
+    assert Q[0, 0] == pytest.approx(3.3333333333333343e-4, rel=1e-15)
+
+
+def test_control_table_accumulates_dt(oracle, golden):
+    for dt in (0.1, 0.5, 1.0):
+        u = oracle.control_table(dt)
+        assert u.shape == (2000,)
+        assert np.array_equal(u, golden[f"u_{dt}"])
+    # j += dt, NOT i*dt (system_models.hpp:54): differs from the closed form at the 1e-11 level
+    u = oracle.control_table(0.1)
+    closed = 2 * np.cos(0.75 * 0.1 * np.arange(2000))
+    assert 0 < np.abs(u - closed).max() < 1e-10
+
+
+def test_riccati_known_answers(oracle, golden):
+    tr = oracle.riccati_trace(0.1, 1.0, 0.1, 201)
+    assert rel_err(tr, golden["riccati_0.1"]) < TOL
+    # SURVEY 8(c) Riccati KAT (q=1, r=0.1, dt=0.1, P0=I)
+    assert tr[0, 0] == pytest.approx(2.0103333333333335, rel=1e-14)
+    assert tr[0, 1] == pytest.approx(0.5025700547172939, rel=1e-14)
+    assert tr[0, 2] == pytest.approx(0.05223014425468413, rel=1e-14)
+    assert tr[1, 0] == pytest.approx(1.5242945752500967, rel=1e-14)
+    assert tr[200, 0] == pytest.approx(1.2859356657862273, rel=1e-13)
+    assert tr[200, 6] == pytest.approx(0.7473678281766549, rel=1e-13)
+    tr = oracle.riccati_trace(1.0, 0.1, 0.01, 201)
+    assert rel_err(tr, golden["riccati_1.0"]) < TOL
+
+
+def test_supplied_noise_trials_match_numpy_restatement(oracle, golden):
+    B = int(golden["meta"][1])
+    for d, (dt, T) in enumerate(golden["sample_times"]):
+        for c, (qe, re) in enumerate(golden["candidates"]):
+            pt = oracle.eval_supplied(dt, int(T), qe, re, golden[f"x0noise_{d}"], golden[f"w_{d}"], golden[f"v_{d}"])
+            assert pt.shape == (4, B)
+            assert rel_err(pt, golden[f"per_trial_{d}_{c}"]) < TOL, (d, c)
+
+
+def test_cost_assembly_matches_numpy_restatement(oracle, golden):
+    B, cores = int(golden["meta"][1]), int(golden["meta"][2])
+    for d, (dt, T) in enumerate(golden["sample_times"]):
+        for c in range(len(golden["candidates"])):
+            pt = golden[f"per_trial_{d}_{c}"]
+            for i, choice in enumerate(["JNEES", "CNEES", "JNIS", "CNIS"]):
+                out = oracle.cost_from_per_trial(pt, int(T), B, cores, cost_choice=choice)
+                assert rel_err(out[:4], golden[f"avg_{d}_{c}"]) < TOL
+                assert out[4] == pytest.approx(golden[f"J_{d}_{c}"][i], rel=1e-11, abs=1e-13)
+
+
+def test_thread_chunking_integer_semantics(oracle):
+    # trial.cpp:19,28: n = nsimruns/cores trials run, but k_average = (T*nsimruns)/cores (int division of the product)
+    rng = np.random.default_rng(0)
+    T, nsim, cores = 201, 23, 4
+    n = nsim // cores
+    pt = rng.uniform(1, 3, size=(4, n * cores))
+    avg = oracle.thread_averages(pt, 0, T, nsim, cores)
+    assert avg[0] == pytest.approx(pt[0, :n].sum() / float(T * nsim // cores), rel=1e-14)
+    assert avg[2] == pytest.approx(pt[2, :n].sum() * cores / nsim, rel=1e-14)
+    assert float(T * nsim // cores) != T * n  # the reference's averages are biased when nsim % cores != 0
+
+
+def test_max_cost_takes_first_maximum(oracle):
+    assert oracle.max_cost([0.3, 0.7]) == (0.7, 1)
+    assert oracle.max_cost([0.7, 0.3]) == (0.7, 0)
+    assert oracle.max_cost([0.5, 0.5]) == (0.5, 0)     # std::max_element: first on ties (trial_node.cpp:118-119)
+    assert oracle.max_cost([0.1, 0.9, 0.9, 0.2]) == (0.9, 1)
+
+
+def test_philox4x32_10_known_answers(oracle):
+    # Random123 kat_vectors (philox4x32 10)
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+        ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+        ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+    ]
+    for ctr, key, want in kat:
+        assert tuple(int(x) for x in oracle.philox4x32_10(ctr, key)) == want
+
+
+def test_mt19937_known_answer(oracle):
+    # ISO C++ [rand.predef]: the 10000th output of a default-constructed mt19937 is 4123659995
+    assert oracle.mt19937_nth(5489, 10000) == 4123659995
+
+
+def test_normal_pair_mapping(oracle):
+    # m1 = 0 -> u1 = 1 -> radius 0
+    assert oracle.normal_pair((0, 0, 0x12345678, 0)) == (0.0, 0.0)
+    # m1 max -> u1 = 2^-52; t = 0 -> (r, 0)
+    a, b = oracle.normal_pair((0xffffffff, 0xffffffff, 0, 0))
+    assert a == pytest.approx(np.sqrt(-2 * np.log(2.0**-52)), rel=1e-15) and b == 0.0
+    # t = 1/2 (m2 = 2^50): quarter turn -> (0, r); t = 1 -> (-r, 0)
+    a, b = oracle.normal_pair((0x80000000, 0, 0x40000000, 0))
+    r = np.sqrt(-2 * np.log(0.5))
+    assert abs(a) < 1e-16 and b == pytest.approx(r, rel=1e-15)
+    a, b = oracle.normal_pair((0x80000000, 0, 0x80000000, 0))
+    assert a == pytest.approx(-r, rel=1e-15) and abs(b) < 1e-16
+    # moments of the stream
+    n = 40000
+    z = np.array([oracle.normal_pair(oracle.philox4x32_10((i, 7, 1, 0), (11, 22))) for i in range(n)]).ravel()
+    assert abs(z.mean()) < 4 / np.sqrt(2 * n)
+    assert abs(z.var() - 1) < 4 * np.sqrt(2 / (2 * n))
+    assert abs((z**4).mean() - 3) < 0.15
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 4 / np.sqrt(n)
+
+
+def test_noise_transforms_reproduce_covariance(oracle):
+    for q, dt in [(1.0, 0.1), (1.0, 1.0), (2.5, 0.5)]:
+        _, Qd = oracle.discretize(q, dt)
+        L, sr = oracle.noise_transform(Qd, 0.1 / dt)
+        Lm = np.array([[L[0], 0], [L[1], L[2]]])
+        np.testing.assert_allclose(Lm @ Lm.T, Qd, rtol=1e-14)
+        assert sr == pytest.approx(np.sqrt(0.1 / dt))
+        Tm = oracle.eig_transform2(Qd)      # eigenmvn.h:126-130
+        np.testing.assert_allclose(Tm @ Tm.T, Qd, rtol=1e-13, atol=1e-18)
+
+
+def test_philox_eval_is_shard_invariant(oracle):
+    # counters use the global trial index: evaluating [0,24) at once == [0,10) and [10,24) separately
+    args = (0x1234, 5, 0.1, 61, 1.0, 0.1, 0.7, 0.2)
+    full = oracle.eval_philox(*args, 0, 24)
+    a, b = oracle.eval_philox(*args, 0, 10), oracle.eval_philox(*args, 10, 14)
+    assert np.array_equal(full, np.concatenate([a, b], axis=1))
+    # different stream -> different draws
+    other = oracle.eval_philox(0x1234, 6, 0.1, 61, 1.0, 0.1, 0.7, 0.2, 0, 24)
+    assert not np.allclose(full, other)
+
+
+def test_statistical_anchors_philox(oracle):
+    # matched filter -> E[NEES]=2 (state dof), E[NIS]=1; q_est=0.1 -> NEES ~ 10.0 at dt=0.1
+    B, T = 4000, 201
+    pt = oracle.eval_philox(42, 0, 0.1, T, 1.0, 0.1, 1.0, 0.1, 0, B)
+    nees = pt[0] / T
+    se = nees.std(ddof=1) / np.sqrt(B)
+    assert abs(nees.mean() - 1.9988) < 5 * se
+    assert abs((pt[1] / T).mean() - 1.0) < 5 * (pt[1] / T).std(ddof=1) / np.sqrt(B)
+    assert abs(pt[2].mean() - 3.857) < 0.15 and abs(pt[3].mean() - 2.001) < 0.08
+    pt = oracle.eval_philox(42, 1, 0.1, T, 1.0, 0.1, 0.1, 0.1, 0, B)
+    nees = pt[0] / T
+    assert abs(nees.mean() - 10.035) < 5 * nees.std(ddof=1) / np.sqrt(B)
+
+
+def test_statistical_anchors_threaded_mt(oracle):
+    # the timed CPU baseline path (mt19937 + polar normals + eigen transform, threaded like trial_node.cpp:54-67)
+    out = oracle.eval_mt(0.1, 201, 1.0, 0.1, 1.0, 0.1, 8000, 8, seed=3)
+    assert abs(out[0] - 1.9988) < 0.03 and abs(out[1] - 1.0) < 0.01
+    assert out[4] == pytest.approx(abs(np.log(out[0] / 2)), rel=1e-14)
+    out = oracle.eval_mt(1.0, 201, 1.0, 0.1, 0.1, 0.1, 8000, 8, seed=4, cost_choice="JNIS")
+    assert abs(out[0] - 9.776) < 0.15
+    assert out[4] == pytest.approx(abs(np.log(out[1] / 1)), rel=1e-14)
+    with pytest.raises(ValueError):
+        oracle.eval_mt(0.1, 2001, 1.0, 0.1, 1.0, 0.1, 80, 8)   # T > 2000: control table limit
