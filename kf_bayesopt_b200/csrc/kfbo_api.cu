@@ -13,9 +13,9 @@
 #include <string>
 #include <vector>
 
-#include "kfbo_device.cuh"
 #include "kfbo_host.h"
 #include "kfbo_kernels.h"
+#include "kfbo_math.cuh"
 
 using kfbo::Case;
 
@@ -65,6 +65,7 @@ struct kfbo_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // tables
     double2 *d_gu = nullptr;          // [D][kMaxSteps] = (g0*u, g1*u)
+    kfbo::math::LogTables *d_logtab = nullptr;   // -2 ln(u) tables of the noise generator
     double truth_l[KFBO_MAX_SAMPLE_TIMES][3]{};
     double truth_sr[KFBO_MAX_SAMPLE_TIMES]{};
     double fd01[KFBO_MAX_SAMPLE_TIMES]{};
@@ -229,6 +230,7 @@ void kfbo_destroy(kfbo_handle *h)
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (int i = 0; i < 5; ++i) if (h->d_scratch[i]) cudaFree(h->d_scratch[i]);
     if (h->d_gu) cudaFree(h->d_gu);
+    if (h->d_logtab) cudaFree(h->d_logtab);
     if (h->d_cases) cudaFree(h->d_cases);
     if (h->h_cases) cudaFreeHost(h->h_cases);
     if (h->d_partials) cudaFree(h->d_partials);
@@ -292,6 +294,13 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
     }
     if (cu(cudaMalloc(&h->d_gu, gu.size() * sizeof(double2)), "cudaMalloc(gu)")) return bail(KFBO_ECUDA);
     if (cu(cudaMemcpy(h->d_gu, gu.data(), gu.size() * sizeof(double2), cudaMemcpyHostToDevice), "cudaMemcpy(gu)")) return bail(KFBO_ECUDA);
+    {
+        static kfbo::math::LogTables tabs;   // built once per process, identical for every handle
+        static bool built = false;
+        if (!built) { kfbo::math::build_log_tables(&tabs); built = true; }
+        if (cu(cudaMalloc(&h->d_logtab, sizeof tabs), "cudaMalloc(logtab)")) return bail(KFBO_ECUDA);
+        if (cu(cudaMemcpy(h->d_logtab, &tabs, sizeof tabs, cudaMemcpyHostToDevice), "cudaMemcpy(logtab)")) return bail(KFBO_ECUDA);
+    }
 
     // ---- evaluation buffers
     h->cases_cap = p->max_candidates * h->D;
@@ -355,7 +364,7 @@ int kfbo_eval_batch(kfbo_handle *h, int32_t C, const double *q_est, const double
         const int step = cases_per_launch(h, tiles);
         for (int first = 0; first < ncases; first += step) {
             const int n = std::min(step, ncases - first);
-            KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, h->d_gu, h->max_T, h->p.seed, (uint32_t)t0, ntrials,
+            KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, h->d_gu, h->d_logtab, h->max_T, h->p.seed, (uint32_t)t0, ntrials,
                                                      nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream));
             ++h->last_launches;
         }
@@ -489,7 +498,7 @@ int kfbo_eval_philox_trials(kfbo_handle *h, int32_t k, double q_est, double r_es
     unsigned *d_ticket = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(d_case) + ((sizeof(Case) + 7) / 8) * 8);
     KFBO_CUDA(h, cudaMemcpyAsync(d_case, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     KFBO_CUDA(h, cudaMemsetAsync(d_ticket, 0, sizeof(unsigned), h->stream));
-    KFBO_CUDA(h, kfbo::launch_rollout_philox(d_case, 1, h->d_gu, h->max_T, h->p.seed, trial0, (uint32_t)ntrials, h->d_scratch[4],
+    KFBO_CUDA(h, kfbo::launch_rollout_philox(d_case, 1, h->d_gu, h->d_logtab, h->max_T, h->p.seed, trial0, (uint32_t)ntrials, h->d_scratch[4],
                                              (size_t)ntrials, d_partials, d_ticket, d_sums, h->stream));
     KFBO_CUDA(h, cudaMemcpyAsync(per_trial, h->d_scratch[4], 4 * (size_t)ntrials * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     KFBO_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -12,69 +12,43 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "kfbo_kernels.h"
+#include "kfbo_math.cuh"
+
 namespace kfbo {
-
-constexpr int kThreads = 128;        // threads per CTA (4 warps, one per SMSP)
-constexpr int kMaxSteps = 2000;      // include/system_models.hpp:51
-
-// Constants of one (candidate, sample time) pair, built on the host (kfbo_host.h).
-// The robot1d model has Fd = [[1, f],[0, 1]] and H = [1 0] exactly
-// (include/system_models.hpp:35-37,141-142 through continuous2discrete.hpp:8-32), so the
-// products with the structural 0/1 entries are dropped: x*1 and x+0*y are exact in IEEE-754,
-// the results are bit-identical to the dense 2x2 products for finite values.
-struct Case {
-    double f;                    // Fd(0,1) = dt
-    double q00, q01, q10, q11;   // estimator Qd (kalman_filter.cpp:23)
-    double r_est;                // estimator R = onoise_est/dt (system_models.hpp:143)
-    double l00, l10, l11;        // Cholesky factor of the truth Qd  (replaces eigenmvn.h:126-130)
-    double sr;                   // sqrt(truth R)
-    int32_t T;                   // max_iterations_
-    int32_t k;                   // sample-time index (selects the g*u table)
-    uint32_t stream;             // Philox stream of this (evaluation, candidate, sample time)
-    int32_t out_slot;            // row of the [n][4] sums / per-trial output this case writes
-};
 
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Counter-based: no state, no races -- replaces the
 // process-wide static std::mt19937 of include/eigenmvn.h:51,62.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1)
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &key)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t lo0 = 0xD2511F53u * c0, hi0 = __umulhi(0xD2511F53u, c0);
         const uint32_t lo1 = 0xCD9E8D57u * c2, hi1 = __umulhi(0xCD9E8D57u, c2);
-        c0 = hi1 ^ c1 ^ k0;
+        c0 = hi1 ^ c1 ^ key.k0[r];
         c1 = lo1;
-        c2 = hi0 ^ c3 ^ k1;
+        c2 = hi0 ^ c3 ^ key.k1[r];
         c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
 }
 
-// 128 random bits -> two independent N(0,1) draws (Box-Muller), bit-manipulated so that no
-// int->double conversion is needed:
-//   m1 = top 52 bits of (x:y), m2 = top 52 bits of (z:w)
-//   u1 = 1 - m1*2^-52 in [2^-52, 1]      (= 2 - [1,2))
-//   t  = m2*2^-51     in [0, 2)          (= [2,4) - 2)
-//   na = sqrt(-2 ln u1) cos(pi t),  nb = sqrt(-2 ln u1) sin(pi t)
-__device__ __forceinline__ void normal_pair(uint4 r, double &na, double &nb)
+// 128 random bits -> two independent N(0,1) draws: the spec is in kfbo_math.cuh (normal_pair_bits).
+__device__ __forceinline__ void normal_pair(uint4 r, const double (*logtab)[2], const double *ktab, double &na, double &nb)
 {
-    const uint32_t hi1 = 0x3FF00000u | (r.x >> 12);
-    const uint32_t lo1 = (r.x << 20) | (r.y >> 12);
-    const uint32_t hi2 = 0x40000000u | (r.z >> 12);
-    const uint32_t lo2 = (r.z << 20) | (r.w >> 12);
-    const double u1 = 2.0 - __hiloint2double((int)hi1, (int)lo1);
-    const double t = __hiloint2double((int)hi2, (int)lo2) - 2.0;
-    const double rad = sqrt(-2.0 * log(u1));
-    double s, c;
-    sincospi(t, &s, &c);
-    na = rad * c;
-    nb = rad * s;
+    math::normal_pair_bits(r.x, r.y, r.z, r.w, logtab, ktab, na, nb);
 }
+
+// 1/S and 1/det(P): S and det(P) come out of a covariance recursion and are normal, well-scaled
+// numbers, so the division's slow path (denormal / huge operands) is never needed; two Newton steps
+// on the MUFU seed give <= 1 ulp.  -DKFBO_EXACT_DIV restores the correctly rounded IEEE division.
+#if defined(KFBO_EXACT_DIV)
+#define KFBO_RCP(x) (1.0 / (x))
+#else
+#define KFBO_RCP(x) ::kfbo::math::rcp(x)
+#endif
 
 // Per-trajectory register state.
 struct Traj {
@@ -115,7 +89,7 @@ __device__ __forceinline__ void filter_step(Traj &t, const Case &m, double2 gu, 
     const double pp11 = t.p11 + m.q11;
     // ---- gain: c = Ppred H^T ; S = H c + R ; K = c * (1/S)
     const double s = pp00 + m.r_est;
-    const double sinv = 1.0 / s;
+    const double sinv = KFBO_RCP(s);      // sob_.inverse() of a 1x1 (kalman_filter.cpp:28)
     const double k0 = pp00 * sinv;
     const double k1 = pp10 * sinv;
     // ---- update: nu = z - H xpred ; xest = xpred + K nu ; P = (I - K H) Ppred
@@ -130,16 +104,17 @@ __device__ __forceinline__ void filter_step(Traj &t, const Case &m, double2 gu, 
     // ---- NEES = (e^T P^-1) e with the closed-form 2x2 inverse; NIS = (nu / S) nu
     const double e0 = t.x0 - t.xh0, e1 = t.x1 - t.xh1;
     const double det = fma(t.p00, t.p11, -(t.p10 * t.p01));
-    const double invdet = 1.0 / det;
+    const double invdet = KFBO_RCP(det);
     const double i00 = t.p11 * invdet, i01 = -t.p01 * invdet;
     const double i10 = -t.p10 * invdet, i11 = t.p00 * invdet;
     const double r0 = fma(e1, i10, e0 * i00);
     const double r1 = fma(e1, i11, e0 * i01);
-    const double nees = fma(r1, e1, r0 * e0);
-    const double nis = (nu * sinv) * nu;
-    // ---- accumulate, shifted by the first sample of the trial
-    if (kFirst) { t.kn = nees; t.ki = nis; }
-    const double dn = nees - t.kn, di = nis - t.ki;
+    const double nu_s = nu * sinv;
+    // ---- accumulate, shifted by the first sample of the trial (kn, ki): the shifted values
+    // nees - kn and nis - ki come straight out of the last fused multiply-add of each form
+    if (kFirst) { t.kn = fma(r1, e1, r0 * e0); t.ki = nu_s * nu; }
+    const double dn = fma(r1, e1, fma(r0, e0, -t.kn));
+    const double di = fma(nu_s, nu, -t.ki);
     t.sdn += dn; t.sqn = fma(dn, dn, t.sqn);
     t.sdi += di; t.sqi = fma(di, di, t.sqi);
 }

@@ -72,19 +72,26 @@ __device__ __forceinline__ void block_reduce_and_publish(const double out[4], in
 //                          step 2p uses n0,n1 (process) n2 (observation); step 2p+1 uses n3,n4,n5
 // -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-rollout_philox(const Case *__restrict__ cases, const double2 *__restrict__ gu_tables, uint32_t key0, uint32_t key1,
-               uint32_t trial0, uint32_t ntrials, int tiles, double *__restrict__ per_trial, size_t per_trial_ld,
-               double *__restrict__ partials, unsigned *__restrict__ tickets, double *__restrict__ sums)
+rollout_philox(const Case *__restrict__ cases, const double2 *__restrict__ gu_tables,
+               const math::LogTables *__restrict__ logtab, const PhiloxKeys key, uint32_t trial0, uint32_t ntrials,
+               int tiles, double *__restrict__ per_trial, size_t per_trial_ld, double *__restrict__ partials,
+               unsigned *__restrict__ tickets, double *__restrict__ sums)
 {
     extern __shared__ double2 s_gu[];
+    __shared__ math::LogTables s_log;
     const int case_idx = blockIdx.x / tiles, tile = blockIdx.x - case_idx * tiles;
     const Case m = cases[case_idx];
     const int T = m.T;
     {
         const double2 *src = gu_tables + (size_t)m.k * kMaxSteps;
         for (int i = threadIdx.x; i < T; i += kThreads) s_gu[i] = src[i];
+        const double *ls = reinterpret_cast<const double *>(logtab);
+        double *ld = reinterpret_cast<double *>(&s_log);
+        for (int i = threadIdx.x; i < (int)(sizeof(math::LogTables) / sizeof(double)); i += kThreads) ld[i] = ls[i];
     }
     __syncthreads();
+    const double (*lt)[2] = s_log.invc_logc;
+    const double *kt = s_log.k2ln2;
 
     const uint32_t local = (uint32_t)tile * kThreads + threadIdx.x;
     const bool active = local < ntrials;
@@ -94,15 +101,15 @@ rollout_philox(const Case *__restrict__ cases, const double2 *__restrict__ gu_ta
         Traj t;
         {
             double a, b;
-            normal_pair(philox4x32_10(trial, m.stream, 0u, 0u, key0, key1), a, b);
+            normal_pair(philox4x32_10(trial, m.stream, 0u, 0u, key), lt, kt, a, b);
             traj_init(t, a, b);
         }
         const int npairs = T >> 1;
         for (int p = 0; p < npairs; ++p) {
             double n0, n1, n2, n3, n4, n5;
-            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)p + 1u, 0u, key0, key1), n0, n1);
-            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)p + 1u, 1u, key0, key1), n2, n3);
-            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)p + 1u, 2u, key0, key1), n4, n5);
+            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)p + 1u, 0u, key), lt, kt, n0, n1);
+            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)p + 1u, 1u, key), lt, kt, n2, n3);
+            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)p + 1u, 2u, key), lt, kt, n4, n5);
             const double2 g0 = s_gu[2 * p], g1 = s_gu[2 * p + 1];
             if (p == 0)
                 filter_step<true>(t, m, g0, m.l00 * n0, fma(m.l11, n1, m.l10 * n0), m.sr * n2);
@@ -112,8 +119,8 @@ rollout_philox(const Case *__restrict__ cases, const double2 *__restrict__ gu_ta
         }
         if (T & 1) {
             double n0, n1, n2, n3;
-            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)npairs + 1u, 0u, key0, key1), n0, n1);
-            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)npairs + 1u, 1u, key0, key1), n2, n3);
+            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)npairs + 1u, 0u, key), lt, kt, n0, n1);
+            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)npairs + 1u, 1u, key), lt, kt, n2, n3);
             filter_step<false>(t, m, s_gu[T - 1], m.l00 * n0, fma(m.l11, n1, m.l10 * n0), m.sr * n2);
         }
         traj_finish(t, T, out);
@@ -218,16 +225,28 @@ __global__ void __launch_bounds__(256) dfma_chain(double *out, int iters, double
 }
 
 // ------------------------------- launchers (host) -------------------------------------------
-cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const double2 *d_gu, int max_T, uint64_t seed,
-                                  uint32_t trial0, uint32_t ntrials, double *d_per_trial, size_t per_trial_ld,
-                                  double *d_partials, unsigned *d_tickets, double *d_sums, cudaStream_t stream)
+PhiloxKeys expand_philox_key(uint64_t seed)
+{
+    PhiloxKeys k;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        k.k0[r] = k0; k.k1[r] = k1;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;   // Weyl sequence of Philox4x32
+    }
+    return k;
+}
+
+cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const double2 *d_gu, const void *d_logtab, int max_T,
+                                  uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
+                                  size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
+                                  cudaStream_t stream)
 {
     if (ncases <= 0 || ntrials == 0) return cudaSuccess;
     const int tiles = (int)((ntrials + kThreads - 1) / kThreads);
     const size_t smem = (size_t)max_T * sizeof(double2);
     rollout_philox<<<(unsigned)(ncases * (size_t)tiles), kThreads, smem, stream>>>(
-        d_cases, d_gu, (uint32_t)seed, (uint32_t)(seed >> 32), trial0, ntrials, tiles, d_per_trial, per_trial_ld,
-        d_partials, d_tickets, d_sums);
+        d_cases, d_gu, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0, ntrials, tiles,
+        d_per_trial, per_trial_ld, d_partials, d_tickets, d_sums);
     return cudaGetLastError();
 }
 

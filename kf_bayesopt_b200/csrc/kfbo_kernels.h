@@ -6,14 +6,40 @@
 
 namespace kfbo {
 
-struct Case;  // kfbo_device.cuh
+constexpr int kThreads = 128;        // threads per CTA (4 warps, one per SMSP)
+constexpr int kMaxSteps = 2000;      // include/system_models.hpp:51
 
-// d_cases[ncases]; d_gu[D][kMaxSteps] = (g0*u, g1*u); trials [trial0, trial0+ntrials).
-// d_per_trial (optional) is [slots][4][per_trial_ld]; d_partials [ncases][tiles][4];
-// d_tickets [ncases] zero-initialised once; d_sums [slots][4].
-cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const double2 *d_gu, int max_T, uint64_t seed,
-                                  uint32_t trial0, uint32_t ntrials, double *d_per_trial, size_t per_trial_ld,
-                                  double *d_partials, unsigned *d_tickets, double *d_sums, cudaStream_t stream);
+// Constants of one (candidate, sample time) pair, built on the host (kfbo_api.cu: build_case).
+// The robot1d model has Fd = [[1, f],[0, 1]] and H = [1 0] exactly
+// (include/system_models.hpp:35-37,141-142 through continuous2discrete.hpp:8-32), so the
+// products with the structural 0/1 entries are dropped: x*1 and x+0*y are exact in IEEE-754,
+// the results are bit-identical to the dense 2x2 products for finite values.
+struct Case {
+    double f;                    // Fd(0,1) = dt
+    double q00, q01, q10, q11;   // estimator Qd (kalman_filter.cpp:23)
+    double r_est;                // estimator R = onoise_est/dt (system_models.hpp:143)
+    double l00, l10, l11;        // Cholesky factor of the truth Qd  (replaces eigenmvn.h:126-130)
+    double sr;                   // sqrt(truth R)
+    int32_t T;                   // max_iterations_
+    int32_t k;                   // sample-time index (selects the g*u table)
+    uint32_t stream;             // Philox stream of this (evaluation, candidate, sample time)
+    int32_t out_slot;            // row of the [n][4] sums / per-trial output this case writes
+};
+
+// The 10 Philox4x32 round keys (key + r*Weyl), expanded on the host so the kernel reads them from
+// the parameter bank instead of re-deriving them per call.
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+PhiloxKeys expand_philox_key(uint64_t seed);
+
+// d_cases[ncases]; d_gu[D][kMaxSteps] = (g0*u, g1*u); d_logtab = math::LogTables on the device;
+// trials [trial0, trial0+ntrials).  d_per_trial (optional) is [slots][4][per_trial_ld];
+// d_partials [ncases][tiles][4]; d_tickets [ncases] zero-initialised once; d_sums [slots][4].
+cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const double2 *d_gu, const void *d_logtab, int max_T,
+                                  uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
+                                  size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
+                                  cudaStream_t stream);
 
 cudaError_t launch_rollout_supplied(const Case *d_cases, int ncases, const double2 *d_gu, int max_T, const double *d_x0noise,
                                     const double *d_w, const double *d_v, size_t B, double *d_per_trial,

@@ -403,13 +403,15 @@ class RunTrial:
 
     def __init__(self, rv: Optional[ReadParaVehicle] = None, second_sample_time=CODE_SECOND_SAMPLE_TIME,
                  n_init_samples: int = 20, publish=None, device: int = -1, seed: int = 0x4B46424F20260101,
-                 verbose: bool = False):
+                 verbose: bool = False, evaluator: Optional[CostEvaluator] = None):
         self.rv_ = rv or ReadParaVehicle()
         self.n_init_samples_ = n_init_samples                     # rb_.n_init_samples_ (trial_node.cpp:121)
         self.it_count_ = self.dt0_count_ = self.dt1_count_ = 0    # trial_node.cpp:140
         self.publish_, self.verbose_ = publish, verbose
         self.last_result: Optional[Result] = None
-        self._ev = CostEvaluator(self.rv_, sample_times_from(self.rv_, second_sample_time), seed=seed, device=device)
+        # the device-side batch launcher; built once, not per callback like the reference's vector<Trial>
+        self._ev = evaluator or CostEvaluator(self.rv_, sample_times_from(self.rv_, second_sample_time), seed=seed,
+                                              device=device)
 
     def ProcessNoiseCallback(self, msg: Float64MultiArray) -> Float64:
         npn = msg.layout.dim[0].size                               # trial_node.cpp:29

@@ -287,27 +287,30 @@ void ko_philox4x32_10(const uint32_t *ctr, const uint32_t *key, uint32_t *out)
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* 128 random bits -> two independent standard normals (Box-Muller):
- * m1 = top 52 bits of (w0:w1), m2 = top 52 bits of (w2:w3);
- * u1 = 1 - m1*2^-52 in [2^-52, 1], t = m2*2^-51 in [0, 2);
- * n_a = sqrt(-2 ln u1) cos(pi t), n_b = sqrt(-2 ln u1) sin(pi t). */
+/* 128 random bits -> two independent standard normals (Box-Muller), the product's spec:
+ *   radius: m1 = top 52 bits of (w0:w1) with the lowest bit forced to 1;
+ *           u1 = 1 - m1*2^-52 in [2^-52, 1-2^-52];  rad = sqrt(-2 ln u1)
+ *   angle : o = top 3 bits of w2 (octant), f = next 52 bits of (w2:w3) * 2^-52 in [0,1);
+ *           theta = (pi/4)(o + f)
+ *   n_a = rad cos(theta), n_b = rad sin(theta)
+ * theta is reduced to its octant exactly (1-f is exact) so libm sees |arg| <= pi/4. */
 void ko_normal_pair(const uint32_t *w, double *na, double *nb)
 {
-    const uint64_t m1 = ((uint64_t)w[0] << 20) | (w[1] >> 12);
-    const uint64_t m2 = ((uint64_t)w[2] << 20) | (w[3] >> 12);
+    const uint64_t m1 = (((uint64_t)w[0] << 20) | (w[1] >> 12)) | 1u;
     const double u1 = 1.0 - (double)m1 * 0x1p-52;
-    const double t = (double)m2 * 0x1p-51;
     const double r = sqrt(-2.0 * log(u1));
-    /* exact quadrant reduction so that libm's sin/cos see |arg| <= pi/4 */
-    const double q = floor(t * 2.0 + 0.5); /* nearest multiple of 1/2 */
-    const double f = t - q * 0.5;          /* exact, |f| <= 1/4 */
-    const double s = sin(M_PI * f), c = cos(M_PI * f);
+    const unsigned o = w[2] >> 29;
+    const uint64_t fbits = ((uint64_t)(w[2] & 0x1FFFFFFFu) << 23) | (w[3] >> 9);
+    const double f = (double)fbits * 0x1p-52;
+    const double x = (o & 1u) ? 1.0 - f : f;           /* position inside the octant, mirrored for odd octants */
+    const double sx = sin(M_PI_4 * x), cx = cos(M_PI_4 * x);
+    const double sa = (o & 1u) ? cx : sx, ca = (o & 1u) ? sx : cx; /* angle within the quadrant */
     double sn, cs;
-    switch ((int)q & 3) {
-    case 0: sn = s; cs = c; break;
-    case 1: sn = c; cs = -s; break;
-    case 2: sn = -s; cs = -c; break;
-    default: sn = -c; cs = s; break;
+    switch (o >> 1) {
+    case 0: sn = sa; cs = ca; break;
+    case 1: sn = ca; cs = -sa; break;
+    case 2: sn = -sa; cs = -ca; break;
+    default: sn = -ca; cs = sa; break;
     }
     *na = r * cs;
     *nb = r * sn;
