@@ -17,7 +17,8 @@ COST_CHOICES = {"JNEES": JNEES, "CNEES": CNEES, "JNIS": JNIS, "CNIS": CNIS}
 SHARD_TRIALS, SHARD_CANDIDATES = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkfbo.so")
+# KFBO_LIB_PATH: load another build of the same library (kernel tuning experiments only)
+LIB_PATH = os.environ.get("KFBO_LIB_PATH") or os.path.join(_HERE, "libkfbo.so")
 
 
 class KfboParams(C.Structure):

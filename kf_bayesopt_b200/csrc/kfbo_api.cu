@@ -70,6 +70,7 @@ struct kfbo_handle {
     double truth_sr[KFBO_MAX_SAMPLE_TIMES]{};
     double fd01[KFBO_MAX_SAMPLE_TIMES]{};
     int max_T = 0;
+    kfbo::SampleTimeConsts st{};       // per-sample-time constants, passed to the kernels by value
     // per-evaluation buffers (sized at create)
     Case *d_cases = nullptr, *h_cases = nullptr;
     int cases_cap = 0;
@@ -155,9 +156,11 @@ int cases_per_launch(const kfbo_handle *h, int tiles)
     size_t n = h->partials_cap / per_case;
     if (n < 1) n = 1;
     if (n > (size_t)h->cases_cap) n = (size_t)h->cases_cap;
-    // keep the 1-D grid below 2^31-1 blocks
-    const size_t grid_cap = 0x7fffffffu / (size_t)tiles;
-    if (n > grid_cap) n = grid_cap;
+    // whole candidates only (grid.z = D sample times per candidate), grid.y <= 65535 candidates
+    const size_t D = (size_t)h->D;
+    if (n > 65535 * D) n = 65535 * D;
+    n = n / D * D;
+    if (n < D) n = D;
     return (int)n;
 }
 
@@ -290,6 +293,8 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
         h->truth_l[k][1] = Qd[2] / h->truth_l[k][0];
         h->truth_l[k][2] = std::sqrt(Qd[3] - h->truth_l[k][1] * h->truth_l[k][1]);
         h->truth_sr[k] = std::sqrt(p->onoise_truth / dt);  // R = onoise/dt (system_models.hpp:143)
+        h->st.f[k] = Fd[1]; h->st.l00[k] = h->truth_l[k][0]; h->st.l10[k] = h->truth_l[k][1];
+        h->st.l11[k] = h->truth_l[k][2]; h->st.sr[k] = h->truth_sr[k];
         h->max_T = std::max(h->max_T, p->max_iterations[k]);
     }
     if (cu(cudaMalloc(&h->d_gu, gu.size() * sizeof(double2)), "cudaMalloc(gu)")) return bail(KFBO_ECUDA);
@@ -307,7 +312,7 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
     const int tiles = kfbo::rollout_tiles((size_t)h->b_eff);
     size_t part = (size_t)h->cases_cap * tiles * 4;
     const size_t budget = kPartialsBudgetBytes / sizeof(double);
-    if (part > budget) part = std::max(budget, (size_t)tiles * 4);
+    if (part > budget) part = std::max(budget, (size_t)tiles * 4 * h->D);   // at least one whole candidate per launch
     h->partials_cap = part;
     if (cu(cudaMalloc(&h->d_cases, h->cases_cap * sizeof(Case)), "cudaMalloc(cases)") ||
         cu(cudaMallocHost(&h->h_cases, h->cases_cap * sizeof(Case)), "cudaMallocHost(cases)") ||
@@ -360,11 +365,13 @@ int kfbo_eval_batch(kfbo_handle *h, int32_t C, const double *q_est, const double
     KFBO_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     const uint32_t ntrials = (uint32_t)(t1 - t0);
     if (ncases > 0 && ntrials > 0) {
-        const int tiles = kfbo::rollout_tiles(ntrials);
+        const int tiles = kfbo::philox_tiles(ntrials);
         const int step = cases_per_launch(h, tiles);
         for (int first = 0; first < ncases; first += step) {
             const int n = std::min(step, ncases - first);
-            KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, h->d_gu, h->d_logtab, h->max_T, h->p.seed, (uint32_t)t0, ntrials,
+            kfbo::SampleTimeConsts st = h->st;
+            st.k0 = 0; st.nk = D;   // cases are laid out [candidate][sample time]; chunks hold whole candidates
+            KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, st, h->d_gu, h->d_logtab, h->max_T, h->p.seed, (uint32_t)t0, ntrials,
                                                      nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream));
             ++h->last_launches;
         }
@@ -411,7 +418,7 @@ static int supplied_impl(kfbo_handle *h, int32_t k, int32_t C, const double *q_e
                          double *h_per_trial, double *sums)
 {
     const int tiles = kfbo::rollout_tiles((size_t)B);
-    if ((size_t)C > (size_t)0x7fffffff / (size_t)tiles) return fail(h, KFBO_ERANGE, "supplied: grid too large");
+    if (C > 65535) return fail(h, KFBO_ERANGE, "kfbo_eval_supplied: at most 65535 candidates per call");
     std::vector<Case> cases((size_t)C);
     for (int c = 0; c < C; ++c) {
         const int rc = build_case(h, k, q_est[c], r_est[c], 0u, c, &cases[c]);
@@ -426,7 +433,9 @@ static int supplied_impl(kfbo_handle *h, int32_t k, int32_t C, const double *q_e
     KFBO_CUDA(h, cudaMemcpyAsync(d_cases, cases.data(), (size_t)C * sizeof(Case), cudaMemcpyHostToDevice, h->stream));
     KFBO_CUDA(h, cudaMemsetAsync(d_tickets, 0, (size_t)C * sizeof(unsigned), h->stream));
     KFBO_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    KFBO_CUDA(h, kfbo::launch_rollout_supplied(d_cases, C, h->d_gu, h->p.max_iterations[k], d_x0, d_w, d_v, (size_t)B, d_per_trial,
+    kfbo::SampleTimeConsts st = h->st;
+    st.k0 = k; st.nk = 1;
+    KFBO_CUDA(h, kfbo::launch_rollout_supplied(d_cases, C, st, h->d_gu, h->p.max_iterations[k], d_x0, d_w, d_v, (size_t)B, d_per_trial,
                                                d_partials, d_tickets, d_sums, h->stream));
     KFBO_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     h->last_launches = 1;
@@ -498,7 +507,9 @@ int kfbo_eval_philox_trials(kfbo_handle *h, int32_t k, double q_est, double r_es
     unsigned *d_ticket = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(d_case) + ((sizeof(Case) + 7) / 8) * 8);
     KFBO_CUDA(h, cudaMemcpyAsync(d_case, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     KFBO_CUDA(h, cudaMemsetAsync(d_ticket, 0, sizeof(unsigned), h->stream));
-    KFBO_CUDA(h, kfbo::launch_rollout_philox(d_case, 1, h->d_gu, h->d_logtab, h->max_T, h->p.seed, trial0, (uint32_t)ntrials, h->d_scratch[4],
+    kfbo::SampleTimeConsts st = h->st;
+    st.k0 = k; st.nk = 1;
+    KFBO_CUDA(h, kfbo::launch_rollout_philox(d_case, 1, st, h->d_gu, h->d_logtab, h->max_T, h->p.seed, trial0, (uint32_t)ntrials, h->d_scratch[4],
                                              (size_t)ntrials, d_partials, d_ticket, d_sums, h->stream));
     KFBO_CUDA(h, cudaMemcpyAsync(per_trial, h->d_scratch[4], 4 * (size_t)ntrials * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     KFBO_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -20,13 +20,35 @@ namespace kfbo {
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Counter-based: no state, no races -- replaces the
 // process-wide static std::mt19937 of include/eigenmvn.h:51,62.
+//
+// Cost on B200 (tools/microbench/imad_wide.cu): the 32x32->64 multiply IMAD.WIDE.U32 takes ~5
+// cycles per warp on a pipe it SHARES with FP64 (it does not overlap with DFMA), IMAD.HI.U32 ~4,
+// while the 32-bit IMAD (low half) takes 2 cycles on a pipe that does overlap.  One Philox call is
+// 20 such multiplies = 80-100 FP64-pipe cycles, as much as 45 DFMAs -- random bits are the
+// expensive resource of this kernel, which is why a normal pair consumes 84 of them, not 128.
 // ---------------------------------------------------------------------------------------
+#ifndef KFBO_PHILOX_SPLIT_MUL
+#define KFBO_PHILOX_SPLIT_MUL 1
+#endif
+__device__ __forceinline__ void mulhilo32(uint32_t m, uint32_t a, uint32_t &hi, uint32_t &lo)
+{
+#if KFBO_PHILOX_SPLIT_MUL
+    // keep the halves apart: IMAD.HI (shared pipe, 4 cycles) + IMAD (free pipe) beats IMAD.WIDE (5)
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(a), "r"(m));
+    asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(lo) : "r"(a), "r"(m));
+#else
+    lo = m * a;
+    hi = __umulhi(m, a);
+#endif
+}
+
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &key)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t lo0 = 0xD2511F53u * c0, hi0 = __umulhi(0xD2511F53u, c0);
-        const uint32_t lo1 = 0xCD9E8D57u * c2, hi1 = __umulhi(0xCD9E8D57u, c2);
+        uint32_t lo0, hi0, lo1, hi1;
+        mulhilo32(0xD2511F53u, c0, hi0, lo0);
+        mulhilo32(0xCD9E8D57u, c2, hi1, lo1);
         c0 = hi1 ^ c1 ^ key.k0[r];
         c1 = lo1;
         c2 = hi0 ^ c3 ^ key.k1[r];
@@ -35,10 +57,14 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
-// 128 random bits -> two independent N(0,1) draws: the spec is in kfbo_math.cuh (normal_pair_bits).
-__device__ __forceinline__ void normal_pair(uint4 r, const double (*logtab)[2], const double *ktab, double &na, double &nb)
+// The random words of one step pair: two Philox calls A, B -> three normal pairs
+//   pair 0: radius (A.x : A.w[31:12]), angle A.y      pair 1: radius (B.x : B.w[31:12]), angle B.y
+//   pair 2: radius (A.z : A.w[11:0] B.w[7:0]), angle B.z
+__device__ __forceinline__ void normals_of_pair(const uint4 &A, const uint4 &B, const double (*lt)[2], const double *kt, double n[6])
 {
-    math::normal_pair_bits(r.x, r.y, r.z, r.w, logtab, ktab, na, nb);
+    math::normal_pair_bits(A.x, A.w >> 12, A.y, lt, kt, n[0], n[1]);
+    math::normal_pair_bits(B.x, B.w >> 12, B.y, lt, kt, n[2], n[3]);
+    math::normal_pair_bits(A.z, ((A.w & 0xFFFu) << 8) | (B.w & 0xFFu), B.z, lt, kt, n[4], n[5]);
 }
 
 // 1/S and 1/det(P): S and det(P) come out of a covariance recursion and are normal, well-scaled
@@ -71,21 +97,22 @@ __device__ __forceinline__ void traj_init(Traj &t, double x0n0, double x0n1)
 
 // One filter-step: truth step, Kalman predict/update, NEES/NIS accumulation.
 // gu = g*u[step] = (0.5 dt^2 u, dt u), rounded products exactly as the reference forms them.
+// f = Fd(0,1) comes in as a uniform value (SampleTimeConsts), the candidate's Qd / R from the Case.
 template <bool kFirst>
-__device__ __forceinline__ void filter_step(Traj &t, const Case &m, double2 gu, double w0, double w1, double v)
+__device__ __forceinline__ void filter_step(Traj &t, const Case &m, const double f, double2 gu, double w0, double w1, double v)
 {
     // ---- truth: x = Fd x + g u + w ; z = H x + v
-    t.x0 = (fma(m.f, t.x1, t.x0) + gu.x) + w0;
+    t.x0 = (fma(f, t.x1, t.x0) + gu.x) + w0;
     t.x1 = (t.x1 + gu.y) + w1;
     const double z = t.x0 + v;
     // ---- predict: xpred = Fd xest + g u ; Ppred = (Fd P) Fd^T + Qd
-    const double xp0 = fma(m.f, t.xh1, t.xh0) + gu.x;
+    const double xp0 = fma(f, t.xh1, t.xh0) + gu.x;
     const double xp1 = t.xh1 + gu.y;
-    const double fp00 = fma(m.f, t.p10, t.p00);
-    const double fp01 = fma(m.f, t.p11, t.p01);
-    const double pp00 = fma(fp01, m.f, fp00) + m.q00;
+    const double fp00 = fma(f, t.p10, t.p00);
+    const double fp01 = fma(f, t.p11, t.p01);
+    const double pp00 = fma(fp01, f, fp00) + m.q00;
     const double pp01 = fp01 + m.q01;
-    const double pp10 = fma(t.p11, m.f, t.p10) + m.q10;
+    const double pp10 = fma(t.p11, f, t.p10) + m.q10;
     const double pp11 = t.p11 + m.q11;
     // ---- gain: c = Ppred H^T ; S = H c + R ; K = c * (1/S)
     const double s = pp00 + m.r_est;

@@ -3,13 +3,22 @@
 //   rollout_philox    on-device Philox4x32-10 + Box-Muller noise (FP64-pipe bound)
 //   rollout_supplied  noise streamed from HBM, SoA [step][component][trial] (HBM bound)
 //
-// Grid: 1-D, block b -> (case = b / tiles, tile = b % tiles); one trajectory per thread.
+// Grid: (tiles, candidates, sample times): blockIdx.y/z give the case without any division, so the
+// case and its sample-time constants are provably uniform (uniform registers / parameter bank).
 // Reduction: warp shuffle -> shared -> one [4] partial per CTA -> the LAST CTA of each case
 // (ticket counter) sums the partials in a fixed order, so sums are deterministic run to run.
 #include "kfbo_device.cuh"
 #include "kfbo_kernels.h"
 
 namespace kfbo {
+
+// Select entry k of a small per-sample-time table held in the parameter bank WITHOUT dynamic
+// indexing: a register-indexed LDC lands in a vector register, a chain of selects on the uniform
+// blockIdx.z stays in the uniform datapath.
+__device__ __forceinline__ double pick4(const double (&a)[4], unsigned k)
+{
+    return k == 0 ? a[0] : k == 1 ? a[1] : k == 2 ? a[2] : a[3];
+}
 
 // CTA partial -> global; last CTA of the case reduces all partials of the case in fixed order.
 __device__ __forceinline__ void block_reduce_and_publish(const double out[4], int case_idx, int tile, int tiles,
@@ -67,23 +76,42 @@ __device__ __forceinline__ void block_reduce_and_publish(const double out[4], in
 // -----------------------------------------------------------------------------------------
 // Philox rollout.  Noise stream layout (restated draw for draw by oracle/kfbo_oracle.c):
 //   key = (seed_lo, seed_hi); counter = (trial, case.stream, block, sub)
-//   block 0, sub 0      -> the N(0,P0) draw added to x0
-//   block p+1, sub j<3  -> normals n[2j], n[2j+1] of the step pair (2p, 2p+1):
+//   block 0, sub 0      -> the N(0,P0) draw added to x0 (radius x : w[31:12], angle y)
+//   block p+1, sub 0,1  -> calls A, B of the step pair (2p, 2p+1) -> normals n0..n5 (normals_of_pair):
 //                          step 2p uses n0,n1 (process) n2 (observation); step 2p+1 uses n3,n4,n5
 // -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-rollout_philox(const Case *__restrict__ cases, const double2 *__restrict__ gu_tables,
-               const math::LogTables *__restrict__ logtab, const PhiloxKeys key, uint32_t trial0, uint32_t ntrials,
+// kPhiloxPerThread independent trajectories (adjacent tiles of the same case) advance in lock-step
+// in every thread.  Measured on B200 (tools/microbench/fp64_latency.cu): DFMA has an 8-cycle
+// dependent latency and the FP64 pipe only reaches its 2-cycles-per-warp-instruction peak when each
+// warp offers several INDEPENDENT FP64 instructions back to back (1 chain/warp: 3.2 cycles per DFMA
+// even with 8 warps per scheduler; 2 chains: 2.6; 4 chains: 2.25).  The filter recursion is one
+// long dependent chain per trajectory, so the second trajectory supplies the missing ILP.
+#ifndef KFBO_PHILOX_PER_THREAD
+#define KFBO_PHILOX_PER_THREAD 2
+#endif
+#ifndef KFBO_PHILOX_MIN_BLOCKS
+#define KFBO_PHILOX_MIN_BLOCKS 1
+#endif
+constexpr int kPhiloxPerThread = KFBO_PHILOX_PER_THREAD;
+
+__global__ void __launch_bounds__(kThreads, KFBO_PHILOX_MIN_BLOCKS)
+rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTimeConsts st,
+               const double2 *__restrict__ gu_tables, const math::LogTables *__restrict__ logtab,
+               const __grid_constant__ PhiloxKeys key, uint32_t trial0, uint32_t ntrials,
                int tiles, double *__restrict__ per_trial, size_t per_trial_ld, double *__restrict__ partials,
                unsigned *__restrict__ tickets, double *__restrict__ sums)
 {
+    constexpr int K = kPhiloxPerThread;
     extern __shared__ double2 s_gu[];
     __shared__ math::LogTables s_log;
-    const int case_idx = blockIdx.x / tiles, tile = blockIdx.x - case_idx * tiles;
+    const int case_idx = blockIdx.y * gridDim.z + blockIdx.z, tile = blockIdx.x;
     const Case m = cases[case_idx];
     const int T = m.T;
+    const unsigned kk = st.k0 + blockIdx.z;   // == m.k, but provably uniform
+    const double f = pick4(st.f, kk), l00 = pick4(st.l00, kk), l10 = pick4(st.l10, kk), l11 = pick4(st.l11, kk),
+                 sr = pick4(st.sr, kk);
     {
-        const double2 *src = gu_tables + (size_t)m.k * kMaxSteps;
+        const double2 *src = gu_tables + (size_t)kk * kMaxSteps;
         for (int i = threadIdx.x; i < T; i += kThreads) s_gu[i] = src[i];
         const double *ls = reinterpret_cast<const double *>(logtab);
         double *ld = reinterpret_cast<double *>(&s_log);
@@ -93,40 +121,71 @@ rollout_philox(const Case *__restrict__ cases, const double2 *__restrict__ gu_ta
     const double (*lt)[2] = s_log.invc_logc;
     const double *kt = s_log.k2ln2;
 
-    const uint32_t local = (uint32_t)tile * kThreads + threadIdx.x;
-    const bool active = local < ntrials;
-    double out[4] = {0.0, 0.0, 0.0, 0.0};
-    if (active) {
-        const uint32_t trial = trial0 + local;
-        Traj t;
-        {
-            double a, b;
-            normal_pair(philox4x32_10(trial, m.stream, 0u, 0u, key), lt, kt, a, b);
-            traj_init(t, a, b);
-        }
-        const int npairs = T >> 1;
-        for (int p = 0; p < npairs; ++p) {
-            double n0, n1, n2, n3, n4, n5;
-            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)p + 1u, 0u, key), lt, kt, n0, n1);
-            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)p + 1u, 1u, key), lt, kt, n2, n3);
-            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)p + 1u, 2u, key), lt, kt, n4, n5);
-            const double2 g0 = s_gu[2 * p], g1 = s_gu[2 * p + 1];
-            if (p == 0)
-                filter_step<true>(t, m, g0, m.l00 * n0, fma(m.l11, n1, m.l10 * n0), m.sr * n2);
-            else
-                filter_step<false>(t, m, g0, m.l00 * n0, fma(m.l11, n1, m.l10 * n0), m.sr * n2);
-            filter_step<false>(t, m, g1, m.l00 * n3, fma(m.l11, n4, m.l10 * n3), m.sr * n5);
-        }
-        if (T & 1) {
-            double n0, n1, n2, n3;
-            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)npairs + 1u, 0u, key), lt, kt, n0, n1);
-            normal_pair(philox4x32_10(trial, m.stream, (uint32_t)npairs + 1u, 1u, key), lt, kt, n2, n3);
-            filter_step<false>(t, m, s_gu[T - 1], m.l00 * n0, fma(m.l11, n1, m.l10 * n0), m.sr * n2);
-        }
-        traj_finish(t, T, out);
-        if (per_trial != nullptr) {
+    // trajectory j of this thread: local trial (tile*K + j)*kThreads + threadIdx.x (coalesced outputs)
+    uint32_t local[K], trial[K];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) per_trial[((size_t)m.out_slot * 4 + k) * per_trial_ld + local] = out[k];
+    for (int j = 0; j < K; ++j) {
+        local[j] = ((uint32_t)tile * K + j) * kThreads + threadIdx.x;
+        trial[j] = trial0 + local[j];   // past-the-end trajectories of the last tile are computed and discarded
+    }
+    Traj t[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        double a, b;
+        const uint4 w = philox4x32_10(trial[j], m.stream, 0u, 0u, key);
+        math::normal_pair_bits(w.x, w.w >> 12, w.y, lt, kt, a, b);
+        traj_init(t[j], a, b);
+    }
+    // The counter-based generator lets the random bits of step pair p+1 be produced while the FP64
+    // work of pair p is in flight: integer (Philox) and FP64 instructions interleave inside a warp.
+    const int npairs = (T + 1) >> 1;     // an odd T leaves the second half of the last pair unused
+    uint4 r[K][2];
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) r[j][c] = philox4x32_10(trial[j], m.stream, 1u, (uint32_t)c, key);
+    for (int p = 0; p < npairs; ++p) {
+        uint4 q[K][2];
+        double n[K][6];
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) q[j][c] = philox4x32_10(trial[j], m.stream, (uint32_t)p + 2u, (uint32_t)c, key);
+#pragma unroll
+        for (int j = 0; j < K; ++j) normals_of_pair(r[j][0], r[j][1], lt, kt, n[j]);
+        const double2 g0 = s_gu[2 * p];
+        if (p == 0) {
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                filter_step<true>(t[j], m, f, g0, l00 * n[j][0], fma(l11, n[j][1], l10 * n[j][0]), sr * n[j][2]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                filter_step<false>(t[j], m, f, g0, l00 * n[j][0], fma(l11, n[j][1], l10 * n[j][0]), sr * n[j][2]);
+        }
+        if (2 * p + 1 < T) {
+            const double2 g1 = s_gu[2 * p + 1];
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                filter_step<false>(t[j], m, f, g1, l00 * n[j][3], fma(l11, n[j][4], l10 * n[j][3]), sr * n[j][5]);
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) r[j][c] = q[j][c];
+    }
+    double out[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        double o[4];
+        traj_finish(t[j], T, o);
+        if (local[j] < ntrials) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out[k] += o[k];
+            if (per_trial != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) per_trial[((size_t)m.out_slot * 4 + k) * per_trial_ld + local[j]] = o[k];
+            }
         }
     }
     block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums);
@@ -147,17 +206,20 @@ __device__ __forceinline__ double ld_stream(const double *p)
 }
 
 __global__ void __launch_bounds__(kThreads)
-rollout_supplied(const Case *__restrict__ cases, const double2 *__restrict__ gu_tables, const double *__restrict__ x0noise,
+rollout_supplied(const Case *__restrict__ cases, const __grid_constant__ SampleTimeConsts st,
+                 const double2 *__restrict__ gu_tables, const double *__restrict__ x0noise,
                  const double *__restrict__ w, const double *__restrict__ v, size_t B, int tiles,
                  double *__restrict__ per_trial, double *__restrict__ partials, unsigned *__restrict__ tickets,
                  double *__restrict__ sums)
 {
     extern __shared__ double2 s_gu[];
-    const int case_idx = blockIdx.x / tiles, tile = blockIdx.x - case_idx * tiles;
+    const int case_idx = blockIdx.y * gridDim.z + blockIdx.z, tile = blockIdx.x;
     const Case m = cases[case_idx];
     const int T = m.T;
+    const unsigned kk = st.k0 + blockIdx.z;
+    const double f = pick4(st.f, kk);
     {
-        const double2 *src = gu_tables + (size_t)m.k * kMaxSteps;
+        const double2 *src = gu_tables + (size_t)kk * kMaxSteps;
         for (int i = threadIdx.x; i < T; i += kThreads) s_gu[i] = src[i];
     }
     __syncthreads();
@@ -191,8 +253,8 @@ rollout_supplied(const Case *__restrict__ cases, const double2 *__restrict__ gu_
             for (int j = 0; j < kPrefetch; ++j) {
                 const int s = s0 + j;
                 if (s < T) {
-                    if (s == 0) filter_step<true>(t, m, s_gu[s], cw0[j], cw1[j], cv[j]);
-                    else        filter_step<false>(t, m, s_gu[s], cw0[j], cw1[j], cv[j]);
+                    if (s == 0) filter_step<true>(t, m, f, s_gu[s], cw0[j], cw1[j], cv[j]);
+                    else        filter_step<false>(t, m, f, s_gu[s], cw0[j], cw1[j], cv[j]);
                 }
             }
 #pragma unroll
@@ -236,29 +298,31 @@ PhiloxKeys expand_philox_key(uint64_t seed)
     return k;
 }
 
-cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const double2 *d_gu, const void *d_logtab, int max_T,
+cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, int max_T,
                                   uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
                                   size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
                                   cudaStream_t stream)
 {
     if (ncases <= 0 || ntrials == 0) return cudaSuccess;
-    const int tiles = (int)((ntrials + kThreads - 1) / kThreads);
+    const int tiles = philox_tiles(ntrials);
     const size_t smem = (size_t)max_T * sizeof(double2);
-    rollout_philox<<<(unsigned)(ncases * (size_t)tiles), kThreads, smem, stream>>>(
-        d_cases, d_gu, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0, ntrials, tiles,
+    const dim3 grid((unsigned)tiles, (unsigned)(ncases / st.nk), (unsigned)st.nk);   // ncases = candidates x nk
+    rollout_philox<<<grid, kThreads, smem, stream>>>(
+        d_cases, st, d_gu, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0, ntrials, tiles,
         d_per_trial, per_trial_ld, d_partials, d_tickets, d_sums);
     return cudaGetLastError();
 }
 
-cudaError_t launch_rollout_supplied(const Case *d_cases, int ncases, const double2 *d_gu, int max_T, const double *d_x0noise,
+cudaError_t launch_rollout_supplied(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, int max_T, const double *d_x0noise,
                                     const double *d_w, const double *d_v, size_t B, double *d_per_trial,
                                     double *d_partials, unsigned *d_tickets, double *d_sums, cudaStream_t stream)
 {
     if (ncases <= 0 || B == 0) return cudaSuccess;
     const int tiles = (int)((B + kThreads - 1) / kThreads);
     const size_t smem = (size_t)max_T * sizeof(double2);
-    rollout_supplied<<<(unsigned)(ncases * (size_t)tiles), kThreads, smem, stream>>>(
-        d_cases, d_gu, d_x0noise, d_w, d_v, B, tiles, d_per_trial, d_partials, d_tickets, d_sums);
+    const dim3 grid((unsigned)tiles, (unsigned)(ncases / st.nk), (unsigned)st.nk);
+    rollout_supplied<<<grid, kThreads, smem, stream>>>(
+        d_cases, st, d_gu, d_x0noise, d_w, d_v, B, tiles, d_per_trial, d_partials, d_tickets, d_sums);
     return cudaGetLastError();
 }
 
@@ -269,5 +333,6 @@ cudaError_t launch_dfma_chain(double *d_out, int blocks, int iters, cudaStream_t
 }
 
 int rollout_tiles(size_t ntrials) { return (int)((ntrials + kThreads - 1) / kThreads); }
+int philox_tiles(size_t ntrials) { return (int)((ntrials + (size_t)kThreads * kPhiloxPerThread - 1) / ((size_t)kThreads * kPhiloxPerThread)); }
 
 }  // namespace kfbo

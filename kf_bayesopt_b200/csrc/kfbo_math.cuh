@@ -5,8 +5,14 @@
 // UMOV pairs; in the rollout loop that made ~420 issued instructions and ~190 FP64 instructions
 // per filter-step (profiles/ncu_philox_r1_first.txt).  The arguments here are known to be well
 // scaled (u1 in [2^-52, 1), S and det(P) of a covariance recursion, angle in one octant), so the
-// special cases are dropped and the coefficients sit in __constant__ memory where DFMA reads
-// them as c[bank][offset] operands.
+// special cases are dropped.
+//
+// Measured on B200 (tools/microbench/, DESIGN.md "What the FP64 pipe really costs"): a DFMA whose
+// three sources are three DISTINCT vector registers occupies the FP64 pipe for 3 cycles per warp
+// instead of 2.  A Horner step fma(p, x2, C) is therefore only full-rate when C is NOT a vector
+// register: the low-order coefficients live in __constant__ memory (loaded once into uniform
+// registers), the high-order ones are rounded to doubles whose low 32 bits are zero, which the
+// assembler encodes as immediates (the rounding moves the results by < 1e-16 relative).
 //
 // Under nvcc the functions are __device__; compiled as plain C++ (g++) the same source gives host
 // functions, which is how tests/native/math_check.cpp checks the accuracy against long-double
@@ -142,15 +148,22 @@ KFBO_HD double sqrt_pos(double a)
 #define KFBO_CONST static const
 #endif
 
-// -2 ln(1+r)/r = -2 + r - (2/3) r^2 + (2/4) r^3 - (2/5) r^4 + (2/6) r^5 ; |r| <= 2^-9: rel. err 8e-18
-KFBO_CONST double kLogPoly[6] = {-2.0, 1.0, -2.0 / 3.0, 0.5, -0.4, 1.0 / 3.0};
-// sin(pi/4 x) = x (S0 + S1 x^2 + ... + S7 x^14), cos(pi/4 x) = C0 + C1 x^2 + ... + C8 x^16, x in [0,1]
-// (Taylor coefficients with the powers of pi/4 folded in; truncation 6.5e-17 / 2.9e-18 relative)
-KFBO_CONST double kSinPoly[8] = {0x1.921fb54442d18p-1,  -0x1.4abbce625be53p-4, 0x1.466bc6775aae2p-9,  -0x1.32d2cce62bd86p-15,
-                                 0x1.50783487ee782p-22, -0x1.e3074fde8871fp-30, 0x1.e8f434d018d63p-38, -0x1.6fadb9f155744p-46};
-KFBO_CONST double kCosPoly[9] = {1.0,                   -0x1.3bd3cc9be45dep-2, 0x1.03c1f081b5ac4p-6,  -0x1.55d3c7e3cbffap-12,
-                                 0x1.e1f506891babbp-19, -0x1.a6d1f2a204a8cp-26, 0x1.f9d38a3763cc3p-34, -0x1.b6e24f44b128fp-42,
-                                 0x1.20c62c2f2d7f5p-50};
+// -2 ln(1+r)/r = -2 + r - (2/3) r^2 + (2/4) r^3 - (2/5) r^4 + (2/6) r^5 ; |r| <= 2^-9: rel. err 8e-18.
+// -2, 1, 1/2 and the hi32-rounded 1/3 are immediates; -2/3 and -2/5 need full precision.
+KFBO_CONST double kLogPolyU[2] = {-2.0 / 3.0, -0.4};
+#define KFBO_LOG_C5 0x1.5555500000000p-2
+// sin(pi/4 x) = x (S0 + S1 x^2 + ... + S7 x^14), cos(pi/4 x) = C0 + C1 x^2 + ... + C8 x^16, x in [-1,1]:
+// Taylor coefficients with the powers of pi/4 folded in; S6, S7, C6, C7, C8 rounded to hi32
+// immediates (max relative error of the polynomials in exact arithmetic: 1.2e-16 / 6.0e-17).
+KFBO_CONST double kSinPolyU[6] = {0x1.921fb54442d18p-1,  -0x1.4abbce625be53p-4, 0x1.466bc6775aae2p-9,
+                                  -0x1.32d2cce62bd86p-15, 0x1.50783487ee782p-22, -0x1.e3074fde8871fp-30};
+#define KFBO_SIN_C6 0x1.e8f4300000000p-38
+#define KFBO_SIN_C7 -0x1.6fadc00000000p-46
+KFBO_CONST double kCosPolyU[5] = {-0x1.3bd3cc9be45dep-2, 0x1.03c1f081b5ac4p-6, -0x1.55d3c7e3cbffap-12,
+                                  0x1.e1f506891babbp-19, -0x1.a6d1f2a204a8cp-26};
+#define KFBO_COS_C6 0x1.f9d3900000000p-34
+#define KFBO_COS_C7 -0x1.b6e2500000000p-42
+#define KFBO_COS_C8 0x1.20c6300000000p-50
 
 // L = -2 ln(u) for u in [2^-52, 1): table-driven, no division, no branch.
 //   u = 2^k z, z in [0.6875, 1.375);  i = top 8 bits of (bits(z) - OFF);  r = z/c_i - 1, |r| <= 2^-9
@@ -165,12 +178,11 @@ KFBO_HD double neg2_log(double u, const double (*tab)[2], const double *ktab)
     const double z = make_double(hi - ((uint32_t)tmp & 0xFFF00000u), lo);
     const double invc = tab[i][0], logc2 = tab[i][1];
     const double r = fma(z, invc, -1.0);
-    double s = kLogPoly[5];
-    s = fma(s, r, kLogPoly[4]);
-    s = fma(s, r, kLogPoly[3]);
-    s = fma(s, r, kLogPoly[2]);
-    s = fma(s, r, kLogPoly[1]);
-    s = fma(s, r, kLogPoly[0]);
+    double s = fma(KFBO_LOG_C5, r, kLogPolyU[1]);
+    s = fma(s, r, 0.5);
+    s = fma(s, r, kLogPolyU[0]);
+    s = fma(s, r, 1.0);
+    s = fma(s, r, -2.0);
     return fma(r, s, ktab[-k] + logc2);
 }
 
@@ -178,37 +190,40 @@ KFBO_HD double neg2_log(double u, const double (*tab)[2], const double *ktab)
 KFBO_HD void sincos_octant(double x, double &s, double &c)
 {
     const double x2 = x * x;
-    double ps = kSinPoly[7], pc = kCosPoly[8];
-    pc = fma(pc, x2, kCosPoly[7]);
-    ps = fma(ps, x2, kSinPoly[6]); pc = fma(pc, x2, kCosPoly[6]);
-    ps = fma(ps, x2, kSinPoly[5]); pc = fma(pc, x2, kCosPoly[5]);
-    ps = fma(ps, x2, kSinPoly[4]); pc = fma(pc, x2, kCosPoly[4]);
-    ps = fma(ps, x2, kSinPoly[3]); pc = fma(pc, x2, kCosPoly[3]);
-    ps = fma(ps, x2, kSinPoly[2]); pc = fma(pc, x2, kCosPoly[2]);
-    ps = fma(ps, x2, kSinPoly[1]); pc = fma(pc, x2, kCosPoly[1]);
-    ps = fma(ps, x2, kSinPoly[0]); pc = fma(pc, x2, kCosPoly[0]);
+    double ps = fma(KFBO_SIN_C7, x2, KFBO_SIN_C6);
+    double pc = fma(KFBO_COS_C8, x2, KFBO_COS_C7);
+    pc = fma(pc, x2, KFBO_COS_C6);
+    ps = fma(ps, x2, kSinPolyU[5]); pc = fma(pc, x2, kCosPolyU[4]);
+    ps = fma(ps, x2, kSinPolyU[4]); pc = fma(pc, x2, kCosPolyU[3]);
+    ps = fma(ps, x2, kSinPolyU[3]); pc = fma(pc, x2, kCosPolyU[2]);
+    ps = fma(ps, x2, kSinPolyU[2]); pc = fma(pc, x2, kCosPolyU[1]);
+    ps = fma(ps, x2, kSinPolyU[1]); pc = fma(pc, x2, kCosPolyU[0]);
+    ps = fma(ps, x2, kSinPolyU[0]); pc = fma(pc, x2, 1.0);
     s = ps * x;
     c = pc;
 }
 
-// 128 random bits -> two independent N(0,1) draws (Box-Muller).  THE SPEC (restated draw for draw
+// 84 random bits -> two independent N(0,1) draws (Box-Muller).  THE SPEC (restated draw for draw
 // by the CPU checker):
-//   radius: m1 = top 52 bits of (w0:w1) with the lowest bit forced to 1; u1 = 1 - m1 2^-52 in
-//           [2^-52, 1 - 2^-52]; rad = sqrt(-2 ln u1)
-//   angle : o = top 3 bits of w2 (octant), f = the next 52 bits of (w2:w3) times 2^-52 in [0,1);
+//   radius: m1 = (rad_hi << 20 | rad_lo20) with the lowest bit forced to 1 (52 bits);
+//           u1 = 1 - m1 2^-52 in [2^-52, 1 - 2^-52]; rad = sqrt(-2 ln u1)
+//   angle : o = top 3 bits of ang (octant), f = low 29 bits of ang times 2^-29 in [0,1);
 //           theta = (pi/4)(o + f)
 //   na = rad cos(theta), nb = rad sin(theta)
+// (32 angle bits: 2^32 directions, 1.5e-9 rad apart; the radius keeps 52 bits, so each normal is
+// continuous to FP64 resolution and the tails reach 8.5 sigma.  Random bits are the expensive part
+// on this chip -- see the Philox note in kfbo_device.cuh.)
 // Evaluated per octant: x = f (even o) or 1-f (odd o); sin/cos of (pi/4)x; swap and signs from o.
-KFBO_HD void normal_pair_bits(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, const double (*tab)[2],
+KFBO_HD void normal_pair_bits(uint32_t rad_hi, uint32_t rad_lo20, uint32_t ang, const double (*tab)[2],
                               const double *ktab, double &na, double &nb)
 {
     // ---- radius
-    const double y1 = make_double(0x3FF00000u | (w0 >> 12), (w0 << 20) | (w1 >> 12) | 1u);   // [1,2)
+    const double y1 = make_double(0x3FF00000u | (rad_hi >> 12), (rad_hi << 20) | rad_lo20 | 1u);   // [1,2)
     const double u1 = 2.0 - y1;
     double rad = sqrt_pos(neg2_log(u1, tab, ktab));
     // ---- angle
-    const uint32_t o = w2 >> 29;
-    const double y2 = make_double(0x3FF00000u | ((w2 >> 9) & 0xFFFFFu), (w2 << 23) | (w3 >> 9));  // 1 + f
+    const uint32_t o = ang >> 29;
+    const double y2 = make_double(0x3FF00000u | ((ang >> 9) & 0xFFFFFu), ang << 23);   // 1 + f
     const uint32_t odd = o & 1u;
     const uint32_t swap = (o ^ (o >> 1)) & 1u;             // sin(theta) takes the cos polynomial
     const uint32_t neg_sin = (o >> 2) & 1u;                // quadrants 2,3
@@ -219,10 +234,9 @@ KFBO_HD void normal_pair_bits(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3
     const uint32_t neg_ps = swap ? neg_cos : neg_sin;      // sign wanted on the sin-polynomial value
     rad = make_double(hi_word(rad) ^ (neg_pc << 31), lo_word(rad));
     const uint32_t flip_x = neg_ps ^ neg_pc;               // rad already carries neg_pc
-    // x = +-(y2 - 1) for even octants, +-(2 - y2) for odd ones: x = fma(y2, sx, cx)
-    const double sx = make_double((0x3FF00000u) ^ ((odd ^ flip_x) << 31), 0u);                 // +-1
-    const double cx = make_double((odd ? 0x40000000u : 0x3FF00000u) ^ ((odd ^ flip_x ^ 1u) << 31), 0u);  // -+1 or +-2
-    const double x = fma(y2, sx, cx);
+    // t = f (even octant) or f - 1 (odd); |x| = f or 1 - f = -t; then the sign flip
+    const double t = y2 + make_double(odd ? 0xC0000000u : 0xBFF00000u, 0u);     // y2 - 2 or y2 - 1
+    const double x = make_double(hi_word(t) ^ ((odd ^ flip_x) << 31), lo_word(t));
     double ps, pc;
     sincos_octant(x, ps, pc);
     const double a = rad * pc, b = rad * ps;

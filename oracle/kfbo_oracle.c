@@ -287,21 +287,20 @@ void ko_philox4x32_10(const uint32_t *ctr, const uint32_t *key, uint32_t *out)
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* 128 random bits -> two independent standard normals (Box-Muller), the product's spec:
- *   radius: m1 = top 52 bits of (w0:w1) with the lowest bit forced to 1;
+/* 84 random bits -> two independent standard normals (Box-Muller), the product's spec:
+ *   radius: m1 = (rad_hi << 20 | rad_lo20) with the lowest bit forced to 1 (52 bits);
  *           u1 = 1 - m1*2^-52 in [2^-52, 1-2^-52];  rad = sqrt(-2 ln u1)
- *   angle : o = top 3 bits of w2 (octant), f = next 52 bits of (w2:w3) * 2^-52 in [0,1);
+ *   angle : o = top 3 bits of ang (octant), f = low 29 bits of ang * 2^-29 in [0,1);
  *           theta = (pi/4)(o + f)
  *   n_a = rad cos(theta), n_b = rad sin(theta)
  * theta is reduced to its octant exactly (1-f is exact) so libm sees |arg| <= pi/4. */
-void ko_normal_pair(const uint32_t *w, double *na, double *nb)
+void ko_normal_pair(uint32_t rad_hi, uint32_t rad_lo20, uint32_t ang, double *na, double *nb)
 {
-    const uint64_t m1 = (((uint64_t)w[0] << 20) | (w[1] >> 12)) | 1u;
+    const uint64_t m1 = (((uint64_t)rad_hi << 20) | (rad_lo20 & 0xFFFFFu)) | 1u;
     const double u1 = 1.0 - (double)m1 * 0x1p-52;
     const double r = sqrt(-2.0 * log(u1));
-    const unsigned o = w[2] >> 29;
-    const uint64_t fbits = ((uint64_t)(w[2] & 0x1FFFFFFFu) << 23) | (w[3] >> 9);
-    const double f = (double)fbits * 0x1p-52;
+    const unsigned o = ang >> 29;
+    const double f = (double)(ang & 0x1FFFFFFFu) * 0x1p-29;
     const double x = (o & 1u) ? 1.0 - f : f;           /* position inside the octant, mirrored for odd octants */
     const double sx = sin(M_PI_4 * x), cx = cos(M_PI_4 * x);
     const double sa = (o & 1u) ? cx : sx, ca = (o & 1u) ? sx : cx; /* angle within the quadrant */
@@ -314,6 +313,16 @@ void ko_normal_pair(const uint32_t *w, double *na, double *nb)
     }
     *na = r * cs;
     *nb = r * sn;
+}
+
+/* The random words of one step pair: two Philox calls A, B -> three normal pairs n[0..5]:
+ *   pair 0: radius (A[0] : A[3]>>12), angle A[1]     pair 1: radius (B[0] : B[3]>>12), angle B[1]
+ *   pair 2: radius (A[2] : A[3][11:0] B[3][7:0]), angle B[2] */
+void ko_normals_of_pair(const uint32_t *A, const uint32_t *B, double *n)
+{
+    ko_normal_pair(A[0], A[3] >> 12, A[1], &n[0], &n[1]);
+    ko_normal_pair(B[0], B[3] >> 12, B[1], &n[2], &n[3]);
+    ko_normal_pair(A[2], ((A[3] & 0xFFFu) << 8) | (B[3] & 0xFFu), B[2], &n[4], &n[5]);
 }
 
 /* Closed-form Cholesky of the truth Qd and sqrt(R): any T with T T^T = Qd is
@@ -338,12 +347,12 @@ static void philox_noise(void *p, int step, double *w0, double *w1, double *v)
     philox_ctx *c = (philox_ctx *)p;
     const int pair = step >> 1;
     if (pair != c->cached_pair) {
-        for (uint32_t j = 0; j < 3; ++j) {
+        uint32_t out[2][4];
+        for (uint32_t j = 0; j < 2; ++j) {
             const uint32_t ctr[4] = {c->trial, c->stream, (uint32_t)pair + 1u, j};
-            uint32_t out[4];
-            ko_philox4x32_10(ctr, c->key, out);
-            ko_normal_pair(out, &c->n[2 * j], &c->n[2 * j + 1]);
+            ko_philox4x32_10(ctr, c->key, out[j]);
         }
+        ko_normals_of_pair(out[0], out[1], c->n);
         c->cached_pair = pair;
     }
     const double *n = c->n + 3 * (step & 1);
@@ -373,7 +382,7 @@ int ko_eval_philox(uint64_t seed, uint32_t stream, double dt, int T, double q_tr
         uint32_t o[4];
         double x0n[2], out[4];
         ko_philox4x32_10(ctr, c.key, o);
-        ko_normal_pair(o, &x0n[0], &x0n[1]); /* P0 = I: transform is the identity */
+        ko_normal_pair(o[0], o[3] >> 12, o[1], &x0n[0], &x0n[1]); /* P0 = I: transform is the identity */
         run_trial(truth, est, T, x0n, philox_noise, &c, hn, hi, out);
         for (int k = 0; k < 4; ++k) per_trial[(long)k * ntrials + i] = out[k];
     }

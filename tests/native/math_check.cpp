@@ -57,13 +57,12 @@ int main()
     { double s, c; sincos_octant(1.0, s, c); e_sin = std::fmax(e_sin, ulp_err(s, sinl(PI4))); e_cos = std::fmax(e_cos, ulp_err(c, cosl(PI4))); }
     // the full pair against the spec evaluated in long double (absolute error: |n| <= 8.5)
     for (int i = 0; i < 2000000; ++i) {
-        const uint32_t w0 = (uint32_t)g(), w1 = (uint32_t)g(), w2 = (uint32_t)g(), w3 = (uint32_t)g();
+        const uint32_t rad_hi = (uint32_t)g(), lo20 = (uint32_t)g() & 0xFFFFFu, ang = (uint32_t)g();
         double na, nb;
-        normal_pair_bits(w0, w1, w2, w3, t.invc_logc, t.k2ln2, na, nb);
-        const uint64_t m1 = (((uint64_t)w0 << 20) | (w1 >> 12)) | 1u;
+        normal_pair_bits(rad_hi, lo20, ang, t.invc_logc, t.k2ln2, na, nb);
+        const uint64_t m1 = (((uint64_t)rad_hi << 20) | lo20) | 1u;
         const long double u1 = 1.0L - (long double)m1 * 0x1p-52L;
-        const uint64_t fbits = (((uint64_t)(w2 & 0x1FFFFFFFu)) << 23) | (w3 >> 9);
-        const long double theta = PI4 * ((long double)(w2 >> 29) + (long double)fbits * 0x1p-52L);
+        const long double theta = PI4 * ((long double)(ang >> 29) + (long double)(ang & 0x1FFFFFFFu) * 0x1p-29L);
         const long double rad = sqrtl(-2.0L * logl(u1));
         e_na = std::fmax(e_na, (double)fabsl((long double)na - rad * cosl(theta)));
         e_nb = std::fmax(e_nb, (double)fabsl((long double)nb - rad * sinl(theta)));

@@ -1,0 +1,63 @@
+// imad_wide.cu -- which pipe does IMAD.WIDE.U32 / IMAD.HI.U32 use on sm_100a: does it overlap with DFMA?
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k(double *out, int iters, double a, double b, uint32_t m)
+{
+    double x[8];
+    uint32_t y[8], z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { x[j] = threadIdx.x + j; y[j] = threadIdx.x * 7 + j; z[j] = y[j] ^ 0x55555555u; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (MODE == 0 || MODE == 2 || MODE == 4 || MODE == 6) x[j] = fma(x[j], a, b);
+                if (MODE == 1 || MODE == 2) { const uint64_t p = (uint64_t)y[j] * m; y[j] = (uint32_t)p; z[j] ^= (uint32_t)(p >> 32); }   // IMAD.WIDE + LOP3
+                if (MODE == 3 || MODE == 4) { y[j] = __umulhi(y[j], m) ^ z[j]; }                                                            // IMAD.HI + LOP3
+                if (MODE == 5 || MODE == 6) { y[j] = (y[j] & 0xffffu) * (m & 0xffffu) + z[j]; }                                            // LOP3 + IMAD (16x16)
+            }
+    }
+    double s = 0;
+    uint32_t t = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s += x[j]; t += y[j] + z[j]; }
+    if (s == 123.456 || t == 0xdeadbeef) out[0] = s + t;
+}
+
+template <int MODE>
+void run(double *d, const char *name)
+{
+    cudaDeviceProp p;
+    cudaGetDeviceProperties(&p, 0);
+    const int blocks = p.multiProcessorCount * 4, iters = 2048;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k<MODE><<<blocks, 256>>>(d, iters, 0.999999, 1e-9, 0xD2511F53u);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    k<MODE><<<blocks, 256>>>(d, iters, 0.999999, 1e-9, 0xD2511F53u);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double rounds_per_smsp = (double)iters * 8 * (blocks * 256 / 32) / (p.multiProcessorCount * 4);
+    std::printf("%-36s %.2f SMSP-cycles per round of 8\n", name, ms * 1e-3 * p.clockRate * 1e3 / rounds_per_smsp);
+}
+
+int main()
+{
+    double *d;
+    cudaMalloc(&d, 64);
+    run<0>(d, "8 DFMA");
+    run<1>(d, "8 (IMAD.WIDE + LOP3)");
+    run<2>(d, "8 DFMA + 8 (IMAD.WIDE + LOP3)");
+    run<3>(d, "8 (IMAD.HI + LOP3)");
+    run<4>(d, "8 DFMA + 8 (IMAD.HI + LOP3)");
+    run<5>(d, "8 (LOP3 + IMAD 16x16)");
+    run<6>(d, "8 DFMA + 8 (LOP3 + IMAD 16x16)");
+    return 0;
+}
