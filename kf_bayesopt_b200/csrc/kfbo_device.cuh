@@ -28,15 +28,19 @@ namespace kfbo {
 // expensive resource of this kernel, which is why a normal pair consumes 84 of them, not 128.
 // ---------------------------------------------------------------------------------------
 #ifndef KFBO_PHILOX_SPLIT_MUL
-#define KFBO_PHILOX_SPLIT_MUL 1
+#define KFBO_PHILOX_SPLIT_MUL 0
 #endif
-__device__ __forceinline__ void mulhilo32(uint32_t m, uint32_t a, uint32_t &hi, uint32_t &lo)
+__device__ __forceinline__ void mulhilo32(uint32_t m, uint32_t a, uint32_t zero, uint32_t &hi, uint32_t &lo)
 {
 #if KFBO_PHILOX_SPLIT_MUL
-    // keep the halves apart: IMAD.HI (shared pipe, 4 cycles) + IMAD (free pipe) beats IMAD.WIDE (5)
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(a), "r"(m));
-    asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(lo) : "r"(a), "r"(m));
+    // experiment: keep the halves apart, IMAD.HI (shared pipe, ~4 cycles) + IMAD (free pipe) instead of
+    // IMAD.WIDE (~5).  Measured SLOWER in the kernel (20.99 vs 20.08 ms), hence off by default.
+    // ptxas fuses mul.hi + mul.lo of the same operands back into IMAD.WIDE, so the low half is a
+    // multiply-add with an addend it cannot prove to be zero (a kernel parameter that is always 0).
+    hi = __umulhi(m, a);
+    lo = m * a + zero;
 #else
+    (void)zero;
     lo = m * a;
     hi = __umulhi(m, a);
 #endif
@@ -47,8 +51,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t lo0, hi0, lo1, hi1;
-        mulhilo32(0xD2511F53u, c0, hi0, lo0);
-        mulhilo32(0xCD9E8D57u, c2, hi1, lo1);
+        mulhilo32(0xD2511F53u, c0, key.zero, hi0, lo0);
+        mulhilo32(0xCD9E8D57u, c2, key.zero, hi1, lo1);
         c0 = hi1 ^ c1 ^ key.k0[r];
         c1 = lo1;
         c2 = hi0 ^ c3 ^ key.k1[r];

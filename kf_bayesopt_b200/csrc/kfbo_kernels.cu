@@ -80,14 +80,12 @@ __device__ __forceinline__ void block_reduce_and_publish(const double out[4], in
 //   block p+1, sub 0,1  -> calls A, B of the step pair (2p, 2p+1) -> normals n0..n5 (normals_of_pair):
 //                          step 2p uses n0,n1 (process) n2 (observation); step 2p+1 uses n3,n4,n5
 // -----------------------------------------------------------------------------------------
-// kPhiloxPerThread independent trajectories (adjacent tiles of the same case) advance in lock-step
-// in every thread.  Measured on B200 (tools/microbench/fp64_latency.cu): DFMA has an 8-cycle
-// dependent latency and the FP64 pipe only reaches its 2-cycles-per-warp-instruction peak when each
-// warp offers several INDEPENDENT FP64 instructions back to back (1 chain/warp: 3.2 cycles per DFMA
-// even with 8 warps per scheduler; 2 chains: 2.6; 4 chains: 2.25).  The filter recursion is one
-// long dependent chain per trajectory, so the second trajectory supplies the missing ILP.
+// kPhiloxPerThread independent trajectories (adjacent tiles of the same case) can advance in
+// lock-step in every thread (more ILP per warp).  Measured on B200 (profiles/NOTES_r1.md): the kernel
+// is bound by the pipe that FP64 and IMAD.WIDE share, not by latency, so 1 and 2 trajectories per
+// thread run at the same speed (19.96 vs 20.08 ms for cfg3) and 1 needs half the registers.
 #ifndef KFBO_PHILOX_PER_THREAD
-#define KFBO_PHILOX_PER_THREAD 2
+#define KFBO_PHILOX_PER_THREAD 1
 #endif
 #ifndef KFBO_PHILOX_MIN_BLOCKS
 #define KFBO_PHILOX_MIN_BLOCKS 1
@@ -290,6 +288,7 @@ __global__ void __launch_bounds__(256) dfma_chain(double *out, int iters, double
 PhiloxKeys expand_philox_key(uint64_t seed)
 {
     PhiloxKeys k;
+    k.zero = 0u;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     for (int r = 0; r < 10; ++r) {
         k.k0[r] = k0; k.k1[r] = k1;
