@@ -249,7 +249,7 @@ def main():
 
     # ---- supplied-noise leg: HBM roofline, inputs resident in HBM and larger than L2
     if rank == 0 and not args.no_supplied:
-        Bs, Ts = 1 << 17, 1000                                    # 3.1 GB of noise >> 126 MB L2
+        Bs, Ts = 1 << 20, 1000                                    # 25 GB of noise >> 126 MB L2; 8192 CTAs = 7 waves
         g = torch.Generator(device="cuda").manual_seed(1)
         x0n = torch.randn((2, Bs), dtype=torch.float64, device="cuda", generator=g)
         w = torch.randn((Ts, 2, Bs), dtype=torch.float64, device="cuda", generator=g) * 0.1
@@ -285,7 +285,7 @@ def main():
                            "sample_times": SAMPLE_TIMES, "candidate": {"pnoise": CANDIDATE[0], "onoise": CANDIDATE[1]},
                            "sharding": f"trials over {world} rank(s), one ncclAllReduce of {D * 4} doubles" if world > 1 else "single GPU",
                            "l2": "n/a for the Philox path: no HBM-resident inputs (noise is generated on the fly); "
-                                 "the supplied-noise leg streams 3.1 GB >> L2"},
+                                 "the supplied-noise leg streams 25 GB >> L2"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "result": {"J_NEES": [float(c) for c in res.cost], "cost": float(res.max_cost), "index_max": res.index_max}}
         line.update(line_extra)

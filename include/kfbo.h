@@ -146,6 +146,14 @@ int kfbo_last_kernel_ms(const kfbo_handle *h, double *ms, int32_t *launches);
 /* Run subsequent launches on this CUDA stream (a cudaStream_t); NULL = the handle's own. */
 int kfbo_set_cuda_stream(kfbo_handle *h, void *cuda_stream);
 
+/* Tuning knobs (none changes results).  KFBO_OPT_SUPPLIED_KERNEL: which supplied-noise kernel
+ * kfbo_eval_supplied* launch -- AUTO = the bulk-copy (cp.async.bulk + mbarrier) kernel whenever the
+ * streams are 16-byte aligned and B is even, else the per-thread-load kernel. */
+enum { KFBO_OPT_SUPPLIED_KERNEL = 1, KFBO_OPT_BULK_SMEM_PAD = 2 /* extra dynamic shared memory (bytes) per CTA of the
+                                        bulk-copy kernel: lowers the CTAs resident per SM */ };
+enum { KFBO_SUPPLIED_AUTO = 0, KFBO_SUPPLIED_LDG = 1, KFBO_SUPPLIED_BULK = 2 };
+int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value);
+
 /* ---- multi-GPU: one process per GPU, one NCCL allreduce of the cost sums per evaluation ---- */
 #define KFBO_NCCL_ID_BYTES 128
 int kfbo_nccl_unique_id(void *id_bytes /*[KFBO_NCCL_ID_BYTES]*/);

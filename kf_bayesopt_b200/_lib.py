@@ -15,6 +15,9 @@ NCCL_ID_BYTES = 128
 JNEES, CNEES, JNIS, CNIS = 0, 1, 2, 3
 COST_CHOICES = {"JNEES": JNEES, "CNEES": CNEES, "JNIS": JNIS, "CNIS": CNIS}
 SHARD_TRIALS, SHARD_CANDIDATES = 0, 1
+OPT_SUPPLIED_KERNEL = 1
+OPT_BULK_SMEM_PAD = 2
+SUPPLIED_AUTO, SUPPLIED_LDG, SUPPLIED_BULK = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # KFBO_LIB_PATH: load another build of the same library (kernel tuning experiments only)
@@ -74,6 +77,7 @@ SIGNATURES = {
     "kfbo_last_sums": (C.c_int, [_vp, _dp, C.c_int32]),
     "kfbo_last_kernel_ms": (C.c_int, [_vp, _dp, C.POINTER(C.c_int32)]),
     "kfbo_set_cuda_stream": (C.c_int, [_vp, _vp]),
+    "kfbo_set_option": (C.c_int, [_vp, C.c_int32, C.c_int64]),
     "kfbo_nccl_unique_id": (C.c_int, [_vp]),
     "kfbo_comm_init": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32]),
     "kfbo_shard_range": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

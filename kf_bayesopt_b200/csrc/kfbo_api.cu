@@ -86,6 +86,8 @@ struct kfbo_handle {
     int rank = 0, nranks = 1, shard_mode = KFBO_SHARD_TRIALS;
     // Philox stream bookkeeping
     uint32_t stream_base = 0, eval_counter = 0;
+    int supplied_kernel = kfbo::kSuppliedAuto;
+    int bulk_smem_pad = 0;
     // last evaluation
     int last_ncand = 0, last_launches = 0;
     double last_ms = 0.0;
@@ -300,9 +302,8 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
     if (cu(cudaMalloc(&h->d_gu, gu.size() * sizeof(double2)), "cudaMalloc(gu)")) return bail(KFBO_ECUDA);
     if (cu(cudaMemcpy(h->d_gu, gu.data(), gu.size() * sizeof(double2), cudaMemcpyHostToDevice), "cudaMemcpy(gu)")) return bail(KFBO_ECUDA);
     {
-        static kfbo::math::LogTables tabs;   // built once per process, identical for every handle
-        static bool built = false;
-        if (!built) { kfbo::math::build_log_tables(&tabs); built = true; }
+        // built once per process (thread-safe: Trial::Run creates handles from several threads)
+        static const kfbo::math::LogTables tabs = [] { kfbo::math::LogTables t; kfbo::math::build_log_tables(&t); return t; }();
         if (cu(cudaMalloc(&h->d_logtab, sizeof tabs), "cudaMalloc(logtab)")) return bail(KFBO_ECUDA);
         if (cu(cudaMemcpy(h->d_logtab, &tabs, sizeof tabs, cudaMemcpyHostToDevice), "cudaMemcpy(logtab)")) return bail(KFBO_ECUDA);
     }
@@ -328,6 +329,23 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
 
 int kfbo_set_stream_base(kfbo_handle *h, uint32_t base) { if (!h) return KFBO_EINVAL; h->stream_base = base; return KFBO_OK; }
 int kfbo_set_eval_counter(kfbo_handle *h, uint32_t e) { if (!h) return KFBO_EINVAL; h->eval_counter = e; return KFBO_OK; }
+
+int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value)
+{
+    if (!h) return KFBO_EINVAL;
+    switch (option) {
+    case KFBO_OPT_SUPPLIED_KERNEL:
+        if (value < KFBO_SUPPLIED_AUTO || value > KFBO_SUPPLIED_BULK) return fail(h, KFBO_EINVAL, "kfbo_set_option: supplied kernel %lld", (long long)value);
+        h->supplied_kernel = (int)value;
+        return KFBO_OK;
+    case KFBO_OPT_BULK_SMEM_PAD:
+        if (value < 0 || value > (128 << 10)) return fail(h, KFBO_EINVAL, "kfbo_set_option: smem pad %lld", (long long)value);
+        h->bulk_smem_pad = (int)value;
+        return KFBO_OK;
+    default:
+        return fail(h, KFBO_EINVAL, "kfbo_set_option: unknown option %d", option);
+    }
+}
 
 int kfbo_set_cuda_stream(kfbo_handle *h, void *cuda_stream)
 {
@@ -436,7 +454,7 @@ static int supplied_impl(kfbo_handle *h, int32_t k, int32_t C, const double *q_e
     kfbo::SampleTimeConsts st = h->st;
     st.k0 = k; st.nk = 1;
     KFBO_CUDA(h, kfbo::launch_rollout_supplied(d_cases, C, st, h->d_gu, h->p.max_iterations[k], d_x0, d_w, d_v, (size_t)B, d_per_trial,
-                                               d_partials, d_tickets, d_sums, h->stream));
+                                               d_partials, d_tickets, d_sums, h->supplied_kernel, h->bulk_smem_pad, h->stream));
     KFBO_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     h->last_launches = 1;
     std::vector<double> hs((size_t)C * 4);

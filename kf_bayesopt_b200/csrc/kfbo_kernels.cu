@@ -21,9 +21,11 @@ __device__ __forceinline__ double pick4(const double (&a)[4], unsigned k)
 }
 
 // CTA partial -> global; last CTA of the case reduces all partials of the case in fixed order.
+// s_red: kThreads x 4 doubles of shared memory the caller no longer needs (or a static array).
 __device__ __forceinline__ void block_reduce_and_publish(const double out[4], int case_idx, int tile, int tiles,
                                                          int out_slot, double *__restrict__ partials,
-                                                         unsigned *__restrict__ tickets, double *__restrict__ sums)
+                                                         unsigned *__restrict__ tickets, double *__restrict__ sums,
+                                                         double (*s_red)[4])
 {
     __shared__ double s_part[kThreads / 32][4];
     __shared__ bool s_last;
@@ -58,7 +60,6 @@ __device__ __forceinline__ void block_reduce_and_publish(const double out[4], in
 #pragma unroll
         for (int m = 0; m < 4; ++m) a[m] += __ldcg(p + m);
     }
-    __shared__ double s_red[kThreads][4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) s_red[threadIdx.x][m] = a[m];
     __syncthreads();
@@ -186,7 +187,8 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
             }
         }
     }
-    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums);
+    __shared__ double s_red[kThreads][4];
+    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, s_red);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -264,7 +266,160 @@ rollout_supplied(const Case *__restrict__ cases, const __grid_constant__ SampleT
             for (int k = 0; k < 4; ++k) per_trial[((size_t)m.out_slot * 4 + k) * B + i] = out[k];
         }
     }
-    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums);
+    __shared__ double s_red[kThreads][4];
+    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, s_red);
+}
+
+// -----------------------------------------------------------------------------------------
+// Supplied-noise rollout, bulk-copy variant (the default when the streams are 16-byte aligned and
+// B is even).  The noise of a 128-trial tile is staged through shared memory by the bulk-copy
+// engine (cp.async.bulk, completion on an mbarrier) kBulkSteps steps at a time in a ring of
+// kBulkStages stages: no per-thread address arithmetic (the 64-bit IMAD.WIDE address products of
+// the LDG variant sit on the pipe FP64 shares), no prefetch registers (106 -> ~70 registers, 6 CTAs
+// per SM instead of 4), and the bytes in flight are held by the copy engine, not by the warps.
+//   stage = { w[kBulkSteps][2][128], v[kBulkSteps][128], gu[kBulkSteps] }  (12 KB + 64 B at 4 steps)
+//   full[s]  : 1 arrival (the expect_tx of the issuing lane) + the bytes of the stage
+//   empty[s] : one arrival per warp once all its lanes have consumed the stage
+// Warp 0 is also the producer: before it consumes chunk c it refills the stage chunk c-1 used.
+// Measured on B200, 1M trials x 1000 steps (profiles/NOTES_r1.md): 4 steps x 2 stages (24 KB, 8 CTAs
+// = 32 warps per SM) streams 5.85 TB/s = 89% of the measured HBM peak; the LDG variant 5.25 TB/s;
+// deeper rings or larger chunks lower the CTAs per SM and lose more than they gain.
+// -----------------------------------------------------------------------------------------
+#ifndef KFBO_BULK_STEPS
+#define KFBO_BULK_STEPS 4
+#endif
+#ifndef KFBO_BULK_STAGES
+#define KFBO_BULK_STAGES 2
+#endif
+constexpr int kBulkSteps = KFBO_BULK_STEPS;
+constexpr int kBulkStages = KFBO_BULK_STAGES;
+static_assert(kMaxSteps % kBulkSteps == 0, "the g*u table is read in whole chunks");
+static_assert(3 * kBulkSteps + 1 <= 32, "one lane of warp 0 per bulk copy of a stage");
+
+struct __align__(128) BulkStage {
+    double w[kBulkSteps][2][kThreads];
+    double v[kBulkSteps][kThreads];
+    double2 gu[kBulkSteps];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned); read-once data: L2 evict_first
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads)
+rollout_supplied_bulk(const Case *__restrict__ cases, const __grid_constant__ SampleTimeConsts st,
+                      const double2 *__restrict__ gu_tables, const double *__restrict__ x0noise,
+                      const double *__restrict__ w, const double *__restrict__ v, size_t B, int tiles,
+                      double *__restrict__ per_trial, double *__restrict__ partials, unsigned *__restrict__ tickets,
+                      double *__restrict__ sums)
+{
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    BulkStage *stage = reinterpret_cast<BulkStage *>(s_raw);
+    __shared__ __align__(8) uint64_t s_full[kBulkStages], s_empty[kBulkStages];
+    const int case_idx = blockIdx.y * gridDim.z + blockIdx.z, tile = blockIdx.x;
+    const Case m = cases[case_idx];
+    const int T = m.T;
+    const unsigned kk = st.k0 + blockIdx.z;
+    const double f = pick4(st.f, kk);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t col0 = (size_t)tile * kThreads;
+    const uint32_t ncols = (uint32_t)(B - col0 < (size_t)kThreads ? B - col0 : (size_t)kThreads);
+    const uint32_t row_bytes = ncols * (uint32_t)sizeof(double);
+    const int nchunks = (T + kBulkSteps - 1) / kBulkSteps;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kBulkStages; ++s) { mbar_init(&s_full[s], 1u); mbar_init(&s_empty[s], kThreads / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    uint64_t policy = 0;
+    const double2 *gu_src = gu_tables + (size_t)kk * kMaxSteps;
+    // lane l of warp 0 issues copy l of a stage: l < 2*nv -> w row, l < 3*nv -> v row, l == 3*nv -> g*u chunk
+    auto issue = [&](int chunk) {
+        BulkStage &sg = stage[chunk % kBulkStages];
+        uint64_t *bar = &s_full[chunk % kBulkStages];
+        const int s0 = chunk * kBulkSteps;
+        const int nv = T - s0 < kBulkSteps ? T - s0 : kBulkSteps;        // steps of this chunk that exist
+        if (lane == 0) mbar_arrive_expect_tx(bar, 3u * (uint32_t)nv * row_bytes + (uint32_t)(kBulkSteps * sizeof(double2)));
+        if (lane < 2 * nv)
+            bulk_g2s(&sg.w[lane >> 1][lane & 1][0], w + ((size_t)(2 * s0 + lane)) * B + col0, row_bytes, bar, policy);
+        else if (lane < 3 * nv)
+            bulk_g2s(&sg.v[lane - 2 * nv][0], v + ((size_t)(s0 + lane - 2 * nv)) * B + col0, row_bytes, bar, policy);
+        else if (lane == 3 * nv)
+            bulk_g2s(&sg.gu[0], gu_src + s0, (uint32_t)(kBulkSteps * sizeof(double2)), bar, policy);
+    };
+    if (warp == 0) {
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        for (int c = 0; c < kBulkStages - 1 && c < nchunks; ++c) issue(c);
+    }
+
+    const size_t i = col0 + threadIdx.x;
+    const bool active = threadIdx.x < ncols;
+    Traj t;
+    traj_init(t, active ? ld_stream(x0noise + i) : 0.0, active ? ld_stream(x0noise + B + i) : 0.0);
+    for (int c = 0; c < nchunks; ++c) {
+        if (warp == 0) {
+            const int nx = c + kBulkStages - 1;       // refill the stage chunk c-1 lived in
+            if (nx < nchunks) {
+                if (nx >= kBulkStages) mbar_wait(&s_empty[nx % kBulkStages], (uint32_t)((nx / kBulkStages - 1) & 1));
+                issue(nx);
+            }
+        }
+        const int sidx = c % kBulkStages;
+        mbar_wait(&s_full[sidx], (uint32_t)((c / kBulkStages) & 1));
+        const BulkStage &sg = stage[sidx];
+        const int s0 = c * kBulkSteps;
+#pragma unroll
+        for (int j = 0; j < kBulkSteps; ++j) {
+            if (s0 + j < T) {
+                const double w0 = sg.w[j][0][threadIdx.x], w1 = sg.w[j][1][threadIdx.x], vv = sg.v[j][threadIdx.x];
+                const double2 g = sg.gu[j];
+                if (j == 0 && c == 0) filter_step<true>(t, m, f, g, w0, w1, vv);
+                else                  filter_step<false>(t, m, f, g, w0, w1, vv);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[sidx]);
+    }
+    double out[4] = {0.0, 0.0, 0.0, 0.0};
+    if (active) {
+        traj_finish(t, T, out);
+        if (per_trial != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) per_trial[((size_t)m.out_slot * 4 + k) * B + i] = out[k];
+        }
+    }
+    // every chunk that was issued has been consumed by every thread: the ring is free to reuse
+    static_assert(sizeof(BulkStage) * kBulkStages >= sizeof(double) * 4 * kThreads, "ring too small for the reduction scratch");
+    __syncthreads();
+    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, reinterpret_cast<double (*)[4]>(s_raw));
 }
 
 // -----------------------------------------------------------------------------------------
@@ -314,15 +469,33 @@ cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleT
 
 cudaError_t launch_rollout_supplied(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, int max_T, const double *d_x0noise,
                                     const double *d_w, const double *d_v, size_t B, double *d_per_trial,
-                                    double *d_partials, unsigned *d_tickets, double *d_sums, cudaStream_t stream)
+                                    double *d_partials, unsigned *d_tickets, double *d_sums, int variant, int smem_pad,
+                                    cudaStream_t stream)
 {
     if (ncases <= 0 || B == 0) return cudaSuccess;
     const int tiles = (int)((B + kThreads - 1) / kThreads);
-    const size_t smem = (size_t)max_T * sizeof(double2);
     const dim3 grid((unsigned)tiles, (unsigned)(ncases / st.nk), (unsigned)st.nk);
-    rollout_supplied<<<grid, kThreads, smem, stream>>>(
-        d_cases, st, d_gu, d_x0noise, d_w, d_v, B, tiles, d_per_trial, d_partials, d_tickets, d_sums);
+    if (supplied_variant_for(variant, d_w, d_v, B) == kSuppliedBulk) {
+        // per device (the attribute lives in the current context), a few microseconds per call
+        const size_t smem = kBulkStages * sizeof(BulkStage) + (size_t)(smem_pad > 0 ? smem_pad : 0);   // pad: caps the CTAs per SM
+        const cudaError_t attr = cudaFuncSetAttribute(rollout_supplied_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (attr != cudaSuccess) return attr;
+        rollout_supplied_bulk<<<grid, kThreads, smem, stream>>>(
+            d_cases, st, d_gu, d_x0noise, d_w, d_v, B, tiles, d_per_trial, d_partials, d_tickets, d_sums);
+    } else {
+        const size_t smem = (size_t)max_T * sizeof(double2);
+        rollout_supplied<<<grid, kThreads, smem, stream>>>(
+            d_cases, st, d_gu, d_x0noise, d_w, d_v, B, tiles, d_per_trial, d_partials, d_tickets, d_sums);
+    }
     return cudaGetLastError();
+}
+
+int supplied_variant_for(int requested, const double *d_w, const double *d_v, size_t B)
+{
+    // bulk copies need 16-byte aligned rows: aligned bases and an even number of trials per row
+    const bool can_bulk = (reinterpret_cast<uintptr_t>(d_w) % 16 == 0) && (reinterpret_cast<uintptr_t>(d_v) % 16 == 0) && (B % 2 == 0);
+    if (requested == kSuppliedLdg || !can_bulk) return kSuppliedLdg;
+    return kSuppliedBulk;
 }
 
 cudaError_t launch_dfma_chain(double *d_out, int blocks, int iters, cudaStream_t stream)

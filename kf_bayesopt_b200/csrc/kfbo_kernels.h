@@ -6,7 +6,10 @@
 
 namespace kfbo {
 
-constexpr int kThreads = 128;        // threads per CTA (4 warps, one per SMSP)
+#ifndef KFBO_THREADS
+#define KFBO_THREADS 128
+#endif
+constexpr int kThreads = KFBO_THREADS;   // threads per CTA (128 = 4 warps, one per SMSP)
 constexpr int kMaxSteps = 2000;      // include/system_models.hpp:51
 
 // Constants of one (candidate, sample time) pair, built on the host (kfbo_api.cu: build_case).
@@ -53,7 +56,13 @@ cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleT
 
 cudaError_t launch_rollout_supplied(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, int max_T, const double *d_x0noise,
                                     const double *d_w, const double *d_v, size_t B, double *d_per_trial,
-                                    double *d_partials, unsigned *d_tickets, double *d_sums, cudaStream_t stream);
+                                    double *d_partials, unsigned *d_tickets, double *d_sums, int variant, int smem_pad,
+                                    cudaStream_t stream);
+
+// Which supplied-noise kernel runs: kSuppliedAuto picks the bulk-copy (cp.async.bulk + mbarrier)
+// variant whenever the streams allow it (16-byte aligned, even B), else the LDG variant.
+enum { kSuppliedAuto = 0, kSuppliedLdg = 1, kSuppliedBulk = 2 };
+int supplied_variant_for(int requested, const double *d_w, const double *d_v, size_t B);
 
 cudaError_t launch_dfma_chain(double *d_out, int blocks, int iters, cudaStream_t stream);
 

@@ -263,6 +263,9 @@ class CostEvaluator:
     def set_eval_counter(self, e: int) -> None:
         self._check(self._lib.kfbo_set_eval_counter(self._h, e))
 
+    def set_option(self, option: int, value: int) -> None:
+        self._check(self._lib.kfbo_set_option(self._h, option, value))
+
     def set_cuda_stream(self, stream_ptr: int) -> None:
         self._check(self._lib.kfbo_set_cuda_stream(self._h, stream_ptr or None))
 

@@ -241,3 +241,23 @@ def test_supplied_device_pointers_and_linearity(kfbo, oracle):
         pt_host, s_host = ev.eval_supplied(0, 0.9, 0.12, x0n, w, v)
     assert np.array_equal(out.cpu().numpy(), pt_host) and np.array_equal(s, s_host)
     assert rel_err(out.cpu().numpy()[0], oracle.eval_supplied(dt, T, 0.9, 0.12, x0n, w, v)) < RTOL
+
+
+def test_supplied_kernels_ldg_and_bulk_agree_bit_for_bit(kfbo, oracle):
+    # the bulk-copy (cp.async.bulk + mbarrier) kernel and the per-thread-load kernel run the same
+    # arithmetic: identical per-trial outputs, for full tiles, a ragged last tile, and step counts that
+    # are / are not a multiple of the staging depth
+    from kf_bayesopt_b200 import _lib
+    rng = np.random.default_rng(11)
+    for B, T, dt in [(256, 201, 0.1), (130, 7, 0.5), (2, 2, 1.0), (1026, 2000, 0.1), (4096, 211, 0.5)]:
+        rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
+        x0n, w, v = _noise(rng, oracle, dt, T, B)
+        out = {}
+        with kfbo.CostEvaluator(rv, [(dt, T)], max_candidates=2) as ev:
+            for name, variant in (("ldg", _lib.SUPPLIED_LDG), ("bulk", _lib.SUPPLIED_BULK)):
+                ev.set_option(_lib.OPT_SUPPLIED_KERNEL, variant)
+                out[name] = ev.eval_supplied(0, [0.8, 2.0], [0.15, 0.05], x0n, w, v)
+        assert np.array_equal(out["ldg"][0], out["bulk"][0]), (B, T)
+        assert np.array_equal(out["ldg"][1], out["bulk"][1]), (B, T)
+        want = oracle.eval_supplied(dt, T, 0.8, 0.15, x0n, w, v)
+        assert rel_err(out["bulk"][0][0], want) < RTOL, (B, T)
