@@ -316,8 +316,24 @@ public:
     {
     }
 
-    void Run()
+    // Like the reference's, Run() is void and runs on a std::thread: a failure (no CUDA device, ...)
+    // must not escape the thread, so it is recorded instead -- ok()/error() -- and the getters stay NaN.
+    void Run() noexcept
     {
+        try {
+            RunOrThrow();
+        } catch (const std::exception &e) {
+            error_ = e.what();
+        } catch (...) {
+            error_ = "unknown failure";
+        }
+    }
+    bool ok() const { return error_.empty(); }
+    const std::string &error() const { return error_; }
+
+    void RunOrThrow()
+    {
+        error_.clear();
         const ReadParaVehicle &sim = param_vehicle_;
         const int n = sim.nsimruns_ / sim.cpu_core_number_;                                   // trial.cpp:28
         const int T = sim.max_iterations_;                                                    // trial.cpp:45
@@ -351,6 +367,7 @@ private:
     ReadParaVehicle param_vehicle_, estimator_parameters_;
     int device_;
     uint64_t seed_;
+    std::string error_;
 };
 
 // ------------------------------------------------------------------------------------------

@@ -53,6 +53,8 @@ int main(int nargs, char *args[])
             for (int i = 0; i < rv_gt.cpu_core_number_; i++) t.push_back(kfbo::Trial(rv_gt, rv, device, seed));
             for (int i = 0; i < rv_gt.cpu_core_number_; i++) th.push_back(std::thread(&kfbo::Trial::Run, &t[i]));
             for (int i = 0; i < rv_gt.cpu_core_number_; i++) th[i].join();
+            for (int i = 0; i < rv_gt.cpu_core_number_; i++)
+                if (!t[i].ok()) throw std::runtime_error("Trial " + std::to_string(i) + ": " + t[i].error());
             for (int i = 0; i < rv_gt.cpu_core_number_; i++) {   // src/test_trial.cpp:70-72,82-84
                 average_nees += t[i].get_average_nees() / rv_gt.cpu_core_number_;
                 average_var_nees += t[i].get_average_var_nees() / rv_gt.cpu_core_number_;

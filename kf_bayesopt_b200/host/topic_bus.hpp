@@ -6,6 +6,7 @@
 #include <deque>
 #include <functional>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -34,7 +35,8 @@ public:
                     if (p->topic == topic && p->sub == i) { pending_.erase(p); break; }
             }
             auto copy = std::make_shared<M>(m);
-            pending_.push_back(Pending{topic, i, [copy, &s]() { s.call(copy.get()); }});
+            auto call = s.call;   // by value: later Subscribe() calls may move the subscriber table
+            pending_.push_back(Pending{topic, i, [copy, call]() { call(copy.get()); }});
         }
     }
     // Runs the callbacks queued so far (callbacks may publish; those run on the next spinOnce).

@@ -1,0 +1,66 @@
+"""GPU tests of the C++ host programs (kf_bayesopt_b200/host/): the reference-shaped callers
+(test_trial, the "noise" -> "cost" node, the BO loop) running on the CUDA evaluator."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_host_cpp import BIN, host_bins, yamls  # noqa: F401  (fixtures)
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(exe, *args, stdin=None):
+    out = subprocess.run([os.path.join(BIN, exe), *map(str, args)], input=stdin, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    return out.stdout
+
+
+def test_test_trial_matched_filter_is_consistent(host_bins, yamls):
+    # launch/robot1d_test_trail.launch:4-5: estimator == truth -> J_NEES ~ 0; both the
+    # reference-shaped caller (CPUcoreNumber Trial objects on std::threads) and the fused launch
+    for extra in ([], ["--fused"]):
+        out = _run("kfbo_test_trial", "--vehicle", yamls[0], "--nsimruns", 4000, *extra)
+        j = float(next(l for l in out.splitlines() if l.startswith("cost JNEES")).split()[-1])
+        var = float(next(l for l in out.splitlines() if l.startswith("variance NEES")).split()[-1])
+        assert j < 0.02, out                      # SE(avg NEES) ~ 0.4/sqrt(4000) -> J ~ 0.003
+        assert 3.0 < var < 5.0, out               # anchor: avgVarNEES ~ 3.86 at dt = 0.1
+    out = _run("kfbo_test_trial", "--vehicle", yamls[0], "--nsimruns", 4000, "--pnoise_est", 0.1, "--fused")
+    j = float(next(l for l in out.splitlines() if l.startswith("cost JNEES")).split()[-1])
+    assert abs(j - 1.613) < 0.05, out             # anchor: q_est = 0.1 -> J_NEES ~ 1.613 at dt = 0.1
+
+
+def test_node_stdin_contract_matches_python_run_trial(host_bins, yamls, kfbo):
+    seed = 424242
+    msgs = [([0.7], [0.2]), ([1.0], [0.1]), ([3.0], [0.05])]
+    lines = "".join(f"noise 1 1 {pn[0]} {on[0]}\n" for pn, on in msgs)
+    out = _run("kfbo_robot1d_kf", "--vehicle", yamls[0], "--seed", seed, "--quiet", stdin=lines)
+    got = [l.split() for l in out.splitlines() if l.startswith("cost ")]
+    rv = kfbo.ReadParaVehicle.from_yaml(yamls[0])
+    rt = kfbo.RunTrial(rv, seed=seed)
+    assert len(got) == len(msgs)
+    for g, (pn, on) in zip(got, msgs):
+        cost = rt.ProcessNoiseCallback(kfbo.Float64MultiArray.noise(pn, on))
+        assert float(g[1]) == cost.data                       # same Philox streams -> bit-identical cost
+        assert int(g[2]) == rt.last_result.index_max
+        assert [float(x) for x in g[3:]] == list(rt.last_result.cost)
+    # the batched message: candidate c of a batch == evaluation with the same stream bookkeeping
+    out = _run("kfbo_robot1d_kf", "--vehicle", yamls[0], "--seed", seed, "--quiet", "--max_candidates", 3,
+               stdin="batch 3 0.7 0.2 1.0 0.1 3.0 0.05\n")
+    got = [l.split() for l in out.splitlines() if l.startswith("cost ")]
+    with kfbo.CostEvaluator(rv, kfbo.sample_times_from(rv), seed=seed, max_candidates=3) as ev:
+        want = ev.eval_batch([0.7, 1.0, 3.0], [0.2, 0.1, 0.05])
+    assert [float(g[1]) for g in got] == [w.max_cost for w in want]
+
+
+def test_bo_loop_runs_the_topic_contract_end_to_end(host_bins, yamls):
+    out = _run("kfbo_bo_loop", "--vehicle", yamls[0], "--bayes", yamls[1], "--iterations", 25, "--init", 10,
+               "--nsimruns", 2000, "--quiet")
+    line = json.loads(next(l for l in out.splitlines() if l.startswith("{")))
+    assert line["iterations"] == 35 and line["nsimruns"] == 2000 and line["sample_times"] == 2
+    assert line["best_cost"] < 0.05                           # a consistent filter was found
+    assert 0.1 <= line["best_x"][0] <= 5.0 and 0.01 <= line["best_x"][1] <= 1.0
+    assert line["dt0_count"] + line["dt1_count"] == 25        # trial_node.cpp:121-126 bookkeeping
+    assert line["evaluator_s"] <= line["wall_s"]
