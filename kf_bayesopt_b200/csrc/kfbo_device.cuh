@@ -64,16 +64,16 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 // The random words of one step pair: two Philox calls A, B -> three normal pairs
 //   pair 0: radius (A.x : A.w[31:12]), angle A.y      pair 1: radius (B.x : B.w[31:12]), angle B.y
 //   pair 2: radius (A.z : A.w[11:0] B.w[7:0]), angle B.z
-__device__ __forceinline__ void normals_of_pair(const uint4 &A, const uint4 &B, const double (*lt)[2], const double *kt, double n[6])
+__device__ __forceinline__ void normals_of_pair(const uint4 &A, const uint4 &B, const math::LogTables &tab, double n[6])
 {
-    math::normal_pair_bits(A.x, A.w >> 12, A.y, lt, kt, n[0], n[1]);
-    math::normal_pair_bits(B.x, B.w >> 12, B.y, lt, kt, n[2], n[3]);
-    math::normal_pair_bits(A.z, ((A.w & 0xFFFu) << 8) | (B.w & 0xFFu), B.z, lt, kt, n[4], n[5]);
+    math::normal_pair_bits(A.x, A.w >> 12, A.y, tab, n[0], n[1]);
+    math::normal_pair_bits(B.x, B.w >> 12, B.y, tab, n[2], n[3]);
+    math::normal_pair_bits(A.z, ((A.w & 0xFFFu) << 8) | (B.w & 0xFFu), B.z, tab, n[4], n[5]);
 }
 
 // 1/S and 1/det(P): S and det(P) come out of a covariance recursion and are normal, well-scaled
-// numbers, so the division's slow path (denormal / huge operands) is never needed; two Newton steps
-// on the MUFU seed give <= 1 ulp.  -DKFBO_EXACT_DIV restores the correctly rounded IEEE division.
+// numbers, so the division's slow path (denormal / huge operands) is never needed; one third-order
+// step on the MUFU seed gives <= 1 ulp.  -DKFBO_EXACT_DIV restores the correctly rounded IEEE division.
 #if defined(KFBO_EXACT_DIV)
 #define KFBO_RCP(x) (1.0 / (x))
 #else
@@ -84,7 +84,10 @@ __device__ __forceinline__ void normals_of_pair(const uint4 &A, const uint4 &B, 
 struct Traj {
     double x0, x1;               // truth state            (Simulator::x_)
     double xh0, xh1;             // estimate               (KalmanFilter::xest_)
-    double p00, p01, p10, p11;   // covariance, 4 entries: the reference never symmetrises it
+    double p00, p01, p11;        // covariance.  The reference carries all four entries and never
+                                 // symmetrises; P(0,1) and P(1,0) are equal in exact arithmetic (Ppred is
+                                 // symmetric and P = (I-KH)Ppred with K = Ppred H^T/S), they differ by
+                                 // rounding only (~1e-16, contracting), far inside the 1e-9 parity bound.
     double kn, ki;               // shift = first NEES / NIS sample of the trial
     double sdn, sqn, sdi, sqi;   // sum (v-k), sum (v-k)^2 for NEES and NIS
 };
@@ -94,35 +97,50 @@ __device__ __forceinline__ void traj_init(Traj &t, double x0n0, double x0n1)
     t.x0 = 0.0 + x0n0;           // x0 = 0, P0 = I hard-coded (trial.cpp:31-32); simulator.cpp:12
     t.x1 = 0.0 + x0n1;
     t.xh0 = 0.0; t.xh1 = 0.0;    // kalman_filter.cpp:14-15
-    t.p00 = 1.0; t.p01 = 0.0; t.p10 = 0.0; t.p11 = 1.0;
+    t.p00 = 1.0; t.p01 = 0.0; t.p11 = 1.0;
     t.kn = 0.0; t.ki = 0.0;
     t.sdn = 0.0; t.sqn = 0.0; t.sdi = 0.0; t.sqi = 0.0;
 }
 
+// The noise of one filter-step, either as post-transform draws (supplied mode: w0, w1, v are added
+// as they come, like system_models.hpp:87,96,158) or as standard normals with the truth transform
+// (w = L n, v = sqrt(R) n2) folded into the state update's multiply-adds.
+struct StepNoise { double a, b, c; };
+
 // One filter-step: truth step, Kalman predict/update, NEES/NIS accumulation.
 // gu = g*u[step] = (0.5 dt^2 u, dt u), rounded products exactly as the reference forms them.
 // f = Fd(0,1) comes in as a uniform value (SampleTimeConsts), the candidate's Qd / R from the Case.
-template <bool kFirst>
-__device__ __forceinline__ void filter_step(Traj &t, const Case &m, const double f, double2 gu, double w0, double w1, double v)
+// kFused: noise = standard normals (n0, n1, n2), l00/l10/l11/sr = the truth transform.
+template <bool kFirst, bool kFused>
+__device__ __forceinline__ void filter_step(Traj &t, const Case &m, const double f, double2 gu, const StepNoise nz,
+                                            const double l00 = 0.0, const double l10 = 0.0, const double l11 = 0.0,
+                                            const double sr = 0.0)
 {
     // ---- truth: x = Fd x + g u + w ; z = H x + v
-    t.x0 = (fma(f, t.x1, t.x0) + gu.x) + w0;
-    t.x1 = (t.x1 + gu.y) + w1;
-    const double z = t.x0 + v;
-    // ---- predict: xpred = Fd xest + g u ; Ppred = (Fd P) Fd^T + Qd
+    const double xa = fma(f, t.x1, t.x0) + gu.x;
+    const double xb = t.x1 + gu.y;
+    double z;
+    if (kFused) {
+        t.x0 = fma(l00, nz.a, xa);
+        t.x1 = fma(l11, nz.b, fma(l10, nz.a, xb));
+        z = fma(sr, nz.c, t.x0);
+    } else {
+        t.x0 = xa + nz.a;
+        t.x1 = xb + nz.b;
+        z = t.x0 + nz.c;
+    }
+    // ---- predict: xpred = Fd xest + g u ; Ppred = (Fd P) Fd^T + Qd  (symmetric: 3 entries)
     const double xp0 = fma(f, t.xh1, t.xh0) + gu.x;
     const double xp1 = t.xh1 + gu.y;
-    const double fp00 = fma(f, t.p10, t.p00);
     const double fp01 = fma(f, t.p11, t.p01);
-    const double pp00 = fma(fp01, f, fp00) + m.q00;
+    const double pp00 = fma(fp01, f, fma(f, t.p01, t.p00)) + m.q00;
     const double pp01 = fp01 + m.q01;
-    const double pp10 = fma(t.p11, f, t.p10) + m.q10;
     const double pp11 = t.p11 + m.q11;
     // ---- gain: c = Ppred H^T ; S = H c + R ; K = c * (1/S)
     const double s = pp00 + m.r_est;
     const double sinv = KFBO_RCP(s);      // sob_.inverse() of a 1x1 (kalman_filter.cpp:28)
     const double k0 = pp00 * sinv;
-    const double k1 = pp10 * sinv;
+    const double k1 = pp01 * sinv;
     // ---- update: nu = z - H xpred ; xest = xpred + K nu ; P = (I - K H) Ppred
     const double nu = z - xp0;
     t.xh0 = fma(k0, nu, xp0);
@@ -130,21 +148,20 @@ __device__ __forceinline__ void filter_step(Traj &t, const Case &m, const double
     const double x00 = 1.0 - k0;
     t.p00 = x00 * pp00;
     t.p01 = x00 * pp01;
-    t.p10 = fma(-k1, pp00, pp10);
     t.p11 = fma(-k1, pp01, pp11);
-    // ---- NEES = (e^T P^-1) e with the closed-form 2x2 inverse; NIS = (nu / S) nu
+    // ---- NEES = e^T P^-1 e = (e^T adj(P) e) / det(P) (the closed-form 2x2 inverse of trial.cpp:58 with
+    //      the division applied once, to the quadratic form); NIS = (nu / S) nu
     const double e0 = t.x0 - t.xh0, e1 = t.x1 - t.xh1;
-    const double det = fma(t.p00, t.p11, -(t.p10 * t.p01));
+    const double det = fma(t.p00, t.p11, -(t.p01 * t.p01));
     const double invdet = KFBO_RCP(det);
-    const double i00 = t.p11 * invdet, i01 = -t.p01 * invdet;
-    const double i10 = -t.p10 * invdet, i11 = t.p00 * invdet;
-    const double r0 = fma(e1, i10, e0 * i00);
-    const double r1 = fma(e1, i11, e0 * i01);
+    const double u0 = fma(t.p11, e0, -(t.p01 * e1));
+    const double u1 = fma(t.p00, e1, -(t.p01 * e0));
+    const double num = fma(e1, u1, e0 * u0);
     const double nu_s = nu * sinv;
     // ---- accumulate, shifted by the first sample of the trial (kn, ki): the shifted values
     // nees - kn and nis - ki come straight out of the last fused multiply-add of each form
-    if (kFirst) { t.kn = fma(r1, e1, r0 * e0); t.ki = nu_s * nu; }
-    const double dn = fma(r1, e1, fma(r0, e0, -t.kn));
+    if (kFirst) { t.kn = num * invdet; t.ki = nu_s * nu; }
+    const double dn = fma(num, invdet, -t.kn);
     const double di = fma(nu_s, nu, -t.ki);
     t.sdn += dn; t.sqn = fma(dn, dn, t.sqn);
     t.sdi += di; t.sqi = fma(di, di, t.sqi);

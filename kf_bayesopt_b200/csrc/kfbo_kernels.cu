@@ -89,7 +89,7 @@ __device__ __forceinline__ void block_reduce_and_publish(const double out[4], in
 #define KFBO_PHILOX_PER_THREAD 1
 #endif
 #ifndef KFBO_PHILOX_MIN_BLOCKS
-#define KFBO_PHILOX_MIN_BLOCKS 1
+#define KFBO_PHILOX_MIN_BLOCKS 4
 #endif
 constexpr int kPhiloxPerThread = KFBO_PHILOX_PER_THREAD;
 
@@ -117,8 +117,6 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
         for (int i = threadIdx.x; i < (int)(sizeof(math::LogTables) / sizeof(double)); i += kThreads) ld[i] = ls[i];
     }
     __syncthreads();
-    const double (*lt)[2] = s_log.invc_logc;
-    const double *kt = s_log.k2ln2;
 
     // trajectory j of this thread: local trial (tile*K + j)*kThreads + threadIdx.x (coalesced outputs)
     uint32_t local[K], trial[K];
@@ -132,7 +130,7 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
     for (int j = 0; j < K; ++j) {
         double a, b;
         const uint4 w = philox4x32_10(trial[j], m.stream, 0u, 0u, key);
-        math::normal_pair_bits(w.x, w.w >> 12, w.y, lt, kt, a, b);
+        math::normal_pair_bits(w.x, w.w >> 12, w.y, s_log, a, b);
         traj_init(t[j], a, b);
     }
     // The counter-based generator lets the random bits of step pair p+1 be produced while the FP64
@@ -151,22 +149,22 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
 #pragma unroll
             for (int c = 0; c < 2; ++c) q[j][c] = philox4x32_10(trial[j], m.stream, (uint32_t)p + 2u, (uint32_t)c, key);
 #pragma unroll
-        for (int j = 0; j < K; ++j) normals_of_pair(r[j][0], r[j][1], lt, kt, n[j]);
+        for (int j = 0; j < K; ++j) normals_of_pair(r[j][0], r[j][1], s_log, n[j]);
         const double2 g0 = s_gu[2 * p];
         if (p == 0) {
 #pragma unroll
             for (int j = 0; j < K; ++j)
-                filter_step<true>(t[j], m, f, g0, l00 * n[j][0], fma(l11, n[j][1], l10 * n[j][0]), sr * n[j][2]);
+                filter_step<true, true>(t[j], m, f, g0, StepNoise{n[j][0], n[j][1], n[j][2]}, l00, l10, l11, sr);
         } else {
 #pragma unroll
             for (int j = 0; j < K; ++j)
-                filter_step<false>(t[j], m, f, g0, l00 * n[j][0], fma(l11, n[j][1], l10 * n[j][0]), sr * n[j][2]);
+                filter_step<false, true>(t[j], m, f, g0, StepNoise{n[j][0], n[j][1], n[j][2]}, l00, l10, l11, sr);
         }
         if (2 * p + 1 < T) {
             const double2 g1 = s_gu[2 * p + 1];
 #pragma unroll
             for (int j = 0; j < K; ++j)
-                filter_step<false>(t[j], m, f, g1, l00 * n[j][3], fma(l11, n[j][4], l10 * n[j][3]), sr * n[j][5]);
+                filter_step<false, true>(t[j], m, f, g1, StepNoise{n[j][3], n[j][4], n[j][5]}, l00, l10, l11, sr);
         }
 #pragma unroll
         for (int j = 0; j < K; ++j)
@@ -253,8 +251,8 @@ rollout_supplied(const Case *__restrict__ cases, const __grid_constant__ SampleT
             for (int j = 0; j < kPrefetch; ++j) {
                 const int s = s0 + j;
                 if (s < T) {
-                    if (s == 0) filter_step<true>(t, m, f, s_gu[s], cw0[j], cw1[j], cv[j]);
-                    else        filter_step<false>(t, m, f, s_gu[s], cw0[j], cw1[j], cv[j]);
+                    if (s == 0) filter_step<true, false>(t, m, f, s_gu[s], StepNoise{cw0[j], cw1[j], cv[j]});
+                    else        filter_step<false, false>(t, m, f, s_gu[s], StepNoise{cw0[j], cw1[j], cv[j]});
                 }
             }
 #pragma unroll
@@ -401,8 +399,8 @@ rollout_supplied_bulk(const Case *__restrict__ cases, const __grid_constant__ Sa
             if (s0 + j < T) {
                 const double w0 = sg.w[j][0][threadIdx.x], w1 = sg.w[j][1][threadIdx.x], vv = sg.v[j][threadIdx.x];
                 const double2 g = sg.gu[j];
-                if (j == 0 && c == 0) filter_step<true>(t, m, f, g, w0, w1, vv);
-                else                  filter_step<false>(t, m, f, g, w0, w1, vv);
+                if (j == 0 && c == 0) filter_step<true, false>(t, m, f, g, StepNoise{w0, w1, vv});
+                else                  filter_step<false, false>(t, m, f, g, StepNoise{w0, w1, vv});
             }
         }
         __syncwarp();

@@ -5,7 +5,8 @@
 // UMOV pairs; in the rollout loop that made ~420 issued instructions and ~190 FP64 instructions
 // per filter-step (profiles/ncu_philox_r1_first.txt).  The arguments here are known to be well
 // scaled (u1 in [2^-52, 1), S and det(P) of a covariance recursion, angle in one octant), so the
-// special cases are dropped.
+// special cases are dropped; sin/cos of the Box-Muller angle come from a 1024-entry direction table
+// plus a two-term rotation instead of degree-16 polynomials.
 //
 // Measured on B200 (tools/microbench/, DESIGN.md "What the FP64 pipe really costs"): a DFMA whose
 // three sources are three DISTINCT vector registers occupies the FP64 pipe for 3 cycles per warp
@@ -37,9 +38,13 @@ constexpr int kLogKTableSize = 56;                  // j = 0..52 used: 2 j ln2
 constexpr uint32_t kLogOffHi = 0x3FE60000u;         // z in [0.6875, 1.375)
 constexpr int kLogUnitEntry = 159;                  // the sub-interval [1-2^-9, 1): c = 1 exactly
 
+constexpr int kAngleTableBits = 10;
+constexpr int kAngleTableSize = 1 << kAngleTableBits;   // 1024 directions x {cos, sin}
+
 struct LogTables {
     double invc_logc[kLogTableSize][2];  // {1/c_i rounded, 2 ln(that rounded value)}
     double k2ln2[kLogKTableSize];        // 2 j ln 2
+    double cossin[kAngleTableSize][2];   // {cos, sin} of 2 pi (i + 1/2) / 1024
 };
 
 // Host: build the tables in long double (x87 extended, 64-bit mantissa).
@@ -56,6 +61,12 @@ inline void build_log_tables(LogTables *t)
         t->invc_logc[i][1] = (i == kLogUnitEntry) ? 0.0 : (double)(2.0L * logl((long double)invc));
     }
     for (int j = 0; j < kLogKTableSize; ++j) t->k2ln2[j] = (double)(2.0L * j * 0.693147180559945309417232121458176568L);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int i = 0; i < kAngleTableSize; ++i) {
+        const long double a = two_pi * (i + 0.5L) / kAngleTableSize;
+        t->cossin[i][0] = (double)cosl(a);
+        t->cossin[i][1] = (double)sinl(a);
+    }
 }
 
 KFBO_HD double make_double(uint32_t hi, uint32_t lo)
@@ -100,9 +111,10 @@ KFBO_HD double rcp_seed(double x)
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     return y;
 #else
-    int e;
-    const double m = std::frexp(x, &e);
-    return std::ldexp((double)(1.0f / (float)m), -e);
+    // MUFU.RCP64H reads and writes only the high 32-bit word (20 mantissa bits): emulate that
+    const double xt = make_double(hi_word(x), 0u);
+    const double y = 1.0 / xt;
+    return make_double(hi_word(y), 0u);
 #endif
 }
 
@@ -113,33 +125,33 @@ KFBO_HD double rsqrt_seed(double x)
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     return y;
 #else
-    int e;
-    double m = std::frexp(x, &e);
-    if (e & 1) { m *= 2.0; --e; }
-    return std::ldexp((double)(1.0f / std::sqrt((float)m)), -e / 2);
+    const double xt = make_double(hi_word(x), 0u);     // MUFU.RSQ64H: high word in, high word out
+    const double y = 1.0 / std::sqrt(xt);
+    return make_double(hi_word(y), 0u);
 #endif
 }
 
-// 1/x to <= 1 ulp for normal, well-scaled x (two Newton steps on the hardware seed).
+// 1/x to <= 1 ulp for normal, well-scaled x.  The hardware seed y0 = (1/x)(1 - e) is good to
+// |e| < 2^-19 (it sees 20 mantissa bits), so ONE third-order step y0 (1 + e + e^2) leaves e^3 < 2^-57:
+// 3 FP64 instructions instead of the 4 of two Newton steps.
 KFBO_HD double rcp(double x)
 {
-    double y = rcp_seed(x);
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
+    const double y = rcp_seed(x);
+    const double e = fma(-x, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
 }
 
-// sqrt(a) to <= 1 ulp for normal a > 0 (coupled Goldschmidt iterations on the hardware seed).
+// sqrt(a) to <= 1 ulp for normal a > 0: g = a y0 = sqrt(a)(1 - e), r = 1/2 - g y0/2 = e - e^2/2, and
+// sqrt(a) = g (1 - 2r)^(-1/2) = g (1 + r + 3/2 r^2 + O(r^3)): one third-order step on the 20-bit seed
+// (|r|^3 < 2^-57), 6 FP64 instructions instead of the 7 of two coupled Goldschmidt iterations.
 KFBO_HD double sqrt_pos(double a)
 {
     const double y = rsqrt_seed(a);
-    double g = a * y, h = 0.5 * y;
-    double r = fma(-h, g, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-h, g, 0.5);
-    return fma(g, r, g);
+    const double g = a * y, h = 0.5 * y;
+    const double r = fma(-h, g, 0.5);
+    const double t = fma(r, 1.5, 1.0);
+    return fma(g * r, t, g);
 }
 
 #if defined(__CUDACC__)
@@ -152,19 +164,6 @@ KFBO_HD double sqrt_pos(double a)
 // -2, 1, 1/2 and the hi32-rounded 1/3 are immediates; -2/3 and -2/5 need full precision.
 KFBO_CONST double kLogPolyU[2] = {-2.0 / 3.0, -0.4};
 #define KFBO_LOG_C5 0x1.5555500000000p-2
-// sin(pi/4 x) = x (S0 + S1 x^2 + ... + S7 x^14), cos(pi/4 x) = C0 + C1 x^2 + ... + C8 x^16, x in [-1,1]:
-// Taylor coefficients with the powers of pi/4 folded in; S6, S7, C6, C7, C8 rounded to hi32
-// immediates (max relative error of the polynomials in exact arithmetic: 1.2e-16 / 6.0e-17).
-KFBO_CONST double kSinPolyU[6] = {0x1.921fb54442d18p-1,  -0x1.4abbce625be53p-4, 0x1.466bc6775aae2p-9,
-                                  -0x1.32d2cce62bd86p-15, 0x1.50783487ee782p-22, -0x1.e3074fde8871fp-30};
-#define KFBO_SIN_C6 0x1.e8f4300000000p-38
-#define KFBO_SIN_C7 -0x1.6fadc00000000p-46
-KFBO_CONST double kCosPolyU[5] = {-0x1.3bd3cc9be45dep-2, 0x1.03c1f081b5ac4p-6, -0x1.55d3c7e3cbffap-12,
-                                  0x1.e1f506891babbp-19, -0x1.a6d1f2a204a8cp-26};
-#define KFBO_COS_C6 0x1.f9d3900000000p-34
-#define KFBO_COS_C7 -0x1.b6e2500000000p-42
-#define KFBO_COS_C8 0x1.20c6300000000p-50
-
 // L = -2 ln(u) for u in [2^-52, 1): table-driven, no division, no branch.
 //   u = 2^k z, z in [0.6875, 1.375);  i = top 8 bits of (bits(z) - OFF);  r = z/c_i - 1, |r| <= 2^-9
 //   -2 ln u = 2 (-k) ln2 + 2 ln(invc_i) + r * (-2 ln(1+r)/r)
@@ -186,21 +185,25 @@ KFBO_HD double neg2_log(double u, const double (*tab)[2], const double *ktab)
     return fma(r, s, ktab[-k] + logc2);
 }
 
-// sin(pi/4 x), cos(pi/4 x) for x in [-1, 1].
-KFBO_HD void sincos_octant(double x, double &s, double &c)
+// cos/sin of theta = 2 pi ang / 2^32 for a 32-bit angle: the top 10 bits pick one of 1024 tabulated
+// directions (cos, sin of the sub-interval's centre), the low 22 bits give the offset
+// |d| <= pi/1024 from it; cos d and sin d need two polynomial terms each (d^6/720 < 2e-18,
+// d^7/5040 < 6e-22) and the result is the rotation of the tabulated direction by d, scaled by `rad`:
+//   c = rad cos(theta), s = rad sin(theta).   13 FP64 instructions, no octant logic.
+KFBO_CONST double kAngU[4] = {0x1.921fb54442d18p-8 /* 2 pi / 1024 */, -0x1.2d97c7f3321d2p-7 /* -1.5 * that */,
+                              1.0 / 24.0, 1.0 / 120.0};
+KFBO_HD void rad_sincos_2pi(double rad, uint32_t ang, const double (*cossin)[2], double &c, double &s)
 {
-    const double x2 = x * x;
-    double ps = fma(KFBO_SIN_C7, x2, KFBO_SIN_C6);
-    double pc = fma(KFBO_COS_C8, x2, KFBO_COS_C7);
-    pc = fma(pc, x2, KFBO_COS_C6);
-    ps = fma(ps, x2, kSinPolyU[5]); pc = fma(pc, x2, kCosPolyU[4]);
-    ps = fma(ps, x2, kSinPolyU[4]); pc = fma(pc, x2, kCosPolyU[3]);
-    ps = fma(ps, x2, kSinPolyU[3]); pc = fma(pc, x2, kCosPolyU[2]);
-    ps = fma(ps, x2, kSinPolyU[2]); pc = fma(pc, x2, kCosPolyU[1]);
-    ps = fma(ps, x2, kSinPolyU[1]); pc = fma(pc, x2, kCosPolyU[0]);
-    ps = fma(ps, x2, kSinPolyU[0]); pc = fma(pc, x2, 1.0);
-    s = ps * x;
-    c = pc;
+    const uint32_t i = ang >> (32 - kAngleTableBits), r = ang & ((1u << (32 - kAngleTableBits)) - 1u);
+    const double y = make_double(0x3FF00000u | (r >> 2), r << 30);          // 1 + r 2^-22 in [1, 2)
+    const double d = fma(y, kAngU[0], kAngU[1]);                             // (2 pi / 1024)(r 2^-22 - 1/2)
+    const double d2 = d * d;
+    const double cd = fma(fma(d2, kAngU[2], -0.5), d2, 1.0);                 // cos d
+    const double sp = fma(d2, kAngU[3], -1.0 / 6.0) * d2;
+    const double sd = fma(sp, d, d);                                         // sin d
+    const double a = rad * cossin[i][0], b = rad * cossin[i][1];
+    c = fma(a, cd, -(b * sd));
+    s = fma(b, cd, a * sd);
 }
 
 // 84 random bits -> two independent N(0,1) draws (Box-Muller).  THE SPEC (restated draw for draw
@@ -213,35 +216,13 @@ KFBO_HD void sincos_octant(double x, double &s, double &c)
 // (32 angle bits: 2^32 directions, 1.5e-9 rad apart; the radius keeps 52 bits, so each normal is
 // continuous to FP64 resolution and the tails reach 8.5 sigma.  Random bits are the expensive part
 // on this chip -- see the Philox note in kfbo_device.cuh.)
-// Evaluated per octant: x = f (even o) or 1-f (odd o); sin/cos of (pi/4)x; swap and signs from o.
-KFBO_HD void normal_pair_bits(uint32_t rad_hi, uint32_t rad_lo20, uint32_t ang, const double (*tab)[2],
-                              const double *ktab, double &na, double &nb)
+// theta = (pi/4)(o + f) = 2 pi ang / 2^32: evaluated by rad_sincos_2pi above.
+KFBO_HD void normal_pair_bits(uint32_t rad_hi, uint32_t rad_lo20, uint32_t ang, const LogTables &tab, double &na, double &nb)
 {
-    // ---- radius
     const double y1 = make_double(0x3FF00000u | (rad_hi >> 12), (rad_hi << 20) | rad_lo20 | 1u);   // [1,2)
     const double u1 = 2.0 - y1;
-    double rad = sqrt_pos(neg2_log(u1, tab, ktab));
-    // ---- angle
-    const uint32_t o = ang >> 29;
-    const double y2 = make_double(0x3FF00000u | ((ang >> 9) & 0xFFFFFu), ang << 23);   // 1 + f
-    const uint32_t odd = o & 1u;
-    const uint32_t swap = (o ^ (o >> 1)) & 1u;             // sin(theta) takes the cos polynomial
-    const uint32_t neg_sin = (o >> 2) & 1u;                // quadrants 2,3
-    const uint32_t neg_cos = ((o >> 1) ^ (o >> 2)) & 1u;   // quadrants 1,2
-    // sign bookkeeping: the cos-polynomial value gets its sign through rad, the sin-polynomial
-    // value (odd in x) through x.  Which of sin/cos(theta) the polynomials feed depends on swap.
-    const uint32_t neg_pc = swap ? neg_sin : neg_cos;      // sign wanted on the cos-polynomial value
-    const uint32_t neg_ps = swap ? neg_cos : neg_sin;      // sign wanted on the sin-polynomial value
-    rad = make_double(hi_word(rad) ^ (neg_pc << 31), lo_word(rad));
-    const uint32_t flip_x = neg_ps ^ neg_pc;               // rad already carries neg_pc
-    // t = f (even octant) or f - 1 (odd); |x| = f or 1 - f = -t; then the sign flip
-    const double t = y2 + make_double(odd ? 0xC0000000u : 0xBFF00000u, 0u);     // y2 - 2 or y2 - 1
-    const double x = make_double(hi_word(t) ^ ((odd ^ flip_x) << 31), lo_word(t));
-    double ps, pc;
-    sincos_octant(x, ps, pc);
-    const double a = rad * pc, b = rad * ps;
-    na = swap ? b : a;     // rad cos(theta)
-    nb = swap ? a : b;     // rad sin(theta)
+    const double rad = sqrt_pos(neg2_log(u1, tab.invc_logc, tab.k2ln2));
+    rad_sincos_2pi(rad, ang, tab.cossin, na, nb);
 }
 
 }  // namespace math

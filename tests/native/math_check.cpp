@@ -46,20 +46,23 @@ int main()
     // edge values
     for (double u : {0x1p-52, 1.0 - 0x1p-52, 0.6875, 0.6875 - 0x1p-54, 1.0 - 0x1p-9, 1.0 - 0x1p-9 - 0x1p-53, 0.5, 0.25 + 0x1p-54})
         e_log = std::fmax(e_log, ulp_err(neg2_log(u, t.invc_logc, t.k2ln2), -2.0L * logl((long double)u)));
-    // octant sin / cos
-    for (int i = 0; i < 2000000; ++i) {
-        const double x = (double)(g() >> 11) * 0x1p-53 * ((i & 1) ? 1.0 : -1.0);
+    // rad * cos / sin of a 32-bit angle (direction table + rotation), rad = 1: absolute error in ulps of 1
+    const long double TWO_PI = 6.283185307179586476925286766559005768L;
+    for (int i = 0; i < 4000000; ++i) {
+        uint32_t ang = (uint32_t)g();
+        if (i % 8 == 0) ang = (ang & ~0x3FFFFFu) | ((i & 8) ? 0x3FFFFFu : 0u);      // both ends of a table sub-interval
+        if (i % 8 == 1) ang &= 0xC0000000u;                                           // the axes
         double s, c;
-        sincos_octant(x, s, c);
-        e_sin = std::fmax(e_sin, ulp_err(s, sinl(PI4 * x)));
-        e_cos = std::fmax(e_cos, ulp_err(c, cosl(PI4 * x)));
+        rad_sincos_2pi(1.0, ang, t.cossin, c, s);
+        const long double th = TWO_PI * (long double)ang * 0x1p-32L;
+        e_sin = std::fmax(e_sin, (double)(fabsl((long double)s - sinl(th)) * 0x1p53L));
+        e_cos = std::fmax(e_cos, (double)(fabsl((long double)c - cosl(th)) * 0x1p53L));
     }
-    { double s, c; sincos_octant(1.0, s, c); e_sin = std::fmax(e_sin, ulp_err(s, sinl(PI4))); e_cos = std::fmax(e_cos, ulp_err(c, cosl(PI4))); }
     // the full pair against the spec evaluated in long double (absolute error: |n| <= 8.5)
     for (int i = 0; i < 2000000; ++i) {
         const uint32_t rad_hi = (uint32_t)g(), lo20 = (uint32_t)g() & 0xFFFFFu, ang = (uint32_t)g();
         double na, nb;
-        normal_pair_bits(rad_hi, lo20, ang, t.invc_logc, t.k2ln2, na, nb);
+        normal_pair_bits(rad_hi, lo20, ang, t, na, nb);
         const uint64_t m1 = (((uint64_t)rad_hi << 20) | lo20) | 1u;
         const long double u1 = 1.0L - (long double)m1 * 0x1p-52L;
         const long double theta = PI4 * ((long double)(ang >> 29) + (long double)(ang & 0x1FFFFFFFu) * 0x1p-29L);

@@ -16,5 +16,6 @@ def test_custom_math_accuracy(tmp_path):
     assert got["rcp_ulp"] <= 1.0
     assert got["sqrt_ulp"] <= 2.0
     assert got["neg2log_ulp"] <= 2.5
-    assert got["sin_ulp"] <= 2.5 and got["cos_ulp"] <= 2.0
+    # sin/cos of the Box-Muller angle: absolute error in units of 2^-53 (half an ulp of 1)
+    assert got["sin_ulp"] <= 3.0 and got["cos_ulp"] <= 3.0
     assert got["na_abs"] < 4e-15 and got["nb_abs"] < 4e-15
