@@ -21,29 +21,35 @@ namespace kfbo {
 // Philox4x32-10 (Salmon et al., SC'11).  Counter-based: no state, no races -- replaces the
 // process-wide static std::mt19937 of include/eigenmvn.h:51,62.
 //
-// Cost on B200 (tools/microbench/imad_wide.cu): the 32x32->64 multiply IMAD.WIDE.U32 takes ~5
-// cycles per warp on a pipe it SHARES with FP64 (it does not overlap with DFMA), IMAD.HI.U32 ~4,
-// while the 32-bit IMAD (low half) takes 2 cycles on a pipe that does overlap.  One Philox call is
-// 20 such multiplies = 80-100 FP64-pipe cycles, as much as 45 DFMAs -- random bits are the
-// expensive resource of this kernel, which is why a normal pair consumes 84 of them, not 128.
+// Cost on B200 (tools/microbench/imad_wide.cu, pipe_mix.cu): the 32x32->64 multiply IMAD.WIDE.U32
+// takes ~5.1 cycles per warp, ~75% of which do NOT overlap with DFMA (8 DFMA 17.6 cycles, 8 WIDE 40.7,
+// both 53.9); IMAD.HI.U32 ~4.1 (half exclusive); the 32-bit IMAD takes 2 cycles and overlaps fully.
+// One Philox call is up to 20 such multiplies ~ 80-100 pipe cycles, as much as 45 DFMAs -- random bits
+// are the expensive resource of this kernel, which is why a normal pair consumes 84 of them, not 128.
 // ---------------------------------------------------------------------------------------
-#ifndef KFBO_PHILOX_SPLIT_MUL
-#define KFBO_PHILOX_SPLIT_MUL 0
+// KFBO_PHILOX_SPLIT16_ROUNDS: how many of the 10 rounds form their two 32x32->64 products from four
+// 16x16->32 products (IMAD on the FMA pipe + shifts/adds on the ALU pipe, ~11 instructions that all
+// overlap with FP64) instead of one IMAD.WIDE (1 instruction, ~5 cycles, ~75% of them exclusive with
+// FP64 -- tools/microbench/imad_wide.cu).  Trades issue slots for shared-pipe cycles.
+#ifndef KFBO_PHILOX_SPLIT16_ROUNDS
+#define KFBO_PHILOX_SPLIT16_ROUNDS 0
 #endif
-__device__ __forceinline__ void mulhilo32(uint32_t m, uint32_t a, uint32_t zero, uint32_t &hi, uint32_t &lo)
+template <uint32_t M>
+__device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t &hi, uint32_t &lo)
 {
-#if KFBO_PHILOX_SPLIT_MUL
-    // experiment: keep the halves apart, IMAD.HI (shared pipe, ~4 cycles) + IMAD (free pipe) instead of
-    // IMAD.WIDE (~5).  Measured SLOWER in the kernel (20.99 vs 20.08 ms), hence off by default.
-    // ptxas fuses mul.hi + mul.lo of the same operands back into IMAD.WIDE, so the low half is a
-    // multiply-add with an addend it cannot prove to be zero (a kernel parameter that is always 0).
-    hi = __umulhi(m, a);
-    lo = m * a + zero;
-#else
-    (void)zero;
-    lo = m * a;
-    hi = __umulhi(m, a);
-#endif
+    lo = M * a;
+    hi = __umulhi(M, a);
+}
+template <uint32_t M>
+__device__ __forceinline__ void mulhilo32_split16(uint32_t a, uint32_t &hi, uint32_t &lo)
+{
+    constexpr uint32_t Mh = M >> 16, Ml = M & 0xFFFFu;
+    const uint32_t al = a & 0xFFFFu, ah = a >> 16;
+    const uint32_t p0 = al * Ml;                       // < 2^32
+    const uint32_t m1 = al * Mh + (p0 >> 16);          // <= (2^16-1)^2 + 2^16-1 < 2^32
+    const uint32_t m2 = ah * Ml + (m1 & 0xFFFFu);      // < 2^32
+    hi = ah * Mh + (m1 >> 16) + (m2 >> 16);
+    lo = M * a;
 }
 
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &key)
@@ -51,8 +57,13 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t lo0, hi0, lo1, hi1;
-        mulhilo32(0xD2511F53u, c0, key.zero, hi0, lo0);
-        mulhilo32(0xCD9E8D57u, c2, key.zero, hi1, lo1);
+        if (r >= 10 - KFBO_PHILOX_SPLIT16_ROUNDS) {
+            mulhilo32_split16<0xD2511F53u>(c0, hi0, lo0);
+            mulhilo32_split16<0xCD9E8D57u>(c2, hi1, lo1);
+        } else {
+            mulhilo32<0xD2511F53u>(c0, hi0, lo0);
+            mulhilo32<0xCD9E8D57u>(c2, hi1, lo1);
+        }
         c0 = hi1 ^ c1 ^ key.k0[r];
         c1 = lo1;
         c2 = hi0 ^ c3 ^ key.k1[r];

@@ -12,12 +12,17 @@
 
 namespace kfbo {
 
-// Select entry k of a small per-sample-time table held in the parameter bank WITHOUT dynamic
-// indexing: a register-indexed LDC lands in a vector register, a chain of selects on the uniform
-// blockIdx.z stays in the uniform datapath.
+// Select entry k of a small per-sample-time table held in the parameter bank so that the result
+// lands in a UNIFORM register pair: a register-indexed LDC, and also a chain of selects on the
+// doubles themselves (predicated LDC.64), end up in vector registers, and a DFMA whose three sources
+// are distinct vector registers costs 3 FP64-pipe cycles instead of 2.  Selecting the two 32-bit
+// halves with integer selects on the uniform blockIdx.z keeps them in the uniform datapath
+// (SASS: DFMA R, R, UR, R).
 __device__ __forceinline__ double pick4(const double (&a)[4], unsigned k)
 {
-    return k == 0 ? a[0] : k == 1 ? a[1] : k == 2 ? a[2] : a[3];
+    const int lo = k == 0 ? __double2loint(a[0]) : k == 1 ? __double2loint(a[1]) : k == 2 ? __double2loint(a[2]) : __double2loint(a[3]);
+    const int hi = k == 0 ? __double2hiint(a[0]) : k == 1 ? __double2hiint(a[1]) : k == 2 ? __double2hiint(a[2]) : __double2hiint(a[3]);
+    return __hiloint2double(hi, lo);
 }
 
 // CTA partial -> global; last CTA of the case reduces all partials of the case in fixed order.
@@ -441,7 +446,6 @@ __global__ void __launch_bounds__(256) dfma_chain(double *out, int iters, double
 PhiloxKeys expand_philox_key(uint64_t seed)
 {
     PhiloxKeys k;
-    k.zero = 0u;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     for (int r = 0; r < 10; ++r) {
         k.k0[r] = k0; k.k1[r] = k1;

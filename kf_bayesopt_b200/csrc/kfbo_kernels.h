@@ -42,7 +42,6 @@ struct SampleTimeConsts {
 // the parameter bank instead of re-deriving them per call.
 struct PhiloxKeys {
     uint32_t k0[10], k1[10];
-    uint32_t zero;   // always 0: an addend the assembler cannot see through (keeps IMAD.HI and IMAD apart)
 };
 PhiloxKeys expand_philox_key(uint64_t seed);
 
