@@ -30,6 +30,10 @@ sys.path.insert(0, ROOT)
 TRIALS = 1 << 20
 STEPS_PER_TRIAL = 1000
 SAMPLE_TIMES = [(0.1, STEPS_PER_TRIAL), (0.5, STEPS_PER_TRIAL)]
+# --workload cfg4 (BASELINE.json configs[3]): 64 x 64 candidates over the yaml bounds x 1024 trials x the README
+# sample-time pair, candidates sharded over the ranks, one ncclAllReduce of the [4096][2][4] sums
+CFG4_GRID, CFG4_TRIALS, CFG4_SAMPLE_TIMES = 64, 1024, [(0.1, 201), (0.5, 211)]
+CFG4_BOUNDS = ((0.1, 5.0), (0.01, 1.0))   # config/bayesParams.yaml:18-19
 Q_TRUTH, R_TRUTH = 1.0, 0.1          # config/vehicleParams.yaml:18-19
 CANDIDATE = ([1.0], [0.1])           # launch/robot1d_test_trail.launch:4-5 (estimator == truth)
 FLOPS_PER_STEP = 137.0               # reference-faithful dense 2x2 count, RNG excluded
@@ -39,6 +43,16 @@ METRIC = "filter-steps/sec (trials x timesteps x sample times); ms_per_step = ms
 UNIT = "filter-steps/s"
 WORKLOAD = ("cfg3: robot1d J_NEES, %d trials x %d steps x %d sample times (dt 0.1/0.5) per evaluation, "
             "FP64, on-device Philox4x32-10 noise" % (TRIALS, STEPS_PER_TRIAL, len(SAMPLE_TIMES)))
+
+
+def profiled_traffic(kernel: str, workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` at this bench's size, from the committed
+    `ncu --set full` capture (profiles/traffic.json, written by tools/ncu_traffic.py); None if there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(f"{kernel}:{workload}", {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -141,6 +155,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kfbo", choices=["kfbo", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4"],
+                    help="cfg3 (default, the configuration the metric is quoted on) or the cfg4 candidate sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-supplied", action="store_true", help="skip the supplied-noise (HBM roofline) leg")
     args = ap.parse_args()
@@ -173,17 +189,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    rv = kf.ReadParaVehicle(nsimruns_=TRIALS, cpu_core_number_=1, pnoise_=[Q_TRUTH], onoise_=[R_TRUTH])
-    ev = kf.CostEvaluator(rv, SAMPLE_TIMES, seed=0x4B46424F00002026, device=local_rank)
+    cfg4 = args.workload == "cfg4"
+    if cfg4:
+        trials, sample_times = CFG4_TRIALS, CFG4_SAMPLE_TIMES
+        qq = np.repeat(np.geomspace(*CFG4_BOUNDS[0], CFG4_GRID), CFG4_GRID)
+        rr = np.tile(np.geomspace(*CFG4_BOUNDS[1], CFG4_GRID), CFG4_GRID)
+        n_cand, shard = qq.size, kf.SHARD_CANDIDATES
+        workload = ("cfg4: cost-surface sweep, %d candidates x %d trials x %d sample times (dt 0.1 T 201 / dt 0.5 T 211), "
+                    "FP64, on-device Philox4x32-10 noise" % (n_cand, trials, len(sample_times)))
+    else:
+        trials, sample_times, n_cand, shard, workload = TRIALS, SAMPLE_TIMES, 1, kf.SHARD_TRIALS, WORKLOAD
+    rv = kf.ReadParaVehicle(nsimruns_=trials, cpu_core_number_=1, pnoise_=[Q_TRUTH], onoise_=[R_TRUTH])
+    ev = kf.CostEvaluator(rv, sample_times, seed=0x4B46424F00002026, device=local_rank, max_candidates=n_cand)
     stream = torch.cuda.Stream()           # the stream every kernel of the evaluator is launched on
     ev.set_cuda_stream(stream.cuda_stream)
     if world > 1:
-        init_comm(ev, kf.SHARD_TRIALS)
-    steps_per_eval = float(TRIALS) * STEPS_PER_TRIAL * len(SAMPLE_TIMES)
+        init_comm(ev, shard)
+    steps_per_eval = float(trials) * n_cand * sum(T for _, T in sample_times)
+
+    def evaluate():
+        if cfg4:
+            return ev.eval_batch(qq, rr)[0]
+        return ev.eval(*CANDIDATE)
 
     # ---- device-timed throughput: K evaluations, CUDA events on the launching stream, max over ranks
     for _ in range(args.warmup):
-        res = ev.eval(*CANDIDATE)
+        res = evaluate()
     try:
         gpu_id = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
     except Exception:
@@ -197,7 +228,7 @@ def main():
     t0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
-        res = ev.eval(*CANDIDATE)
+        res = evaluate()
         ms, n = ev.last_kernel_ms()
         kernel_ms.append(ms)
         launches += n
@@ -215,21 +246,24 @@ def main():
     # (host buffers; the per-step H2D is the candidate's model constants, the D2H the cost sums)
     rt = kf.RunTrial(rv, evaluator=ev)
     msg = kf.Float64MultiArray.noise(*CANDIDATE)
+    e2e_call = (lambda: ev.eval_batch_costs(qq, rr)) if cfg4 else (lambda: rt.ProcessNoiseCallback(msg))
     for _ in range(2):
-        rt.ProcessNoiseCallback(msg)
+        e2e_call()
     barrier()
     w0 = time.perf_counter()
     for _ in range(args.steps):
-        cost = rt.ProcessNoiseCallback(msg)
+        e2e_call()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = steps_per_eval * args.steps / float(e2e_s.item())
-    D = len(SAMPLE_TIMES)
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 96 * D, "d2h_bytes_per_step": 32 * D,
+    D = len(sample_times)
+    # per evaluation: H2D = the (candidate, sample time) constants (struct Case, 96 B each), D2H = the [C][D][4] sums
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 96 * D * n_cand, "d2h_bytes_per_step": 32 * D * n_cand,
            "ms_per_eval": float(e2e_s.item()) / args.steps * 1e3,
-           "api": "RunTrial.ProcessNoiseCallback (Float64MultiArray 'noise' -> Float64 'cost') over the C ABI kfbo_eval"}
+           "api": ("CostEvaluator.eval_batch_costs (host candidate arrays -> host costs) over the C ABI kfbo_eval_batch" if cfg4 else
+                   "RunTrial.ProcessNoiseCallback (Float64MultiArray 'noise' -> Float64 'cost') over the C ABI kfbo_eval")}
 
     # ---- roofline of the dominant kernel (rollout_philox): FP64 pipe
     k_ms = float(np.mean(kernel_ms))
@@ -239,7 +273,7 @@ def main():
         fp64_peak = kf.measure_fp64_peak(local_rank, 400.0)
         achieved = FLOPS_PER_STEP * local_steps / (k_ms * 1e-3) / 1e12
         roofline = {"bound": "fp64", "kernel": "rollout_philox", "achieved": achieved, "peak": fp64_peak,
-                    "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": profiled_traffic("rollout_philox", args.workload),
                     "peak_source": "measured live on this GPU: DFMA-chain microbenchmark (kfbo_measure_fp64_peak); "
                                    "MEASURED_PEAKS.json has no FP64 figure",
                     "flops_per_filter_step": FLOPS_PER_STEP, "kernel_ms": k_ms,
@@ -268,12 +302,13 @@ def main():
         ach = byts / (float(np.mean(ms_s)) * 1e-3) / 1e9
         line_extra["roofline_supplied"] = {
             "bound": "hbm", "kernel": "rollout_supplied", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": src, "kernel_ms": float(np.mean(ms_s)),
+            "frac": ach / peaks["hbm_gbs"], "traffic": profiled_traffic("rollout_supplied_bulk", "supplied"), "peak_source": src,
+            "kernel_ms": float(np.mean(ms_s)),
             "filter_steps_per_s": Bs * Ts / (float(np.mean(ms_s)) * 1e-3),
             "workload": f"{Bs} trials x {Ts} steps, supplied noise resident in HBM ({byts / 1e9:.2f} GB > L2)"}
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle's threaded path on a bounded sample
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not cfg4:
         cb, _, _ = cpu_reference_run(steps=3, warmup=1, budget_s=16.0)
         line_extra["cpu_baseline"] = cb
 
@@ -281,9 +316,11 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "trials": TRIALS, "steps_per_trial": STEPS_PER_TRIAL,
-                           "sample_times": SAMPLE_TIMES, "candidate": {"pnoise": CANDIDATE[0], "onoise": CANDIDATE[1]},
-                           "sharding": f"trials over {world} rank(s), one ncclAllReduce of {D * 4} doubles" if world > 1 else "single GPU",
+                "config": {"workload": workload, "trials": trials, "candidates": n_cand,
+                           "sample_times": sample_times,
+                           "candidate": "64 x 64 log grid over q in [0.1,5], r in [0.01,1]" if cfg4 else {"pnoise": CANDIDATE[0], "onoise": CANDIDATE[1]},
+                           "sharding": (f"{'candidates' if cfg4 else 'trials'} over {world} rank(s), one ncclAllReduce of "
+                                        f"{n_cand * D * 4} doubles") if world > 1 else "single GPU",
                            "l2": "n/a for the Philox path: no HBM-resident inputs (noise is generated on the fly); "
                                  "the supplied-noise leg streams 25 GB >> L2"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

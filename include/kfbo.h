@@ -150,7 +150,16 @@ int kfbo_set_cuda_stream(kfbo_handle *h, void *cuda_stream);
  * kfbo_eval_supplied* launch -- AUTO = the bulk-copy (cp.async.bulk + mbarrier) kernel whenever the
  * streams are 16-byte aligned and B is even, else the per-thread-load kernel. */
 enum { KFBO_OPT_SUPPLIED_KERNEL = 1, KFBO_OPT_BULK_SMEM_PAD = 2 /* extra dynamic shared memory (bytes) per CTA of the
-                                        bulk-copy kernel: lowers the CTAs resident per SM */ };
+                                        bulk-copy kernel: lowers the CTAs resident per SM */,
+       KFBO_OPT_ROLLOUT_FORM = 3 };
+/* KFBO_OPT_ROLLOUT_FORM, for the on-device-noise evaluations (kfbo_eval, kfbo_eval_batch, kfbo_eval_philox_trials):
+ *   KFBO_FORM_REFERENCE (default): every trajectory carries truth state, estimate and covariance and runs
+ *       simulator.cpp:15-19 + kalman_filter.cpp:18-38 + trial.cpp:53-60 step by step, as north_star prescribes.
+ *   KFBO_FORM_REDUCED: the data-independent covariance / gain recursion is tabulated once per (candidate,
+ *       sample time) and each trajectory propagates only the error e = x - xhat (the control and the truth
+ *       state cancel in it).  Same per-trial NEES/NIS to rounding (tests: 1e-9 relative), ~2.5x fewer FP64
+ *       instructions in the filter part.  The supplied-noise parity entry points always use the reference form. */
+enum { KFBO_FORM_REFERENCE = 0, KFBO_FORM_REDUCED = 1 };
 enum { KFBO_SUPPLIED_AUTO = 0, KFBO_SUPPLIED_LDG = 1, KFBO_SUPPLIED_BULK = 2 };
 int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value);
 

@@ -17,6 +17,8 @@ COST_CHOICES = {"JNEES": JNEES, "CNEES": CNEES, "JNIS": JNIS, "CNIS": CNIS}
 SHARD_TRIALS, SHARD_CANDIDATES = 0, 1
 OPT_SUPPLIED_KERNEL = 1
 OPT_BULK_SMEM_PAD = 2
+OPT_ROLLOUT_FORM = 3
+FORM_REFERENCE, FORM_REDUCED = 0, 1
 SUPPLIED_AUTO, SUPPLIED_LDG, SUPPLIED_BULK = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

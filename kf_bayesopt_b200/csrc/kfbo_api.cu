@@ -53,6 +53,7 @@ NcclApi &nccl()
 }
 
 constexpr size_t kPartialsBudgetBytes = 64u << 20;  // per-launch partial-sum scratch cap
+constexpr size_t kGainsBudgetBytes = 256u << 20;    // per-launch gain-table cap (reduced form)
 
 }  // namespace
 
@@ -87,6 +88,9 @@ struct kfbo_handle {
     // Philox stream bookkeeping
     uint32_t stream_base = 0, eval_counter = 0;
     int supplied_kernel = kfbo::kSuppliedAuto;
+    int rollout_form = KFBO_FORM_REFERENCE;
+    kfbo::GainStep *d_gains = nullptr;   // reduced form only: [cases per launch][gain stride]
+    size_t gains_cap = 0;                // entries
     int bulk_smem_pad = 0;
     // last evaluation
     int last_ncand = 0, last_launches = 0;
@@ -234,6 +238,7 @@ void kfbo_destroy(kfbo_handle *h)
     if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (int i = 0; i < 5; ++i) if (h->d_scratch[i]) cudaFree(h->d_scratch[i]);
+    if (h->d_gains) cudaFree(h->d_gains);
     if (h->d_gu) cudaFree(h->d_gu);
     if (h->d_logtab) cudaFree(h->d_logtab);
     if (h->d_cases) cudaFree(h->d_cases);
@@ -338,6 +343,21 @@ int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value)
         if (value < KFBO_SUPPLIED_AUTO || value > KFBO_SUPPLIED_BULK) return fail(h, KFBO_EINVAL, "kfbo_set_option: supplied kernel %lld", (long long)value);
         h->supplied_kernel = (int)value;
         return KFBO_OK;
+    case KFBO_OPT_ROLLOUT_FORM: {
+        if (value != KFBO_FORM_REFERENCE && value != KFBO_FORM_REDUCED) return fail(h, KFBO_EINVAL, "kfbo_set_option: rollout form %lld", (long long)value);
+        if (value == KFBO_FORM_REDUCED && !h->d_gains) {
+            // gain table for as many cases as one launch may hold (whole candidates), at most kGainsBudgetBytes
+            KFBO_CUDA(h, cudaSetDevice(h->device));
+            const size_t stride = (size_t)kfbo::gain_stride_for(h->max_T);
+            size_t ncases = kGainsBudgetBytes / (stride * sizeof(kfbo::GainStep));
+            ncases = std::max<size_t>(ncases / h->D * h->D, (size_t)h->D);
+            ncases = std::min<size_t>(ncases, (size_t)h->cases_cap);
+            KFBO_CUDA(h, cudaMalloc(&h->d_gains, ncases * stride * sizeof(kfbo::GainStep)));
+            h->gains_cap = ncases;
+        }
+        h->rollout_form = (int)value;
+        return KFBO_OK;
+    }
     case KFBO_OPT_BULK_SMEM_PAD:
         if (value < 0 || value > (128 << 10)) return fail(h, KFBO_EINVAL, "kfbo_set_option: smem pad %lld", (long long)value);
         h->bulk_smem_pad = (int)value;
@@ -383,15 +403,23 @@ int kfbo_eval_batch(kfbo_handle *h, int32_t C, const double *q_est, const double
     KFBO_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     const uint32_t ntrials = (uint32_t)(t1 - t0);
     if (ncases > 0 && ntrials > 0) {
-        const int tiles = kfbo::philox_tiles(ntrials);
-        const int step = cases_per_launch(h, tiles);
+        const bool reduced = h->rollout_form == KFBO_FORM_REDUCED;
+        const int tiles = reduced ? kfbo::rollout_tiles(ntrials) : kfbo::philox_tiles(ntrials);
+        int step = cases_per_launch(h, tiles);
+        if (reduced) step = std::max(D, std::min(step, (int)h->gains_cap));
         for (int first = 0; first < ncases; first += step) {
             const int n = std::min(step, ncases - first);
             kfbo::SampleTimeConsts st = h->st;
             st.k0 = 0; st.nk = D;   // cases are laid out [candidate][sample time]; chunks hold whole candidates
-            KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, st, h->d_gu, h->d_logtab, h->max_T, h->p.seed, (uint32_t)t0, ntrials,
-                                                     nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream));
-            ++h->last_launches;
+            if (reduced) {
+                KFBO_CUDA(h, kfbo::launch_rollout_philox_reduced(h->d_cases + first, n, st, h->d_gains, h->d_logtab, h->max_T, h->p.seed, (uint32_t)t0,
+                                                                 ntrials, nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream));
+                h->last_launches += 2;
+            } else {
+                KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, st, h->d_gu, h->d_logtab, h->max_T, h->p.seed, (uint32_t)t0, ntrials,
+                                                         nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream));
+                ++h->last_launches;
+            }
         }
     }
     KFBO_CUDA(h, cudaEventRecord(h->ev1, h->stream));
@@ -527,8 +555,12 @@ int kfbo_eval_philox_trials(kfbo_handle *h, int32_t k, double q_est, double r_es
     KFBO_CUDA(h, cudaMemsetAsync(d_ticket, 0, sizeof(unsigned), h->stream));
     kfbo::SampleTimeConsts st = h->st;
     st.k0 = k; st.nk = 1;
-    KFBO_CUDA(h, kfbo::launch_rollout_philox(d_case, 1, st, h->d_gu, h->d_logtab, h->max_T, h->p.seed, trial0, (uint32_t)ntrials, h->d_scratch[4],
-                                             (size_t)ntrials, d_partials, d_ticket, d_sums, h->stream));
+    if (h->rollout_form == KFBO_FORM_REDUCED)
+        KFBO_CUDA(h, kfbo::launch_rollout_philox_reduced(d_case, 1, st, h->d_gains, h->d_logtab, h->max_T, h->p.seed, trial0, (uint32_t)ntrials,
+                                                         h->d_scratch[4], (size_t)ntrials, d_partials, d_ticket, d_sums, h->stream));
+    else
+        KFBO_CUDA(h, kfbo::launch_rollout_philox(d_case, 1, st, h->d_gu, h->d_logtab, h->max_T, h->p.seed, trial0, (uint32_t)ntrials, h->d_scratch[4],
+                                                 (size_t)ntrials, d_partials, d_ticket, d_sums, h->stream));
     KFBO_CUDA(h, cudaMemcpyAsync(per_trial, h->d_scratch[4], 4 * (size_t)ntrials * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     KFBO_CUDA(h, cudaStreamSynchronize(h->stream));
     h->last_launches = 1;

@@ -426,6 +426,169 @@ rollout_supplied_bulk(const Case *__restrict__ cases, const __grid_constant__ Sa
 }
 
 // -----------------------------------------------------------------------------------------
+// REDUCED FORM of the Philox rollout (opt-in: KFBO_OPT_ROLLOUT_FORM = KFBO_FORM_REDUCED).
+//
+// Two exact identities of the reference recursion remove work that every trajectory of a case
+// repeats identically:
+//   1. the covariance recursion P, S, K (kalman_filter.cpp:23-37) does not depend on the data: it is
+//      the same for all trials of a (candidate, sample time).  riccati_gains runs it ONCE per case
+//      and tabulates, per step, the gain K, 1/S and P^-1 (what NEES / NIS need);
+//   2. the error e = x - xhat obeys e- = Fd e + w, nu = H e- + v, e = e- - K nu: the control g u and
+//      the truth state itself cancel (trial.cpp:53 only ever uses x - xhat).
+// Per trajectory that leaves 19 FP64 instructions per filter-step instead of 48 (plus the noise).
+// The per-trial NEES/NIS agree with the reference form to rounding (no x - xhat cancellation here,
+// so this form is the more accurate one); tests bound the difference by 1e-9 relative like every other
+// parity check.  It is NOT the formulation north_star prescribes (covariance per thread), so it is
+// off by default and bench.py reports it on its own line with its own instruction count.
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) riccati_gains(const Case *__restrict__ cases, int ncases, GainStep *__restrict__ table, int stride)
+{
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    if (i >= ncases) return;
+    const Case m = cases[i];
+    const double f = m.f;
+    double p00 = 1.0, p01 = 0.0, p11 = 1.0;                       // P0 = I (trial.cpp:32)
+    GainStep *out = table + (size_t)i * stride;
+    for (int s = 0; s < m.T; ++s) {
+        const double fp01 = fma(f, p11, p01);                     // same operations as filter_step
+        const double pp00 = fma(fp01, f, fma(f, p01, p00)) + m.q00;
+        const double pp01 = fp01 + m.q01;
+        const double pp11 = p11 + m.q11;
+        const double sv = pp00 + m.r_est;
+        const double sinv = KFBO_RCP(sv);
+        const double k0 = pp00 * sinv, k1 = pp01 * sinv;
+        const double x00 = 1.0 - k0;
+        p00 = x00 * pp00;
+        p01 = x00 * pp01;
+        p11 = fma(-k1, pp01, pp11);
+        const double det = fma(p00, p11, -(p01 * p01));
+        const double invdet = KFBO_RCP(det);
+        GainStep g;
+        g.k0 = k0; g.k1 = k1; g.sinv = sinv;
+        g.a = p11 * invdet; g.b = -2.0 * (p01 * invdet); g.c = p00 * invdet;   // P^-1 = [[a, b/2], [b/2, c]]
+        out[s] = g;
+    }
+}
+
+constexpr int kGainChunk = 16;    // steps per stage of the gain ring (768 B)
+constexpr int kGainStages = 3;
+
+template <bool kFirst>
+__device__ __forceinline__ void reduced_step(double &e0, double &e1, double &kn, double &ki, double &sdn, double &sqn,
+                                             double &sdi, double &sqi, const GainStep &g, const double f, const double l00,
+                                             const double l10, const double l11, const double sr, const double n0,
+                                             const double n1, const double n2)
+{
+    const double em0 = fma(l00, n0, fma(f, e1, e0));            // e- = Fd e + w,  w = L n
+    const double em1 = fma(l11, n1, fma(l10, n0, e1));
+    const double nu = fma(sr, n2, em0);                          // nu = H e- + v
+    e0 = fma(-g.k0, nu, em0);                                    // e = e- - K nu
+    e1 = fma(-g.k1, nu, em1);
+    const double t2 = fma(g.b, e1, g.a * e0);                    // NEES = a e0^2 + b e0 e1 + c e1^2
+    const double q = (g.c * e1) * e1;
+    const double nu_s = nu * g.sinv;
+    if (kFirst) { kn = fma(e0, t2, q); ki = nu_s * nu; }
+    const double dn = fma(e0, t2, q - kn);
+    const double di = fma(nu_s, nu, -ki);
+    sdn += dn; sqn = fma(dn, dn, sqn);
+    sdi += di; sqi = fma(di, di, sqi);
+}
+
+__global__ void __launch_bounds__(kThreads)
+rollout_philox_reduced(const Case *__restrict__ cases, const __grid_constant__ SampleTimeConsts st,
+                       const GainStep *__restrict__ gains, int gain_stride, const math::LogTables *__restrict__ logtab,
+                       const __grid_constant__ PhiloxKeys key, uint32_t trial0, uint32_t ntrials, int tiles,
+                       double *__restrict__ per_trial, size_t per_trial_ld, double *__restrict__ partials,
+                       unsigned *__restrict__ tickets, double *__restrict__ sums)
+{
+    __shared__ math::LogTables s_log;
+    __shared__ __align__(128) GainStep s_gain[kGainStages][kGainChunk];
+    __shared__ __align__(8) uint64_t s_full[kGainStages], s_empty[kGainStages];
+    const int case_idx = blockIdx.y * gridDim.z + blockIdx.z, tile = blockIdx.x;
+    const Case m = cases[case_idx];
+    const int T = m.T;
+    const unsigned kk = st.k0 + blockIdx.z;
+    const double f = pick4(st.f, kk), l00 = pick4(st.l00, kk), l10 = pick4(st.l10, kk), l11 = pick4(st.l11, kk),
+                 sr = pick4(st.sr, kk);
+    const int lane = threadIdx.x & 31;
+    {
+        const double *ls = reinterpret_cast<const double *>(logtab);
+        double *ld = reinterpret_cast<double *>(&s_log);
+        for (int i = threadIdx.x; i < (int)(sizeof(math::LogTables) / sizeof(double)); i += kThreads) ld[i] = ls[i];
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kGainStages; ++s) { mbar_init(&s_full[s], 1u); mbar_init(&s_empty[s], kThreads / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nchunks = (T + kGainChunk - 1) / kGainChunk;
+    const GainStep *gsrc = gains + (size_t)case_idx * gain_stride;      // stride is a multiple of kGainChunk
+    uint64_t policy = 0;
+    auto issue = [&](int chunk) {
+        uint64_t *bar = &s_full[chunk % kGainStages];
+        mbar_arrive_expect_tx(bar, (uint32_t)sizeof(s_gain[0]));
+        bulk_g2s(&s_gain[chunk % kGainStages][0], gsrc + (size_t)chunk * kGainChunk, (uint32_t)sizeof(s_gain[0]), bar, policy);
+    };
+    if (threadIdx.x == 0) {
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));   // every CTA of the case re-reads it
+        for (int c = 0; c < kGainStages - 1 && c < nchunks; ++c) issue(c);
+    }
+
+    const uint32_t local = (uint32_t)tile * kThreads + threadIdx.x;
+    const uint32_t trial = trial0 + local;    // past-the-end trajectories of the last tile are computed and discarded
+    double e0, e1, kn = 0.0, ki = 0.0, sdn = 0.0, sqn = 0.0, sdi = 0.0, sqi = 0.0;
+    {
+        const uint4 w = philox4x32_10(trial, m.stream, 0u, 0u, key);
+        math::normal_pair_bits(w.x, w.w >> 12, w.y, s_log, e0, e1);    // e = x0 + N(0,P0) - xhat0 = the draw itself
+    }
+    uint4 r0 = philox4x32_10(trial, m.stream, 1u, 0u, key), r1 = philox4x32_10(trial, m.stream, 1u, 1u, key);
+    for (int c = 0; c < nchunks; ++c) {
+        if (threadIdx.x == 0) {
+            const int nx = c + kGainStages - 1;
+            if (nx < nchunks) {
+                if (nx >= kGainStages) mbar_wait(&s_empty[nx % kGainStages], (uint32_t)((nx / kGainStages - 1) & 1));
+                issue(nx);
+            }
+        }
+        const int sidx = c % kGainStages;
+        mbar_wait(&s_full[sidx], (uint32_t)((c / kGainStages) & 1));
+        const GainStep *g = s_gain[sidx];
+        const int s0 = c * kGainChunk;
+#pragma unroll 1
+        for (int j = 0; j < kGainChunk && s0 + j < T; j += 2) {
+            const uint32_t p = (uint32_t)((s0 + j) >> 1);
+            const uint4 q0 = philox4x32_10(trial, m.stream, p + 2u, 0u, key), q1 = philox4x32_10(trial, m.stream, p + 2u, 1u, key);
+            double n[6];
+            normals_of_pair(r0, r1, s_log, n);
+            if (s0 + j == 0) reduced_step<true>(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j], f, l00, l10, l11, sr, n[0], n[1], n[2]);
+            else             reduced_step<false>(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j], f, l00, l10, l11, sr, n[0], n[1], n[2]);
+            if (s0 + j + 1 < T) reduced_step<false>(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j + 1], f, l00, l10, l11, sr, n[3], n[4], n[5]);
+            r0 = q0; r1 = q1;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[sidx]);
+    }
+    double out[4] = {0.0, 0.0, 0.0, 0.0};
+    {
+        Traj t;
+        t.kn = kn; t.ki = ki; t.sdn = sdn; t.sqn = sqn; t.sdi = sdi; t.sqi = sqi;
+        double o[4];
+        traj_finish(t, T, o);
+        if (local < ntrials) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out[k] = o[k];
+            if (per_trial != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) per_trial[((size_t)m.out_slot * 4 + k) * per_trial_ld + local] = o[k];
+            }
+        }
+    }
+    __shared__ double s_red[kThreads][4];
+    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, s_red);
+}
+
+// -----------------------------------------------------------------------------------------
 // DFMA-chain microbenchmark: 8 independent FMA chains per thread.
 // -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_chain(double *out, int iters, double a, double b)
@@ -463,8 +626,31 @@ cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleT
     const int tiles = philox_tiles(ntrials);
     const size_t smem = (size_t)max_T * sizeof(double2);
     const dim3 grid((unsigned)tiles, (unsigned)(ncases / st.nk), (unsigned)st.nk);   // ncases = candidates x nk
+    // static tables (25 KB) + the g*u table pass the default 48 KB of shared memory for T > ~1400: opt in
+    const cudaError_t attr = cudaFuncSetAttribute(rollout_philox, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (attr != cudaSuccess) return attr;
     rollout_philox<<<grid, kThreads, smem, stream>>>(
         d_cases, st, d_gu, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0, ntrials, tiles,
+        d_per_trial, per_trial_ld, d_partials, d_tickets, d_sums);
+    return cudaGetLastError();
+}
+
+int gain_stride_for(int max_T) { return (max_T + kGainChunk - 1) / kGainChunk * kGainChunk; }
+
+cudaError_t launch_rollout_philox_reduced(const Case *d_cases, int ncases, const SampleTimeConsts &st, GainStep *d_gains, const void *d_logtab,
+                                          int max_T, uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
+                                          size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
+                                          cudaStream_t stream)
+{
+    if (ncases <= 0 || ntrials == 0) return cudaSuccess;
+    const int stride = gain_stride_for(max_T);
+    riccati_gains<<<(ncases + 31) / 32, 32, 0, stream>>>(d_cases, ncases, d_gains, stride);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int tiles = rollout_tiles(ntrials);
+    const dim3 grid((unsigned)tiles, (unsigned)(ncases / st.nk), (unsigned)st.nk);
+    rollout_philox_reduced<<<grid, kThreads, 0, stream>>>(
+        d_cases, st, d_gains, stride, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0, ntrials, tiles,
         d_per_trial, per_trial_ld, d_partials, d_tickets, d_sums);
     return cudaGetLastError();
 }

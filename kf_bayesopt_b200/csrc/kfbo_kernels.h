@@ -53,6 +53,15 @@ cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleT
                                   size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
                                   cudaStream_t stream);
 
+// Reduced form (opt-in): per step of a case the gain K, 1/S and P^-1 = [[a, b/2], [b/2, c]], tabulated once
+// per case by riccati_gains; d_gains holds ncases x gain_stride_for(max_T) entries.
+struct GainStep { double k0, k1, sinv, a, b, c; };
+int gain_stride_for(int max_T);
+cudaError_t launch_rollout_philox_reduced(const Case *d_cases, int ncases, const SampleTimeConsts &st, GainStep *d_gains, const void *d_logtab,
+                                          int max_T, uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
+                                          size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
+                                          cudaStream_t stream);
+
 cudaError_t launch_rollout_supplied(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, int max_T, const double *d_x0noise,
                                     const double *d_w, const double *d_v, size_t B, double *d_per_trial,
                                     double *d_partials, unsigned *d_tickets, double *d_sums, int variant, int smem_pad,
