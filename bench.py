@@ -159,6 +159,7 @@ def main():
                     help="cfg3 (default, the configuration the metric is quoted on) or the cfg4 candidate sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-supplied", action="store_true", help="skip the supplied-noise (HBM roofline) leg")
+    ap.add_argument("--no-reduced", action="store_true", help="skip the reduced-form leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "kfbo" else args.warmup
 
@@ -207,9 +208,13 @@ def main():
         init_comm(ev, shard)
     steps_per_eval = float(trials) * n_cand * sum(T for _, T in sample_times)
 
+    class _First:   # the first candidate of a batch, shaped like Result where the JSON line reads it
+        def __init__(self, rec):
+            self.cost, self.max_cost, self.index_max = rec["cost"][:len(sample_times)], float(rec["max_cost"]), int(rec["index_max"])
+
     def evaluate():
         if cfg4:
-            return ev.eval_batch(qq, rr)[0]
+            return _First(ev.eval_batch_raw(qq, rr)[0])
         return ev.eval(*CANDIDATE)
 
     # ---- device-timed throughput: K evaluations, CUDA events on the launching stream, max over ranks
@@ -280,6 +285,29 @@ def main():
                     "filter_steps_per_launch": local_steps,
                     "note": "tensor cores do not apply (2x2 FP64 recursion); RNG flops are excluded from 'achieved'"}
         line_extra["roofline"] = roofline
+
+    # ---- the opt-in reduced form (KFBO_FORM_REDUCED) on the same workload and streams: reported on its own
+    # line with its own instruction count -- it is not the per-thread-covariance formulation north_star names
+    if not args.no_reduced:
+        from kf_bayesopt_b200 import _lib as L
+        ev.set_option(L.OPT_ROLLOUT_FORM, L.FORM_REDUCED)
+        red_ms = []
+        for i in range(3 + 5):
+            r2 = evaluate()
+            if i >= 3:
+                red_ms.append(ev.last_kernel_ms()[0])
+        ev.set_option(L.OPT_ROLLOUT_FORM, L.FORM_REFERENCE)
+        red = torch.tensor([float(np.mean(red_ms))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            line_extra["reduced_form"] = {
+                "value": steps_per_eval / (float(red.item()) * 1e-3), "unit": UNIT, "kernel_ms": float(red.item()),
+                "kernels": "riccati_gains + rollout_philox_reduced",
+                "fp64_instructions_per_filter_step": {"filter": 19, "noise": 42, "reference_form_filter": 48},
+                "J": [float(c) for c in r2.cost],
+                "note": "opt-in; gain/covariance recursion tabulated once per (candidate, sample time), trajectories "
+                        "propagate the error state; same per-trial NEES/NIS to rounding (tests: 1e-9 relative)"}
 
     # ---- supplied-noise leg: HBM roofline, inputs resident in HBM and larger than L2
     if rank == 0 and not args.no_supplied:

@@ -82,6 +82,11 @@ struct kfbo_handle {
     // grow-only scratch for the supplied-noise / per-trial entry points
     double *d_scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_cap[5] = {0, 0, 0, 0, 0};
+    // memo of the estimator-side discretisation by (pnoise, sample time): a candidate sweep repeats each
+    // pnoise value many times (a 64 x 64 grid has 64 of them), and the 4x4 matrix exponential is the only
+    // non-trivial host work per case
+    struct DiscMemo { uint64_t qbits = 0; int k = -1; double f = 0, Qd[4] = {0, 0, 0, 0}; };
+    DiscMemo disc_memo[256];
     // NCCL
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1, shard_mode = KFBO_SHARD_TRIALS;
@@ -140,11 +145,18 @@ int ensure_scratch(kfbo_handle *h, int slot, size_t doubles)
 // estimator (kalman_filter.cpp:6-10) plus the truth-side noise transform (simulator.cpp:5).
 int build_case(kfbo_handle *h, int k, double q_est, double r_est, uint32_t stream, int out_slot, Case *c)
 {
-    double Fd[4], Qd[4];
-    kfbo::host::discretize(q_est, h->p.dt[k], Fd, Qd);
-    if (Fd[0] != 1.0 || Fd[2] != 0.0 || Fd[3] != 1.0)
-        return fail(h, KFBO_EINVAL, "discretised Fd lost its [[1,f],[0,1]] structure");
-    c->f = Fd[1];
+    uint64_t qbits;
+    std::memcpy(&qbits, &q_est, sizeof qbits);
+    kfbo_handle::DiscMemo &memo = h->disc_memo[((qbits * 0x9E3779B97F4A7C15ull) >> 56) ^ (uint64_t)k];
+    if (memo.k != k || memo.qbits != qbits) {
+        double Fd[4];
+        kfbo::host::discretize(q_est, h->p.dt[k], Fd, memo.Qd);
+        if (Fd[0] != 1.0 || Fd[2] != 0.0 || Fd[3] != 1.0)
+            return fail(h, KFBO_EINVAL, "discretised Fd lost its [[1,f],[0,1]] structure");
+        memo.f = Fd[1]; memo.k = k; memo.qbits = qbits;
+    }
+    const double *Qd = memo.Qd;
+    c->f = memo.f;
     c->q00 = Qd[0]; c->q01 = Qd[1]; c->q10 = Qd[2]; c->q11 = Qd[3];
     c->r_est = r_est / h->p.dt[k];                       // system_models.hpp:143
     c->l00 = h->truth_l[k][0]; c->l10 = h->truth_l[k][1]; c->l11 = h->truth_l[k][2];

@@ -22,6 +22,11 @@ from ._lib import COST_CHOICES, KfboParams, KfboResult, MAX_SAMPLE_TIMES, SHARD_
 
 _dp = C.POINTER(C.c_double)
 
+# struct kfbo_result as a numpy record (same layout as _lib.KfboResult; checked in tests/test_host_abi.py)
+RESULT_DTYPE = np.dtype([("average_nees", "f8", (MAX_SAMPLE_TIMES,)), ("average_nis", "f8", (MAX_SAMPLE_TIMES,)),
+                         ("average_var_nees", "f8", (MAX_SAMPLE_TIMES,)), ("average_var_nis", "f8", (MAX_SAMPLE_TIMES,)),
+                         ("cost", "f8", (MAX_SAMPLE_TIMES,)), ("max_cost", "f8"), ("index_max", "i4"), ("reserved", "i4")])
+
 # trial_node.cpp:105-114: pass 0 uses the yaml (dt, t_end); pass 1 overwrites them with these.
 CODE_SECOND_SAMPLE_TIME = (1.0, 201.0)
 # the variant commented out at trial_node.cpp:109-112 and described in README.md:96 / BASELINE.json
@@ -213,10 +218,20 @@ class CostEvaluator:
         self._check(self._lib.kfbo_eval_batch(self._h, q.size, _ptr(q), _ptr(r), res))
         return [Result.from_c(x, self.D) for x in res]
 
+    def eval_batch_raw(self, q_est, r_est) -> np.ndarray:
+        """The kfbo_result array of a candidate batch as ONE structured numpy array (fields of struct
+        kfbo_result; no per-candidate Python objects -- a 4096-candidate sweep costs microseconds of host time)."""
+        q, r = _f64(q_est), _f64(r_est)
+        if q.shape != r.shape or q.ndim != 1:
+            raise ValueError("q_est and r_est must be 1-D arrays of equal length")
+        res = np.empty(q.size, dtype=RESULT_DTYPE)
+        self._check(self._lib.kfbo_eval_batch(self._h, q.size, _ptr(q), _ptr(r), res.ctypes.data_as(C.POINTER(KfboResult))))
+        return res
+
     def eval_batch_costs(self, q_est, r_est) -> Tuple[np.ndarray, np.ndarray]:
         """(cost[C][D], max_cost[C]) of a candidate batch."""
-        rs = self.eval_batch(q_est, r_est)
-        return np.stack([x.cost for x in rs]), np.array([x.max_cost for x in rs])
+        res = self.eval_batch_raw(q_est, r_est)
+        return res["cost"][:, :self.D].copy(), res["max_cost"].copy()
 
     def last_sums(self, n_candidates: int = 1) -> np.ndarray:
         out = np.empty((n_candidates, self.D, 4))

@@ -28,6 +28,14 @@ def test_library_exports_every_declared_symbol(kfbo):
     assert b"sm_100a" in lib.kfbo_version()
 
 
+def test_numpy_result_record_matches_the_struct(kfbo):
+    import ctypes
+    from kf_bayesopt_b200 import _lib, evaluator
+    assert evaluator.RESULT_DTYPE.itemsize == ctypes.sizeof(_lib.KfboResult)
+    for name, _ in _lib.KfboResult._fields_:
+        assert evaluator.RESULT_DTYPE.fields[name][1] == getattr(_lib.KfboResult, name).offset
+
+
 def test_struct_layout_matches_header(kfbo):
     from kf_bayesopt_b200 import _lib
     # sizes implied by include/kfbo.h with natural alignment

@@ -14,7 +14,7 @@ python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:rollout_philox -s 3 -c 1 -f -o $OUT/prof_philox_$TAG \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-supplied > $OUT/ncu_full_philox_$TAG.log 2>&1; echo "ncu philox rc=$?"
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-supplied --no-reduced > $OUT/ncu_full_philox_$TAG.log 2>&1; echo "ncu philox rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:rollout_supplied_bulk -s 3 -c 1 -f -o $OUT/prof_supplied_$TAG \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_supplied_$TAG.log 2>&1; echo "ncu supplied rc=$?"
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-reduced > $OUT/ncu_full_supplied_$TAG.log 2>&1; echo "ncu supplied rc=$?"
 ls -la $OUT | tail -16
