@@ -146,7 +146,19 @@ def run_reference(args, rank: int):
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line, on the real stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# Everything else that writes to fd 1 (NCCL prints its version banner there, libraries may print warnings) goes
+# to stderr, so stdout carries exactly one JSON line.
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -354,7 +366,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "result": {"J_NEES": [float(c) for c in res.cost], "cost": float(res.max_cost), "index_max": res.index_max}}
         line.update(line_extra)
-        print(json.dumps(line), flush=True)
+        emit(line)
     ev.close()
     if world > 1:
         dist.barrier()
