@@ -149,6 +149,49 @@ def run_reference(args, rank: int):
     emit(line)
 
 
+def run_bo_loop(args):
+    """BASELINE.json configs[4]: the BO loop (20 initial + 180 iterations = 200 cost evaluations of the default
+    vehicleParams.yaml workload: 200 trials x 201 steps x 2 sample times) driving the GPU evaluator over the
+    noise/cost topic contract -- the C++ program kf_bayesopt_b200/bin/kfbo_bo_loop (in-process topic bus, GP/EI
+    stand-in for the absent bayesopt library).  CPU arm: the same 200 evaluations on the oracle's threaded path with
+    the yaml's CPUcoreNumber = 10 threads, thread pool created per evaluation like trial_node.cpp:54-67."""
+    exe = os.path.join(ROOT, "kf_bayesopt_b200", "bin", "kfbo_bo_loop")
+    if not os.path.exists(exe):
+        raise SystemExit("bench.py: build the host programs first (make -C kf_bayesopt_b200/host)")
+    iters, init, B, T, D = 180, 20, 200, 201, 2
+    out = subprocess.run([exe, "--iterations", str(iters), "--init", str(init), "--quiet"], capture_output=True, text=True, check=True)
+    loop = json.loads(next(l for l in out.stdout.splitlines() if l.startswith("{")))
+    n = loop["iterations"]
+    steps_total = float(n) * B * T * D
+    line = {"metric": METRIC, "value": steps_total / loop["wall_s"], "unit": UNIT, "n_gpus": 1, "steps": n, "warmup": 0,
+            "ms_per_step": loop["wall_s"] / n * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg5: full Bayesian-optimisation loop, %d cost evaluations (20 initial + %d iterations) of "
+                                   "%d trials x %d steps x %d sample times over the noise/cost topic contract" % (n, iters, B, T, D),
+                       "optimiser": "GP (Matern-3/2 ARD) + EI stand-in for the absent bayesopt library; settings of bayesParams.yaml"},
+            "bo_loop": loop,
+            "e2e": {"value": steps_total / loop["wall_s"], "unit": UNIT, "h2d_bytes_per_step": 96 * D, "d2h_bytes_per_step": 32 * D,
+                    "wall_s": loop["wall_s"], "evaluator_s": loop["evaluator_s"],
+                    "wall_s_with_reference_sleeps": loop["wall_s"] + 0.5 * n,
+                    "api": "kfbo_bo_loop: Robot1D::evaluateSample contract -> topic bus -> kfbo::RunTrial::ProcessNoiseCallback -> C ABI"},
+            "gpu_launches": n}
+    if not args.no_cpu_baseline:
+        from oracle import oracle as o
+        cores = 10                                          # config/vehicleParams.yaml:1
+        t = time.perf_counter()
+        for i in range(n):
+            for dt in (0.1, 1.0):                           # trial_node.cpp:105-114
+                o.eval_mt(dt, T, Q_TRUTH, R_TRUTH, 1.0 + 0.01 * i, 0.1, B, cores, seed=i)
+        cpu_s = time.perf_counter() - t
+        line["cpu_baseline"] = {"value": steps_total / cpu_s, "unit": UNIT, "cores": min(cores, os.cpu_count() or 1), "kind": "port",
+                                "sample": f"{n} evaluations of {B} trials x {T} steps x {D} sample times on {cores} threads "
+                                          f"(yaml CPUcoreNumber), {cpu_s:.2f} s",
+                                "evaluator_s": cpu_s,
+                                "loop_wall_s_estimate": cpu_s + loop["optimiser_s"],
+                                "loop_wall_s_estimate_with_reference_sleeps": cpu_s + loop["optimiser_s"] + 0.5 * n}
+    emit(line)
+
+
 def emit(line: dict) -> None:
     """The ONE JSON line, on the real stdout."""
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
@@ -167,8 +210,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kfbo", choices=["kfbo", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4"],
-                    help="cfg3 (default, the configuration the metric is quoted on) or the cfg4 candidate sweep")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4", "cfg5"],
+                    help="cfg3 (default, the configuration the metric is quoted on), the cfg4 candidate sweep, or the "
+                         "cfg5 Bayesian-optimisation loop over the noise/cost topic contract (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-supplied", action="store_true", help="skip the supplied-noise (HBM roofline) leg")
     ap.add_argument("--no-reduced", action="store_true", help="skip the reduced-form leg")
@@ -180,6 +224,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload == "cfg5":
+        if rank == 0:
+            run_bo_loop(args)
         return
 
     import numpy as np

@@ -130,6 +130,12 @@ int kfbo_eval_supplied_dev(kfbo_handle *h, int32_t k, int32_t n_candidates, cons
 int kfbo_eval_philox_trials(kfbo_handle *h, int32_t k, double q_est, double r_est, uint32_t stream,
                             uint32_t trial0, int64_t ntrials, double *per_trial);
 
+/* The Nsimruns == 1 path of Trial::Run (trial.cpp:69-78,116-129: the error inside its 95 % band): trajectory
+ * `trial` of Philox stream `stream` at sample time k, replayed step by step.
+ * trace[T][9] (host) = {time, e1, e2, lb1, ub1, lb2, ub2, nees, nis}, lb/ub = -/+ 2 sqrt(P_ii) of the posterior. */
+#define KFBO_TRACE_COLUMNS 9
+int kfbo_trace_trial(kfbo_handle *h, int32_t k, double q_est, double r_est, uint32_t stream, uint32_t trial, double *trace);
+
 /* Philox stream bookkeeping: evaluation e of candidate c at sample time k uses stream
  * base + (e*max_candidates + c)*n_sample_times + k.  kfbo_eval* advance e by one per call. */
 int kfbo_set_stream_base(kfbo_handle *h, uint32_t base);

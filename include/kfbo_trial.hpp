@@ -242,6 +242,14 @@ public:
         if (launches) *launches = n;
         return ms;
     }
+    // The Nsimruns == 1 record of trial.cpp:69-78: rows {time, e1, e2, lb1, ub1, lb2, ub2, nees, nis} of one trajectory.
+    std::vector<double> TraceTrial(int k, double q_est, double r_est, uint32_t stream, uint32_t trial)
+    {
+        std::vector<double> t((size_t)p_.max_iterations[k] * KFBO_TRACE_COLUMNS);
+        Check(kfbo_trace_trial(h_, k, q_est, r_est, stream, trial, t.data()));
+        return t;
+    }
+    void SetOption(int option, long long value) { Check(kfbo_set_option(h_, option, value)); }
     void SetStreamBase(uint32_t base) { Check(kfbo_set_stream_base(h_, base)); }
     void SetEvalCounter(uint32_t e) { Check(kfbo_set_eval_counter(h_, e)); }
     void CommInit(const void *nccl_id, int rank, int nranks, int shard_mode) { Check(kfbo_comm_init(h_, nccl_id, rank, nranks, shard_mode)); }

@@ -74,6 +74,7 @@ SIGNATURES = {
     "kfbo_eval_supplied": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
     "kfbo_eval_supplied_dev": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp, _dp, C.c_int64, _vp, _vp, _vp, _vp, _dp]),
     "kfbo_eval_philox_trials": (C.c_int, [_vp, C.c_int32, C.c_double, C.c_double, C.c_uint32, C.c_uint32, C.c_int64, _dp]),
+    "kfbo_trace_trial": (C.c_int, [_vp, C.c_int32, C.c_double, C.c_double, C.c_uint32, C.c_uint32, _dp]),
     "kfbo_set_stream_base": (C.c_int, [_vp, C.c_uint32]),
     "kfbo_set_eval_counter": (C.c_int, [_vp, C.c_uint32]),
     "kfbo_last_sums": (C.c_int, [_vp, _dp, C.c_int32]),

@@ -579,6 +579,28 @@ int kfbo_eval_philox_trials(kfbo_handle *h, int32_t k, double q_est, double r_es
     return KFBO_OK;
 }
 
+int kfbo_trace_trial(kfbo_handle *h, int32_t k, double q_est, double r_est, uint32_t stream, uint32_t trial, double *trace)
+{
+    if (!h) return KFBO_EINVAL;
+    if (!trace || k < 0 || k >= h->D) return fail(h, KFBO_EINVAL, "kfbo_trace_trial: bad argument");
+    KFBO_CUDA(h, cudaSetDevice(h->device));
+    Case c;
+    int rc = build_case(h, k, q_est, r_est, stream, 0, &c);
+    if (rc) return rc;
+    const size_t T = (size_t)h->p.max_iterations[k];
+    if ((rc = ensure_scratch(h, 3, (sizeof(Case) + 7) / 8 + 1))) return rc;
+    if ((rc = ensure_scratch(h, 4, 9 * T))) return rc;
+    Case *d_case = reinterpret_cast<Case *>(h->d_scratch[3]);
+    KFBO_CUDA(h, cudaMemcpyAsync(d_case, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
+    kfbo::SampleTimeConsts st = h->st;
+    st.k0 = k; st.nk = 1;
+    KFBO_CUDA(h, kfbo::launch_trace_philox(d_case, st, h->d_gu, h->d_logtab, h->p.seed, trial, h->p.dt[k], h->d_scratch[4], h->stream));
+    KFBO_CUDA(h, cudaMemcpyAsync(trace, h->d_scratch[4], 9 * T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    KFBO_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->last_launches = 1;
+    return KFBO_OK;
+}
+
 int kfbo_nccl_unique_id(void *id_bytes)
 {
     static_assert(sizeof(ncclUniqueId) == KFBO_NCCL_ID_BYTES, "ncclUniqueId size");

@@ -118,6 +118,9 @@ __device__ __forceinline__ void traj_init(Traj &t, double x0n0, double x0n1)
 // (w = L n, v = sqrt(R) n2) folded into the state update's multiply-adds.
 struct StepNoise { double a, b, c; };
 
+// What the single-trial trace (trial.cpp:69-78) records of a step, beyond the trajectory state.
+struct StepProbe { double nees, nis; };
+
 // One filter-step: truth step, Kalman predict/update, NEES/NIS accumulation.
 // gu = g*u[step] = (0.5 dt^2 u, dt u), rounded products exactly as the reference forms them.
 // f = Fd(0,1) comes in as a uniform value (SampleTimeConsts), the candidate's Qd / R from the Case.
@@ -125,7 +128,7 @@ struct StepNoise { double a, b, c; };
 template <bool kFirst, bool kFused>
 __device__ __forceinline__ void filter_step(Traj &t, const Case &m, const double f, double2 gu, const StepNoise nz,
                                             const double l00 = 0.0, const double l10 = 0.0, const double l11 = 0.0,
-                                            const double sr = 0.0)
+                                            const double sr = 0.0, StepProbe *probe = nullptr)
 {
     // ---- truth: x = Fd x + g u + w ; z = H x + v
     const double xa = fma(f, t.x1, t.x0) + gu.x;
@@ -171,6 +174,7 @@ __device__ __forceinline__ void filter_step(Traj &t, const Case &m, const double
     const double nu_s = nu * sinv;
     // ---- accumulate, shifted by the first sample of the trial (kn, ki): the shifted values
     // nees - kn and nis - ki come straight out of the last fused multiply-add of each form
+    if (probe != nullptr) { probe->nees = num * invdet; probe->nis = nu_s * nu; }
     if (kFirst) { t.kn = num * invdet; t.ki = nu_s * nu; }
     const double dn = fma(num, invdet, -t.kn);
     const double di = fma(nu_s, nu, -t.ki);

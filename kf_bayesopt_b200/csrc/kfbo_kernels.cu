@@ -589,6 +589,46 @@ rollout_philox_reduced(const Case *__restrict__ cases, const __grid_constant__ S
 }
 
 // -----------------------------------------------------------------------------------------
+// Single-trial trace (the Nsimruns == 1 path of trial.cpp:69-78,116-129, which plots the estimation
+// error inside its +-2 sigma band): one thread replays ONE trajectory of the Philox rollout -- same
+// streams, same filter_step -- and records per step
+//   {time, e1, e2, lb1, ub1, lb2, ub2, nees, nis},  lb/ub = -/+ 2 sqrt(P_ii).
+// -----------------------------------------------------------------------------------------
+__global__ void trace_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTimeConsts st,
+                             const double2 *__restrict__ gu_tables, const math::LogTables *__restrict__ logtab,
+                             const __grid_constant__ PhiloxKeys key, uint32_t trial, double dt, double *__restrict__ trace)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const Case m = cases[0];
+    const unsigned kk = st.k0;
+    const double f = st.f[kk], l00 = st.l00[kk], l10 = st.l10[kk], l11 = st.l11[kk], sr = st.sr[kk];
+    const double2 *gu = gu_tables + (size_t)kk * kMaxSteps;
+    const math::LogTables &tab = *logtab;
+    Traj t;
+    {
+        double a, b;
+        const uint4 w = philox4x32_10(trial, m.stream, 0u, 0u, key);
+        math::normal_pair_bits(w.x, w.w >> 12, w.y, tab, a, b);
+        traj_init(t, a, b);
+    }
+    for (int s = 0; s < m.T; ++s) {
+        const uint32_t p = (uint32_t)(s >> 1);
+        double n[6];
+        normals_of_pair(philox4x32_10(trial, m.stream, p + 1u, 0u, key), philox4x32_10(trial, m.stream, p + 1u, 1u, key), tab, n);
+        const int o = (s & 1) * 3;
+        StepProbe probe;
+        if (s == 0) filter_step<true, true>(t, m, f, gu[s], StepNoise{n[o], n[o + 1], n[o + 2]}, l00, l10, l11, sr, &probe);
+        else        filter_step<false, true>(t, m, f, gu[s], StepNoise{n[o], n[o + 1], n[o + 2]}, l00, l10, l11, sr, &probe);
+        double *row = trace + (size_t)s * 9;
+        const double b1 = 2.0 * sqrt(t.p00), b2 = 2.0 * sqrt(t.p11);
+        row[0] = s * dt;                       // trial.cpp:70
+        row[1] = t.x0 - t.xh0; row[2] = t.x1 - t.xh1;
+        row[3] = -b1; row[4] = b1; row[5] = -b2; row[6] = b2;
+        row[7] = probe.nees; row[8] = probe.nis;
+    }
+}
+
+// -----------------------------------------------------------------------------------------
 // DFMA-chain microbenchmark: 8 independent FMA chains per thread.
 // -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_chain(double *out, int iters, double a, double b)
@@ -632,6 +672,13 @@ cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleT
     rollout_philox<<<grid, kThreads, smem, stream>>>(
         d_cases, st, d_gu, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0, ntrials, tiles,
         d_per_trial, per_trial_ld, d_partials, d_tickets, d_sums);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_philox(const Case *d_case, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, uint64_t seed,
+                                uint32_t trial, double dt, double *d_trace, cudaStream_t stream)
+{
+    trace_philox<<<1, 32, 0, stream>>>(d_case, st, d_gu, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial, dt, d_trace);
     return cudaGetLastError();
 }
 

@@ -72,6 +72,10 @@ cudaError_t launch_rollout_supplied(const Case *d_cases, int ncases, const Sampl
 enum { kSuppliedAuto = 0, kSuppliedLdg = 1, kSuppliedBulk = 2 };
 int supplied_variant_for(int requested, const double *d_w, const double *d_v, size_t B);
 
+// One trajectory replayed step by step: d_trace[T][9] = {time, e1, e2, lb1, ub1, lb2, ub2, nees, nis}; st.k0 = sample time.
+cudaError_t launch_trace_philox(const Case *d_case, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, uint64_t seed,
+                                uint32_t trial, double dt, double *d_trace, cudaStream_t stream);
+
 cudaError_t launch_dfma_chain(double *d_out, int blocks, int iters, cudaStream_t stream);
 
 int rollout_tiles(size_t ntrials);   // CTAs per case of the supplied-noise kernel (upper bound for the Philox one)

@@ -271,6 +271,12 @@ class CostEvaluator:
         self._check(self._lib.kfbo_eval_philox_trials(self._h, k, q_est, r_est, stream, trial0, ntrials, _ptr(out)))
         return out
 
+    def trace_trial(self, k: int, q_est: float, r_est: float, stream: int, trial: int) -> np.ndarray:
+        """The Nsimruns == 1 record of trial.cpp:69-78: [T][9] = time, e1, e2, lb1, ub1, lb2, ub2, nees, nis."""
+        out = np.empty((self.sample_times[k][1], 9))
+        self._check(self._lib.kfbo_trace_trial(self._h, k, q_est, r_est, stream, trial, _ptr(out)))
+        return out
+
     # -- Philox stream control / CUDA stream / NCCL
     def set_stream_base(self, base: int) -> None:
         self._check(self._lib.kfbo_set_stream_base(self._h, base))

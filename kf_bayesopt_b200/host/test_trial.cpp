@@ -3,11 +3,13 @@
 // evaluation with a fixed estimator (pnoise_est, onoise_est), printed the same way.
 //
 //   kfbo_test_trial [--vehicle config/vehicleParams.yaml] [--pnoise_est 1.0] [--onoise_est 0.1]
-//                   [--nsimruns N] [--device D] [--seed S] [--fused]
+//                   [--nsimruns N] [--device D] [--seed S] [--fused] [--trace out.csv]
 //
 // Default path = the reference's caller shape: CPUcoreNumber Trial objects, one std::thread each
 // (src/test_trial.cpp:41-51), every Trial::Run() rolling its share out on the GPU.  --fused runs the
 // whole batch as ONE launch through the evaluator (what RunTrial does per sample time).
+// --trace FILE: the reference's Nsimruns == 1 path (trial.cpp:69-78,116-129 plots the estimation error inside
+// its 95 % band with matplotlibcpp): the same per-step record of trajectory 0, written as CSV instead.
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -21,6 +23,7 @@ int main(int nargs, char *args[])
     int device = -1, nsimruns = -1;
     uint64_t seed = kfbo::kDefaultSeed;
     bool fused = false;
+    std::string trace_path;
     for (int i = 1; i < nargs; ++i) {
         auto next = [&](const char *name) -> const char * {
             if (i + 1 >= nargs) { std::cerr << name << " needs a value\n"; std::exit(64); }
@@ -33,6 +36,7 @@ int main(int nargs, char *args[])
         else if (!std::strcmp(args[i], "--device")) device = std::atoi(next("--device"));
         else if (!std::strcmp(args[i], "--seed")) seed = std::strtoull(next("--seed"), nullptr, 0);
         else if (!std::strcmp(args[i], "--fused")) fused = true;
+        else if (!std::strcmp(args[i], "--trace")) trace_path = next("--trace");
         else { std::cerr << "unknown argument " << args[i] << "\n"; return 64; }
     }
     try {
@@ -69,6 +73,16 @@ int main(int nargs, char *args[])
             int launches = 0;
             const double ms = ev.LastKernelMs(&launches);
             std::cout << "rollout kernel " << ms << " ms, " << launches << " launch(es)" << std::endl;
+        }
+        if (!trace_path.empty()) {
+            kfbo::Evaluator ev(kfbo::MakeParams(rv_gt, kfbo::SampleTimesFrom(rv_gt, nullptr), "JNEES", seed, 1, device));
+            const std::vector<double> tr = ev.TraceTrial(0, rv.pnoise_[0], rv.onoise_[0], 0u, 0u);
+            std::ofstream f(trace_path);
+            f.precision(17);
+            f << "time,e1,e2,lb1,ub1,lb2,ub2,nees,nis\n";
+            for (size_t s = 0; s < tr.size() / KFBO_TRACE_COLUMNS; ++s)
+                for (int c = 0; c < KFBO_TRACE_COLUMNS; ++c) f << tr[s * KFBO_TRACE_COLUMNS + c] << (c + 1 < KFBO_TRACE_COLUMNS ? "," : "\n");
+            std::cout << "trace of trajectory 0 written to " << trace_path << " (" << tr.size() / KFBO_TRACE_COLUMNS << " steps)" << std::endl;
         }
         if (rv.cost_choice_ == "JNEES" || rv.cost_choice_ == "CNEES") {
             const double J_NEES = std::abs(std::log(average_nees / rv.state_dof_));

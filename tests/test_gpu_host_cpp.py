@@ -64,3 +64,20 @@ def test_bo_loop_runs_the_topic_contract_end_to_end(host_bins, yamls):
     assert 0.1 <= line["best_x"][0] <= 5.0 and 0.01 <= line["best_x"][1] <= 1.0
     assert line["dt0_count"] + line["dt1_count"] == 25        # trial_node.cpp:121-126 bookkeeping
     assert line["evaluator_s"] <= line["wall_s"]
+
+
+def test_trace_csv_and_cost_surface_cli(host_bins, yamls, tmp_path):
+    trace = tmp_path / "trace.csv"
+    out = _run("kfbo_test_trial", "--vehicle", yamls[0], "--nsimruns", 10, "--fused", "--trace", trace)
+    assert "trace of trajectory 0" in out
+    t = np.loadtxt(trace, delimiter=",", skiprows=1)
+    assert t.shape == (201, 9) and np.all(t[:, 4] > 0) and np.all(t[:, 7] >= 0) and np.all(t[:, 8] >= 0)
+    np.testing.assert_allclose(t[:, 0], np.arange(201) * 0.1, rtol=1e-12)
+    surf = tmp_path / "surface.csv"
+    out = _run("kfbo_cost_surface", "--vehicle", yamls[0], "--bayes", yamls[1], "--grid", 12, "--nsimruns", 2000, "--out", surf)
+    s = np.loadtxt(surf, delimiter=",", skiprows=1)
+    assert s.shape == (144, 6)
+    assert np.all(s[:, 4] == np.maximum(s[:, 2], s[:, 3]))        # max_cost = max over the sample times
+    assert np.all((s[:, 5] == 0) | (s[:, 5] == 1))
+    best = s[np.argmin(s[:, 4])]
+    assert best[4] < 0.2 and 0.2 < best[0] < 5.0

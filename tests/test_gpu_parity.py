@@ -319,3 +319,30 @@ def test_reduced_form_full_size_and_chunked_gain_table(kfbo):
         c_red, _ = ev.eval_batch_costs(q, r)
         assert ev.last_kernel_ms()[1] > 2 * launches_ref          # 256 MB of gains hold 2796 cases of 2000 steps
     np.testing.assert_allclose(c_red, c_ref, rtol=1e-9, atol=1e-12)
+
+
+def test_single_trial_trace_matches_rollout_and_oracle_covariance(kfbo, oracle):
+    # the Nsimruns == 1 record (trial.cpp:69-78): replaying one trajectory step by step gives the per-step
+    # NEES/NIS whose sums / time-variances are that trial's rollout outputs, and +-2 sqrt(P_ii) bands that
+    # follow the oracle's (data-independent) covariance recursion
+    seed = 99
+    rv = kfbo.ReadParaVehicle(nsimruns_=64, cpu_core_number_=1)
+    times = [(0.1, 201), (0.5, 212)]
+    with kfbo.CostEvaluator(rv, times, seed=seed) as ev:
+        for k, (dt, T) in enumerate(times):
+            for qe, re, stream, trial in [(1.0, 0.1, 0, 0), (0.4, 0.3, 11, 37)]:
+                tr = ev.trace_trial(k, qe, re, stream, trial)
+                assert tr.shape == (T, 9)
+                np.testing.assert_allclose(tr[:, 0], np.arange(T) * dt, rtol=1e-15)
+                pt = ev.eval_philox_trials(k, qe, re, stream, trial, 1)[:, 0]
+                want = [tr[:, 7].sum(), tr[:, 8].sum(), tr[:, 7].var(ddof=1), tr[:, 8].var(ddof=1)]   # trial.cpp:62-63,84-96
+                np.testing.assert_allclose(pt, want, rtol=1e-9)
+                ric = oracle.riccati_trace(dt, qe, re, T)        # columns: S, K0, K1, P00, P01, P10, P11
+                np.testing.assert_allclose(tr[:, 4], 2 * np.sqrt(ric[:, 3]), rtol=1e-9)
+                np.testing.assert_allclose(tr[:, 6], 2 * np.sqrt(ric[:, 6]), rtol=1e-9)
+                assert np.array_equal(tr[:, 3], -tr[:, 4]) and np.array_equal(tr[:, 5], -tr[:, 6])
+                want_pt = oracle.eval_philox(seed, stream, dt, T, Q_TRUTH, R_TRUTH, qe, re, trial, 1)[:, 0]
+                np.testing.assert_allclose(want, want_pt, rtol=1e-9)
+                # a consistent filter keeps the error inside its 95 % band most of the time
+                if (qe, re) == (1.0, 0.1):
+                    assert np.mean(np.abs(tr[:, 1]) <= tr[:, 4]) > 0.85
