@@ -77,9 +77,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 //   pair 2: radius (A.z : A.w[11:0] B.w[7:0]), angle B.z
 __device__ __forceinline__ void normals_of_pair(const uint4 &A, const uint4 &B, const math::LogTables &tab, double n[6])
 {
-    math::normal_pair_bits(A.x, A.w >> 12, A.y, tab, n[0], n[1]);
-    math::normal_pair_bits(B.x, B.w >> 12, B.y, tab, n[2], n[3]);
-    math::normal_pair_bits(A.z, ((A.w & 0xFFFu) << 8) | (B.w & 0xFFu), B.z, tab, n[4], n[5]);
+    math::normal_pair_bits(A.x, A.w, A.y, tab, n[0], n[1]);                           // low 20 bits: A.w[31:12]
+    math::normal_pair_bits(B.x, B.w, B.y, tab, n[2], n[3]);                           //              B.w[31:12]
+    math::normal_pair_bits(A.z, math::funnel_l(B.w << 24, A.w, 20), B.z, tab, n[4], n[5]);   // A.w[11:0] : B.w[7:0]
 }
 
 // 1/S and 1/det(P): S and det(P) come out of a covariance recursion and are normal, well-scaled

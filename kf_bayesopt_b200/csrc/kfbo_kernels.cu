@@ -1,7 +1,13 @@
 // kfbo_kernels.cu -- the rollout kernels (sm_100a) and their launchers.
 //
-//   rollout_philox    on-device Philox4x32-10 + Box-Muller noise (FP64-pipe bound)
-//   rollout_supplied  noise streamed from HBM, SoA [step][component][trial] (HBM bound)
+//   rollout_philox          on-device Philox4x32-10 + Box-Muller noise, the reference form:
+//                           truth state, estimate and covariance per thread (FP64-pipe bound)
+//   rollout_supplied_bulk   noise streamed from HBM, SoA [step][component][trial], staged through
+//                           shared memory by cp.async.bulk + mbarriers (HBM bound)
+//   rollout_supplied        the same with per-thread loads (streams that are not 16-byte aligned)
+//   riccati_gains +
+//   rollout_philox_reduced  opt-in reduced form: gain table once per case, error-state trajectories
+//   trace_philox            one trajectory replayed step by step (the Nsimruns == 1 record)
 //
 // Grid: (tiles, candidates, sample times): blockIdx.y/z give the case without any division, so the
 // case and its sample-time constants are provably uniform (uniform registers / parameter bank).
@@ -135,7 +141,7 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
     for (int j = 0; j < K; ++j) {
         double a, b;
         const uint4 w = philox4x32_10(trial[j], m.stream, 0u, 0u, key);
-        math::normal_pair_bits(w.x, w.w >> 12, w.y, s_log, a, b);
+        math::normal_pair_bits(w.x, w.w, w.y, s_log, a, b);
         traj_init(t[j], a, b);
     }
     // The counter-based generator lets the random bits of step pair p+1 be produced while the FP64
@@ -540,7 +546,7 @@ rollout_philox_reduced(const Case *__restrict__ cases, const __grid_constant__ S
     double e0, e1, kn = 0.0, ki = 0.0, sdn = 0.0, sqn = 0.0, sdi = 0.0, sqi = 0.0;
     {
         const uint4 w = philox4x32_10(trial, m.stream, 0u, 0u, key);
-        math::normal_pair_bits(w.x, w.w >> 12, w.y, s_log, e0, e1);    // e = x0 + N(0,P0) - xhat0 = the draw itself
+        math::normal_pair_bits(w.x, w.w, w.y, s_log, e0, e1);    // e = x0 + N(0,P0) - xhat0 = the draw itself
     }
     uint4 r0 = philox4x32_10(trial, m.stream, 1u, 0u, key), r1 = philox4x32_10(trial, m.stream, 1u, 1u, key);
     for (int c = 0; c < nchunks; ++c) {
@@ -608,7 +614,7 @@ __global__ void trace_philox(const Case *__restrict__ cases, const __grid_consta
     {
         double a, b;
         const uint4 w = philox4x32_10(trial, m.stream, 0u, 0u, key);
-        math::normal_pair_bits(w.x, w.w >> 12, w.y, tab, a, b);
+        math::normal_pair_bits(w.x, w.w, w.y, tab, a, b);
         traj_init(t, a, b);
     }
     for (int s = 0; s < m.T; ++s) {

@@ -43,7 +43,7 @@ constexpr int kAngleTableSize = 1 << kAngleTableBits;   // 1024 directions x {co
 
 struct LogTables {
     double invc_logc[kLogTableSize][2];  // {1/c_i rounded, 2 ln(that rounded value)}
-    double k2ln2[kLogKTableSize];        // 2 j ln 2
+    double k2ln2[kLogKTableSize];        // entry 52 + k: -2 k ln 2
     double cossin[kAngleTableSize][2];   // {cos, sin} of 2 pi (i + 1/2) / 1024
 };
 
@@ -60,7 +60,8 @@ inline void build_log_tables(LogTables *t)
         t->invc_logc[i][0] = invc;
         t->invc_logc[i][1] = (i == kLogUnitEntry) ? 0.0 : (double)(2.0L * logl((long double)invc));
     }
-    for (int j = 0; j < kLogKTableSize; ++j) t->k2ln2[j] = (double)(2.0L * j * 0.693147180559945309417232121458176568L);
+    for (int j = 0; j < kLogKTableSize; ++j)   // indexed by 52 + k, k = exponent of u in [-52, 0]: a non-negative index
+        t->k2ln2[j] = (double)(2.0L * (kLogKTableSize - 4 - j) * 0.693147180559945309417232121458176568L);
     const long double two_pi = 6.283185307179586476925286766559005768L;
     for (int i = 0; i < kAngleTableSize; ++i) {
         const long double a = two_pi * (i + 0.5L) / kAngleTableSize;
@@ -89,6 +90,17 @@ KFBO_HD uint32_t hi_word(double d)
     uint64_t b;
     std::memcpy(&b, &d, sizeof b);
     return (uint32_t)(b >> 32);
+#endif
+}
+
+// (hi : lo) << n, upper word: SHF.L.W on the device (the ALU pipe -- a plain C shift may become an IMAD
+// on the FMA-heavy pipe, which this kernel cannot spare).  0 < n < 32.
+KFBO_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t n)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, n);
+#else
+    return (hi << n) | (lo >> (32u - n));
 #endif
 }
 
@@ -182,7 +194,12 @@ KFBO_HD double neg2_log(double u, const double (*tab)[2], const double *ktab)
     s = fma(s, r, kLogPolyU[0]);
     s = fma(s, r, 1.0);
     s = fma(s, r, -2.0);
-    return fma(r, s, ktab[-k] + logc2);
+#if defined(KFBO_LOG_K_I2F) && defined(__CUDA_ARCH__)
+    (void)ktab;
+    return fma(r, s, fma(__int2double_rn(k), -0x1.62e42fefa39efp+0 /* -2 ln 2 */, logc2));
+#else
+    return fma(r, s, ktab[kLogKTableSize - 4 + k] + logc2);    // entry j holds 2 (52 - j) ln 2, j = 52 + k >= 0
+#endif
 }
 
 // cos/sin of theta = 2 pi ang / 2^32 for a 32-bit angle: the top 10 bits pick one of 1024 tabulated
@@ -195,7 +212,7 @@ KFBO_CONST double kAngU[4] = {0x1.921fb54442d18p-8 /* 2 pi / 1024 */, -0x1.2d97c
 KFBO_HD void rad_sincos_2pi(double rad, uint32_t ang, const double (*cossin)[2], double &c, double &s)
 {
     const uint32_t i = ang >> (32 - kAngleTableBits), r = ang & ((1u << (32 - kAngleTableBits)) - 1u);
-    const double y = make_double(0x3FF00000u | (r >> 2), r << 30);          // 1 + r 2^-22 in [1, 2)
+    const double y = make_double(0x3FF00000u | (r >> 2), funnel_l(0u, r, 30));   // 1 + r 2^-22 in [1, 2)
     const double d = fma(y, kAngU[0], kAngU[1]);                             // (2 pi / 1024)(r 2^-22 - 1/2)
     const double d2 = d * d;
     const double cd = fma(fma(d2, kAngU[2], -0.5), d2, 1.0);                 // cos d
@@ -208,7 +225,7 @@ KFBO_HD void rad_sincos_2pi(double rad, uint32_t ang, const double (*cossin)[2],
 
 // 84 random bits -> two independent N(0,1) draws (Box-Muller).  THE SPEC (restated draw for draw
 // by the CPU checker):
-//   radius: m1 = (rad_hi << 20 | rad_lo20) with the lowest bit forced to 1 (52 bits);
+//   radius: m1 = (rad_hi << 20 | rad_lo20) with the lowest bit forced to 1 (52 bits), rad_lo20 = rad_lo_top20 >> 12;
 //           u1 = 1 - m1 2^-52 in [2^-52, 1 - 2^-52]; rad = sqrt(-2 ln u1)
 //   angle : o = top 3 bits of ang (octant), f = low 29 bits of ang times 2^-29 in [0,1);
 //           theta = (pi/4)(o + f)
@@ -217,9 +234,10 @@ KFBO_HD void rad_sincos_2pi(double rad, uint32_t ang, const double (*cossin)[2],
 // continuous to FP64 resolution and the tails reach 8.5 sigma.  Random bits are the expensive part
 // on this chip -- see the Philox note in kfbo_device.cuh.)
 // theta = (pi/4)(o + f) = 2 pi ang / 2^32: evaluated by rad_sincos_2pi above.
-KFBO_HD void normal_pair_bits(uint32_t rad_hi, uint32_t rad_lo20, uint32_t ang, const LogTables &tab, double &na, double &nb)
+// rad_lo_top20: a word whose TOP 20 bits are the low 20 bits of the radius mantissa (one funnel shift joins them).
+KFBO_HD void normal_pair_bits(uint32_t rad_hi, uint32_t rad_lo_top20, uint32_t ang, const LogTables &tab, double &na, double &nb)
 {
-    const double y1 = make_double(0x3FF00000u | (rad_hi >> 12), (rad_hi << 20) | rad_lo20 | 1u);   // [1,2)
+    const double y1 = make_double(0x3FF00000u | (rad_hi >> 12), funnel_l(rad_lo_top20, rad_hi, 20) | 1u);   // [1,2)
     const double u1 = 2.0 - y1;
     const double rad = sqrt_pos(neg2_log(u1, tab.invc_logc, tab.k2ln2));
     rad_sincos_2pi(rad, ang, tab.cossin, na, nb);

@@ -62,7 +62,7 @@ int main()
     for (int i = 0; i < 2000000; ++i) {
         const uint32_t rad_hi = (uint32_t)g(), lo20 = (uint32_t)g() & 0xFFFFFu, ang = (uint32_t)g();
         double na, nb;
-        normal_pair_bits(rad_hi, lo20, ang, t, na, nb);
+        normal_pair_bits(rad_hi, lo20 << 12 | (uint32_t)(g() & 0xFFFu), ang, t, na, nb);
         const uint64_t m1 = (((uint64_t)rad_hi << 20) | lo20) | 1u;
         const long double u1 = 1.0L - (long double)m1 * 0x1p-52L;
         const long double theta = PI4 * ((long double)(ang >> 29) + (long double)(ang & 0x1FFFFFFFu) * 0x1p-29L);
