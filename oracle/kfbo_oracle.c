@@ -6,13 +6,22 @@
  * bench.py may load it, and only as the checker / timed CPU baseline.  The
  * product path (kf_bayesopt_b200/ + include/kfbo.h) never links or calls it.
  *
- * PARITY UNPINNED: the reference (arpg/kf_bayesopt, mounted at /root/reference)
- * ships no tests, fixtures or golden vectors for this path (CMakeLists.txt:221-232
- * is commented out), seeds every RNG from the wall clock (system_models.hpp:74,147;
- * simulator.cpp:9) and cannot be compiled here (Eigen3, ROS, Boost, bayesopt are
- * absent).  This file is therefore a plain-C restatement of the reference
- * arithmetic, pinned only by (i) an independent numpy/scipy restatement
- * (tests/golden/make_golden.py) and (ii) data-independent known answers.
+ * WHAT PINS IT.  The reference (arpg/kf_bayesopt, mounted at /root/reference) ships no tests,
+ * fixtures or golden vectors for this path (CMakeLists.txt:221-232 is commented out) and seeds
+ * every RNG from the wall clock (system_models.hpp:74,147; simulator.cpp:9), so there is nothing
+ * of its own to check against -- by that measure parity is UNPINNED.  Its dependencies (Eigen3,
+ * ROS, Boost, bayesopt) are absent here, so its build cannot run either.  What this repo does
+ * instead: oracle/Makefile compiles the reference's OWN hot-path sources (trial.cpp, simulator.cpp,
+ * kalman_filter.cpp, read_para_vehicle.cpp, include/*.hpp) from where they lie into
+ * oracle/_ref/libkfbo_ref.so, with oracle/ref_shim/ standing in for the few pieces of Eigen3 / ROS /
+ * matplotlibcpp they use and a counter for the wall clock.  This file is checked against that
+ * library (tests/test_oracle_vs_ref.py: models, Van Loan discretisation, KalmanFilter::Step,
+ * Trial::Run end to end with the reference's RNG discipline replayed) and against vectors it
+ * produced (tests/golden/ref_vectors.npz, for machines without the reference tree).  What stays
+ * restated rather than linked is Eigen's internal arithmetic for 1x1 / 2x2 / 4x4 matrices (product
+ * order, closed-form inverse, expm, the eigen-solver's sign convention) -- see ref_shim/Eigen/Dense.
+ * Independent pins besides: a numpy/scipy restatement (tests/golden/make_golden.py) and
+ * data-independent known answers.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference).  Compile with -O2 -ffp-contract=off: the reference's catkin
@@ -605,6 +614,114 @@ int ko_eval_mt(double dt, int T, double q_truth, double r_truth, double q_est, d
     ko_cost_from_threads(ta, cores, state_dof, obs_dof, cost_choice, out);
     free(ta); free(jobs); free(th);
     return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Replay of ONE Trial object exactly as the reference's own code runs it when  */
+/* its clock is the counter of oracle/ref_shim/fake_clock.h -- the check of     */
+/* this file against oracle/_ref (the reference's sources compiled here).       */
+/* What the reference does with its static generator (eigenmvn.h:51-62,91-98):  */
+/*   * every sampler construction re-seeds it: Trial's constructor reads the    */
+/*     clock twice (truth ProcessModel, truth ObservationModel,                 */
+/*     system_models.hpp:74,147) and the estimator's default-constructed        */
+/*     samplers re-seed it to 5489 -- all overwritten before any draw, because  */
+/*   * Simulator::Initialize re-seeds from the clock at the start of EVERY      */
+/*     trial (simulator.cpp:9-10): trial i uses seed (unsigned)(clock0 + 2 + i);*/
+/*   * samples(n) hands the generator functor to NullaryExpr BY VALUE           */
+/*     (eigenmvn.h:135-138): each call starts from a normal_distribution        */
+/*     without a saved value, so a 2-vector consumes one polar pair and the     */
+/*     1x1 observation draw consumes one pair and DROPS its second half.        */
+/* ------------------------------------------------------------------------- */
+typedef struct { mt19937_t *g; double Tq[4], sr; } refclock_ctx;
+
+static void refclock_noise(void *p, int step, double *w0, double *w1, double *v)
+{
+    (void)step;
+    refclock_ctx *c = (refclock_ctx *)p;
+    normal_t pn = {0, 0.0}, on = {0, 0.0};
+    const double n0 = mt_normal(c->g, &pn), n1 = mt_normal(c->g, &pn);   /* system_models.hpp:87 */
+    *w0 = c->Tq[0] * n0 + c->Tq[1] * n1;
+    *w1 = c->Tq[2] * n0 + c->Tq[3] * n1;
+    *v = c->sr * mt_normal(c->g, &on);                                    /* system_models.hpp:158 */
+}
+
+int ko_trial_run_refclock(double dt, int T, double q_truth, double r_truth, double q_est, double r_est,
+                          int nsimruns, int cores, long long clock0, double *avg4)
+{
+    if (T < 2 || T > KO_U_TABLE || cores < 1 || nsimruns < cores) return -1;
+    ko_model *truth = malloc(sizeof *truth), *est = malloc(sizeof *est);
+    ko_model_init(truth, q_truth, r_truth, dt);
+    ko_model_init(est, q_est, r_est, dt);
+    mt19937_t *g = malloc(sizeof *g);
+    refclock_ctx c; c.g = g;
+    ko_eig_transform2(truth->Qd, c.Tq);
+    c.sr = sqrt(truth->R > 0 ? truth->R : 0);
+    const int n = nsimruns / cores;
+    double *hn = malloc(sizeof(double) * T), *hi = malloc(sizeof(double) * T);
+    double *pt = malloc(sizeof(double) * 4 * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        mt_seed(g, (uint32_t)(unsigned long long)(clock0 + 2 + i));      /* simulator.cpp:9-10 */
+        normal_t ic = {0, 0.0};
+        double x0n[2], out[4];
+        x0n[0] = mt_normal(g, &ic);   /* P0 = I: V*sqrt(Lambda) = I (simulator.cpp:10-12) */
+        x0n[1] = mt_normal(g, &ic);
+        run_trial(truth, est, T, x0n, refclock_noise, &c, hn, hi, out);
+        for (int k = 0; k < 4; ++k) pt[(long)k * n + i] = out[k];
+    }
+    ko_thread_averages(pt, n, 0, T, nsimruns, cores, avg4);
+    free(truth); free(est); free(g); free(hn); free(hi); free(pt);
+    return 0;
+}
+
+/* The post-transform noise draws of trial i of that replay: x0n[2], w[T][2], v[T] -- what
+ * Simulator::Initialize / ProcessModel::Predict / ObservationModel::Predict add (simulator.cpp:12,
+ * system_models.hpp:96,158).  Feeding them to a supplied-noise evaluation reproduces the trial. */
+int ko_refclock_draws(double dt, int T, double q_truth, double r_truth, long long clock0, int i,
+                      double *x0n, double *w, double *v)
+{
+    if (T < 1 || T > KO_U_TABLE) return -1;
+    ko_model *truth = malloc(sizeof *truth);
+    ko_model_init(truth, q_truth, r_truth, dt);
+    mt19937_t *g = malloc(sizeof *g);
+    refclock_ctx c; c.g = g;
+    ko_eig_transform2(truth->Qd, c.Tq);
+    c.sr = sqrt(truth->R > 0 ? truth->R : 0);
+    mt_seed(g, (uint32_t)(unsigned long long)(clock0 + 2 + i));
+    normal_t ic = {0, 0.0};
+    x0n[0] = mt_normal(g, &ic);
+    x0n[1] = mt_normal(g, &ic);
+    for (int s = 0; s < T; ++s) refclock_noise(&c, s, &w[2 * s], &w[2 * s + 1], &v[s]);
+    free(truth); free(g);
+    return 0;
+}
+
+/* KalmanFilter::Initialize(0, I) then Step(z[k], k) (kalman_filter.cpp:12-38) on a supplied measurement
+ * sequence.  out[k] = {xest0, xest1, P00, P01, P10, P11, nu, S}. */
+int ko_kf_run(double q_est, double r_est, double dt, int T, const double *z, double *out)
+{
+    if (T < 1 || T > KO_U_TABLE) return -1;
+    ko_model *est = malloc(sizeof *est);
+    ko_model_init(est, q_est, r_est, dt);
+    ko_kf f;
+    f.xest[0] = f.xest[1] = 0; f.pest[0] = 1; f.pest[1] = 0; f.pest[2] = 0; f.pest[3] = 1; f.nu = 0; f.sob = 1;
+    for (int k = 0; k < T; ++k) {
+        kf_step(est, &f, z[k], k);
+        double *o = out + 8 * k;
+        o[0] = f.xest[0]; o[1] = f.xest[1];
+        o[2] = f.pest[0]; o[3] = f.pest[1]; o[4] = f.pest[2]; o[5] = f.pest[3];
+        o[6] = f.nu; o[7] = f.sob;
+    }
+    free(est);
+    return 0;
+}
+
+/* g*u[count] as ProcessModel::Predict adds it (system_models.hpp:46-56,82): out[n][2]. */
+void ko_gu_table(double dt, int n, double *out)
+{
+    ko_model *m = malloc(sizeof *m);
+    ko_model_init(m, 1.0, 1.0, dt);
+    for (int i = 0; i < n && i < KO_U_TABLE; ++i) { out[2 * i] = m->g[0] * m->u[i]; out[2 * i + 1] = m->g[1] * m->u[i]; }
+    free(m);
 }
 
 /* Data-independent Riccati trace for known-answer tests: S, K, P after step k

@@ -21,7 +21,7 @@ COST_CHOICES = {"JNEES": 0, "CNEES": 1, "JNIS": 2, "CNIS": 3}
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "kfbo_oracle.c")
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libkfbo_oracle.so"])
     return _SO
 
 
@@ -53,6 +53,14 @@ def lib() -> C.CDLL:
         L.ko_eig_transform2.argtypes = [_dp, _dp]
         L.ko_mt19937_nth.argtypes = [C.c_uint32, C.c_int]
         L.ko_mt19937_nth.restype = C.c_uint32
+        L.ko_trial_run_refclock.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                                            C.c_int, C.c_longlong, _dp]
+        L.ko_trial_run_refclock.restype = C.c_int
+        L.ko_refclock_draws.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_longlong, C.c_int, _dp, _dp, _dp]
+        L.ko_refclock_draws.restype = C.c_int
+        L.ko_kf_run.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, _dp, _dp]
+        L.ko_kf_run.restype = C.c_int
+        L.ko_gu_table.argtypes = [C.c_double, C.c_int, _dp]
         _lib = L
     return _lib
 
@@ -172,3 +180,37 @@ def eig_transform2(cov) -> np.ndarray:
 
 def mt19937_nth(seed: int, n: int) -> int:
     return int(lib().ko_mt19937_nth(seed, n))
+
+
+def trial_run_refclock(dt, T, q_truth, r_truth, q_est, r_est, nsimruns, cores, clock0) -> np.ndarray:
+    """The four getters of ONE Trial object replayed with the reference's own RNG discipline under the counter
+    clock of oracle/ref_shim/fake_clock.h (checked against oracle/_ref in tests/test_oracle_vs_ref.py)."""
+    out = np.empty(4)
+    rc = lib().ko_trial_run_refclock(dt, T, q_truth, r_truth, q_est, r_est, nsimruns, cores, clock0, _p(out))
+    if rc:
+        raise ValueError(f"ko_trial_run_refclock rc={rc}")
+    return out
+
+
+def kf_run(q_est, r_est, dt, z) -> np.ndarray:
+    z = _f64(z)
+    out = np.empty((z.size, 8))
+    rc = lib().ko_kf_run(q_est, r_est, dt, z.size, _p(z), _p(out))
+    if rc:
+        raise ValueError(f"ko_kf_run rc={rc}")
+    return out
+
+
+def gu_table(dt, n=2000) -> np.ndarray:
+    out = np.empty((n, 2))
+    lib().ko_gu_table(dt, n, _p(out))
+    return out
+
+
+def refclock_draws(dt, T, q_truth, r_truth, clock0, i=0):
+    """(x0n[2], w[T][2], v[T]): the noise trial i of trial_run_refclock adds."""
+    x0n, w, v = np.empty(2), np.empty((T, 2)), np.empty(T)
+    rc = lib().ko_refclock_draws(dt, T, q_truth, r_truth, clock0, i, _p(x0n), _p(w), _p(v))
+    if rc:
+        raise ValueError(f"ko_refclock_draws rc={rc}")
+    return x0n, w, v

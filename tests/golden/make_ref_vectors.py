@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ref_vectors.npz: outputs of THE REFERENCE'S OWN CODE (oracle/_ref/libkfbo_ref.so, built by
+oracle/Makefile from /root/reference's trial.cpp, simulator.cpp, kalman_filter.cpp, read_para_vehicle.cpp and headers)
+for fixed inputs, so that machines without the reference tree (the GPU box) can still check against it.
+
+  kf_*     KalmanFilter::Step on seeded measurement sequences: {xest, P (4 entries), nu, S} per step
+  models_* Fd, Qd, g*u table, R of ProcessModel / ObservationModel
+  trial_*  Trial::Run with Nsimruns = CPUcoreNumber = 1 under the counter clock: the four getters, plus the noise
+           draws of that trial (x0n, w, v) as replayed by the oracle -- the replay is what
+           tests/test_oracle_vs_ref.py checks against the reference end to end, so feeding these draws to a
+           supplied-noise evaluation must reproduce the reference's getters.
+Run here (the reference tree must be present):  python tests/golden/make_ref_vectors.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as o   # noqa: E402
+from oracle import ref           # noqa: E402
+
+out = {}
+rng = np.random.default_rng(20261019)
+kf_cases = [(1.0, 0.1, 0.1, 201), (0.3, 0.7, 0.5, 211), (5.0, 0.01, 1.0, 201), (0.1, 1.0, 0.1, 2000)]
+out["kf_cases"] = np.array(kf_cases)
+for i, (q, r, dt, T) in enumerate(kf_cases):
+    z = np.cumsum(rng.normal(size=T)) * 0.3
+    out[f"kf_z_{i}"] = z
+    out[f"kf_out_{i}"] = ref.kf_run(q, r, dt, z)
+    Fd, Qd, gu, H, R = ref.models(q, r, dt)
+    out[f"models_{i}"] = np.concatenate([Fd.ravel(), Qd.ravel(), H, [R]])
+    out[f"models_gu_{i}"] = gu
+trial_cases = [  # dt, t_end, q_truth, r_truth, q_est, r_est, clock0
+    (0.1, 20.1, 1.0, 0.1, 1.0, 0.1, 1000), (0.1, 20.1, 1.0, 0.1, 0.1, 0.1, 1001), (0.1, 20.1, 1.0, 0.1, 5.0, 1.0, 1002),
+    (1.0, 201.0, 1.0, 0.1, 1.0, 0.1, 2000), (1.0, 201.0, 1.0, 0.1, 2.5, 0.01, 2001),
+    (0.5, 105.5, 1.0, 0.1, 1.0, 0.1, 3000), (0.5, 105.5, 1.0, 0.1, 0.37, 0.62, 3001), (0.1, 200.0, 1.0, 0.1, 1.3, 0.07, 4000)]
+out["trial_cases"] = np.array(trial_cases, dtype=np.float64)
+for i, (dt, t_end, qt, rt, qe, re, clock0) in enumerate(trial_cases):
+    getters, calls, T = ref.trial_run(dt, t_end, 1, 1, qt, rt, qe, re, int(clock0))
+    assert calls == 3
+    replay = o.trial_run_refclock(dt, T, qt, rt, qe, re, 1, 1, int(clock0))
+    assert np.max(np.abs(replay - getters) / np.abs(getters)) < 1e-9, (i, replay, getters)
+    x0n, w, v = o.refclock_draws(dt, T, qt, rt, int(clock0), 0)
+    out[f"trial_T_{i}"] = np.array(T)
+    out[f"trial_getters_{i}"] = getters        # average_nees_, average_nis_, average_var_nees_, average_var_nis_
+    out[f"trial_x0n_{i}"], out[f"trial_w_{i}"], out[f"trial_v_{i}"] = x0n, w, v
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_vectors.npz"), **out)
+print("wrote ref_vectors.npz:", len(out), "arrays")
