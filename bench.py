@@ -11,8 +11,8 @@ meet in one ncclAllReduce inside libkfbo.so.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-Prints ONE JSON line on rank 0.  --impl reference times the reference's threaded CPU path
-(restated by oracle/kfbo_oracle.c: the reference itself cannot be compiled here) on the host cores.
+Prints ONE JSON line on rank 0.  --impl reference times the reference's threaded CPU path on the host cores:
+the reference's own sources as compiled into oracle/_ref (cpu_baseline.kind "reference"), else the oracle's port.
 """
 from __future__ import annotations
 
@@ -101,17 +101,26 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(rows), "reasons": reasons}
 
 
-def cpu_reference_run(steps: int, warmup: int, budget_s: float):
-    """The reference's threaded CPU trial path (trial_node.cpp:54-67 -> Trial::Run), restated by the
-    oracle, on all host cores; each step a bounded sample of the cfg3 workload (same T, D, candidate)."""
+def cpu_reference_run(steps: int, warmup: int, budget_s: float, kind: str = "auto"):
+    """The reference's threaded CPU trial path (trial_node.cpp:54-75: CPUcoreNumber Trial objects, one std::thread
+    per Trial::Run, getters averaged) on all host cores; each step a bounded sample of the cfg3 workload (same T, D,
+    candidate).  kind "reference": the reference's OWN trial.cpp / simulator.cpp / kalman_filter.cpp / headers as
+    compiled into oracle/_ref/libkfbo_ref.so (oracle/Makefile; Eigen3 is not installed, oracle/ref_shim stands in for
+    it).  kind "port": the oracle's restatement (heap-free, one mt19937 per thread).  "auto": reference if built."""
     from oracle import oracle as o
+    from oracle import ref
     cores = os.cpu_count() or 1
+    use_ref = kind == "reference" or (kind == "auto" and ref.available())
 
     def one_eval(nsim):
         for dt, T in SAMPLE_TIMES:
-            o.eval_mt(dt, T, Q_TRUTH, R_TRUTH, CANDIDATE[0][0], CANDIDATE[1][0], nsim, cores, seed=12345)
+            if use_ref:
+                _, T_ref = ref.eval_threads(dt, dt * T, nsim, cores, Q_TRUTH, R_TRUTH, CANDIDATE[0][0], CANDIDATE[1][0], clock0=12345)
+                assert T_ref == T, (T_ref, T)
+            else:
+                o.eval_mt(dt, T, Q_TRUTH, R_TRUTH, CANDIDATE[0][0], CANDIDATE[1][0], nsim, cores, seed=12345)
 
-    cal = 16 * cores
+    cal = (2 if use_ref else 16) * cores
     t = time.perf_counter()
     one_eval(cal)
     rate = cal / (time.perf_counter() - t)                      # trials/s for a D=2 evaluation
@@ -129,16 +138,22 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float):
         model = next(l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name"))
     except Exception:
         pass
-    return {"value": work / el, "unit": UNIT, "cores": cores, "kind": "port",
+    how = ("the reference's own trial.cpp / simulator.cpp / kalman_filter.cpp / eigenmvn.h: Trial::Run on one std::thread per "
+           "core sharing the reference's static mt19937 (trial_node.cpp:54-75), compiled by oracle/Makefile with a stand-in "
+           "for Eigen3, which is not installed" if use_ref else
+           "mt19937 + polar normals per thread; heap-free restatement (oracle/kfbo_oracle.c), faster than the Eigen-dynamic original")
+    return {"value": work / el, "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port",
             "sample": f"{steps} evaluations of {nsim} trials x {STEPS_PER_TRIAL} steps x {len(SAMPLE_TIMES)} sample times "
-                      f"({el:.1f} s; mt19937 + polar normals per thread; heap-free restatement, faster than the "
-                      f"Eigen-dynamic original)", "cpu_model": model}, el / steps * 1e3, nsim
+                      f"({el:.1f} s; {how})", "cpu_model": model}, el / steps * 1e3, nsim
 
 
 def run_reference(args, rank: int):
     if rank != 0:
         return
     cb, ms, nsim = cpu_reference_run(args.steps, args.warmup, budget_s=120.0)
+    if cb["kind"] == "reference":      # the oracle's restatement beside it, for scale (a few seconds)
+        port, _, _ = cpu_reference_run(2, 1, budget_s=6.0, kind="port")
+        cb["port"] = {k: port[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -398,6 +413,9 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only): the oracle's threaded path on a bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not cfg4:
         cb, _, _ = cpu_reference_run(steps=3, warmup=1, budget_s=16.0)
+        if cb["kind"] == "reference":
+            port, _, _ = cpu_reference_run(2, 1, budget_s=6.0, kind="port")
+            cb["port"] = {k: port[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line_extra["cpu_baseline"] = cb
 
     if rank == 0:

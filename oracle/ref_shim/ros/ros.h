@@ -1,15 +1,125 @@
-// ros/ros.h -- stand-in so that the reference's read_para_vehicle.h / .cpp compile without ROS (test
-// infrastructure, see Eigen/Dense in this directory).  The parameter server is empty: getParam finds nothing;
-// oracle/ref_driver.cpp fills the ReadParaVehicle members directly.
+// ros/ros.h -- stand-in so that the reference's read_para_vehicle.{h,cpp}, read_para_bayes.{h,cpp} and
+// trial_node.cpp compile without ROS (test infrastructure, see Eigen/Dense in this directory).
+//
+// What it restates of roscpp's published behaviour, and nothing more:
+//   * the parameter server: a process-wide name -> value map that oracle/ref_driver.cpp fills (from the
+//     reference's own yaml files, parsed by the tests); NodeHandle::getParam returns false for a missing name or
+//     a type it cannot convert (an int parameter reads as double, like XmlRpc ints do in roscpp);
+//   * topics: advertise<T>() returns a Publisher whose publish() appends the message to the topic's outbox;
+//     subscribe() registers a member-function callback; ros::spin() delivers every message queued in the
+//     topic's inbox to the callbacks, in order, on the calling thread, and returns (roscpp's spin() returns on
+//     shutdown; here "the inbox is empty" is the shutdown).
+// In- and outboxes hold type-erased shared_ptr<void>; the driver knows the message types of the two topics of
+// the contract ("noise": std_msgs::Float64MultiArray, "cost": std_msgs::Float64).
 #pragma once
+#include <algorithm>   // roscpp's headers pull it in; trial_node.cpp relies on that for max_element
+#include <deque>
+#include <functional>
+#include <map>
+#include <memory>
 #include <string>
+#include <vector>
+
 namespace ros {
+
+struct ShimParam {
+    enum Kind { kInt, kDouble, kString, kDoubleVector } kind = kInt;
+    long long i = 0;
+    double d = 0.0;
+    std::string s;
+    std::vector<double> v;
+};
+
+struct ShimMaster {
+    std::map<std::string, ShimParam> params;
+    std::map<std::string, std::deque<std::shared_ptr<void>>> inbox, outbox;
+    std::map<std::string, std::vector<std::function<void(const std::shared_ptr<void> &)>>> callbacks;
+    static ShimMaster &get()
+    {
+        static ShimMaster m;
+        return m;
+    }
+};
+
+class Publisher {
+public:
+    Publisher() {}
+    explicit Publisher(const std::string &topic) : topic_(topic) {}
+    template <typename M> void publish(const M &msg) const
+    {
+        ShimMaster::get().outbox[topic_].push_back(std::make_shared<M>(msg));
+    }
+private:
+    std::string topic_;
+};
+
+class Subscriber {};
+
 class NodeHandle {
 public:
-    template <typename T> bool getParam(const std::string &, T &) const { return false; }
+    bool getParam(const std::string &name, int &out) const
+    {
+        const ShimParam *p = find(name);
+        if (!p || p->kind != ShimParam::kInt) return false;
+        out = (int)p->i;
+        return true;
+    }
+    bool getParam(const std::string &name, double &out) const
+    {
+        const ShimParam *p = find(name);
+        if (!p || (p->kind != ShimParam::kDouble && p->kind != ShimParam::kInt)) return false;
+        out = p->kind == ShimParam::kDouble ? p->d : (double)p->i;
+        return true;
+    }
+    bool getParam(const std::string &name, std::string &out) const
+    {
+        const ShimParam *p = find(name);
+        if (!p || p->kind != ShimParam::kString) return false;
+        out = p->s;
+        return true;
+    }
+    bool getParam(const std::string &name, std::vector<double> &out) const
+    {
+        const ShimParam *p = find(name);
+        if (!p || p->kind != ShimParam::kDoubleVector) return false;
+        out = p->v;
+        return true;
+    }
+    template <typename M> Publisher advertise(const std::string &topic, unsigned /*queue_size*/) { return Publisher(topic); }
+    template <typename M, typename T>
+    Subscriber subscribe(const std::string &topic, unsigned /*queue_size*/, void (T::*fp)(const std::shared_ptr<const M> &), T *obj)
+    {
+        ShimMaster::get().callbacks[topic].push_back([fp, obj](const std::shared_ptr<void> &m) {
+            const std::shared_ptr<const M> typed = std::static_pointer_cast<const M>(m);
+            (obj->*fp)(typed);
+        });
+        return Subscriber();
+    }
+private:
+    static const ShimParam *find(const std::string &name)
+    {
+        const auto &ps = ShimMaster::get().params;
+        const auto it = ps.find(name);
+        return it == ps.end() ? nullptr : &it->second;
+    }
 };
+
+inline void init(int &, char **, const std::string &) {}
 inline bool ok() { return true; }
 inline void shutdown() {}
+inline void spin()
+{
+    ShimMaster &m = ShimMaster::get();
+    for (auto &kv : m.callbacks) {
+        std::deque<std::shared_ptr<void>> &q = m.inbox[kv.first];
+        while (!q.empty()) {
+            const std::shared_ptr<void> msg = q.front();
+            q.pop_front();
+            for (auto &cb : kv.second) cb(msg);
+        }
+    }
+    m.callbacks.clear();      // the node object the callbacks point into dies when its main() returns
+}
 }  // namespace ros
 #define ROS_INFO(...) ((void)0)
 #define ROS_WARN(...) ((void)0)

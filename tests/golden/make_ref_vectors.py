@@ -9,6 +9,9 @@ for fixed inputs, so that machines without the reference tree (the GPU box) can 
            draws of that trial (x0n, w, v) as replayed by the oracle -- the replay is what
            tests/test_oracle_vs_ref.py checks against the reference end to end, so feeding these draws to a
            supplied-noise evaluation must reproduce the reference's getters.
+  node_*   THE NODE: trial_node.cpp's main() -> RunTrial::ProcessNoiseCallback on queued "noise" messages (CPUcoreNumber = 1
+           so that the static generator is not raced; the reference's own vehicleParams.yaml / bayesParams.yaml otherwise):
+           the "cost" messages it published for each costChoice, plus the noise draws of every trial of every pass.
 Run here (the reference tree must be present):  python tests/golden/make_ref_vectors.py"""
 import os
 import sys
@@ -45,5 +48,33 @@ for i, (dt, t_end, qt, rt, qe, re, clock0) in enumerate(trial_cases):
     out[f"trial_T_{i}"] = np.array(T)
     out[f"trial_getters_{i}"] = getters        # average_nees_, average_nis_, average_var_nees_, average_var_nis_
     out[f"trial_x0n_{i}"], out[f"trial_w_{i}"], out[f"trial_v_{i}"] = x0n, w, v
+
+# ---- the node (trial_node.cpp): "noise" messages in, "cost" messages out
+REF = "/root/reference"
+NODE_NSIM, NODE_CLOCK0 = 6, 5000
+node_msgs = [([0.3], [0.5]), ([2.0], [0.05]), ([1.0], [0.1])]
+yaml_params = ref.load_yaml_params(f"{REF}/config/vehicleParams.yaml", f"{REF}/config/bayesParams.yaml")
+out["node_msgs"] = np.array([[pn[0], on[0]] for pn, on in node_msgs])
+out["node_meta"] = np.array([NODE_NSIM, NODE_CLOCK0, yaml_params["dt"], yaml_params["t_end"], 1.0, 201.0])   # + trial_node.cpp:105-108
+qt, rt = yaml_params["pnoise"][0], yaml_params["onoise"][0]
+passes = [(yaml_params["dt"], yaml_params["t_end"]), (1.0, 201.0)]            # (dt, t_end) of the callback's two passes
+for choice in ("JNEES", "CNEES", "JNIS", "CNIS"):
+    ref.set_params(dict(yaml_params, CPUcoreNumber=1, Nsimruns=NODE_NSIM, costChoice=choice))
+    costs, calls = ref.node_run(node_msgs, clock0=NODE_CLOCK0)
+    assert len(costs) == len(node_msgs) and calls == len(node_msgs) * 2 * (2 + NODE_NSIM)
+    out[f"node_costs_{choice}"] = costs
+clock = NODE_CLOCK0
+for m, (pn, on) in enumerate(node_msgs):
+    for k, (dt, t_end) in enumerate(passes):
+        want, _, T = ref.trial_run(dt, t_end, NODE_NSIM, 1, qt, rt, pn[0], on[0], clock)
+        g = o.trial_run_refclock(dt, T, qt, rt, pn[0], on[0], NODE_NSIM, 1, clock)
+        assert np.max(np.abs(g - want) / np.abs(want)) < 1e-9
+        draws = [o.refclock_draws(dt, T, qt, rt, clock, i) for i in range(NODE_NSIM)]
+        out[f"node_x0n_{m}_{k}"] = np.stack([d[0] for d in draws], axis=1)            # [2][B]
+        out[f"node_w_{m}_{k}"] = np.stack([d[1] for d in draws], axis=2)              # [T][2][B]
+        out[f"node_v_{m}_{k}"] = np.stack([d[2] for d in draws], axis=1)              # [T][B]
+        out[f"node_getters_{m}_{k}"] = want
+        out[f"node_T_{m}_{k}"] = np.array(T)
+        clock += 2 + NODE_NSIM
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_vectors.npz"), **out)
 print("wrote ref_vectors.npz:", len(out), "arrays")
