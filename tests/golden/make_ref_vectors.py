@@ -12,6 +12,9 @@ for fixed inputs, so that machines without the reference tree (the GPU box) can 
   node_*   THE NODE: trial_node.cpp's main() -> RunTrial::ProcessNoiseCallback on queued "noise" messages (CPUcoreNumber = 1
            so that the static generator is not raced; the reference's own vehicleParams.yaml / bayesParams.yaml otherwise):
            the "cost" messages it published for each costChoice, plus the noise draws of every trial of every pass.
+  stat_*   statistical anchors FROM THE REFERENCE'S OWN RNG PATH (mt19937 + eigenmvn): Trial::Run on 10 independent
+           blocks of 2000 trials per case -> mean and standard error over the blocks of the four getters; the on-device
+           Philox path has to agree with these within the Monte Carlo standard error (north_star).
 Run here (the reference tree must be present):  python tests/golden/make_ref_vectors.py"""
 import os
 import sys
@@ -76,5 +79,19 @@ for m, (pn, on) in enumerate(node_msgs):
         out[f"node_getters_{m}_{k}"] = want
         out[f"node_T_{m}_{k}"] = np.array(T)
         clock += 2 + NODE_NSIM
+
+# ---- statistical anchors of the reference's own noise path
+stat_cases = [  # dt, t_end, q_est, r_est      (truth q = 1.0, r = 0.1: config/vehicleParams.yaml)
+    (0.1, 20.1, 1.0, 0.1), (0.1, 20.1, 0.1, 0.1), (0.1, 20.1, 5.0, 0.1), (0.1, 20.1, 1.0, 0.01), (0.1, 20.1, 1.0, 1.0),
+    (1.0, 201.0, 1.0, 0.1), (1.0, 201.0, 0.1, 0.1), (0.5, 105.5, 1.0, 0.1), (0.5, 105.5, 5.0, 1.0)]
+STAT_BLOCKS, STAT_BLOCK_TRIALS = 10, 2000
+out["stat_cases"] = np.array(stat_cases)
+out["stat_meta"] = np.array([STAT_BLOCKS, STAT_BLOCK_TRIALS])
+for i, (dt, t_end, qe, re) in enumerate(stat_cases):
+    blocks = np.stack([ref.trial_run(dt, t_end, STAT_BLOCK_TRIALS, 1, qt, rt, qe, re, 10_000_000 * (i + 1) + 100_000 * b)[0]
+                       for b in range(STAT_BLOCKS)])
+    out[f"stat_mean_{i}"] = blocks.mean(axis=0)
+    out[f"stat_se_{i}"] = blocks.std(axis=0, ddof=1) / np.sqrt(STAT_BLOCKS)
+    print("stat", stat_cases[i], out[f"stat_mean_{i}"], out[f"stat_se_{i}"])
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_vectors.npz"), **out)
 print("wrote ref_vectors.npz:", len(out), "arrays")

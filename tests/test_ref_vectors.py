@@ -68,3 +68,42 @@ def test_cuda_path_reproduces_reference_trials(kfbo, refvec):
                 # and the host-side cost assembly on those sums: J_NEES of the reference's formula (trial_node.cpp:77)
                 res = kfbo.finalize(kfbo.make_params(rv, [(dt, T)]), sums[0].reshape(1, 4))
                 assert res.cost[0] == pytest.approx(abs(np.log(want[0] / 2)), rel=1e-8, abs=1e-10)
+
+
+# ---------------------------------------------------------------------------------------------
+# Statistical anchors from the reference's OWN noise path (mt19937 + eigenmvn.h; stat_* arrays): north_star's second
+# correctness clause -- the counter-based Philox noise must agree with the reference within the Monte Carlo standard
+# error.  5 sigma of the combined standard error (the reference's comes from 10 blocks, so it is itself +-25%).
+# ---------------------------------------------------------------------------------------------
+def _stat_cases(refvec):
+    for i, (dt, t_end, qe, re) in enumerate(refvec["stat_cases"]):
+        yield i, float(dt), int((float(t_end) - 0.0) / float(dt)), float(qe), float(re), refvec[f"stat_mean_{i}"], refvec[f"stat_se_{i}"]
+
+
+def _check_against_anchor(per_trial, T, mean, se, what):
+    B = per_trial.shape[1]
+    got = np.array([per_trial[0].mean() / T, per_trial[1].mean() / T, per_trial[2].mean(), per_trial[3].mean()])
+    own = np.array([per_trial[0].std(ddof=1) / T, per_trial[1].std(ddof=1) / T, per_trial[2].std(ddof=1), per_trial[3].std(ddof=1)]) / np.sqrt(B)
+    z = (got - mean) / np.sqrt(se ** 2 + own ** 2)
+    assert np.all(np.abs(z) < 5.0), (what, got, mean, z)
+
+
+def test_oracle_philox_noise_agrees_statistically_with_the_reference_rng(oracle, refvec):
+    for i, dt, T, qe, re, mean, se in _stat_cases(refvec):
+        pt = oracle.eval_philox(20261019, i, dt, T, 1.0, 0.1, qe, re, 0, 20000)
+        _check_against_anchor(pt, T, mean, se, ("oracle philox", i))
+
+
+@pytest.mark.gpu
+def test_cuda_philox_noise_agrees_statistically_with_the_reference_rng(kfbo, refvec):
+    B = 1 << 17
+    for i, dt, T, qe, re, mean, se in _stat_cases(refvec):
+        rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
+        with kfbo.CostEvaluator(rv, [(dt, T)], seed=20261019 + i) as ev:
+            pt = ev.eval_philox_trials(0, qe, re, 0, 0, B)
+            _check_against_anchor(pt, T, mean, se, ("cuda philox", i))
+            # and the whole-evaluation path (in-kernel reduction -> finalize) gives the same averages as its own per-trial rows
+            ev.set_eval_counter(0)
+            res = ev.eval([qe], [re])
+            assert res.average_nees[0] == pytest.approx(pt[0].sum() / (B * T), rel=1e-9)
+            assert res.average_var_nis[0] == pytest.approx(pt[3].mean(), rel=1e-9)
