@@ -307,6 +307,55 @@ inline std::atomic<uint32_t> &TrialStreamCounter()
     static std::atomic<uint32_t> c{0x40000000u};
     return c;
 }
+
+// Evaluator handles shared by the Trial objects of a process.  The reference's callers build CPUcoreNumber fresh
+// Trial objects per sample time per callback (trial_node.cpp:55-63); creating a device handle for each would make
+// every callback pay for allocations.  A Trial borrows a handle with its parameters for the duration of Run() and
+// gives it back; handles are created on demand (as many as Trials run concurrently).  The pool is never destroyed:
+// handles must not be torn down after the CUDA runtime at process exit.
+class EvaluatorPool {
+public:
+    static EvaluatorPool &Get()
+    {
+        static EvaluatorPool *pool = new EvaluatorPool;
+        return *pool;
+    }
+    std::unique_ptr<Evaluator> Borrow(const kfbo_params &p)
+    {
+        const std::string key = Key(p);
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            std::vector<std::unique_ptr<Evaluator>> &free_list = free_[key];
+            if (!free_list.empty()) {
+                std::unique_ptr<Evaluator> ev = std::move(free_list.back());
+                free_list.pop_back();
+                return ev;
+            }
+        }
+        return std::unique_ptr<Evaluator>(new Evaluator(p));
+    }
+    void Return(std::unique_ptr<Evaluator> ev)
+    {
+        const std::string key = Key(ev->params());
+        std::lock_guard<std::mutex> lock(mu_);
+        std::vector<std::unique_ptr<Evaluator>> &free_list = free_[key];
+        if (free_list.size() < kMaxIdlePerKey) free_list.push_back(std::move(ev));
+    }
+
+private:
+    static constexpr size_t kMaxIdlePerKey = 64;
+    static std::string Key(const kfbo_params &p)
+    {
+        std::ostringstream k;
+        k << std::hexfloat << p.n_sample_times;
+        for (int i = 0; i < p.n_sample_times; ++i) k << '|' << p.dt[i] << ':' << p.max_iterations[i];
+        k << '|' << p.nsimruns << '|' << p.cpu_core_number << '|' << p.state_dof << '|' << p.observation_dof << '|' << p.pnoise_truth
+          << '|' << p.onoise_truth << '|' << p.cost_choice << '|' << p.device << '|' << p.seed << '|' << p.max_candidates;
+        return k.str();
+    }
+    std::mutex mu_;
+    std::map<std::string, std::vector<std::unique_ptr<Evaluator>>> free_;
+};
 }  // namespace detail
 
 // ------------------------------------------------------------------------------------------
@@ -314,7 +363,7 @@ inline std::atomic<uint32_t> &TrialStreamCounter()
 // callers keep their shape (trial_node.cpp:55-75, src/test_trial.cpp:41-51):
 //     std::vector<Trial> t; for (cores) t.push_back(Trial(rv_gt, rv));
 //     std::thread(&Trial::Run, &t[i]) ... join ... t[i].get_average_nees() / cores
-// Run() is thread-safe across distinct Trial objects (each owns its handle and Philox stream).
+// Run() is thread-safe across distinct Trial objects (each borrows a pooled handle and takes a fresh Philox stream).
 // ------------------------------------------------------------------------------------------
 class Trial {
 public:
@@ -349,10 +398,13 @@ public:
         ReadParaVehicle one = sim;
         one.nsimruns_ = n;
         one.cpu_core_number_ = 1;
-        Evaluator ev(MakeParams(one, {{sim.dt_, T}}, "JNEES", seed_, 1, device_));
-        ev.SetStreamBase(detail::TrialStreamCounter().fetch_add(1));   // every Trial draws its own noise
-        ev.Eval(estimator_parameters_.pnoise_, estimator_parameters_.onoise_);
-        const std::vector<double> s = ev.LastSums(1);
+        // a pooled handle for these parameters; every Run draws its own noise (a fresh Philox stream)
+        std::unique_ptr<Evaluator> ev = detail::EvaluatorPool::Get().Borrow(MakeParams(one, {{sim.dt_, T}}, "JNEES", seed_, 1, device_));
+        ev->SetStreamBase(detail::TrialStreamCounter().fetch_add(1));
+        ev->SetEvalCounter(0);
+        ev->Eval(estimator_parameters_.pnoise_, estimator_parameters_.onoise_);
+        const std::vector<double> s = ev->LastSums(1);
+        detail::EvaluatorPool::Get().Return(std::move(ev));
         all_nees_ = s[0];
         all_nis_ = s[1];
         average_var_nees_ = s[2] * sim.cpu_core_number_ / sim.nsimruns_;                      // trial.cpp:110

@@ -20,6 +20,8 @@
 #include <string>
 #include <vector>
 
+#include <unistd.h>      // roscpp's headers pull it in; src/test_trial.cpp relies on that for usleep
+
 namespace ros {
 
 struct ShimParam {
