@@ -149,6 +149,14 @@ int kfbo_last_sums(const kfbo_handle *h, double *sums, int32_t n_candidates);
  * and how many kernels the last evaluation launched. */
 int kfbo_last_kernel_ms(const kfbo_handle *h, double *ms, int32_t *launches);
 
+/* Host wall time (microseconds) of the phases of the last kfbo_eval / kfbo_eval_batch on this rank:
+ * us[0] building the per-(candidate, sample time) constants, us[1] enqueueing copies and launches,
+ * us[2] waiting for the device (kernels, all-reduce, result copy), us[3] cost assembly (trial_node.cpp:70-119);
+ * us[4] is device time: the all-reduce of the cost sums (CUDA events around it; 0 without a communicator).
+ * The reference has no counterpart; this is what separates host overhead from kernel time in bench.py. */
+#define KFBO_HOST_PHASES 5
+int kfbo_last_host_us(const kfbo_handle *h, double us[KFBO_HOST_PHASES]);
+
 /* Run subsequent launches on this CUDA stream (a cudaStream_t); NULL = the handle's own. */
 int kfbo_set_cuda_stream(kfbo_handle *h, void *cuda_stream);
 

@@ -79,6 +79,7 @@ SIGNATURES = {
     "kfbo_set_eval_counter": (C.c_int, [_vp, C.c_uint32]),
     "kfbo_last_sums": (C.c_int, [_vp, _dp, C.c_int32]),
     "kfbo_last_kernel_ms": (C.c_int, [_vp, _dp, C.POINTER(C.c_int32)]),
+    "kfbo_last_host_us": (C.c_int, [_vp, _dp]),
     "kfbo_set_cuda_stream": (C.c_int, [_vp, _vp]),
     "kfbo_set_option": (C.c_int, [_vp, C.c_int32, C.c_int64]),
     "kfbo_nccl_unique_id": (C.c_int, [_vp]),

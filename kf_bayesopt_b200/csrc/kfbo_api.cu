@@ -6,11 +6,14 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kfbo_host.h"
@@ -63,7 +66,7 @@ struct kfbo_handle {
     int64_t b_eff = 0;
     int D = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     // tables
     double2 *d_gu = nullptr;          // [D][kMaxSteps] = (g0*u, g1*u)
     kfbo::math::LogTables *d_logtab = nullptr;   // -2 ln(u) tables of the noise generator
@@ -100,6 +103,7 @@ struct kfbo_handle {
     // last evaluation
     int last_ncand = 0, last_launches = 0;
     double last_ms = 0.0;
+    double last_host_us[KFBO_HOST_PHASES] = {0, 0, 0, 0, 0};   // build cases, enqueue, wait for the device, cost assembly, all-reduce (device)
     std::string err;
 };
 
@@ -166,6 +170,25 @@ int build_case(kfbo_handle *h, int k, double q_est, double r_est, uint32_t strea
     c->stream = stream;
     c->out_slot = out_slot;
     return KFBO_OK;
+}
+
+// Cost assembly of a batch (trial_node.cpp:70-119 per candidate).  ~30 ns per candidate (two logs per sample
+// time), which for a 4096-candidate sweep is 0.12 ms after an evaluation of 2-14 ms: large batches are split
+// over a few host threads (candidates are independent; each thread writes its own slice of `out`).
+void finalize_all(const kfbo_handle *h, int C, kfbo_result *out)
+{
+    const int D = h->D;
+    auto run = [h, D, out](int c0, int c1) {
+        for (int c = c0; c < c1; ++c) kfbo::host::finalize(h->p, h->h_sums + (size_t)c * D * 4, &out[c]);
+    };
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nthreads = C >= 1024 ? (int)std::min<unsigned>(4u, hw ? hw : 1u) : 1;
+    if (nthreads <= 1) { run(0, C); return; }
+    std::vector<std::thread> workers;
+    const int per = (C + nthreads - 1) / nthreads;
+    for (int t = 1; t < nthreads; ++t) workers.emplace_back(run, std::min(C, t * per), std::min(C, (t + 1) * per));
+    run(0, std::min(C, per));
+    for (std::thread &w : workers) w.join();
 }
 
 int cases_per_launch(const kfbo_handle *h, int tiles)
@@ -261,6 +284,7 @@ void kfbo_destroy(kfbo_handle *h)
     if (h->h_sums) cudaFreeHost(h->h_sums);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -293,7 +317,8 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
     if (cu(cudaSetDevice(h->device), "cudaSetDevice")) return bail(KFBO_ECUDA);
     if (cu(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail(KFBO_ECUDA);
     h->stream = h->own_stream;
-    if (cu(cudaEventCreate(&h->ev0), "cudaEventCreate") || cu(cudaEventCreate(&h->ev1), "cudaEventCreate")) return bail(KFBO_ECUDA);
+    if (cu(cudaEventCreate(&h->ev0), "cudaEventCreate") || cu(cudaEventCreate(&h->ev1), "cudaEventCreate") ||
+        cu(cudaEventCreate(&h->ev2), "cudaEventCreate")) return bail(KFBO_ECUDA);
 
     // ---- per-sample-time tables: g*u (system_models.hpp:46-56,82) and the truth noise transform
     std::vector<double2> gu((size_t)h->D * kfbo::kMaxSteps);
@@ -400,6 +425,8 @@ int kfbo_eval_batch(kfbo_handle *h, int32_t C, const double *q_est, const double
         else kfbo::host::shard_range(h->b_eff, h->rank, h->nranks, &t0, &t1);
     }
     const int ncases = (int)(c1 - c0) * D;
+    using clk = std::chrono::steady_clock;
+    const clk::time_point w0 = clk::now();
     for (int64_t c = c0; c < c1; ++c)
         for (int k = 0; k < D; ++k) {
             const uint32_t stream = h->stream_base + (h->eval_counter * (uint32_t)h->p.max_candidates + (uint32_t)c) * (uint32_t)D + (uint32_t)k;
@@ -407,6 +434,7 @@ int kfbo_eval_batch(kfbo_handle *h, int32_t C, const double *q_est, const double
             if (rc) return rc;
         }
     const size_t nsums = (size_t)C * D * 4;
+    const clk::time_point w1 = clk::now();
     // ranks that own no case of a slot (candidate sharding) or no trials contribute zeros
     KFBO_CUDA(h, cudaMemsetAsync(h->d_sums, 0, nsums * sizeof(double), h->stream));
     if (ncases > 0)
@@ -435,15 +463,28 @@ int kfbo_eval_batch(kfbo_handle *h, int32_t C, const double *q_est, const double
         }
     }
     KFBO_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-    if (h->comm)
+    if (h->comm) {
         KFBO_NCCL(h, nccl().AllReduce(h->d_sums, h->d_sums, nsums, ncclDouble, ncclSum, h->comm, h->stream));
+        KFBO_CUDA(h, cudaEventRecord(h->ev2, h->stream));
+    }
     KFBO_CUDA(h, cudaMemcpyAsync(h->h_sums, h->d_sums, nsums * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    const clk::time_point w2 = clk::now();
     KFBO_CUDA(h, cudaStreamSynchronize(h->stream));
+    const clk::time_point w3 = clk::now();
     float ms = 0.f;
     KFBO_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms;
     h->last_ncand = C;
-    for (int c = 0; c < C; ++c) kfbo::host::finalize(h->p, h->h_sums + (size_t)c * D * 4, &out[c]);
+    finalize_all(h, C, out);
+    const clk::time_point w4 = clk::now();
+    const clk::time_point w[5] = {w0, w1, w2, w3, w4};
+    for (int i = 0; i < 4; ++i) h->last_host_us[i] = std::chrono::duration<double, std::micro>(w[i + 1] - w[i]).count();
+    h->last_host_us[4] = 0.0;
+    if (h->comm) {
+        float ar = 0.f;
+        KFBO_CUDA(h, cudaEventElapsedTime(&ar, h->ev1, h->ev2));
+        h->last_host_us[4] = 1e3 * ar;
+    }
     ++h->eval_counter;
     return KFBO_OK;
 }
@@ -460,6 +501,13 @@ int kfbo_last_sums(const kfbo_handle *h, double *sums, int32_t n_candidates)
 {
     if (!h || !sums || n_candidates < 1 || n_candidates > h->last_ncand) return KFBO_EINVAL;
     std::memcpy(sums, h->h_sums, (size_t)n_candidates * h->D * 4 * sizeof(double));
+    return KFBO_OK;
+}
+
+int kfbo_last_host_us(const kfbo_handle *h, double us[KFBO_HOST_PHASES])
+{
+    if (!h || !us) return KFBO_EINVAL;
+    for (int i = 0; i < KFBO_HOST_PHASES; ++i) us[i] = h->last_host_us[i];
     return KFBO_OK;
 }
 

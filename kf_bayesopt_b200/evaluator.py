@@ -243,6 +243,12 @@ class CostEvaluator:
         self._check(self._lib.kfbo_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def last_host_us(self) -> dict:
+        """Host wall time (us) of the phases of the last eval / eval_batch on this rank."""
+        us = np.empty(5)
+        self._check(self._lib.kfbo_last_host_us(self._h, _ptr(us)))
+        return dict(zip(("build_cases", "enqueue", "device_wait", "cost_assembly", "allreduce_device"), us.tolist()))
+
     # -- exact-parity entry points
     def eval_supplied(self, k: int, q_est, r_est, x0noise, w, v, per_trial: bool = True):
         """Returns (per_trial[C][4][B] or None, sums[C][4]); x0noise[2][B], w[T][2][B], v[T][B]."""
