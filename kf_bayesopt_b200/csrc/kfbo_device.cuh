@@ -159,9 +159,10 @@ __device__ __forceinline__ void filter_step(Traj &t, const Case &m, const double
     const double nu = z - xp0;
     t.xh0 = fma(k0, nu, xp0);
     t.xh1 = fma(k1, nu, xp1);
-    const double x00 = 1.0 - k0;
-    t.p00 = x00 * pp00;
-    t.p01 = x00 * pp01;
+    // (I - K H) Ppred with K = Ppred H^T / S: (1 - k0) pp00 = (R/S) pp00 = R k0 and (1 - k0) pp01 = R k1 -- the same
+    // numbers without forming 1 - k0 (one FP64 instruction fewer, and no cancellation when k0 -> 1)
+    t.p00 = m.r_est * k0;
+    t.p01 = m.r_est * k1;
     t.p11 = fma(-k1, pp01, pp11);
     // ---- NEES = e^T P^-1 e = (e^T adj(P) e) / det(P) (the closed-form 2x2 inverse of trial.cpp:58 with
     //      the division applied once, to the quadratic form); NIS = (nu / S) nu

@@ -463,9 +463,8 @@ __global__ void __launch_bounds__(32) riccati_gains(const Case *__restrict__ cas
         const double sv = pp00 + m.r_est;
         const double sinv = KFBO_RCP(sv);
         const double k0 = pp00 * sinv, k1 = pp01 * sinv;
-        const double x00 = 1.0 - k0;
-        p00 = x00 * pp00;
-        p01 = x00 * pp01;
+        p00 = m.r_est * k0;
+        p01 = m.r_est * k1;
         p11 = fma(-k1, pp01, pp11);
         const double det = fma(p00, p11, -(p01 * p01));
         const double invdet = KFBO_RCP(det);

@@ -32,11 +32,12 @@
 namespace kfbo {
 namespace math {
 
-constexpr int kLogTableBits = 8;
-constexpr int kLogTableSize = 1 << kLogTableBits;   // 256 entries x {invc, 2 ln(invc)}
+constexpr int kLogTableBits = 10;
+constexpr int kLogTableSize = 1 << kLogTableBits;   // 1024 entries x {invc, 2 ln(invc)}: |r| <= 2^-11, one polynomial term fewer than 256 entries need
 constexpr int kLogKTableSize = 56;                  // j = 0..52 used: 2 j ln2
 constexpr uint32_t kLogOffHi = 0x3FE60000u;         // z in [0.6875, 1.375)
-constexpr int kLogUnitEntry = 159;                  // the sub-interval [1-2^-9, 1): c = 1 exactly
+constexpr int kLogBelowOne = 160 << (kLogTableBits - 8);   // sub-intervals of [0.6875, 1): (1 - 0.6875) 2^(bits+1)
+constexpr int kLogUnitEntry = kLogBelowOne - 1;     // the sub-interval [1-2^-(bits+1), 1): c = 1 exactly
 
 constexpr int kAngleTableBits = 10;
 constexpr int kAngleTableSize = 1 << kAngleTableBits;   // 1024 directions x {cos, sin}
@@ -51,10 +52,10 @@ struct LogTables {
 inline void build_log_tables(LogTables *t)
 {
     for (int i = 0; i < kLogTableSize; ++i) {
-        // sub-interval i of tmp = bits(z) - OFF: [i, i+1) * 2^44; below z = 1 one unit of tmp is
-        // 2^-53 in z, above it 2^-52 (z = 1 sits exactly at i = 160)
-        const long double lo = 0.6875L, w_lo = ldexpl(1.0L, -9), w_hi = ldexpl(1.0L, -8);
-        const long double centre = (i < 160) ? lo + (i + 0.5L) * w_lo : 1.0L + (i - 160 + 0.5L) * w_hi;
+        // sub-interval i of tmp = bits(z) - OFF: [i, i+1) * 2^(52-bits); below z = 1 one unit of tmp is
+        // 2^-53 in z, above it 2^-52 (z = 1 sits exactly at i = kLogBelowOne)
+        const long double lo = 0.6875L, w_lo = ldexpl(1.0L, -(kLogTableBits + 1)), w_hi = ldexpl(1.0L, -kLogTableBits);
+        const long double centre = (i < kLogBelowOne) ? lo + (i + 0.5L) * w_lo : 1.0L + (i - kLogBelowOne + 0.5L) * w_hi;
         double invc = (double)(1.0L / centre);
         if (i == kLogUnitEntry) invc = 1.0;
         t->invc_logc[i][0] = invc;
@@ -156,11 +157,13 @@ KFBO_HD double rcp(double x)
 
 // sqrt(a) to <= 1 ulp for normal a > 0: g = a y0 = sqrt(a)(1 - e), r = 1/2 - g y0/2 = e - e^2/2, and
 // sqrt(a) = g (1 - 2r)^(-1/2) = g (1 + r + 3/2 r^2 + O(r^3)): one third-order step on the 20-bit seed
-// (|r|^3 < 2^-57), 6 FP64 instructions instead of the 7 of two coupled Goldschmidt iterations.
+// (|r|^3 < 2^-57), 5 FP64 instructions instead of the 7 of two coupled Goldschmidt iterations.
 KFBO_HD double sqrt_pos(double a)
 {
     const double y = rsqrt_seed(a);
-    const double g = a * y, h = 0.5 * y;
+    // h = y / 2 exactly, by decrementing the exponent field (y = 1/sqrt(a) is a normal number far from the
+    // subnormal range): one integer add instead of a multiply on the FP64 pipe
+    const double g = a * y, h = make_double(hi_word(y) - 0x00100000u, lo_word(y));
     const double r = fma(-h, g, 0.5);
     const double t = fma(r, 1.5, 1.0);
     return fma(g * r, t, g);
@@ -172,12 +175,14 @@ KFBO_HD double sqrt_pos(double a)
 #define KFBO_CONST static const
 #endif
 
-// -2 ln(1+r)/r = -2 + r - (2/3) r^2 + (2/4) r^3 - (2/5) r^4 + (2/6) r^5 ; |r| <= 2^-9: rel. err 8e-18.
-// -2, 1, 1/2 and the hi32-rounded 1/3 are immediates; -2/3 and -2/5 need full precision.
-KFBO_CONST double kLogPolyU[2] = {-2.0 / 3.0, -0.4};
-#define KFBO_LOG_C5 0x1.5555500000000p-2
+// -2 ln(1+r)/r = -2 + r - (2/3) r^2 + (2/4) r^3 - (2/5) r^4 + ... ; |r| <= 2^-11 (1024 sub-intervals): the first
+// dropped term (1/3) r^5 is < 5e-18 of the leading -2.
+// -2, 1, 1/2 are immediates, the hi32-rounded -2/5 too (its 4e-7 relative rounding is scaled by r^4 < 6e-14);
+// -2/3 needs full precision.
+KFBO_CONST double kLogPolyU[1] = {-2.0 / 3.0};
+#define KFBO_LOG_C4 -0x1.9999900000000p-2
 // L = -2 ln(u) for u in [2^-52, 1): table-driven, no division, no branch.
-//   u = 2^k z, z in [0.6875, 1.375);  i = top 8 bits of (bits(z) - OFF);  r = z/c_i - 1, |r| <= 2^-9
+//   u = 2^k z, z in [0.6875, 1.375);  i = top 10 bits of (bits(z) - OFF);  r = z/c_i - 1, |r| <= 2^-11
 //   -2 ln u = 2 (-k) ln2 + 2 ln(invc_i) + r * (-2 ln(1+r)/r)
 // tab / ktab may live in shared memory (device) or anywhere (host).
 KFBO_HD double neg2_log(double u, const double (*tab)[2], const double *ktab)
@@ -189,8 +194,7 @@ KFBO_HD double neg2_log(double u, const double (*tab)[2], const double *ktab)
     const double z = make_double(hi - ((uint32_t)tmp & 0xFFF00000u), lo);
     const double invc = tab[i][0], logc2 = tab[i][1];
     const double r = fma(z, invc, -1.0);
-    double s = fma(KFBO_LOG_C5, r, kLogPolyU[1]);
-    s = fma(s, r, 0.5);
+    double s = fma(KFBO_LOG_C4, r, 0.5);
     s = fma(s, r, kLogPolyU[0]);
     s = fma(s, r, 1.0);
     s = fma(s, r, -2.0);
