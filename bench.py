@@ -192,14 +192,31 @@ def run_bo_loop(args):
             "gpu_launches": n}
     if not args.no_cpu_baseline:
         from oracle import oracle as o
+        from oracle import ref
         cores = 10                                          # config/vehicleParams.yaml:1
-        t = time.perf_counter()
-        for i in range(n):
-            for dt in (0.1, 1.0):                           # trial_node.cpp:105-114
-                o.eval_mt(dt, T, Q_TRUTH, R_TRUTH, 1.0 + 0.01 * i, 0.1, B, cores, seed=i)
-        cpu_s = time.perf_counter() - t
-        line["cpu_baseline"] = {"value": steps_total / cpu_s, "unit": UNIT, "cores": min(cores, os.cpu_count() or 1), "kind": "port",
-                                "sample": f"{n} evaluations of {B} trials x {T} steps x {D} sample times on {cores} threads "
+        cands = [(1.0 + 0.01 * i, 0.1) for i in range(n)]
+        if ref.available():
+            # the reference's OWN node (trial_node.cpp compiled into oracle/_ref): the same number of "noise" messages
+            # through RunTrial::ProcessNoiseCallback -- 10 Trial objects and std::threads per pass, two passes per message
+            ref.set_params({"CPUcoreNumber": cores, "stateDOF": 2, "observationDOF": 1, "t_start": 0.0, "t_end": 20.1, "dt": 0.1,
+                            "xi0": 0.0, "xidot0": 0.0, "Nsimruns": B, "pnoise": [Q_TRUTH], "onoise": [R_TRUTH],
+                            "optimizationChoice": "all", "costChoice": "JNEES", "n_init_samples": init})   # config/*.yaml
+            ref.node_run([([q], [r]) for q, r in cands[:8]], clock0=1)
+            t = time.perf_counter()
+            costs, _ = ref.node_run([([q], [r]) for q, r in cands], clock0=1)
+            cpu_s = time.perf_counter() - t
+            assert len(costs) == n
+            kind, how = "reference", ("messages through the reference's own RunTrial::ProcessNoiseCallback (trial_node.cpp compiled into "
+                                      "oracle/_ref with stand-ins for Eigen3 / ROS)")
+        else:
+            t = time.perf_counter()
+            for q, r in cands:
+                for dt in (0.1, 1.0):                       # trial_node.cpp:105-114
+                    o.eval_mt(dt, T, Q_TRUTH, R_TRUTH, q, r, B, cores, seed=1)
+            cpu_s = time.perf_counter() - t
+            kind, how = "port", "evaluations by the oracle's threaded restatement"
+        line["cpu_baseline"] = {"value": steps_total / cpu_s, "unit": UNIT, "cores": min(cores, os.cpu_count() or 1), "kind": kind,
+                                "sample": f"{n} {how}: {B} trials x {T} steps x {D} sample times on {cores} threads "
                                           f"(yaml CPUcoreNumber), {cpu_s:.2f} s",
                                 "evaluator_s": cpu_s,
                                 "loop_wall_s_estimate": cpu_s + loop["optimiser_s"],
