@@ -184,6 +184,26 @@ int kfbo_comm_init(kfbo_handle *h, const void *id_bytes, int32_t rank, int32_t n
 /* [begin,end) of n units owned by `rank` of `nranks` (contiguous, remainder to the low ranks). */
 int kfbo_shard_range(int64_t n, int32_t rank, int32_t nranks, int64_t *begin, int64_t *end);
 
+/* ---- multi-GPU from ONE process: a device group ----
+ * What a single-process caller (the ROS node robot1d_kf, src/test_trial.cpp) needs to spread an evaluation over
+ * several GPUs of the box: one host thread drives n_devices devices (devices[i], or 0..n_devices-1 when NULL); each
+ * evaluation launches its shard on every device, then ONE grouped ncclAllReduce of the [C][D][4] cost sums, then the
+ * costs are assembled from the first device's copy.  Sharding, Philox streams and therefore the results are those of
+ * the one-process-per-GPU mode with n_devices ranks.  n_devices == 1 needs no NCCL. */
+typedef struct kfbo_group kfbo_group;
+int kfbo_group_create(const kfbo_params *p, int32_t n_devices, const int32_t *devices, int32_t shard_mode, kfbo_group **out);
+void kfbo_group_destroy(kfbo_group *g);
+const char *kfbo_group_last_error(const kfbo_group *g);      /* g == NULL: last kfbo_group_create failure of this thread */
+int32_t kfbo_group_size(const kfbo_group *g);
+kfbo_handle *kfbo_group_handle(kfbo_group *g, int32_t i);    /* the handle of device i (owned by the group) */
+int kfbo_group_eval(kfbo_group *g, const double *pn, int32_t npn, const double *on, int32_t non, kfbo_result *out);
+int kfbo_group_eval_batch(kfbo_group *g, int32_t n_candidates, const double *q_est, const double *r_est, kfbo_result *out);
+int kfbo_group_last_sums(const kfbo_group *g, double *sums, int32_t n_candidates);
+int kfbo_group_last_kernel_ms(const kfbo_group *g, double *ms_max /* slowest device */, int32_t *launches /* all devices */);
+int kfbo_group_set_option(kfbo_group *g, int32_t option, int64_t value);
+int kfbo_group_set_stream_base(kfbo_group *g, uint32_t base);
+int kfbo_group_set_eval_counter(kfbo_group *g, uint32_t e);
+
 /* ---- host-side pieces of the path, exported so they can be tested without a GPU ---- */
 /* continuousToDiscrete for the robot1d model (continuous2discrete.hpp:8-32, system_models.hpp:33-39,58). */
 int kfbo_discretize(double pnoise0, double dt, double *Fd /*[4]*/, double *Qd /*[4]*/);

@@ -205,40 +205,57 @@ constexpr SecondSampleTime kReadmeSecondSampleTime{0.5, 105.5};
 // ------------------------------------------------------------------------------------------
 class Evaluator {
 public:
-    explicit Evaluator(const kfbo_params &p) : p_(p)
+    // n_gpus > 1: ONE process drives n_gpus devices (a kfbo_group: each evaluation launches its shard on every
+    // device and ends in one grouped ncclAllReduce of the cost sums) -- what a single-process caller like the ROS node
+    // needs to use the whole box.  shard_mode: KFBO_SHARD_TRIALS (one candidate, many trials) or
+    // KFBO_SHARD_CANDIDATES (candidate sweeps).
+    explicit Evaluator(const kfbo_params &p, int n_gpus = 1, int shard_mode = KFBO_SHARD_TRIALS) : p_(p)
     {
-        const int rc = kfbo_create(&p_, &h_);
-        if (rc) throw Error(rc, kfbo_last_error(nullptr));
+        if (n_gpus > 1) {
+            const int rc = kfbo_group_create(&p_, n_gpus, nullptr, shard_mode, &g_);
+            if (rc) throw Error(rc, kfbo_group_last_error(nullptr));
+            h_ = kfbo_group_handle(g_, 0);
+        } else {
+            const int rc = kfbo_create(&p_, &h_);
+            if (rc) throw Error(rc, kfbo_last_error(nullptr));
+        }
     }
-    ~Evaluator() { kfbo_destroy(h_); }
+    ~Evaluator()
+    {
+        if (g_) kfbo_group_destroy(g_);
+        else kfbo_destroy(h_);
+    }
     Evaluator(const Evaluator &) = delete;
     Evaluator &operator=(const Evaluator &) = delete;
 
     kfbo_result Eval(const std::vector<double> &pn, const std::vector<double> &on)
     {
         kfbo_result r;
-        Check(kfbo_eval(h_, pn.data(), (int32_t)pn.size(), on.data(), (int32_t)on.size(), &r));
+        Check(g_ ? kfbo_group_eval(g_, pn.data(), (int32_t)pn.size(), on.data(), (int32_t)on.size(), &r)
+                 : kfbo_eval(h_, pn.data(), (int32_t)pn.size(), on.data(), (int32_t)on.size(), &r));
         return r;
     }
     std::vector<kfbo_result> EvalBatch(const std::vector<double> &q_est, const std::vector<double> &r_est)
     {
         if (q_est.size() != r_est.size() || q_est.empty()) throw Error(KFBO_EINVAL, "EvalBatch: q_est and r_est must have equal, non-zero length");
         std::vector<kfbo_result> out(q_est.size());
-        Check(kfbo_eval_batch(h_, (int32_t)q_est.size(), q_est.data(), r_est.data(), out.data()));
+        Check(g_ ? kfbo_group_eval_batch(g_, (int32_t)q_est.size(), q_est.data(), r_est.data(), out.data())
+                 : kfbo_eval_batch(h_, (int32_t)q_est.size(), q_est.data(), r_est.data(), out.data()));
         return out;
     }
     // sums[n_candidates][D][4] of the last evaluation
     std::vector<double> LastSums(int n_candidates = 1) const
     {
         std::vector<double> s((size_t)n_candidates * p_.n_sample_times * 4);
-        Check(kfbo_last_sums(h_, s.data(), n_candidates));
+        Check(g_ ? kfbo_group_last_sums(g_, s.data(), n_candidates) : kfbo_last_sums(h_, s.data(), n_candidates));
         return s;
     }
+    // device time of the last evaluation's rollout kernel(s): the slowest device of a group
     double LastKernelMs(int *launches = nullptr) const
     {
         double ms = 0;
         int32_t n = 0;
-        Check(kfbo_last_kernel_ms(h_, &ms, &n));
+        Check(g_ ? kfbo_group_last_kernel_ms(g_, &ms, &n) : kfbo_last_kernel_ms(h_, &ms, &n));
         if (launches) *launches = n;
         return ms;
     }
@@ -249,20 +266,27 @@ public:
         Check(kfbo_trace_trial(h_, k, q_est, r_est, stream, trial, t.data()));
         return t;
     }
-    void SetOption(int option, long long value) { Check(kfbo_set_option(h_, option, value)); }
-    void SetStreamBase(uint32_t base) { Check(kfbo_set_stream_base(h_, base)); }
-    void SetEvalCounter(uint32_t e) { Check(kfbo_set_eval_counter(h_, e)); }
-    void CommInit(const void *nccl_id, int rank, int nranks, int shard_mode) { Check(kfbo_comm_init(h_, nccl_id, rank, nranks, shard_mode)); }
+    void SetOption(int option, long long value) { Check(g_ ? kfbo_group_set_option(g_, option, value) : kfbo_set_option(h_, option, value)); }
+    void SetStreamBase(uint32_t base) { Check(g_ ? kfbo_group_set_stream_base(g_, base) : kfbo_set_stream_base(h_, base)); }
+    void SetEvalCounter(uint32_t e) { Check(g_ ? kfbo_group_set_eval_counter(g_, e) : kfbo_set_eval_counter(h_, e)); }
+    // one process per GPU instead (MPI / torchrun style): join the NCCL communicator of the ranks
+    void CommInit(const void *nccl_id, int rank, int nranks, int shard_mode)
+    {
+        if (g_) throw Error(KFBO_ESTATE, "CommInit: this evaluator already drives a device group");
+        Check(kfbo_comm_init(h_, nccl_id, rank, nranks, shard_mode));
+    }
     const kfbo_params &params() const { return p_; }
-    kfbo_handle *handle() { return h_; }
+    kfbo_handle *handle() { return h_; }          // of a group: its first device
+    int n_gpus() const { return g_ ? (int)kfbo_group_size(g_) : 1; }
 
 private:
     void Check(int rc) const
     {
-        if (rc) throw Error(rc, kfbo_last_error(h_));
+        if (rc) throw Error(rc, g_ && *kfbo_group_last_error(g_) ? kfbo_group_last_error(g_) : kfbo_last_error(h_));
     }
     kfbo_params p_;
     kfbo_handle *h_ = nullptr;
+    kfbo_group *g_ = nullptr;
 };
 
 // kfbo_params for the truth side `rv_gt` and a list of (dt, max_iterations) passes.
@@ -471,9 +495,12 @@ public:
 
     explicit RunTrial(const ReadParaVehicle &rv, const SecondSampleTime *second = &kCodeSecondSampleTime,
                       int n_init_samples = 20, Publisher pub_cost = nullptr, bool verbose = true, int device = -1,
-                      uint64_t seed = kDefaultSeed, int max_candidates = 1)
+                      uint64_t seed = kDefaultSeed, int max_candidates = 1, int n_gpus = 1)
         : rv_(rv), n_init_samples_(n_init_samples), pub_cost_(std::move(pub_cost)), verbose_(verbose),
-          ev_(new Evaluator(MakeParams(rv, SampleTimesFrom(rv, second), rv.cost_choice_, seed, max_candidates, device)))
+          // single messages shard their trials over the GPUs; ProcessNoiseBatch sweeps shard the same way (every
+          // device runs every candidate on its slice of the trials)
+          ev_(new Evaluator(MakeParams(rv, SampleTimesFrom(rv, second), rv.cost_choice_, seed, max_candidates, device), n_gpus,
+                            KFBO_SHARD_TRIALS))
     {
     }
 

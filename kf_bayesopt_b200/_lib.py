@@ -84,6 +84,18 @@ SIGNATURES = {
     "kfbo_set_option": (C.c_int, [_vp, C.c_int32, C.c_int64]),
     "kfbo_nccl_unique_id": (C.c_int, [_vp]),
     "kfbo_comm_init": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32]),
+    "kfbo_group_create": (C.c_int, [C.POINTER(KfboParams), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(_vp)]),
+    "kfbo_group_destroy": (None, [_vp]),
+    "kfbo_group_last_error": (C.c_char_p, [_vp]),
+    "kfbo_group_size": (C.c_int32, [_vp]),
+    "kfbo_group_handle": (_vp, [_vp, C.c_int32]),
+    "kfbo_group_eval": (C.c_int, [_vp, _dp, C.c_int32, _dp, C.c_int32, C.POINTER(KfboResult)]),
+    "kfbo_group_eval_batch": (C.c_int, [_vp, C.c_int32, _dp, _dp, C.POINTER(KfboResult)]),
+    "kfbo_group_last_sums": (C.c_int, [_vp, _dp, C.c_int32]),
+    "kfbo_group_last_kernel_ms": (C.c_int, [_vp, _dp, C.POINTER(C.c_int32)]),
+    "kfbo_group_set_option": (C.c_int, [_vp, C.c_int32, C.c_int64]),
+    "kfbo_group_set_stream_base": (C.c_int, [_vp, C.c_uint32]),
+    "kfbo_group_set_eval_counter": (C.c_int, [_vp, C.c_uint32]),
     "kfbo_shard_range": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "kfbo_discretize": (C.c_int, [C.c_double, C.c_double, _dp, _dp]),
     "kfbo_control_table": (C.c_int, [C.c_double, C.c_int32, _dp]),

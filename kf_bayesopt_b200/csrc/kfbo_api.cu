@@ -33,6 +33,9 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -49,7 +52,11 @@ NcclApi &nccl()
         a.AllReduce = (decltype(a.AllReduce))dlsym(a.so, "ncclAllReduce");
         a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.so, "ncclCommDestroy");
         a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.so, "ncclGetErrorString");
-        a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
+        a.CommInitAll = (decltype(a.CommInitAll))dlsym(a.so, "ncclCommInitAll");
+        a.GroupStart = (decltype(a.GroupStart))dlsym(a.so, "ncclGroupStart");
+        a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.so, "ncclGroupEnd");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString && a.CommInitAll &&
+               a.GroupStart && a.GroupEnd;
         return a;
     }();
     return api;
@@ -103,6 +110,7 @@ struct kfbo_handle {
     // last evaluation
     int last_ncand = 0, last_launches = 0;
     double last_ms = 0.0;
+    std::chrono::steady_clock::time_point tp[3];   // phase marks of the evaluation in flight
     double last_host_us[KFBO_HOST_PHASES] = {0, 0, 0, 0, 0};   // build cases, enqueue, wait for the device, cost assembly, all-reduce (device)
     std::string err;
 };
@@ -411,12 +419,20 @@ int kfbo_set_cuda_stream(kfbo_handle *h, void *cuda_stream)
     return KFBO_OK;
 }
 
-int kfbo_eval_batch(kfbo_handle *h, int32_t C, const double *q_est, const double *r_est, kfbo_result *out)
+// An evaluation in three phases, so that a device group (kfbo_group_*) can run each phase on all its devices before
+// the next:  launch (constants, copies, rollout kernels)  ->  reduce (the all-reduce of the cost sums)  ->
+// collect (result copy, wait, cost assembly).  kfbo_eval_batch is the three in a row on one handle.
+static int eval_check(kfbo_handle *h, int32_t C, const double *q_est, const double *r_est, const kfbo_result *out)
 {
-    if (!h) return KFBO_EINVAL;
     if (!q_est || !r_est || !out) return fail(h, KFBO_EINVAL, "kfbo_eval_batch: NULL argument");
     if (C < 1 || C > h->p.max_candidates)
         return fail(h, KFBO_EINVAL, "kfbo_eval_batch: n_candidates %d outside [1, max_candidates=%d]", C, h->p.max_candidates);
+    return KFBO_OK;
+}
+
+static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const double *r_est)
+{
+    using clk = std::chrono::steady_clock;
     KFBO_CUDA(h, cudaSetDevice(h->device));
     const int D = h->D;
     int64_t c0 = 0, c1 = C, t0 = 0, t1 = h->b_eff;
@@ -425,8 +441,7 @@ int kfbo_eval_batch(kfbo_handle *h, int32_t C, const double *q_est, const double
         else kfbo::host::shard_range(h->b_eff, h->rank, h->nranks, &t0, &t1);
     }
     const int ncases = (int)(c1 - c0) * D;
-    using clk = std::chrono::steady_clock;
-    const clk::time_point w0 = clk::now();
+    h->tp[0] = clk::now();
     for (int64_t c = c0; c < c1; ++c)
         for (int k = 0; k < D; ++k) {
             const uint32_t stream = h->stream_base + (h->eval_counter * (uint32_t)h->p.max_candidates + (uint32_t)c) * (uint32_t)D + (uint32_t)k;
@@ -434,7 +449,7 @@ int kfbo_eval_batch(kfbo_handle *h, int32_t C, const double *q_est, const double
             if (rc) return rc;
         }
     const size_t nsums = (size_t)C * D * 4;
-    const clk::time_point w1 = clk::now();
+    h->tp[1] = clk::now();
     // ranks that own no case of a slot (candidate sharding) or no trials contribute zeros
     KFBO_CUDA(h, cudaMemsetAsync(h->d_sums, 0, nsums * sizeof(double), h->stream));
     if (ncases > 0)
@@ -463,21 +478,40 @@ int kfbo_eval_batch(kfbo_handle *h, int32_t C, const double *q_est, const double
         }
     }
     KFBO_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-    if (h->comm) {
-        KFBO_NCCL(h, nccl().AllReduce(h->d_sums, h->d_sums, nsums, ncclDouble, ncclSum, h->comm, h->stream));
-        KFBO_CUDA(h, cudaEventRecord(h->ev2, h->stream));
-    }
-    KFBO_CUDA(h, cudaMemcpyAsync(h->h_sums, h->d_sums, nsums * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    return KFBO_OK;
+}
+
+// in_group: the call sits between ncclGroupStart / ncclGroupEnd of a device group, where NCCL defers the operation to
+// the end of the group -- the event that closes the all-reduce is then recorded by the group, after ncclGroupEnd.
+static int eval_reduce(kfbo_handle *h, int32_t C, bool in_group)
+{
+    if (!h->comm) return KFBO_OK;
+    KFBO_CUDA(h, cudaSetDevice(h->device));
+    const size_t nsums = (size_t)C * h->D * 4;
+    KFBO_NCCL(h, nccl().AllReduce(h->d_sums, h->d_sums, nsums, ncclDouble, ncclSum, h->comm, h->stream));
+    if (!in_group) KFBO_CUDA(h, cudaEventRecord(h->ev2, h->stream));
+    return KFBO_OK;
+}
+
+// out == NULL: wait for the device only (a group collects the results on its first device; after the all-reduce
+// every device holds the same sums).
+static int eval_collect(kfbo_handle *h, int32_t C, kfbo_result *out)
+{
+    using clk = std::chrono::steady_clock;
+    KFBO_CUDA(h, cudaSetDevice(h->device));
+    const int D = h->D;
+    const size_t nsums = (size_t)C * D * 4;
+    if (out) KFBO_CUDA(h, cudaMemcpyAsync(h->h_sums, h->d_sums, nsums * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     const clk::time_point w2 = clk::now();
     KFBO_CUDA(h, cudaStreamSynchronize(h->stream));
     const clk::time_point w3 = clk::now();
     float ms = 0.f;
     KFBO_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms;
-    h->last_ncand = C;
-    finalize_all(h, C, out);
+    h->last_ncand = out ? C : 0;
+    if (out) finalize_all(h, C, out);
     const clk::time_point w4 = clk::now();
-    const clk::time_point w[5] = {w0, w1, w2, w3, w4};
+    const clk::time_point w[5] = {h->tp[0], h->tp[1], w2, w3, w4};
     for (int i = 0; i < 4; ++i) h->last_host_us[i] = std::chrono::duration<double, std::micro>(w[i + 1] - w[i]).count();
     h->last_host_us[4] = 0.0;
     if (h->comm) {
@@ -487,6 +521,16 @@ int kfbo_eval_batch(kfbo_handle *h, int32_t C, const double *q_est, const double
     }
     ++h->eval_counter;
     return KFBO_OK;
+}
+
+int kfbo_eval_batch(kfbo_handle *h, int32_t C, const double *q_est, const double *r_est, kfbo_result *out)
+{
+    if (!h) return KFBO_EINVAL;
+    int rc = eval_check(h, C, q_est, r_est, out);
+    if (rc == KFBO_OK) rc = eval_launch(h, C, q_est, r_est);
+    if (rc == KFBO_OK) rc = eval_reduce(h, C, false);
+    if (rc == KFBO_OK) rc = eval_collect(h, C, out);
+    return rc;
 }
 
 int kfbo_eval(kfbo_handle *h, const double *pn, int32_t npn, const double *on, int32_t non, kfbo_result *out)
@@ -674,6 +718,156 @@ int kfbo_comm_init(kfbo_handle *h, const void *id_bytes, int32_t rank, int32_t n
     std::memcpy(&id, id_bytes, sizeof id);
     KFBO_NCCL(h, nccl().CommInitRank(&h->comm, nranks, id, rank));
     h->rank = rank; h->nranks = nranks; h->shard_mode = shard_mode;
+    return KFBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Device group: ONE host process (one thread) driving several GPUs of the box -- what a single-process caller such as
+// the ROS node needs to use more than one GPU.  A group is one handle per device, joined by ncclCommInitAll; an
+// evaluation launches on every device, then one grouped ncclAllReduce of the cost sums, then the first device's sums
+// are assembled into costs.  Same sharding and the same Philox streams as the one-process-per-GPU mode, so the
+// results are the same numbers.
+// ------------------------------------------------------------------------------------------------------------------
+struct kfbo_group {
+    std::vector<kfbo_handle *> hs;
+    std::string err;
+};
+
+static int group_fail(kfbo_group *g, int code, const std::string &what)
+{
+    if (g) g->err = what; else g_create_error = what;
+    return code;
+}
+
+int kfbo_group_create(const kfbo_params *p, int32_t n_devices, const int32_t *devices, int32_t shard_mode, kfbo_group **out)
+{
+    if (!p || !out) return fail(nullptr, KFBO_EINVAL, "kfbo_group_create: NULL argument");
+    *out = nullptr;
+    if (shard_mode != KFBO_SHARD_TRIALS && shard_mode != KFBO_SHARD_CANDIDATES)
+        return fail(nullptr, KFBO_EINVAL, "kfbo_group_create: shard mode %d", shard_mode);
+    int ndev = 0;
+    const cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev < 1)
+        return fail(nullptr, KFBO_ENODEVICE, "kfbo_group_create: no CUDA device (%s); there is no CPU fallback",
+                    ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+    if (n_devices < 1 || n_devices > ndev)
+        return fail(nullptr, KFBO_ENODEVICE, "kfbo_group_create: %d devices requested, %d present", n_devices, ndev);
+    std::vector<int> devs((size_t)n_devices);
+    for (int i = 0; i < n_devices; ++i) {
+        devs[i] = devices ? devices[i] : i;
+        if (devs[i] < 0 || devs[i] >= ndev) return fail(nullptr, KFBO_ENODEVICE, "kfbo_group_create: device %d of %d", devs[i], ndev);
+        for (int j = 0; j < i; ++j)
+            if (devs[j] == devs[i]) return fail(nullptr, KFBO_EINVAL, "kfbo_group_create: device %d listed twice", devs[i]);
+    }
+    kfbo_group *g = new (std::nothrow) kfbo_group;
+    if (!g) return fail(nullptr, KFBO_EINVAL, "kfbo_group_create: out of host memory");
+    for (int i = 0; i < n_devices; ++i) {
+        kfbo_params pi = *p;
+        pi.device = devs[i];
+        kfbo_handle *h = nullptr;
+        const int rc = kfbo_create(&pi, &h);
+        if (rc) { kfbo_group_destroy(g); return rc; }      // g_create_error holds kfbo_create's text
+        g->hs.push_back(h);
+    }
+    if (n_devices > 1) {
+        if (!nccl().ok) { kfbo_group_destroy(g); return fail(nullptr, KFBO_ENCCL, "libnccl.so.2 could not be loaded"); }
+        std::vector<ncclComm_t> comms((size_t)n_devices);
+        const ncclResult_t r = nccl().CommInitAll(comms.data(), n_devices, devs.data());
+        if (r != ncclSuccess) {
+            kfbo_group_destroy(g);
+            return fail(nullptr, KFBO_ENCCL, "ncclCommInitAll: %s", nccl().GetErrorString(r));
+        }
+        for (int i = 0; i < n_devices; ++i) {
+            g->hs[i]->comm = comms[i];
+            g->hs[i]->rank = i; g->hs[i]->nranks = n_devices; g->hs[i]->shard_mode = shard_mode;
+        }
+    }
+    *out = g;
+    return KFBO_OK;
+}
+
+void kfbo_group_destroy(kfbo_group *g)
+{
+    if (!g) return;
+    for (kfbo_handle *h : g->hs) kfbo_destroy(h);
+    delete g;
+}
+
+const char *kfbo_group_last_error(const kfbo_group *g) { return g ? g->err.c_str() : g_create_error.c_str(); }
+int32_t kfbo_group_size(const kfbo_group *g) { return g ? (int32_t)g->hs.size() : 0; }
+kfbo_handle *kfbo_group_handle(kfbo_group *g, int32_t i) { return (g && i >= 0 && i < (int32_t)g->hs.size()) ? g->hs[i] : nullptr; }
+
+int kfbo_group_eval_batch(kfbo_group *g, int32_t C, const double *q_est, const double *r_est, kfbo_result *out)
+{
+    if (!g || g->hs.empty()) return KFBO_EINVAL;
+    auto check = [g](kfbo_handle *h, int rc) { if (rc) g->err = h->err; return rc; };
+    int rc = check(g->hs[0], eval_check(g->hs[0], C, q_est, r_est, out));
+    if (rc) return rc;
+    for (kfbo_handle *h : g->hs)
+        if ((rc = check(h, eval_launch(h, C, q_est, r_est)))) return rc;
+    if (g->hs.size() > 1) {
+        ncclResult_t r = nccl().GroupStart();
+        if (r != ncclSuccess) return group_fail(g, KFBO_ENCCL, std::string("ncclGroupStart: ") + nccl().GetErrorString(r));
+        for (kfbo_handle *h : g->hs)
+            if ((rc = check(h, eval_reduce(h, C, true)))) break;
+        r = nccl().GroupEnd();
+        if (rc) return rc;
+        if (r != ncclSuccess) return group_fail(g, KFBO_ENCCL, std::string("ncclGroupEnd: ") + nccl().GetErrorString(r));
+        for (kfbo_handle *h : g->hs) {
+            if (cudaSetDevice(h->device) != cudaSuccess || cudaEventRecord(h->ev2, h->stream) != cudaSuccess)
+                return group_fail(g, KFBO_ECUDA, "cudaEventRecord after the grouped all-reduce failed");
+        }
+    }
+    for (size_t i = 0; i < g->hs.size(); ++i)
+        if ((rc = check(g->hs[i], eval_collect(g->hs[i], C, i == 0 ? out : nullptr)))) return rc;
+    return KFBO_OK;
+}
+
+int kfbo_group_eval(kfbo_group *g, const double *pn, int32_t npn, const double *on, int32_t non, kfbo_result *out)
+{
+    if (!g) return KFBO_EINVAL;
+    if (!pn || !on || !out || npn < 1 || non < 1)
+        return group_fail(g, KFBO_EINVAL, "kfbo_group_eval: needs pn[>=1], on[>=1] (system_models.hpp:39,143 read element 0)");
+    return kfbo_group_eval_batch(g, 1, pn, on, out);
+}
+
+int kfbo_group_last_sums(const kfbo_group *g, double *sums, int32_t n_candidates)
+{
+    return (g && !g->hs.empty()) ? kfbo_last_sums(g->hs[0], sums, n_candidates) : KFBO_EINVAL;
+}
+
+int kfbo_group_last_kernel_ms(const kfbo_group *g, double *ms_max, int32_t *launches)
+{
+    if (!g || g->hs.empty()) return KFBO_EINVAL;
+    double mx = 0.0;
+    int32_t n = 0;
+    for (const kfbo_handle *h : g->hs) { mx = std::max(mx, h->last_ms); n += h->last_launches; }
+    if (ms_max) *ms_max = mx;
+    if (launches) *launches = n;
+    return KFBO_OK;
+}
+
+int kfbo_group_set_option(kfbo_group *g, int32_t option, int64_t value)
+{
+    if (!g) return KFBO_EINVAL;
+    for (kfbo_handle *h : g->hs) {
+        const int rc = kfbo_set_option(h, option, value);
+        if (rc) { g->err = h->err; return rc; }
+    }
+    return KFBO_OK;
+}
+
+int kfbo_group_set_stream_base(kfbo_group *g, uint32_t base)
+{
+    if (!g) return KFBO_EINVAL;
+    for (kfbo_handle *h : g->hs) h->stream_base = base;
+    return KFBO_OK;
+}
+
+int kfbo_group_set_eval_counter(kfbo_group *g, uint32_t e)
+{
+    if (!g) return KFBO_EINVAL;
+    for (kfbo_handle *h : g->hs) h->eval_counter = e;
     return KFBO_OK;
 }
 

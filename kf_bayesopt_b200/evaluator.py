@@ -301,6 +301,80 @@ class CostEvaluator:
         self._check(self._lib.kfbo_comm_init(self._h, buf, rank, nranks, shard_mode))
 
 
+class CostEvaluatorGroup:
+    """Owns one kfbo_group: ONE process driving `n_gpus` devices of the box (kfbo_group_* in include/kfbo.h) -- the
+    single-process counterpart of the one-process-per-GPU mode (dist.init_comm); same sharding, same Philox streams,
+    same results."""
+
+    def __init__(self, rv_gt: Optional[ReadParaVehicle] = None, sample_times: Optional[Sequence[Tuple[float, int]]] = None,
+                 n_gpus: int = 1, devices: Optional[Sequence[int]] = None, shard_mode: int = SHARD_TRIALS,
+                 seed: int = 0x4B46424F20260101, max_candidates: int = 1, cost_choice: Optional[str] = None):
+        self._lib = _lib.load()
+        self.rv_gt = rv_gt or ReadParaVehicle()
+        self.sample_times = list(sample_times) if sample_times is not None else sample_times_from(self.rv_gt)
+        self.params = make_params(self.rv_gt, self.sample_times, seed, max_candidates, -1, cost_choice)
+        self.D, self.n_gpus = len(self.sample_times), n_gpus
+        self._g = C.c_void_p()
+        devs = (C.c_int32 * n_gpus)(*devices) if devices is not None else None
+        rc = self._lib.kfbo_group_create(C.byref(self.params), n_gpus, devs, shard_mode, C.byref(self._g))
+        if rc:
+            raise KfboError(rc, (self._lib.kfbo_group_last_error(None) or b"").decode())
+
+    def close(self) -> None:
+        if getattr(self, "_g", None) and self._g.value:
+            self._lib.kfbo_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc:
+            raise KfboError(rc, (self._lib.kfbo_group_last_error(self._g) or b"").decode())
+
+    def eval(self, pn: Sequence[float], on: Sequence[float]) -> Result:
+        pn, on = _f64(pn), _f64(on)
+        r = KfboResult()
+        self._check(self._lib.kfbo_group_eval(self._g, _ptr(pn), pn.size, _ptr(on), on.size, C.byref(r)))
+        return Result.from_c(r, self.D)
+
+    def eval_batch_raw(self, q_est, r_est) -> np.ndarray:
+        q, r = _f64(q_est), _f64(r_est)
+        if q.shape != r.shape or q.ndim != 1:
+            raise ValueError("q_est and r_est must be 1-D arrays of equal length")
+        res = np.empty(q.size, dtype=RESULT_DTYPE)
+        self._check(self._lib.kfbo_group_eval_batch(self._g, q.size, _ptr(q), _ptr(r), res.ctypes.data_as(C.POINTER(KfboResult))))
+        return res
+
+    def last_sums(self, n_candidates: int = 1) -> np.ndarray:
+        out = np.empty((n_candidates, self.D, 4))
+        self._check(self._lib.kfbo_group_last_sums(self._g, _ptr(out), n_candidates))
+        return out
+
+    def last_kernel_ms(self) -> Tuple[float, int]:
+        ms, n = C.c_double(), C.c_int32()
+        self._check(self._lib.kfbo_group_last_kernel_ms(self._g, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def set_option(self, option: int, value: int) -> None:
+        self._check(self._lib.kfbo_group_set_option(self._g, option, value))
+
+    def set_stream_base(self, base: int) -> None:
+        self._check(self._lib.kfbo_group_set_stream_base(self._g, base))
+
+    def set_eval_counter(self, e: int) -> None:
+        self._check(self._lib.kfbo_group_set_eval_counter(self._g, e))
+
+
 def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(_lib.NCCL_ID_BYTES)
     rc = _lib.load().kfbo_nccl_unique_id(buf)

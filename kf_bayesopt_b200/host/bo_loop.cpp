@@ -11,7 +11,7 @@
 //
 //   kfbo_bo_loop [--vehicle vehicleParams.yaml] [--bayes bayesParams.yaml] [--iterations N]
 //                [--init N] [--nsimruns N] [--second code|readme|none] [--reference-sleeps]
-//                [--device D] [--seed S] [--quiet]
+//                [--device D] [--gpus N] [--seed S] [--quiet]     (--gpus N: this one process drives N GPUs)
 #include <unistd.h>
 
 #include <chrono>
@@ -70,7 +70,7 @@ private:
 int main(int nargs, char *args[])
 {
     std::string vehicle, bayes, second = "code";
-    int iterations = -1, init = -1, nsimruns = -1, device = -1;
+    int iterations = -1, init = -1, nsimruns = -1, device = -1, gpus = 1;
     uint64_t seed = kfbo::kDefaultSeed;
     bool sleeps = false, verbose = true;
     for (int i = 1; i < nargs; ++i) {
@@ -86,6 +86,7 @@ int main(int nargs, char *args[])
         else if (!std::strcmp(args[i], "--second")) second = next("--second");
         else if (!std::strcmp(args[i], "--reference-sleeps")) sleeps = true;
         else if (!std::strcmp(args[i], "--device")) device = std::atoi(next("--device"));
+        else if (!std::strcmp(args[i], "--gpus")) gpus = std::atoi(next("--gpus"));
         else if (!std::strcmp(args[i], "--seed")) seed = std::strtoull(next("--seed"), nullptr, 0);
         else if (!std::strcmp(args[i], "--quiet")) verbose = false;
         else { std::cerr << "unknown argument " << args[i] << "\n"; return 64; }
@@ -108,7 +109,7 @@ int main(int nargs, char *args[])
         kfbo::TopicBus bus;
         double eval_s = 0.0;
         int evals = 0;
-        kfbo::RunTrial rT(rv, sec, rb.n_init_samples_, [&](const kfbo::msg::Float64 &c) { bus.Publish("cost", c); }, false, device, seed);
+        kfbo::RunTrial rT(rv, sec, rb.n_init_samples_, [&](const kfbo::msg::Float64 &c) { bus.Publish("cost", c); }, false, device, seed, 1, gpus);
         bus.Subscribe<kfbo::msg::Float64MultiArray>("noise", 10, [&](const kfbo::msg::Float64MultiArray &m) {
             const double t0 = now_s();
             rT.ProcessNoiseCallback(m);

@@ -3,7 +3,7 @@
 // scripts/plot_surrogate_acquisition.py shows of the optimiser's surrogate.
 //
 //   kfbo_cost_surface [--vehicle vehicleParams.yaml] [--bayes bayesParams.yaml] [--grid 64] [--nsimruns N]
-//                     [--second code|readme|none] [--linear] [--out surface.csv] [--device D] [--seed S]
+//                     [--second code|readme|none] [--linear] [--out surface.csv] [--device D] [--gpus N] [--seed S]
 // Columns: pnoise, onoise, cost per sample time..., max_cost, index_max.  Bounds from bayesParams.yaml:18-19.
 #include <cstdlib>
 #include <cstring>
@@ -14,7 +14,7 @@
 int main(int nargs, char *args[])
 {
     std::string vehicle, bayes, second = "code", out_path = "surface.csv";
-    int grid = 64, nsimruns = -1, device = -1;
+    int grid = 64, nsimruns = -1, device = -1, gpus = 1;
     bool linear = false;
     uint64_t seed = kfbo::kDefaultSeed;
     for (int i = 1; i < nargs; ++i) {
@@ -30,6 +30,7 @@ int main(int nargs, char *args[])
         else if (!std::strcmp(args[i], "--linear")) linear = true;
         else if (!std::strcmp(args[i], "--out")) out_path = next("--out");
         else if (!std::strcmp(args[i], "--device")) device = std::atoi(next("--device"));
+        else if (!std::strcmp(args[i], "--gpus")) gpus = std::atoi(next("--gpus"));
         else if (!std::strcmp(args[i], "--seed")) seed = std::strtoull(next("--seed"), nullptr, 0);
         else { std::cerr << "unknown argument " << args[i] << "\n"; return 64; }
     }
@@ -48,7 +49,7 @@ int main(int nargs, char *args[])
         std::vector<double> q, r;
         for (int i = 0; i < grid; ++i)
             for (int j = 0; j < grid; ++j) { q.push_back(axis(0, i)); r.push_back(axis(1, j)); }
-        kfbo::Evaluator ev(kfbo::MakeParams(rv, kfbo::SampleTimesFrom(rv, sec), rv.cost_choice_, seed, grid * grid, device));
+        kfbo::Evaluator ev(kfbo::MakeParams(rv, kfbo::SampleTimesFrom(rv, sec), rv.cost_choice_, seed, grid * grid, device), gpus, KFBO_SHARD_CANDIDATES);
         const std::vector<kfbo_result> res = ev.EvalBatch(q, r);
         const int D = ev.params().n_sample_times;
         std::ofstream f(out_path);

@@ -8,7 +8,7 @@
 //     noise  <npn> <non> <pn...> <on...>         ->  cost <max_cost> <index_max> <pic_max...>
 //     batch  <C> <q_0> <r_0> ... <q_C-1> <r_C-1> ->  C lines "cost ..."
 //   kfbo_robot1d_kf [--vehicle config/vehicleParams.yaml] [--second code|readme|none] [--n_init_samples 20]
-//                   [--max_candidates C] [--device D] [--seed S] [--quiet]
+//                   [--max_candidates C] [--device D] [--gpus N] [--seed S] [--quiet]   (--gpus N: the node drives N GPUs)
 #include <cstdlib>
 #include <cstring>
 #include <iomanip>
@@ -23,7 +23,7 @@
 int main(int nargs, char *args[])
 {
     std::string vehicle, second = "code";
-    int device = -1, n_init = 20, max_cand = 1;
+    int device = -1, n_init = 20, max_cand = 1, gpus = 1;
     uint64_t seed = kfbo::kDefaultSeed;
     bool verbose = true;
 #ifdef KFBO_WITH_ROS
@@ -41,6 +41,7 @@ int main(int nargs, char *args[])
         else if (!std::strcmp(args[i], "--n_init_samples")) n_init = std::atoi(next("--n_init_samples"));
         else if (!std::strcmp(args[i], "--max_candidates")) max_cand = std::atoi(next("--max_candidates"));
         else if (!std::strcmp(args[i], "--device")) device = std::atoi(next("--device"));
+        else if (!std::strcmp(args[i], "--gpus")) gpus = std::atoi(next("--gpus"));
         else if (!std::strcmp(args[i], "--seed")) seed = std::strtoull(next("--seed"), nullptr, 0);
         else if (!std::strcmp(args[i], "--quiet")) verbose = false;
         else { std::cerr << "unknown argument " << args[i] << "\n"; return 64; }
@@ -51,13 +52,13 @@ int main(int nargs, char *args[])
                                           : second == "readme" ? &kfbo::kReadmeSecondSampleTime : nullptr;
 #ifdef KFBO_WITH_ROS
         ros::Publisher pub_cost = n.advertise<std_msgs::Float64>("cost", 10);                     // trial_node.cpp:17
-        kfbo::RunTrial rT(rv, sec, n_init, [&](const std_msgs::Float64 &c) { pub_cost.publish(c); }, verbose, device, seed, max_cand);
+        kfbo::RunTrial rT(rv, sec, n_init, [&](const std_msgs::Float64 &c) { pub_cost.publish(c); }, verbose, device, seed, max_cand, gpus);
         boost::function<void(const std_msgs::Float64MultiArray::ConstPtr &)> cb =
             [&](const std_msgs::Float64MultiArray::ConstPtr &m) { rT.ProcessNoiseCallback(*m); };
         ros::Subscriber sub = n.subscribe<std_msgs::Float64MultiArray>("noise", 10, cb);           // trial_node.cpp:150
         ros::spin();
 #else
-        kfbo::RunTrial rT(rv, sec, n_init, nullptr, verbose, device, seed, max_cand);
+        kfbo::RunTrial rT(rv, sec, n_init, nullptr, verbose, device, seed, max_cand, gpus);
         std::cout << std::setprecision(17);
         std::string line;
         while (std::getline(std::cin, line)) {

@@ -3,7 +3,7 @@
 // evaluation with a fixed estimator (pnoise_est, onoise_est), printed the same way.
 //
 //   kfbo_test_trial [--vehicle config/vehicleParams.yaml] [--pnoise_est 1.0] [--onoise_est 0.1]
-//                   [--nsimruns N] [--device D] [--seed S] [--fused] [--trace out.csv]
+//                   [--nsimruns N] [--device D] [--gpus N] [--seed S] [--fused] [--trace out.csv]   (--gpus applies to --fused)
 //
 // Default path = the reference's caller shape: CPUcoreNumber Trial objects, one std::thread each
 // (src/test_trial.cpp:41-51), every Trial::Run() rolling its share out on the GPU.  --fused runs the
@@ -20,7 +20,7 @@ int main(int nargs, char *args[])
 {
     std::string vehicle;
     double pnoise_est = 1.0, onoise_est = 0.1;   // src/test_trial.cpp:23
-    int device = -1, nsimruns = -1;
+    int device = -1, nsimruns = -1, gpus = 1;
     uint64_t seed = kfbo::kDefaultSeed;
     bool fused = false;
     std::string trace_path;
@@ -34,6 +34,7 @@ int main(int nargs, char *args[])
         else if (!std::strcmp(args[i], "--onoise_est")) onoise_est = std::atof(next("--onoise_est"));
         else if (!std::strcmp(args[i], "--nsimruns")) nsimruns = std::atoi(next("--nsimruns"));
         else if (!std::strcmp(args[i], "--device")) device = std::atoi(next("--device"));
+        else if (!std::strcmp(args[i], "--gpus")) gpus = std::atoi(next("--gpus"));
         else if (!std::strcmp(args[i], "--seed")) seed = std::strtoull(next("--seed"), nullptr, 0);
         else if (!std::strcmp(args[i], "--fused")) fused = true;
         else if (!std::strcmp(args[i], "--trace")) trace_path = next("--trace");
@@ -66,7 +67,7 @@ int main(int nargs, char *args[])
                 average_var_nis += t[i].get_average_var_nis() / rv_gt.cpu_core_number_;
             }
         } else {
-            kfbo::Evaluator ev(kfbo::MakeParams(rv_gt, kfbo::SampleTimesFrom(rv_gt, nullptr), "JNEES", seed, 1, device));
+            kfbo::Evaluator ev(kfbo::MakeParams(rv_gt, kfbo::SampleTimesFrom(rv_gt, nullptr), "JNEES", seed, 1, device), gpus);
             const kfbo_result r = ev.Eval(rv.pnoise_, rv.onoise_);
             average_nees = r.average_nees[0]; average_var_nees = r.average_var_nees[0];
             average_nis = r.average_nis[0]; average_var_nis = r.average_var_nis[0];

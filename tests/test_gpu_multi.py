@@ -22,3 +22,72 @@ def test_two_ranks_nccl_allreduce_matches_single_gpu():
                           os.path.join(ROOT, "tools", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "multi_gpu_check ok" in out.stdout
+
+
+# ---------------------------------------------------------------------------------------------
+# Device group: ONE process driving several GPUs (kfbo_group_*, what the single-process ROS node uses)
+# ---------------------------------------------------------------------------------------------
+def test_group_of_one_device_equals_a_plain_handle(kfbo):
+    import numpy as np
+    rv = kfbo.ReadParaVehicle(nsimruns_=4099, cpu_core_number_=1)
+    times, q, r = [(0.1, 201), (0.5, 211)], np.linspace(0.1, 5.0, 7), np.linspace(0.01, 1.0, 7)
+    with kfbo.CostEvaluator(rv, times, seed=5, max_candidates=7) as ev, \
+            kfbo.CostEvaluatorGroup(rv, times, n_gpus=1, seed=5, max_candidates=7) as gr:
+        a, b = ev.eval_batch_raw(q, r), gr.eval_batch_raw(q, r)
+        assert np.array_equal(ev.last_sums(7), gr.last_sums(7))
+        assert np.array_equal(a["cost"], b["cost"]) and np.array_equal(a["index_max"], b["index_max"])
+        one_a, one_b = ev.eval([1.0], [0.1]), gr.eval([1.0], [0.1])      # second evaluation: fresh streams on both
+        assert np.array_equal(one_a.cost, one_b.cost)
+    with pytest.raises(kfbo.KfboError):
+        kfbo.CostEvaluatorGroup(rv, times, n_gpus=4096)                  # more devices than the box has
+
+
+def test_device_group_matches_single_device(kfbo):
+    import numpy as np
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    G = 2 if n < 4 else 4
+    B, C = 4099, 13                                                     # neither divides by the device count
+    rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
+    times, q, r = [(0.1, 201), (0.5, 211)], np.linspace(0.1, 5.0, C), np.linspace(0.01, 1.0, C)
+    with kfbo.CostEvaluator(rv, times, seed=77, max_candidates=C) as ev:
+        want = ev.eval_batch_raw(q, r)
+        want_sums = ev.last_sums(C)
+        want_one = ev.eval([1.0], [0.1]).cost
+    for mode in (kfbo.SHARD_TRIALS, kfbo.SHARD_CANDIDATES):
+        with kfbo.CostEvaluatorGroup(rv, times, n_gpus=G, shard_mode=mode, seed=77, max_candidates=C) as gr:
+            got = gr.eval_batch_raw(q, r)
+            sums = gr.last_sums(C)
+            one = gr.eval([1.0], [0.1]).cost                            # a second evaluation on the same communicators
+            ms, launches = gr.last_kernel_ms()
+            assert ms > 0 and 1 <= launches <= G                        # one candidate, candidate-sharded: one device has work
+        if mode == kfbo.SHARD_CANDIDATES:                               # every slot written by one device, the others add 0.0
+            assert np.array_equal(sums, want_sums) and np.array_equal(got["cost"], want["cost"])
+        else:                                                           # the same trials, summed in another order
+            np.testing.assert_allclose(sums, want_sums, rtol=1e-12)
+            np.testing.assert_allclose(got["cost"], want["cost"], rtol=1e-10, atol=1e-13)
+        assert np.array_equal(got["index_max"], want["index_max"])
+        np.testing.assert_allclose(one, want_one, rtol=1e-10, atol=1e-13)
+
+
+def test_cpp_node_drives_several_gpus_from_one_process(kfbo, tmp_path):
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    exe = os.path.join(ROOT, "kf_bayesopt_b200", "bin", "kfbo_test_trial")
+    if not os.path.exists(exe):
+        pytest.skip("host programs not built")
+    y = tmp_path / "vehicleParams.yaml"
+    y.write_text("CPUcoreNumber: 10\nstateDOF: 2\nobservationDOF: 1\nt_start: 0.0\nt_end: 20.1\ndt: 0.1\nxi0: 0.0\nxidot0: 0.0\n"
+                 "Nsimruns: 200000\npnoise: [1.0]\nonoise: [0.1]\noptimizationChoice: all\ncostChoice: JNEES\n")
+    outs = []
+    for gpus in (1, 2):
+        out = subprocess.run([exe, "--vehicle", str(y), "--pnoise_est", "0.1", "--fused", "--gpus", str(gpus), "--seed", "9"],
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        outs.append(float(next(l for l in out.stdout.splitlines() if l.startswith("cost JNEES")).split()[-1]))
+    assert outs[0] == pytest.approx(1.613, abs=0.01)
+    assert outs[1] == pytest.approx(outs[0], rel=1e-5)                  # same trials and streams; printed with 6 digits
