@@ -34,11 +34,23 @@ namespace kfbo {
 #ifndef KFBO_PHILOX_SPLIT16_ROUNDS
 #define KFBO_PHILOX_SPLIT16_ROUNDS 0
 #endif
+// KFBO_PHILOX_SPLIT_MUL (experiment, off): keep the two halves of the product apart -- IMAD.HI + IMAD instead of one
+// IMAD.WIDE.  ptxas fuses mul.hi + mul.lo of the same operands back into IMAD.WIDE, so the low half is formed as a
+// multiply-add with an addend it cannot prove to be zero (`zero`: a value loaded from memory that is always 0).
+#ifndef KFBO_PHILOX_SPLIT_MUL
+#define KFBO_PHILOX_SPLIT_MUL 0
+#endif
 template <uint32_t M>
-__device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t &hi, uint32_t &lo)
+__device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t &hi, uint32_t &lo, uint32_t zero = 0u)
 {
+#if KFBO_PHILOX_SPLIT_MUL
+    hi = __umulhi(M, a);
+    lo = M * a + zero;
+#else
+    (void)zero;
     lo = M * a;
     hi = __umulhi(M, a);
+#endif
 }
 template <uint32_t M>
 __device__ __forceinline__ void mulhilo32_split16(uint32_t a, uint32_t &hi, uint32_t &lo)
@@ -52,7 +64,8 @@ __device__ __forceinline__ void mulhilo32_split16(uint32_t a, uint32_t &hi, uint
     lo = M * a;
 }
 
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &key)
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &key,
+                                               uint32_t zero = 0u)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -61,8 +74,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
             mulhilo32_split16<0xD2511F53u>(c0, hi0, lo0);
             mulhilo32_split16<0xCD9E8D57u>(c2, hi1, lo1);
         } else {
-            mulhilo32<0xD2511F53u>(c0, hi0, lo0);
-            mulhilo32<0xCD9E8D57u>(c2, hi1, lo1);
+            mulhilo32<0xD2511F53u>(c0, hi0, lo0, zero);
+            mulhilo32<0xCD9E8D57u>(c2, hi1, lo1, zero);
         }
         c0 = hi1 ^ c1 ^ key.k0[r];
         c1 = lo1;

@@ -117,6 +117,7 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
     const int case_idx = blockIdx.y * gridDim.z + blockIdx.z, tile = blockIdx.x;
     const Case m = cases[case_idx];
     const int T = m.T;
+    const uint32_t zero = (uint32_t)T >> 30;  // 0 (T <= 2000), opaque to the compiler: KFBO_PHILOX_SPLIT_MUL experiment only
     const unsigned kk = st.k0 + blockIdx.z;   // == m.k, but provably uniform
     const double f = pick4(st.f, kk), l00 = pick4(st.l00, kk), l10 = pick4(st.l10, kk), l11 = pick4(st.l11, kk),
                  sr = pick4(st.sr, kk);
@@ -158,7 +159,7 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
 #pragma unroll
         for (int j = 0; j < K; ++j)
 #pragma unroll
-            for (int c = 0; c < 2; ++c) q[j][c] = philox4x32_10(trial[j], m.stream, (uint32_t)p + 2u, (uint32_t)c, key);
+            for (int c = 0; c < 2; ++c) q[j][c] = philox4x32_10(trial[j], m.stream, (uint32_t)p + 2u, (uint32_t)c, key, zero);
 #pragma unroll
         for (int j = 0; j < K; ++j) normals_of_pair(r[j][0], r[j][1], s_log, n[j]);
         const double2 g0 = s_gu[2 * p];
