@@ -48,3 +48,15 @@ def test_cost_choices(kfbo):
         assert out["CNEES"].cost[k] == pytest.approx(a.cost[k] + abs(np.log(0.5 * a.average_var_nees[k] / 2)), rel=1e-12)
         assert out["JNIS"].cost[k] == pytest.approx(abs(np.log(a.average_nis[k] / 1)), rel=1e-12)
         assert out["CNIS"].cost[k] == pytest.approx(out["JNIS"].cost[k] + abs(np.log(0.5 * a.average_var_nis[k] / 1)), rel=1e-12)
+
+
+@pytest.mark.gpu
+def test_every_kernel_runs_on_small_ragged_shapes():
+    # tools/all_kernels_small.py: Philox (both forms, batch, per-trial), both supplied-noise kernels on whole + ragged tiles,
+    # odd trial counts, the gain recursion and the trace, with finite outputs everywhere
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "all_kernels_small.py")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "all_kernels_small ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
