@@ -22,27 +22,26 @@ public:
     ReadParaVehicle() {}
     ReadParaVehicle(ros::NodeHandle nh, bool showReadInfo)
     {
-        nh.getParam("CPUcoreNumber", cpu_core_number_);
-        nh.getParam("stateDOF", state_dof_);
-        nh.getParam("observationDOF", observation_dof_);
-        nh.getParam("dt", dt_);
-        nh.getParam("t_start", t_start_);
-        nh.getParam("t_end", t_end_);
-        nh.getParam("xi0", xi0_);
-        nh.getParam("xidot0", xidot0_);
-        nh.getParam("P0", P0_);
+        nsimruns_ = 10;                                          // the reference's in-class default (read_para_vehicle.h:34)
+        // parameter name -> member, by type; a name the server does not hold leaves its member untouched
+        const struct { const char *name; int *member; } ints[] = {
+            {"CPUcoreNumber", &cpu_core_number_}, {"stateDOF", &state_dof_}, {"observationDOF", &observation_dof_},
+            {"Nsimruns", &nsimruns_}};
+        const struct { const char *name; double *member; } reals[] = {
+            {"dt", &dt_}, {"t_start", &t_start_}, {"t_end", &t_end_}, {"xi0", &xi0_}, {"xidot0", &xidot0_}};
+        const struct { const char *name; std::string *member; } strings[] = {
+            {"P0", &P0_}, {"optimizationChoice", &optimization_choice_}, {"costChoice", &cost_choice_}};
+        for (const auto &e : ints) nh.getParam(e.name, *e.member);
+        for (const auto &e : reals) nh.getParam(e.name, *e.member);
+        for (const auto &e : strings) nh.getParam(e.name, *e.member);
         nh.getParam("disturbance", disturbance_);
-        nsimruns_ = 10;                                          // read_para_vehicle.h:34
-        nh.getParam("Nsimruns", nsimruns_);
-        if (cpu_core_number_ > 0 && nsimruns_ % cpu_core_number_ != 0)
-            ROS_WARN("the nsimruns should be an integral multiple of cpu core number, or the final result may be slightly off");
-        UpdateMaxIterations();                                   // read_para_vehicle.cpp:145
-        if (!nh.getParam("pnoise", pnoise_)) ROS_FATAL("process noise must be set");
-        if (!nh.getParam("onoise", onoise_)) ROS_FATAL("observation noise must be set");
+        const bool have_noise = nh.getParam("pnoise", pnoise_) & nh.getParam("onoise", onoise_);
+        if (!have_noise) ROS_FATAL("process noise and observation noise must be set");          // read_para_vehicle.cpp:95,102
         dim_pn_ = (int)pnoise_.size();
         dim_on_ = (int)onoise_.size();
-        nh.getParam("optimizationChoice", optimization_choice_);
-        nh.getParam("costChoice", cost_choice_);
+        if (cpu_core_number_ > 0 && nsimruns_ % cpu_core_number_ != 0)                            // :141-142
+            ROS_WARN("Nsimruns is not a multiple of CPUcoreNumber: the remainder trials are dropped (trial.cpp:28)");
+        UpdateMaxIterations();                                   // (t_end - t_start)/dt, truncated (:145)
         if (showReadInfo) Print(std::cout);
     }
     double tmpf = 17.32;                                         // read_para_vehicle.h:48
