@@ -25,7 +25,7 @@ namespace kfbo {
 // takes ~5.1 cycles per warp, ~75% of which do NOT overlap with DFMA (8 DFMA 17.6 cycles, 8 WIDE 40.7,
 // both 53.9); IMAD.HI.U32 ~4.1 (half exclusive); the 32-bit IMAD takes 2 cycles and overlaps fully.
 // One Philox call is up to 20 such multiplies ~ 80-100 pipe cycles, as much as 45 DFMAs -- random bits
-// are the expensive resource of this kernel, which is why a normal pair consumes 84 of them, not 128.
+// are the expensive resource of this kernel, which is why a normal pair consumes 64 of them, not 128.
 // ---------------------------------------------------------------------------------------
 // KFBO_PHILOX_SPLIT16_ROUNDS: how many of the 10 rounds form their two 32x32->64 products from four
 // 16x16->32 products (IMAD on the FMA pipe + shifts/adds on the ALU pipe, ~11 instructions that all
@@ -85,14 +85,25 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
-// The random words of one step pair: two Philox calls A, B -> three normal pairs
-//   pair 0: radius (A.x : A.w[31:12]), angle A.y      pair 1: radius (B.x : B.w[31:12]), angle B.y
-//   pair 2: radius (A.z : A.w[11:0] B.w[7:0]), angle B.z
-__device__ __forceinline__ void normals_of_pair(const uint4 &A, const uint4 &B, const math::LogTables &tab, double n[6])
+// Noise stream layout (restated draw for draw by oracle/kfbo_oracle.c):
+//   key = (seed_lo, seed_hi); counter = (trial, case.stream, block, sub)
+//   block 0, sub 0         -> words (x, y): the N(0,P0) draw added to x0
+//   block g+1, sub 0, 1, 2 -> calls A, B, C of the STEP GROUP g = steps 4g .. 4g+3; a call (x, y, z, w) holds the two
+//                             normal pairs (x, y) and (z, w) of math::normal_pair:
+//        step 4g   : process (A.x, A.y)   observation: cos half of (C.x, C.y)
+//        step 4g+1 : process (A.z, A.w)   observation: sin half of (C.x, C.y)
+//        step 4g+2 : process (B.x, B.y)   observation: cos half of (C.z, C.w)
+//        step 4g+3 : process (B.z, B.w)   observation: sin half of (C.z, C.w)
+//   3 calls per 4 steps: all 12 x 32 = 384 bits are used, none is shared between two normals.
+struct GroupWords { uint4 a, b, c; };
+
+__device__ __forceinline__ GroupWords philox_group(uint32_t trial, uint32_t stream, uint32_t group, const PhiloxKeys &key, uint32_t zero = 0u)
 {
-    math::normal_pair_bits(A.x, A.w, A.y, tab, n[0], n[1]);                           // low 20 bits: A.w[31:12]
-    math::normal_pair_bits(B.x, B.w, B.y, tab, n[2], n[3]);                           //              B.w[31:12]
-    math::normal_pair_bits(A.z, math::funnel_l(B.w << 24, A.w, 20), B.z, tab, n[4], n[5]);   // A.w[11:0] : B.w[7:0]
+    GroupWords w;
+    w.a = philox4x32_10(trial, stream, group + 1u, 0u, key, zero);
+    w.b = philox4x32_10(trial, stream, group + 1u, 1u, key, zero);
+    w.c = philox4x32_10(trial, stream, group + 1u, 2u, key, zero);
+    return w;
 }
 
 // 1/S and 1/det(P): S and det(P) come out of a covariance recursion and are normal, well-scaled
@@ -141,7 +152,7 @@ struct StepProbe { double nees, nis; };
 template <bool kFirst, bool kFused>
 __device__ __forceinline__ void filter_step(Traj &t, const Case &m, const double f, double2 gu, const StepNoise nz,
                                             const double l00 = 0.0, const double l10 = 0.0, const double l11 = 0.0,
-                                            const double sr = 0.0, StepProbe *probe = nullptr)
+                                            const double sr = 0.0, StepProbe *probe = nullptr, const bool first_rt = false)
 {
     // ---- truth: x = Fd x + g u + w ; z = H x + v
     const double xa = fma(f, t.x1, t.x0) + gu.x;
@@ -189,7 +200,9 @@ __device__ __forceinline__ void filter_step(Traj &t, const Case &m, const double
     // ---- accumulate, shifted by the first sample of the trial (kn, ki): the shifted values
     // nees - kn and nis - ki come straight out of the last fused multiply-add of each form
     if (probe != nullptr) { probe->nees = num * invdet; probe->nis = nu_s * nu; }
-    if (kFirst) { t.kn = num * invdet; t.ki = nu_s * nu; }
+    // first_rt: the same for callers that only know at run time whether this is the trial's first step (a uniform
+    // predicate on two multiplies instead of a branch, so that a whole step group stays one basic block)
+    if (kFirst || first_rt) { t.kn = num * invdet; t.ki = nu_s * nu; }
     const double dn = fma(num, invdet, -t.kn);
     const double di = fma(nu_s, nu, -t.ki);
     t.sdn += dn; t.sqn = fma(dn, dn, t.sqn);

@@ -86,23 +86,24 @@ __device__ __forceinline__ void block_reduce_and_publish(const double out[4], in
 }
 
 // -----------------------------------------------------------------------------------------
-// Philox rollout.  Noise stream layout (restated draw for draw by oracle/kfbo_oracle.c):
-//   key = (seed_lo, seed_hi); counter = (trial, case.stream, block, sub)
-//   block 0, sub 0      -> the N(0,P0) draw added to x0 (radius x : w[31:12], angle y)
-//   block p+1, sub 0,1  -> calls A, B of the step pair (2p, 2p+1) -> normals n0..n5 (normals_of_pair):
-//                          step 2p uses n0,n1 (process) n2 (observation); step 2p+1 uses n3,n4,n5
+// Philox rollout.  Noise stream layout: kfbo_device.cuh (philox_group) -- three Philox4x32-10 calls per group of four
+// steps, 64 random bits per Box-Muller pair.
+// The counter-based generator lets the random bits of group g+1 be produced while the FP64 work of group g is in
+// flight: integer (Philox) and FP64 instructions interleave inside a warp.
+// Shared memory: the noise tables only (48.4 KB, dynamic); g*u[step] is the same address for the whole warp and comes
+// through the read-only path.  4 CTAs per SM.
 // -----------------------------------------------------------------------------------------
-// kPhiloxPerThread independent trajectories (adjacent tiles of the same case) can advance in
-// lock-step in every thread (more ILP per warp).  Measured on B200 (profiles/NOTES_r1.md): the kernel
-// is bound by the pipe that FP64 and IMAD.WIDE share, not by latency, so 1 and 2 trajectories per
-// thread run at the same speed (19.96 vs 20.08 ms for cfg3) and 1 needs half the registers.
-#ifndef KFBO_PHILOX_PER_THREAD
-#define KFBO_PHILOX_PER_THREAD 1
-#endif
 #ifndef KFBO_PHILOX_MIN_BLOCKS
 #define KFBO_PHILOX_MIN_BLOCKS 4
 #endif
-constexpr int kPhiloxPerThread = KFBO_PHILOX_PER_THREAD;
+
+__device__ __forceinline__ void load_noise_tables(math::LogTables *dst, const math::LogTables *__restrict__ src)
+{
+    const double2 *ls = reinterpret_cast<const double2 *>(src);
+    double2 *ld = reinterpret_cast<double2 *>(dst);
+    static_assert(sizeof(math::LogTables) % sizeof(double2) == 0, "tables are copied 16 bytes at a time");
+    for (int i = threadIdx.x; i < (int)(sizeof(math::LogTables) / sizeof(double2)); i += kThreads) ld[i] = ls[i];
+}
 
 __global__ void __launch_bounds__(kThreads, KFBO_PHILOX_MIN_BLOCKS)
 rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTimeConsts st,
@@ -111,9 +112,8 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
                int tiles, double *__restrict__ per_trial, size_t per_trial_ld, double *__restrict__ partials,
                unsigned *__restrict__ tickets, double *__restrict__ sums)
 {
-    constexpr int K = kPhiloxPerThread;
-    extern __shared__ double2 s_gu[];
-    __shared__ math::LogTables s_log;
+    extern __shared__ __align__(16) unsigned char s_tables_raw[];
+    math::LogTables &s_log = *reinterpret_cast<math::LogTables *>(s_tables_raw);
     const int case_idx = blockIdx.y * gridDim.z + blockIdx.z, tile = blockIdx.x;
     const Case m = cases[case_idx];
     const int T = m.T;
@@ -121,84 +121,74 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
     const unsigned kk = st.k0 + blockIdx.z;   // == m.k, but provably uniform
     const double f = pick4(st.f, kk), l00 = pick4(st.l00, kk), l10 = pick4(st.l10, kk), l11 = pick4(st.l11, kk),
                  sr = pick4(st.sr, kk);
-    {
-        const double2 *src = gu_tables + (size_t)kk * kMaxSteps;
-        for (int i = threadIdx.x; i < T; i += kThreads) s_gu[i] = src[i];
-        const double *ls = reinterpret_cast<const double *>(logtab);
-        double *ld = reinterpret_cast<double *>(&s_log);
-        for (int i = threadIdx.x; i < (int)(sizeof(math::LogTables) / sizeof(double)); i += kThreads) ld[i] = ls[i];
-    }
+    const double2 *__restrict__ gu = gu_tables + (size_t)kk * kMaxSteps;
+    load_noise_tables(&s_log, logtab);
     __syncthreads();
 
-    // trajectory j of this thread: local trial (tile*K + j)*kThreads + threadIdx.x (coalesced outputs)
-    uint32_t local[K], trial[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-        local[j] = ((uint32_t)tile * K + j) * kThreads + threadIdx.x;
-        trial[j] = trial0 + local[j];   // past-the-end trajectories of the last tile are computed and discarded
-    }
-    Traj t[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
+    const uint32_t local = (uint32_t)tile * kThreads + threadIdx.x;
+    const uint32_t trial = trial0 + local;   // past-the-end trajectories of the last tile are computed and discarded
+    Traj t;
+    {
         double a, b;
-        const uint4 w = philox4x32_10(trial[j], m.stream, 0u, 0u, key);
-        math::normal_pair_bits(w.x, w.w, w.y, s_log, a, b);
-        traj_init(t[j], a, b);
+        const uint4 w = philox4x32_10(trial, m.stream, 0u, 0u, key);
+        math::normal_pair(w.x, w.y, s_log, a, b);
+        traj_init(t, a, b);
     }
-    // The counter-based generator lets the random bits of step pair p+1 be produced while the FP64
-    // work of pair p is in flight: integer (Philox) and FP64 instructions interleave inside a warp.
-    const int npairs = (T + 1) >> 1;     // an odd T leaves the second half of the last pair unused
-    uint4 r[K][2];
-#pragma unroll
-    for (int j = 0; j < K; ++j)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) r[j][c] = philox4x32_10(trial[j], m.stream, 1u, (uint32_t)c, key);
-    for (int p = 0; p < npairs; ++p) {
-        uint4 q[K][2];
-        double n[K][6];
-#pragma unroll
-        for (int j = 0; j < K; ++j)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) q[j][c] = philox4x32_10(trial[j], m.stream, (uint32_t)p + 2u, (uint32_t)c, key, zero);
-#pragma unroll
-        for (int j = 0; j < K; ++j) normals_of_pair(r[j][0], r[j][1], s_log, n[j]);
-        const double2 g0 = s_gu[2 * p];
-        if (p == 0) {
-#pragma unroll
-            for (int j = 0; j < K; ++j)
-                filter_step<true, true>(t[j], m, f, g0, StepNoise{n[j][0], n[j][1], n[j][2]}, l00, l10, l11, sr);
-        } else {
-#pragma unroll
-            for (int j = 0; j < K; ++j)
-                filter_step<false, true>(t[j], m, f, g0, StepNoise{n[j][0], n[j][1], n[j][2]}, l00, l10, l11, sr);
+    // Whole groups of four steps: ONE basic block per group (no branch inside), so the scheduler is free to overlap the
+    // table lookups and the log/sqrt chains of one step's normals with the filter recursion of the previous step.
+    const int nfull = T >> 2;
+    GroupWords r = philox_group(trial, m.stream, 0u, key);
+    for (int g = 0; g < nfull; ++g) {
+        const GroupWords q = philox_group(trial, m.stream, (uint32_t)g + 1u, key, zero);
+        const double2 *gs = gu + 4 * g;
+        const double2 g0 = __ldg(gs), g1 = __ldg(gs + 1), g2 = __ldg(gs + 2), g3 = __ldg(gs + 3);
+        double p0a, p0b, p1a, p1b, p2a, p2b, p3a, p3b, o0, o1, o2, o3;
+        math::normal_pair(r.c.x, r.c.y, s_log, o0, o1);
+        math::normal_pair(r.a.x, r.a.y, s_log, p0a, p0b);
+        math::normal_pair(r.a.z, r.a.w, s_log, p1a, p1b);
+        filter_step<false, true>(t, m, f, g0, StepNoise{p0a, p0b, o0}, l00, l10, l11, sr, nullptr, g == 0);
+        math::normal_pair(r.c.z, r.c.w, s_log, o2, o3);
+        math::normal_pair(r.b.x, r.b.y, s_log, p2a, p2b);
+        filter_step<false, true>(t, m, f, g1, StepNoise{p1a, p1b, o1}, l00, l10, l11, sr);
+        math::normal_pair(r.b.z, r.b.w, s_log, p3a, p3b);
+        filter_step<false, true>(t, m, f, g2, StepNoise{p2a, p2b, o2}, l00, l10, l11, sr);
+        filter_step<false, true>(t, m, f, g3, StepNoise{p3a, p3b, o3}, l00, l10, l11, sr);
+        r = q;
+    }
+    // the partial last group (T mod 4 steps); its unused normals are never formed
+    const int rem = T & 3, sT = 4 * nfull;
+    if (rem > 0) {
+        double pa, pb, o0, o1;
+        math::normal_pair(r.c.x, r.c.y, s_log, o0, o1);
+        math::normal_pair(r.a.x, r.a.y, s_log, pa, pb);
+        filter_step<false, true>(t, m, f, __ldg(gu + sT), StepNoise{pa, pb, o0}, l00, l10, l11, sr, nullptr, nfull == 0);
+        if (rem > 1) {
+            math::normal_pair(r.a.z, r.a.w, s_log, pa, pb);
+            filter_step<false, true>(t, m, f, __ldg(gu + sT + 1), StepNoise{pa, pb, o1}, l00, l10, l11, sr);
         }
-        if (2 * p + 1 < T) {
-            const double2 g1 = s_gu[2 * p + 1];
-#pragma unroll
-            for (int j = 0; j < K; ++j)
-                filter_step<false, true>(t[j], m, f, g1, StepNoise{n[j][3], n[j][4], n[j][5]}, l00, l10, l11, sr);
+        if (rem > 2) {
+            math::normal_pair(r.c.z, r.c.w, s_log, o0, o1);
+            math::normal_pair(r.b.x, r.b.y, s_log, pa, pb);
+            filter_step<false, true>(t, m, f, __ldg(gu + sT + 2), StepNoise{pa, pb, o0}, l00, l10, l11, sr);
         }
-#pragma unroll
-        for (int j = 0; j < K; ++j)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) r[j][c] = q[j][c];
     }
     double out[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
+    {
         double o[4];
-        traj_finish(t[j], T, o);
-        if (local[j] < ntrials) {
+        traj_finish(t, T, o);
+        if (local < ntrials) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) out[k] += o[k];
+            for (int k = 0; k < 4; ++k) out[k] = o[k];
             if (per_trial != nullptr) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) per_trial[((size_t)m.out_slot * 4 + k) * per_trial_ld + local[j]] = o[k];
+                for (int k = 0; k < 4; ++k) per_trial[((size_t)m.out_slot * 4 + k) * per_trial_ld + local] = o[k];
             }
         }
     }
-    __shared__ double s_red[kThreads][4];
-    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, s_red);
+    // every thread is past its last table lookup: the table space doubles as the reduction scratch
+    static_assert(sizeof(math::LogTables) >= sizeof(double) * 4 * kThreads, "tables too small for the reduction scratch");
+    __syncthreads();
+    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, reinterpret_cast<double (*)[4]>(s_tables_raw));
 }
 
 // -----------------------------------------------------------------------------------------
@@ -476,14 +466,18 @@ __global__ void __launch_bounds__(32) riccati_gains(const Case *__restrict__ cas
     }
 }
 
+#ifndef KFBO_REDUCED_UNROLL
+#define KFBO_REDUCED_UNROLL 1
+#endif
+constexpr int kReducedUnroll = KFBO_REDUCED_UNROLL;   // groups of the chunk loop unrolled (constant offsets into the stage)
 constexpr int kGainChunk = 16;    // steps per stage of the gain ring (768 B)
 constexpr int kGainStages = 3;
 
-template <bool kFirst>
+// first: whether this is the trial's first step (run-time, uniform: a predicate on two instructions, no branch)
 __device__ __forceinline__ void reduced_step(double &e0, double &e1, double &kn, double &ki, double &sdn, double &sqn,
                                              double &sdi, double &sqi, const GainStep &g, const double f, const double l00,
                                              const double l10, const double l11, const double sr, const double n0,
-                                             const double n1, const double n2)
+                                             const double n1, const double n2, const bool first)
 {
     const double em0 = fma(l00, n0, fma(f, e1, e0));            // e- = Fd e + w,  w = L n
     const double em1 = fma(l11, n1, fma(l10, n0, e1));
@@ -493,7 +487,7 @@ __device__ __forceinline__ void reduced_step(double &e0, double &e1, double &kn,
     const double t2 = fma(g.b, e1, g.a * e0);                    // NEES = a e0^2 + b e0 e1 + c e1^2
     const double q = (g.c * e1) * e1;
     const double nu_s = nu * g.sinv;
-    if (kFirst) { kn = fma(e0, t2, q); ki = nu_s * nu; }
+    if (first) { kn = fma(e0, t2, q); ki = nu_s * nu; }
     const double dn = fma(e0, t2, q - kn);
     const double di = fma(nu_s, nu, -ki);
     sdn += dn; sqn = fma(dn, dn, sqn);
@@ -507,7 +501,8 @@ rollout_philox_reduced(const Case *__restrict__ cases, const __grid_constant__ S
                        double *__restrict__ per_trial, size_t per_trial_ld, double *__restrict__ partials,
                        unsigned *__restrict__ tickets, double *__restrict__ sums)
 {
-    __shared__ math::LogTables s_log;
+    extern __shared__ __align__(16) unsigned char s_tables_raw[];
+    math::LogTables &s_log = *reinterpret_cast<math::LogTables *>(s_tables_raw);
     __shared__ __align__(128) GainStep s_gain[kGainStages][kGainChunk];
     __shared__ __align__(8) uint64_t s_full[kGainStages], s_empty[kGainStages];
     const int case_idx = blockIdx.y * gridDim.z + blockIdx.z, tile = blockIdx.x;
@@ -517,11 +512,7 @@ rollout_philox_reduced(const Case *__restrict__ cases, const __grid_constant__ S
     const double f = pick4(st.f, kk), l00 = pick4(st.l00, kk), l10 = pick4(st.l10, kk), l11 = pick4(st.l11, kk),
                  sr = pick4(st.sr, kk);
     const int lane = threadIdx.x & 31;
-    {
-        const double *ls = reinterpret_cast<const double *>(logtab);
-        double *ld = reinterpret_cast<double *>(&s_log);
-        for (int i = threadIdx.x; i < (int)(sizeof(math::LogTables) / sizeof(double)); i += kThreads) ld[i] = ls[i];
-    }
+    load_noise_tables(&s_log, logtab);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < kGainStages; ++s) { mbar_init(&s_full[s], 1u); mbar_init(&s_empty[s], kThreads / 32); }
@@ -546,9 +537,10 @@ rollout_philox_reduced(const Case *__restrict__ cases, const __grid_constant__ S
     double e0, e1, kn = 0.0, ki = 0.0, sdn = 0.0, sqn = 0.0, sdi = 0.0, sqi = 0.0;
     {
         const uint4 w = philox4x32_10(trial, m.stream, 0u, 0u, key);
-        math::normal_pair_bits(w.x, w.w, w.y, s_log, e0, e1);    // e = x0 + N(0,P0) - xhat0 = the draw itself
+        math::normal_pair(w.x, w.y, s_log, e0, e1);    // e = x0 + N(0,P0) - xhat0 = the draw itself
     }
-    uint4 r0 = philox4x32_10(trial, m.stream, 1u, 0u, key), r1 = philox4x32_10(trial, m.stream, 1u, 1u, key);
+    static_assert(kGainChunk % 4 == 0, "a gain chunk holds whole step groups");
+    GroupWords r = philox_group(trial, m.stream, 0u, key);
     for (int c = 0; c < nchunks; ++c) {
         if (threadIdx.x == 0) {
             const int nx = c + kGainStages - 1;
@@ -560,17 +552,42 @@ rollout_philox_reduced(const Case *__restrict__ cases, const __grid_constant__ S
         const int sidx = c % kGainStages;
         mbar_wait(&s_full[sidx], (uint32_t)((c / kGainStages) & 1));
         const GainStep *g = s_gain[sidx];
-        const int s0 = c * kGainChunk;
-#pragma unroll 1
-        for (int j = 0; j < kGainChunk && s0 + j < T; j += 2) {
-            const uint32_t p = (uint32_t)((s0 + j) >> 1);
-            const uint4 q0 = philox4x32_10(trial, m.stream, p + 2u, 0u, key), q1 = philox4x32_10(trial, m.stream, p + 2u, 1u, key);
-            double n[6];
-            normals_of_pair(r0, r1, s_log, n);
-            if (s0 + j == 0) reduced_step<true>(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j], f, l00, l10, l11, sr, n[0], n[1], n[2]);
-            else             reduced_step<false>(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j], f, l00, l10, l11, sr, n[0], n[1], n[2]);
-            if (s0 + j + 1 < T) reduced_step<false>(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j + 1], f, l00, l10, l11, sr, n[3], n[4], n[5]);
-            r0 = q0; r1 = q1;
+        const int c0 = c * kGainChunk;
+        const int nsteps = T - c0 < kGainChunk ? T - c0 : kGainChunk;     // steps of this chunk that exist
+        const int nfull = nsteps >> 2;
+#pragma unroll kReducedUnroll
+        for (int gi = 0; gi < nfull; ++gi) {                              // whole groups: one basic block each
+            const int j = 4 * gi, s0 = c0 + j;
+            const GroupWords q = philox_group(trial, m.stream, (uint32_t)(s0 >> 2) + 1u, key);
+            double p0a, p0b, p1a, p1b, p2a, p2b, p3a, p3b, o0, o1, o2, o3;
+            math::normal_pair(r.c.x, r.c.y, s_log, o0, o1);
+            math::normal_pair(r.a.x, r.a.y, s_log, p0a, p0b);
+            math::normal_pair(r.a.z, r.a.w, s_log, p1a, p1b);
+            reduced_step(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j], f, l00, l10, l11, sr, p0a, p0b, o0, s0 == 0);
+            math::normal_pair(r.c.z, r.c.w, s_log, o2, o3);
+            math::normal_pair(r.b.x, r.b.y, s_log, p2a, p2b);
+            reduced_step(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j + 1], f, l00, l10, l11, sr, p1a, p1b, o1, false);
+            math::normal_pair(r.b.z, r.b.w, s_log, p3a, p3b);
+            reduced_step(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j + 2], f, l00, l10, l11, sr, p2a, p2b, o2, false);
+            reduced_step(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j + 3], f, l00, l10, l11, sr, p3a, p3b, o3, false);
+            r = q;
+        }
+        const int rem = nsteps & 3;                                       // only the last chunk can end in a partial group
+        if (rem > 0) {
+            const int j = 4 * nfull, s0 = c0 + j;
+            double pa, pb, o0, o1;
+            math::normal_pair(r.c.x, r.c.y, s_log, o0, o1);
+            math::normal_pair(r.a.x, r.a.y, s_log, pa, pb);
+            reduced_step(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j], f, l00, l10, l11, sr, pa, pb, o0, s0 == 0);
+            if (rem > 1) {
+                math::normal_pair(r.a.z, r.a.w, s_log, pa, pb);
+                reduced_step(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j + 1], f, l00, l10, l11, sr, pa, pb, o1, false);
+            }
+            if (rem > 2) {
+                math::normal_pair(r.c.z, r.c.w, s_log, o0, o1);
+                math::normal_pair(r.b.x, r.b.y, s_log, pa, pb);
+                reduced_step(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j + 2], f, l00, l10, l11, sr, pa, pb, o0, false);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[sidx]);
@@ -590,8 +607,8 @@ rollout_philox_reduced(const Case *__restrict__ cases, const __grid_constant__ S
             }
         }
     }
-    __shared__ double s_red[kThreads][4];
-    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, s_red);
+    __syncthreads();
+    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, reinterpret_cast<double (*)[4]>(s_tables_raw));
 }
 
 // -----------------------------------------------------------------------------------------
@@ -614,17 +631,20 @@ __global__ void trace_philox(const Case *__restrict__ cases, const __grid_consta
     {
         double a, b;
         const uint4 w = philox4x32_10(trial, m.stream, 0u, 0u, key);
-        math::normal_pair_bits(w.x, w.w, w.y, tab, a, b);
+        math::normal_pair(w.x, w.y, tab, a, b);
         traj_init(t, a, b);
     }
     for (int s = 0; s < m.T; ++s) {
-        const uint32_t p = (uint32_t)(s >> 1);
-        double n[6];
-        normals_of_pair(philox4x32_10(trial, m.stream, p + 1u, 0u, key), philox4x32_10(trial, m.stream, p + 1u, 1u, key), tab, n);
-        const int o = (s & 1) * 3;
+        // the normals of step s out of its group's words (kfbo_device.cuh: philox_group), formed anew every step
+        const GroupWords w = philox_group(trial, m.stream, (uint32_t)(s >> 2), key);
+        const int q = s & 3;
+        const uint4 pw = q < 2 ? w.a : w.b;
+        double pa, pb, oa, ob;
+        if (q & 1) math::normal_pair(pw.z, pw.w, tab, pa, pb); else math::normal_pair(pw.x, pw.y, tab, pa, pb);
+        if (q < 2) math::normal_pair(w.c.x, w.c.y, tab, oa, ob); else math::normal_pair(w.c.z, w.c.w, tab, oa, ob);
         StepProbe probe;
-        if (s == 0) filter_step<true, true>(t, m, f, gu[s], StepNoise{n[o], n[o + 1], n[o + 2]}, l00, l10, l11, sr, &probe);
-        else        filter_step<false, true>(t, m, f, gu[s], StepNoise{n[o], n[o + 1], n[o + 2]}, l00, l10, l11, sr, &probe);
+        if (s == 0) filter_step<true, true>(t, m, f, gu[s], StepNoise{pa, pb, (q & 1) ? ob : oa}, l00, l10, l11, sr, &probe);
+        else        filter_step<false, true>(t, m, f, gu[s], StepNoise{pa, pb, (q & 1) ? ob : oa}, l00, l10, l11, sr, &probe);
         double *row = trace + (size_t)s * 9;
         const double b1 = 2.0 * sqrt(t.p00), b2 = 2.0 * sqrt(t.p11);
         row[0] = s * dt;                       // trial.cpp:70
@@ -669,10 +689,11 @@ cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleT
                                   cudaStream_t stream)
 {
     if (ncases <= 0 || ntrials == 0) return cudaSuccess;
-    const int tiles = philox_tiles(ntrials);
-    const size_t smem = (size_t)max_T * sizeof(double2);
+    (void)max_T;
+    const int tiles = rollout_tiles(ntrials);
+    const size_t smem = sizeof(math::LogTables);
     const dim3 grid((unsigned)tiles, (unsigned)(ncases / st.nk), (unsigned)st.nk);   // ncases = candidates x nk
-    // static tables (25 KB) + the g*u table pass the default 48 KB of shared memory for T > ~1400: opt in
+    // the noise tables (48.4 KB) pass the default 48 KB of shared memory: opt in (per device, a few microseconds)
     const cudaError_t attr = cudaFuncSetAttribute(rollout_philox, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (attr != cudaSuccess) return attr;
     rollout_philox<<<grid, kThreads, smem, stream>>>(
@@ -702,7 +723,10 @@ cudaError_t launch_rollout_philox_reduced(const Case *d_cases, int ncases, const
     if (e != cudaSuccess) return e;
     const int tiles = rollout_tiles(ntrials);
     const dim3 grid((unsigned)tiles, (unsigned)(ncases / st.nk), (unsigned)st.nk);
-    rollout_philox_reduced<<<grid, kThreads, 0, stream>>>(
+    const size_t smem = sizeof(math::LogTables);
+    e = cudaFuncSetAttribute(rollout_philox_reduced, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rollout_philox_reduced<<<grid, kThreads, smem, stream>>>(
         d_cases, st, d_gains, stride, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0, ntrials, tiles,
         d_per_trial, per_trial_ld, d_partials, d_tickets, d_sums);
     return cudaGetLastError();
@@ -746,6 +770,6 @@ cudaError_t launch_dfma_chain(double *d_out, int blocks, int iters, cudaStream_t
 }
 
 int rollout_tiles(size_t ntrials) { return (int)((ntrials + kThreads - 1) / kThreads); }
-int philox_tiles(size_t ntrials) { return (int)((ntrials + (size_t)kThreads * kPhiloxPerThread - 1) / ((size_t)kThreads * kPhiloxPerThread)); }
+int philox_tiles(size_t ntrials) { return rollout_tiles(ntrials); }
 
 }  // namespace kfbo

@@ -5,8 +5,8 @@
 // UMOV pairs; in the rollout loop that made ~420 issued instructions and ~190 FP64 instructions
 // per filter-step (profiles/ncu_philox_r1_first.txt).  The arguments here are known to be well
 // scaled (u1 in [2^-52, 1), S and det(P) of a covariance recursion, angle in one octant), so the
-// special cases are dropped; sin/cos of the Box-Muller angle come from a 1024-entry direction table
-// plus a two-term rotation instead of degree-16 polynomials.
+// special cases are dropped; the Box-Muller direction is the product of two tabulated unit vectors (a coarse and a
+// fine 1024-entry table: 2^20 equally spaced directions) instead of sin/cos polynomials.
 //
 // Measured on B200 (tools/microbench/, DESIGN.md "What the FP64 pipe really costs"): a DFMA whose
 // three sources are three DISTINCT vector registers occupies the FP64 pipe for 3 cycles per warp
@@ -39,13 +39,16 @@ constexpr uint32_t kLogOffHi = 0x3FE60000u;         // z in [0.6875, 1.375)
 constexpr int kLogBelowOne = 160 << (kLogTableBits - 8);   // sub-intervals of [0.6875, 1): (1 - 0.6875) 2^(bits+1)
 constexpr int kLogUnitEntry = kLogBelowOne - 1;     // the sub-interval [1-2^-(bits+1), 1): c = 1 exactly
 
-constexpr int kAngleTableBits = 10;
-constexpr int kAngleTableSize = 1 << kAngleTableBits;   // 1024 directions x {cos, sin}
+constexpr int kDirTableBits = 10;
+constexpr int kDirTableSize = 1 << kDirTableBits;   // per level: 1024 unit vectors {cos, sin}; two levels -> 2^20 directions
+constexpr int kDirBits = 2 * kDirTableBits;         // direction index bits of a normal pair
+constexpr int kRadiusBits = 64 - kDirBits;          // radius bits of a normal pair (44)
 
 struct LogTables {
     double invc_logc[kLogTableSize][2];  // {1/c_i rounded, 2 ln(that rounded value)}
     double k2ln2[kLogKTableSize];        // entry 52 + k: -2 k ln 2
-    double cossin[kAngleTableSize][2];   // {cos, sin} of 2 pi (i + 1/2) / 1024
+    double dir_coarse[kDirTableSize][2]; // {cos, sin} of 2 pi i / 2^10
+    double dir_fine[kDirTableSize][2];   // {cos, sin} of 2 pi (j + 1/2) / 2^20
 };
 
 // Host: build the tables in long double (x87 extended, 64-bit mantissa).
@@ -64,10 +67,12 @@ inline void build_log_tables(LogTables *t)
     for (int j = 0; j < kLogKTableSize; ++j)   // indexed by 52 + k, k = exponent of u in [-52, 0]: a non-negative index
         t->k2ln2[j] = (double)(2.0L * (kLogKTableSize - 4 - j) * 0.693147180559945309417232121458176568L);
     const long double two_pi = 6.283185307179586476925286766559005768L;
-    for (int i = 0; i < kAngleTableSize; ++i) {
-        const long double a = two_pi * (i + 0.5L) / kAngleTableSize;
-        t->cossin[i][0] = (double)cosl(a);
-        t->cossin[i][1] = (double)sinl(a);
+    for (int i = 0; i < kDirTableSize; ++i) {
+        const long double a = two_pi * i / kDirTableSize, b = two_pi * (i + 0.5L) / ((long double)kDirTableSize * kDirTableSize);
+        t->dir_coarse[i][0] = (double)cosl(a);
+        t->dir_coarse[i][1] = (double)sinl(a);
+        t->dir_fine[i][0] = (double)cosl(b);
+        t->dir_fine[i][1] = (double)sinl(b);
     }
 }
 
@@ -206,45 +211,37 @@ KFBO_HD double neg2_log(double u, const double (*tab)[2], const double *ktab)
 #endif
 }
 
-// cos/sin of theta = 2 pi ang / 2^32 for a 32-bit angle: the top 10 bits pick one of 1024 tabulated
-// directions (cos, sin of the sub-interval's centre), the low 22 bits give the offset
-// |d| <= pi/1024 from it; cos d and sin d need two polynomial terms each (d^6/720 < 2e-18,
-// d^7/5040 < 6e-22) and the result is the rotation of the tabulated direction by d, scaled by `rad`:
-//   c = rad cos(theta), s = rad sin(theta).   13 FP64 instructions, no octant logic.
-KFBO_CONST double kAngU[4] = {0x1.921fb54442d18p-8 /* 2 pi / 1024 */, -0x1.2d97c7f3321d2p-7 /* -1.5 * that */,
-                              1.0 / 24.0, 1.0 / 120.0};
-KFBO_HD void rad_sincos_2pi(double rad, uint32_t ang, const double (*cossin)[2], double &c, double &s)
+// rad * (cos, sin) of direction `dir` out of 2^20: theta = 2 pi (dir + 1/2) / 2^20 = 2 pi i / 2^10 + 2 pi (j + 1/2) / 2^20
+// with dir = i 2^10 + j -- the product of a coarse and a fine tabulated unit vector: 6 FP64 instructions, no polynomial
+// (13 for a table + rotation by a polynomial sin/cos; ~40 for a libdevice sincospi).  Absolute error <= 2.5e-16 rad.
+KFBO_HD void rad_direction(double rad, uint32_t dir, const LogTables &tab, double &c, double &s)
 {
-    const uint32_t i = ang >> (32 - kAngleTableBits), r = ang & ((1u << (32 - kAngleTableBits)) - 1u);
-    const double y = make_double(0x3FF00000u | (r >> 2), funnel_l(0u, r, 30));   // 1 + r 2^-22 in [1, 2)
-    const double d = fma(y, kAngU[0], kAngU[1]);                             // (2 pi / 1024)(r 2^-22 - 1/2)
-    const double d2 = d * d;
-    const double cd = fma(fma(d2, kAngU[2], -0.5), d2, 1.0);                 // cos d
-    const double sp = fma(d2, kAngU[3], -1.0 / 6.0) * d2;
-    const double sd = fma(sp, d, d);                                         // sin d
-    const double a = rad * cossin[i][0], b = rad * cossin[i][1];
-    c = fma(a, cd, -(b * sd));
-    s = fma(b, cd, a * sd);
+    const uint32_t i = (dir >> kDirTableBits) & (kDirTableSize - 1u), j = dir & (kDirTableSize - 1u);
+    const double a = rad * tab.dir_coarse[i][0], b = rad * tab.dir_coarse[i][1];
+    const double c2 = tab.dir_fine[j][0], s2 = tab.dir_fine[j][1];
+    c = fma(a, c2, -(b * s2));
+    s = fma(b, c2, a * s2);
 }
 
-// 84 random bits -> two independent N(0,1) draws (Box-Muller).  THE SPEC (restated draw for draw
-// by the CPU checker):
-//   radius: m1 = (rad_hi << 20 | rad_lo20) with the lowest bit forced to 1 (52 bits), rad_lo20 = rad_lo_top20 >> 12;
-//           u1 = 1 - m1 2^-52 in [2^-52, 1 - 2^-52]; rad = sqrt(-2 ln u1)
-//   angle : o = top 3 bits of ang (octant), f = low 29 bits of ang times 2^-29 in [0,1);
-//           theta = (pi/4)(o + f)
+// 64 random bits (w0, w1) -> two independent N(0,1) draws (Box-Muller).  THE SPEC (restated draw for draw by oracle/kfbo_oracle.c):
+//   radius   : 44 bits  m = (w0 << 12) | (w1 >> 20);  u1 = 1 - (m + 1/2) 2^-44  in [2^-45, 1 - 2^-45];  rad = sqrt(-2 ln u1)
+//   direction: 20 bits  dir = w1 & 0xFFFFF;           theta = 2 pi (dir + 1/2) / 2^20
 //   na = rad cos(theta), nb = rad sin(theta)
-// (32 angle bits: 2^32 directions, 1.5e-9 rad apart; the radius keeps 52 bits, so each normal is
-// continuous to FP64 resolution and the tails reach 8.5 sigma.  Random bits are the expensive part
-// on this chip -- see the Philox note in kfbo_device.cuh.)
-// theta = (pi/4)(o + f) = 2 pi ang / 2^32: evaluated by rad_sincos_2pi above.
-// rad_lo_top20: a word whose TOP 20 bits are the low 20 bits of the radius mantissa (one funnel shift joins them).
-KFBO_HD void normal_pair_bits(uint32_t rad_hi, uint32_t rad_lo_top20, uint32_t ang, const LogTables &tab, double &na, double &nb)
+// Why these widths.  Random bits are the expensive resource on this chip (the 32x32->64 multiplies of Philox share
+// the FP64 issue resource -- kfbo_device.cuh), so a pair takes 64 of them: one Philox4x32-10 call makes two pairs.
+//   * 2^20 equally spaced directions: for a uniform grid of N angles every trigonometric moment E[cos^p sin^q] with
+//     p + q < N equals the continuous one exactly, so all joint moments of (na, nb) up to order 2^20 - 1 are those of
+//     two independent normals, and the marginal densities differ from the normal density by the (super-algebraically
+//     small) trapezoid-rule error of a smooth periodic integrand;
+//   * 44-bit radius variate: each normal is continuous (the radius is) with tails to 7.9 sigma; the mass beyond,
+//     3e-15 per draw, is less than one draw in 10^14.
+KFBO_HD void normal_pair(uint32_t w0, uint32_t w1, const LogTables &tab, double &na, double &nb)
 {
-    const double y1 = make_double(0x3FF00000u | (rad_hi >> 12), funnel_l(rad_lo_top20, rad_hi, 20) | 1u);   // [1,2)
+    // y1 = 1 + (m + 1/2) 2^-44 in [1, 2): mantissa = w0 : w1[31:20] : 1000 0000b
+    const double y1 = make_double(0x3FF00000u | (w0 >> 12), (funnel_l(w1, w0, 20) & 0xFFFFFF00u) | 0x80u);
     const double u1 = 2.0 - y1;
     const double rad = sqrt_pos(neg2_log(u1, tab.invc_logc, tab.k2ln2));
-    rad_sincos_2pi(rad, ang, tab.cossin, na, nb);
+    rad_direction(rad, w1, tab, na, nb);
 }
 
 }  // namespace math

@@ -12,7 +12,7 @@
  * of its own to check against -- by that measure parity is UNPINNED.  Its dependencies (Eigen3,
  * ROS, Boost, bayesopt) are absent here, so its build cannot run either.  What this repo does
  * instead: oracle/Makefile compiles the reference's OWN hot-path sources (trial.cpp, simulator.cpp,
- * kalman_filter.cpp, read_para_vehicle.cpp, include/*.hpp) from where they lie into
+ * kalman_filter.cpp, read_para_vehicle.cpp, the headers under include/) from where they lie into
  * oracle/_ref/libkfbo_ref.so, with oracle/ref_shim/ standing in for the few pieces of Eigen3 / ROS /
  * matplotlibcpp they use and a counter for the wall clock.  This file is checked against that
  * library (tests/test_oracle_vs_ref.py: models, Van Loan discretisation, KalmanFilter::Step,
@@ -296,21 +296,21 @@ void ko_philox4x32_10(const uint32_t *ctr, const uint32_t *key, uint32_t *out)
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* 84 random bits -> two independent standard normals (Box-Muller), the product's spec:
- *   radius: m1 = (rad_hi << 20 | rad_lo20) with the lowest bit forced to 1 (52 bits);
- *           u1 = 1 - m1*2^-52 in [2^-52, 1-2^-52];  rad = sqrt(-2 ln u1)
- *   angle : o = top 3 bits of ang (octant), f = low 29 bits of ang * 2^-29 in [0,1);
- *           theta = (pi/4)(o + f)
+/* 64 random bits (w0, w1) -> two independent standard normals (Box-Muller), the product's spec
+ * (kf_bayesopt_b200/csrc/kfbo_math.cuh: normal_pair), evaluated here with libm:
+ *   radius   : 44 bits  m = (w0 << 12) | (w1 >> 20);  u1 = 1 - (m + 1/2) 2^-44;  rad = sqrt(-2 ln u1)
+ *   direction: 20 bits  dir = w1 & 0xFFFFF;           theta = 2 pi (dir + 1/2) / 2^20
  *   n_a = rad cos(theta), n_b = rad sin(theta)
- * theta is reduced to its octant exactly (1-f is exact) so libm sees |arg| <= pi/4. */
-void ko_normal_pair(uint32_t rad_hi, uint32_t rad_lo20, uint32_t ang, double *na, double *nb)
+ * theta is reduced to its octant exactly (dir + 1/2 and 2^17 - it are exact) so libm sees |arg| <= pi/4. */
+void ko_normal_pair(uint32_t w0, uint32_t w1, double *na, double *nb)
 {
-    const uint64_t m1 = (((uint64_t)rad_hi << 20) | (rad_lo20 & 0xFFFFFu)) | 1u;
-    const double u1 = 1.0 - (double)m1 * 0x1p-52;
+    const uint64_t m = ((uint64_t)w0 << 12) | (w1 >> 20);
+    const double u1 = 1.0 - ((double)m + 0.5) * 0x1p-44;
     const double r = sqrt(-2.0 * log(u1));
-    const unsigned o = ang >> 29;
-    const double f = (double)(ang & 0x1FFFFFFFu) * 0x1p-29;
-    const double x = (o & 1u) ? 1.0 - f : f;           /* position inside the octant, mirrored for odd octants */
+    const uint32_t dir = w1 & 0xFFFFFu;
+    const unsigned o = dir >> 17;                                  /* octant: 2^17 directions each */
+    const double f = ((double)(dir & 0x1FFFFu) + 0.5) * 0x1p-17;   /* position inside the octant, in (0, 1) */
+    const double x = (o & 1u) ? 1.0 - f : f;                       /* mirrored for odd octants */
     const double sx = sin(M_PI_4 * x), cx = cos(M_PI_4 * x);
     const double sa = (o & 1u) ? cx : sx, ca = (o & 1u) ? sx : cx; /* angle within the quadrant */
     double sn, cs;
@@ -324,14 +324,17 @@ void ko_normal_pair(uint32_t rad_hi, uint32_t rad_lo20, uint32_t ang, double *na
     *nb = r * sn;
 }
 
-/* The random words of one step pair: two Philox calls A, B -> three normal pairs n[0..5]:
- *   pair 0: radius (A[0] : A[3]>>12), angle A[1]     pair 1: radius (B[0] : B[3]>>12), angle B[1]
- *   pair 2: radius (A[2] : A[3][11:0] B[3][7:0]), angle B[2] */
-void ko_normals_of_pair(const uint32_t *A, const uint32_t *B, double *n)
+/* The random words of one STEP GROUP (steps 4g .. 4g+3): three Philox calls A, B, C -> six normal pairs:
+ *   process noise of step 4g+s: (A.x,A.y), (A.z,A.w), (B.x,B.y), (B.z,B.w) for s = 0..3  -> pn[s][0..1]
+ *   observation noise: the two halves of (C.x,C.y) for steps 4g, 4g+1, of (C.z,C.w) for 4g+2, 4g+3 -> on[s] */
+void ko_normals_of_group(const uint32_t *A, const uint32_t *B, const uint32_t *Cc, double *pn /*[4][2]*/, double *on /*[4]*/)
 {
-    ko_normal_pair(A[0], A[3] >> 12, A[1], &n[0], &n[1]);
-    ko_normal_pair(B[0], B[3] >> 12, B[1], &n[2], &n[3]);
-    ko_normal_pair(A[2], ((A[3] & 0xFFFu) << 8) | (B[3] & 0xFFu), B[2], &n[4], &n[5]);
+    ko_normal_pair(A[0], A[1], &pn[0], &pn[1]);
+    ko_normal_pair(A[2], A[3], &pn[2], &pn[3]);
+    ko_normal_pair(B[0], B[1], &pn[4], &pn[5]);
+    ko_normal_pair(B[2], B[3], &pn[6], &pn[7]);
+    ko_normal_pair(Cc[0], Cc[1], &on[0], &on[1]);
+    ko_normal_pair(Cc[2], Cc[3], &on[2], &on[3]);
 }
 
 /* Closed-form Cholesky of the truth Qd and sqrt(R): any T with T T^T = Qd is
@@ -347,27 +350,27 @@ void ko_noise_transform(const double *Qd, double R, double *L /*[3]: L00,L10,L11
 typedef struct {
     uint32_t key[2], trial, stream;
     double L[3], sr;
-    int cached_pair;   /* index of the step pair whose 6 normals are in n[] */
-    double n[6];
+    int cached_group;  /* index of the step group whose 12 normals are in pn[], on[] */
+    double pn[8], on[4];
 } philox_ctx;
 
 static void philox_noise(void *p, int step, double *w0, double *w1, double *v)
 {
     philox_ctx *c = (philox_ctx *)p;
-    const int pair = step >> 1;
-    if (pair != c->cached_pair) {
-        uint32_t out[2][4];
-        for (uint32_t j = 0; j < 2; ++j) {
-            const uint32_t ctr[4] = {c->trial, c->stream, (uint32_t)pair + 1u, j};
+    const int group = step >> 2, s = step & 3;
+    if (group != c->cached_group) {
+        uint32_t out[3][4];
+        for (uint32_t j = 0; j < 3; ++j) {
+            const uint32_t ctr[4] = {c->trial, c->stream, (uint32_t)group + 1u, j};
             ko_philox4x32_10(ctr, c->key, out[j]);
         }
-        ko_normals_of_pair(out[0], out[1], c->n);
-        c->cached_pair = pair;
+        ko_normals_of_group(out[0], out[1], out[2], c->pn, c->on);
+        c->cached_group = group;
     }
-    const double *n = c->n + 3 * (step & 1);
-    *w0 = c->L[0] * n[0];
-    *w1 = c->L[1] * n[0] + c->L[2] * n[1];
-    *v = c->sr * n[2];
+    const double n0 = c->pn[2 * s], n1 = c->pn[2 * s + 1], n2 = c->on[s];
+    *w0 = c->L[0] * n0;
+    *w1 = c->L[1] * n0 + c->L[2] * n1;
+    *v = c->sr * n2;
 }
 
 /* Philox-stream evaluation of trials [trial0, trial0+ntrials) of one
@@ -386,12 +389,12 @@ int ko_eval_philox(uint64_t seed, uint32_t stream, double dt, int T, double q_tr
     ko_noise_transform(truth->Qd, truth->R, c.L, &c.sr);
     for (long i = 0; i < ntrials; ++i) {
         c.trial = trial0 + (uint32_t)i;
-        c.cached_pair = -1;
+        c.cached_group = -1;
         const uint32_t ctr[4] = {c.trial, c.stream, 0u, 0u};
         uint32_t o[4];
         double x0n[2], out[4];
         ko_philox4x32_10(ctr, c.key, o);
-        ko_normal_pair(o[0], o[3] >> 12, o[1], &x0n[0], &x0n[1]); /* P0 = I: transform is the identity */
+        ko_normal_pair(o[0], o[1], &x0n[0], &x0n[1]); /* P0 = I: transform is the identity */
         run_trial(truth, est, T, x0n, philox_noise, &c, hn, hi, out);
         for (int k = 0; k < 4; ++k) per_trial[(long)k * ntrials + i] = out[k];
     }

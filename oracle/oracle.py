@@ -38,7 +38,7 @@ def lib() -> C.CDLL:
         L.ko_eval_supplied.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_long, _dp, _dp, _dp, _dp]
         L.ko_eval_supplied.restype = C.c_int
         L.ko_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
-        L.ko_normal_pair.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, _dp, _dp]
+        L.ko_normal_pair.argtypes = [C.c_uint32, C.c_uint32, _dp, _dp]
         L.ko_noise_transform.argtypes = [_dp, C.c_double, _dp, _dp]
         L.ko_eval_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_double, C.c_int, C.c_double, C.c_double,
                                      C.c_double, C.c_double, C.c_uint32, C.c_long, _dp]
@@ -105,10 +105,10 @@ def philox4x32_10(ctr, key) -> np.ndarray:
     return np.array(list(o), dtype=np.uint32)
 
 
-def normal_pair(rad_hi, rad_lo20, ang):
-    """84 random bits -> (rad cos theta, rad sin theta); see ko_normal_pair."""
+def normal_pair(w0, w1):
+    """64 random bits -> (rad cos theta, rad sin theta): 44-bit radius variate, 20-bit direction; see ko_normal_pair."""
     a, b = C.c_double(), C.c_double()
-    lib().ko_normal_pair(int(rad_hi) & 0xFFFFFFFF, int(rad_lo20) & 0xFFFFF, int(ang) & 0xFFFFFFFF, C.byref(a), C.byref(b))
+    lib().ko_normal_pair(int(w0) & 0xFFFFFFFF, int(w1) & 0xFFFFFFFF, C.byref(a), C.byref(b))
     return a.value, b.value
 
 

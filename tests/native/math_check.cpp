@@ -24,7 +24,6 @@ int main()
     static LogTables t;
     build_log_tables(&t);
     std::mt19937_64 g(12345);
-    const long double PI4 = 0.785398163397448309615660845819875721L;
     double e_rcp = 0, e_sqrt = 0, e_log = 0, e_sin = 0, e_cos = 0, e_na = 0, e_nb = 0;
     // rcp / sqrt over 40 decades
     for (int i = 0; i < 2000000; ++i) {
@@ -46,26 +45,28 @@ int main()
     // edge values
     for (double u : {0x1p-52, 1.0 - 0x1p-52, 0.6875, 0.6875 - 0x1p-54, 1.0 - 0x1p-9, 1.0 - 0x1p-9 - 0x1p-53, 0.5, 0.25 + 0x1p-54})
         e_log = std::fmax(e_log, ulp_err(neg2_log(u, t.invc_logc, t.k2ln2), -2.0L * logl((long double)u)));
-    // rad * cos / sin of a 32-bit angle (direction table + rotation), rad = 1: absolute error in ulps of 1
+    // rad * (cos, sin) of one of 2^20 directions (coarse x fine table product), rad = 1: absolute error in ulps of 1
     const long double TWO_PI = 6.283185307179586476925286766559005768L;
     for (int i = 0; i < 4000000; ++i) {
-        uint32_t ang = (uint32_t)g();
-        if (i % 8 == 0) ang = (ang & ~0x3FFFFFu) | ((i & 8) ? 0x3FFFFFu : 0u);      // both ends of a table sub-interval
-        if (i % 8 == 1) ang &= 0xC0000000u;                                           // the axes
+        uint32_t dir = (uint32_t)g() & 0xFFFFFu;
+        if (i % 8 == 0) dir = (dir & ~0x3FFu) | ((i & 8) ? 0x3FFu : 0u);            // both ends of a coarse sub-interval
+        if (i % 8 == 1) dir &= 0xC0000u;                                              // next to the axes
         double s, c;
-        rad_sincos_2pi(1.0, ang, t.cossin, c, s);
-        const long double th = TWO_PI * (long double)ang * 0x1p-32L;
+        rad_direction(1.0, dir | ((uint32_t)g() << 20), t, c, s);                     // the bits above 20 must be ignored
+        const long double th = TWO_PI * ((long double)dir + 0.5L) * 0x1p-20L;
         e_sin = std::fmax(e_sin, (double)(fabsl((long double)s - sinl(th)) * 0x1p53L));
         e_cos = std::fmax(e_cos, (double)(fabsl((long double)c - cosl(th)) * 0x1p53L));
     }
-    // the full pair against the spec evaluated in long double (absolute error: |n| <= 8.5)
+    // the full pair against the spec evaluated in long double (absolute error: |n| <= 7.9)
     for (int i = 0; i < 2000000; ++i) {
-        const uint32_t rad_hi = (uint32_t)g(), lo20 = (uint32_t)g() & 0xFFFFFu, ang = (uint32_t)g();
+        uint32_t w0 = (uint32_t)g(), w1 = (uint32_t)g();
+        if (i % 16 == 0) { w0 = 0xFFFFFFFFu; w1 |= 0xFFF00000u; }                     // the largest radius
+        if (i % 16 == 1) { w0 = 0u; w1 &= 0x000FFFFFu; }                              // the smallest
         double na, nb;
-        normal_pair_bits(rad_hi, lo20 << 12 | (uint32_t)(g() & 0xFFFu), ang, t, na, nb);
-        const uint64_t m1 = (((uint64_t)rad_hi << 20) | lo20) | 1u;
-        const long double u1 = 1.0L - (long double)m1 * 0x1p-52L;
-        const long double theta = PI4 * ((long double)(ang >> 29) + (long double)(ang & 0x1FFFFFFFu) * 0x1p-29L);
+        normal_pair(w0, w1, t, na, nb);
+        const uint64_t m = ((uint64_t)w0 << 12) | (w1 >> 20);
+        const long double u1 = 1.0L - ((long double)m + 0.5L) * 0x1p-44L;
+        const long double theta = TWO_PI * ((long double)(w1 & 0xFFFFFu) + 0.5L) * 0x1p-20L;
         const long double rad = sqrtl(-2.0L * logl(u1));
         e_na = std::fmax(e_na, (double)fabsl((long double)na - rad * cosl(theta)));
         e_nb = std::fmax(e_nb, (double)fabsl((long double)nb - rad * sinl(theta)));

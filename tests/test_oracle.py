@@ -111,39 +111,58 @@ def test_mt19937_known_answer(oracle):
 
 
 def test_normal_pair_mapping(oracle):
-    # m1 = 0 -> forced to 1 -> u1 = 1 - 2^-52 -> radius sqrt(2^-51); octant 0, f = 0 -> (r, 0)
-    a, b = oracle.normal_pair(0, 0, 0)
-    assert a == pytest.approx(np.sqrt(2.0**-51), rel=1e-12) and b == 0.0
-    # m1 max -> u1 = 2^-52: the largest radius, 8.49 sigma
-    a, b = oracle.normal_pair(0xffffffff, 0xfffff, 0)
-    assert a == pytest.approx(np.sqrt(-2 * np.log(2.0**-52)), rel=1e-15) and b == 0.0
-    r = np.sqrt(-2 * np.log(0.5 - 2.0**-52))
-    # octant 2, f = 0: theta = pi/2 -> (0, r); octant 4: theta = pi -> (-r, 0); octant 6 -> (0, -r)
-    for ang, want in [(0x40000000, (0, 1)), (0x80000000, (-1, 0)), (0xC0000000, (0, -1))]:
-        a, b = oracle.normal_pair(0x80000000, 0, ang)
-        assert a == pytest.approx(want[0] * r, rel=1e-15, abs=1e-16) and b == pytest.approx(want[1] * r, rel=1e-15, abs=1e-16)
-    # octant 1, f = 0: theta = pi/4; octant 0, f = 1/2: theta = pi/8
-    a, b = oracle.normal_pair(0x80000000, 0, 0x20000000)
-    assert a == pytest.approx(r * np.sqrt(0.5), rel=1e-15) and b == pytest.approx(r * np.sqrt(0.5), rel=1e-15)
-    a, b = oracle.normal_pair(0x80000000, 0, 0x10000000)
-    assert a == pytest.approx(r * np.cos(np.pi / 8), rel=1e-15) and b == pytest.approx(r * np.sin(np.pi / 8), rel=1e-15)
-    # every octant: the pair is rad*(cos, sin) of theta = (pi/4)(o + f)
+    # the spec of kfbo_math.cuh::normal_pair: radius from m = (w0 << 12 | w1 >> 20), u1 = 1 - (m + 1/2) 2^-44;
+    # direction dir = w1 & 0xFFFFF, theta = 2 pi (dir + 1/2) / 2^20
+    def want(w0, w1):
+        m = (w0 << 12) | (w1 >> 20)
+        u1 = 1.0 - (m + 0.5) * 2.0**-44
+        r = np.sqrt(-2 * np.log(u1))
+        th = 2 * np.pi * ((w1 & 0xFFFFF) + 0.5) / 2.0**20
+        return r * np.cos(th), r * np.sin(th)
+    # m = 0: the smallest radius, sqrt(-2 ln(1 - 2^-45)) ~ 2^-22; m max: u1 = 2^-45, the largest, 7.9 sigma
+    a, b = oracle.normal_pair(0, 0)
+    assert np.hypot(a, b) == pytest.approx(np.sqrt(2.0**-44), rel=1e-12)
+    a, b = oracle.normal_pair(0xffffffff, 0xfff00000)
+    assert np.hypot(a, b) == pytest.approx(np.sqrt(-2 * np.log(2.0**-45)), rel=1e-15) and 7.89 < np.hypot(a, b) < 7.9
+    # the direction only depends on the low 20 bits of w1, the radius on the rest
+    r0 = np.hypot(*oracle.normal_pair(0x12345678, 0xABC00000))
+    for d in (0, 1, 0x3FFFF, 0x40000, 0x80000, 0xC0000, 0xFFFFF, 0x5A5A5):
+        a, b = oracle.normal_pair(0x12345678, 0xABC00000 | d)
+        wa, wb = want(0x12345678, 0xABC00000 | d)
+        assert a == pytest.approx(wa, rel=1e-13, abs=1e-15) and b == pytest.approx(wb, rel=1e-13, abs=1e-15)
+        assert np.hypot(a, b) == pytest.approx(r0, rel=1e-14)
+    # every octant
     for o in range(8):
-        ang = (o << 29) | 0x0ABCDEF1
-        a, b = oracle.normal_pair(0x80000000, 0, ang)
-        th = np.pi / 4 * (o + (ang & 0x1FFFFFFF) * 2.0**-29)
-        assert a == pytest.approx(r * np.cos(th), rel=1e-14, abs=1e-15) and b == pytest.approx(r * np.sin(th), rel=1e-14, abs=1e-15)
-    # moments of the stream
-    n = 40000
+        w1 = 0x7FF00000 | (o << 17) | 0x0BCDE
+        a, b = oracle.normal_pair(0x80000000, w1)
+        wa, wb = want(0x80000000, w1)
+        assert a == pytest.approx(wa, rel=1e-13, abs=1e-15) and b == pytest.approx(wb, rel=1e-13, abs=1e-15)
+    # moments of the stream (a Philox call holds two pairs)
+    n = 20000
     z = []
     for i in range(n):
         w = oracle.philox4x32_10((i, 7, 1, 0), (11, 22))
-        z.append(oracle.normal_pair(w[0], w[3] >> 12, w[1]))
+        z.append(oracle.normal_pair(w[0], w[1]))
+        z.append(oracle.normal_pair(w[2], w[3]))
     z = np.array(z).ravel()
-    assert abs(z.mean()) < 4 / np.sqrt(2 * n)
-    assert abs(z.var() - 1) < 4 * np.sqrt(2 / (2 * n))
+    assert abs(z.mean()) < 4 / np.sqrt(z.size)
+    assert abs(z.var() - 1) < 4 * np.sqrt(2 / z.size)
     assert abs((z**4).mean() - 3) < 0.15
-    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 4 / np.sqrt(n)
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 4 / np.sqrt(z.size / 2)
+
+
+def test_direction_grid_reproduces_the_trigonometric_moments():
+    # why 2^20 equally spaced directions are enough: on a uniform grid of N angles every moment E[cos^p sin^q] with
+    # p + q < N equals the continuous one exactly (aliasing starts at order N), so the joint moments of a Box-Muller pair
+    # are those of two independent normals up to order 2^20 - 1.  Checked numerically on the grid of the spec.
+    from math import gamma, pi
+    N = 1 << 20
+    th = 2 * np.pi * (np.arange(N) + 0.5) / N
+    c, s = np.cos(th), np.sin(th)
+    for p, q in [(2, 0), (0, 2), (1, 1), (4, 0), (2, 2), (6, 2), (8, 8), (3, 1), (20, 10), (40, 40)]:
+        got = np.mean(c**p * s**q)
+        exact = 0.0 if (p % 2 or q % 2) else gamma((p + 1) / 2) * gamma((q + 1) / 2) / (pi * gamma((p + q) / 2 + 1))
+        assert got == pytest.approx(exact, rel=1e-11, abs=1e-15), (p, q)
 
 
 def test_noise_transforms_reproduce_covariance(oracle):
