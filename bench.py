@@ -396,7 +396,7 @@ def main():
             line_extra["reduced_form"] = {
                 "value": steps_per_eval / (float(red.item()) * 1e-3), "unit": UNIT, "kernel_ms": float(red.item()),
                 "kernels": "riccati_gains + rollout_philox_reduced",
-                "fp64_instructions_per_filter_step": {"filter": 19, "noise": 42, "reference_form_filter": 48},
+                "fp64_instructions_per_filter_step": {"filter": 19, "noise": 28.5, "reference_form_filter": 47},
                 "J": [float(c) for c in r2.cost],
                 "note": "opt-in; gain/covariance recursion tabulated once per (candidate, sample time), trajectories "
                         "propagate the error state; same per-trial NEES/NIS to rounding (tests: 1e-9 relative)"}
