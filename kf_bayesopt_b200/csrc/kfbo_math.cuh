@@ -34,7 +34,6 @@ namespace math {
 
 constexpr int kLogTableBits = 10;
 constexpr int kLogTableSize = 1 << kLogTableBits;   // 1024 entries x {invc, 2 ln(invc)}: |r| <= 2^-11, one polynomial term fewer than 256 entries need
-constexpr int kLogKTableSize = 56;                  // j = 0..52 used: 2 j ln2
 constexpr uint32_t kLogOffHi = 0x3FE60000u;         // z in [0.6875, 1.375)
 constexpr int kLogBelowOne = 160 << (kLogTableBits - 8);   // sub-intervals of [0.6875, 1): (1 - 0.6875) 2^(bits+1)
 constexpr int kLogUnitEntry = kLogBelowOne - 1;     // the sub-interval [1-2^-(bits+1), 1): c = 1 exactly
@@ -46,7 +45,6 @@ constexpr int kRadiusBits = 64 - kDirBits;          // radius bits of a normal p
 
 struct LogTables {
     double invc_logc[kLogTableSize][2];  // {1/c_i rounded, 2 ln(that rounded value)}
-    double k2ln2[kLogKTableSize];        // entry 52 + k: -2 k ln 2
     double dir_coarse[kDirTableSize][2]; // {cos, sin} of 2 pi i / 2^10
     double dir_fine[kDirTableSize][2];   // {cos, sin} of 2 pi (j + 1/2) / 2^20
 };
@@ -64,8 +62,6 @@ inline void build_log_tables(LogTables *t)
         t->invc_logc[i][0] = invc;
         t->invc_logc[i][1] = (i == kLogUnitEntry) ? 0.0 : (double)(2.0L * logl((long double)invc));
     }
-    for (int j = 0; j < kLogKTableSize; ++j)   // indexed by 52 + k, k = exponent of u in [-52, 0]: a non-negative index
-        t->k2ln2[j] = (double)(2.0L * (kLogKTableSize - 4 - j) * 0.693147180559945309417232121458176568L);
     const long double two_pi = 6.283185307179586476925286766559005768L;
     for (int i = 0; i < kDirTableSize; ++i) {
         const long double a = two_pi * i / kDirTableSize, b = two_pi * (i + 0.5L) / ((long double)kDirTableSize * kDirTableSize);
@@ -189,8 +185,8 @@ KFBO_CONST double kLogPolyU[1] = {-2.0 / 3.0};
 // L = -2 ln(u) for u in [2^-52, 1): table-driven, no division, no branch.
 //   u = 2^k z, z in [0.6875, 1.375);  i = top 10 bits of (bits(z) - OFF);  r = z/c_i - 1, |r| <= 2^-11
 //   -2 ln u = 2 (-k) ln2 + 2 ln(invc_i) + r * (-2 ln(1+r)/r)
-// tab / ktab may live in shared memory (device) or anywhere (host).
-KFBO_HD double neg2_log(double u, const double (*tab)[2], const double *ktab)
+// tab may live in shared memory (device) or anywhere (host).
+KFBO_HD double neg2_log(double u, const double (*tab)[2])
 {
     const uint32_t hi = hi_word(u), lo = lo_word(u);
     const int32_t tmp = (int32_t)(hi - kLogOffHi);
@@ -203,12 +199,14 @@ KFBO_HD double neg2_log(double u, const double (*tab)[2], const double *ktab)
     s = fma(s, r, kLogPolyU[0]);
     s = fma(s, r, 1.0);
     s = fma(s, r, -2.0);
-#if defined(KFBO_LOG_K_I2F) && defined(__CUDA_ARCH__)
-    (void)ktab;
-    return fma(r, s, fma(__int2double_rn(k), -0x1.62e42fefa39efp+0 /* -2 ln 2 */, logc2));
+    // the exponent's share -2 k ln 2 by one conversion + multiply-add (k in [-52, 0] is exact in FP64); a 53-entry table
+    // would cost a shared-memory lookup, and shared-memory wavefronts are the scarcer resource (measured: 13.42 vs 13.59 ms)
+#if defined(__CUDA_ARCH__)
+    const double kd = __int2double_rn(k);
 #else
-    return fma(r, s, ktab[kLogKTableSize - 4 + k] + logc2);    // entry j holds 2 (52 - j) ln 2, j = 52 + k >= 0
+    const double kd = (double)k;
 #endif
+    return fma(r, s, fma(kd, -0x1.62e42fefa39efp+0 /* -2 ln 2 */, logc2));
 }
 
 // rad * (cos, sin) of direction `dir` out of 2^20: theta = 2 pi (dir + 1/2) / 2^20 = 2 pi i / 2^10 + 2 pi (j + 1/2) / 2^20
@@ -240,7 +238,7 @@ KFBO_HD void normal_pair(uint32_t w0, uint32_t w1, const LogTables &tab, double 
     // y1 = 1 + (m + 1/2) 2^-44 in [1, 2): mantissa = w0 : w1[31:20] : 1000 0000b
     const double y1 = make_double(0x3FF00000u | (w0 >> 12), (funnel_l(w1, w0, 20) & 0xFFFFFF00u) | 0x80u);
     const double u1 = 2.0 - y1;
-    const double rad = sqrt_pos(neg2_log(u1, tab.invc_logc, tab.k2ln2));
+    const double rad = sqrt_pos(neg2_log(u1, tab.invc_logc));
     rad_direction(rad, w1, tab, na, nb);
 }
 

@@ -40,11 +40,11 @@ int main()
         if (i % 4 == 2) m1 |= ~0ull << (g() % 52) >> 12 << 0, m1 &= (1ull << 52) - 1, m1 |= 1;  // u near 2^-52
         const double u = 1.0 - (double)m1 * 0x1p-52;
         if (!(u >= 0x1p-52 && u < 1.0)) continue;
-        e_log = std::fmax(e_log, ulp_err(neg2_log(u, t.invc_logc, t.k2ln2), -2.0L * logl((long double)u)));
+        e_log = std::fmax(e_log, ulp_err(neg2_log(u, t.invc_logc), -2.0L * logl((long double)u)));
     }
     // edge values
     for (double u : {0x1p-52, 1.0 - 0x1p-52, 0.6875, 0.6875 - 0x1p-54, 1.0 - 0x1p-9, 1.0 - 0x1p-9 - 0x1p-53, 0.5, 0.25 + 0x1p-54})
-        e_log = std::fmax(e_log, ulp_err(neg2_log(u, t.invc_logc, t.k2ln2), -2.0L * logl((long double)u)));
+        e_log = std::fmax(e_log, ulp_err(neg2_log(u, t.invc_logc), -2.0L * logl((long double)u)));
     // rad * (cos, sin) of one of 2^20 directions (coarse x fine table product), rad = 1: absolute error in ulps of 1
     const long double TWO_PI = 6.283185307179586476925286766559005768L;
     for (int i = 0; i < 4000000; ++i) {

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(128) k(const Case *cases, const Case pc, doubl
     for (int s = 0; s < steps; ++s) {
         const double2 g = make_double2(1e-3 * (s & 7), 1e-2 * (s & 3));
 #pragma unroll
-        for (int j = 0; j < K; ++j) filter_step<false>(t[j], m, g, w, -w, 0.5 * w);
+        for (int j = 0; j < K; ++j) filter_step<false, false>(t[j], m, m.f, g, StepNoise{w, -w, 0.5 * w});
         w = -w;
     }
     double o[4], acc = 0;

@@ -10,7 +10,8 @@ using namespace kfbo;
 template <int MODE>
 __global__ void __launch_bounds__(128) k(const math::LogTables *logtab, const PhiloxKeys key, double *out, int iters)
 {
-    __shared__ math::LogTables s_log;
+    extern __shared__ __align__(16) unsigned char s_raw[];     // the noise tables (48 KB): dynamic shared memory
+    math::LogTables &s_log = *reinterpret_cast<math::LogTables *>(s_raw);
     {
         const double *ls = reinterpret_cast<const double *>(logtab);
         double *ld = reinterpret_cast<double *>(&s_log);
@@ -30,14 +31,15 @@ __global__ void __launch_bounds__(128) k(const math::LogTables *logtab, const Ph
             for (int c = 0; c < 3; ++c) {
                 r.x = r.x * 1664525u + 1013904223u; r.y ^= r.x >> 3; r.z += r.y; r.w ^= r.z << 5;
                 double a, b;
-                normal_pair(r, s_log.invc_logc, s_log.k2ln2, a, b);
+                math::normal_pair(r.x ^ r.z, r.y ^ r.w, s_log, a, b);
                 acc += a * b;
             }
         } else if (MODE == 2) {   // both
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 double a, b;
-                normal_pair(philox4x32_10(trial, 7u, (uint32_t)i, (uint32_t)c, key), s_log.invc_logc, s_log.k2ln2, a, b);
+                const uint4 q = philox4x32_10(trial, 7u, (uint32_t)i, (uint32_t)c, key);
+                math::normal_pair(q.x ^ q.z, q.y ^ q.w, s_log, a, b);
                 acc += a * b;
             }
         } else if (MODE == 3) {   // 24 IMAD.WIDE.U32 (8 independent chains x 3)
@@ -73,10 +75,11 @@ void run(const math::LogTables *dt, double *d, const char *name, int blocks_per_
     const PhiloxKeys key = {{1, 2, 3, 4, 5, 6, 7, 8, 9, 10}, {11, 12, 13, 14, 15, 16, 17, 18, 19, 20}};
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    k<MODE><<<blocks, 128>>>(dt, key, d, iters);
+    cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(math::LogTables));
+    k<MODE><<<blocks, 128, sizeof(math::LogTables)>>>(dt, key, d, iters);
     cudaDeviceSynchronize();
     cudaEventRecord(e0);
-    k<MODE><<<blocks, 128>>>(dt, key, d, iters);
+    k<MODE><<<blocks, 128, sizeof(math::LogTables)>>>(dt, key, d, iters);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;
