@@ -89,7 +89,8 @@ def test_philox_trials_match_oracle_draw_for_draw(kfbo, oracle):
     # the device RNG path restated by the oracle: same counters -> same normals -> same per-trial outputs
     seed = 0x0123456789ABCDEF
     rv = kfbo.ReadParaVehicle(nsimruns_=300, cpu_core_number_=1)
-    for times in (CODE_TIMES, README_TIMES, [(0.1, 200), (0.5, 2)]):   # odd and even step counts
+    # step counts of every residue mod 4 (the noise comes in groups of four steps), including less than one group
+    for times in (CODE_TIMES, README_TIMES, [(0.1, 200), (0.5, 2)], [(0.1, 3), (0.5, 4), (1.0, 5), (0.2, 6)], [(0.1, 7), (0.5, 1999)]):
         with kfbo.CostEvaluator(rv, times, seed=seed) as ev:
             for k, (dt, T) in enumerate(times):
                 for qe, re, stream, trial0 in [(1.0, 0.1, 0, 0), (0.3, 0.7, 77, 1000), (4.0, 0.02, 0xFFFFFFFE, 0xFFFFFF00)]:
@@ -269,7 +270,7 @@ def test_reduced_form_matches_reference_form_and_oracle(kfbo, oracle):
     from kf_bayesopt_b200 import _lib
     seed = 0xFEEDFACE12345678
     rv = kfbo.ReadParaVehicle(nsimruns_=700, cpu_core_number_=1)
-    for times in (CODE_TIMES, README_TIMES, [(0.1, 2000), (0.5, 2)], [(1.0, 17), (0.1, 33)]):
+    for times in (CODE_TIMES, README_TIMES, [(0.1, 2000), (0.5, 2)], [(1.0, 17), (0.1, 33)], [(0.2, 18), (0.5, 19), (0.1, 3)]):
         with kfbo.CostEvaluator(rv, times, seed=seed, max_candidates=5) as ev:
             for k, (dt, T) in enumerate(times):
                 for qe, re, stream, trial0, n in [(1.0, 0.1, 3, 0, 700), (0.2, 0.9, 9, 123456, 129), (4.5, 0.02, 0xFFFFFFF0, 7, 1)]:
