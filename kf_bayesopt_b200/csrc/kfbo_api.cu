@@ -6,7 +6,10 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <algorithm>
@@ -110,6 +113,7 @@ struct kfbo_handle {
     // last evaluation
     int last_ncand = 0, last_launches = 0;
     double last_ms = 0.0;
+    struct kfbo_assembly_pool *pool = nullptr;   // host threads for the cost assembly of large batches (created on first use)
     std::chrono::steady_clock::time_point tp[3];   // phase marks of the evaluation in flight
     double last_host_us[KFBO_HOST_PHASES] = {0, 0, 0, 0, 0};   // build cases, enqueue, wait for the device, cost assembly, all-reduce (device)
     std::string err;
@@ -181,22 +185,85 @@ int build_case(kfbo_handle *h, int k, double q_est, double r_est, uint32_t strea
 }
 
 // Cost assembly of a batch (trial_node.cpp:70-119 per candidate).  ~30 ns per candidate (two logs per sample
-// time), which for a 4096-candidate sweep is 0.12 ms after an evaluation of 2-14 ms: large batches are split
-// over a few host threads (candidates are independent; each thread writes its own slice of `out`).
-void finalize_all(const kfbo_handle *h, int C, kfbo_result *out)
+// time), which for a 4096-candidate sweep is 0.13 ms after an evaluation of 1.5-11 ms.  Large batches are split over a
+// few PERSISTENT host threads owned by the handle (candidates are independent; each thread writes its own slice of
+// `out`); spawning threads per call costs more than it saves (measured: 147 us against 126 us single-threaded).
+void finalize_range(const kfbo_handle *h, kfbo_result *out, int c0, int c1)
 {
     const int D = h->D;
-    auto run = [h, D, out](int c0, int c1) {
-        for (int c = c0; c < c1; ++c) kfbo::host::finalize(h->p, h->h_sums + (size_t)c * D * 4, &out[c]);
-    };
-    const unsigned hw = std::thread::hardware_concurrency();
-    const int nthreads = C >= 1024 ? (int)std::min<unsigned>(4u, hw ? hw : 1u) : 1;
-    if (nthreads <= 1) { run(0, C); return; }
-    std::vector<std::thread> workers;
-    const int per = (C + nthreads - 1) / nthreads;
-    for (int t = 1; t < nthreads; ++t) workers.emplace_back(run, std::min(C, t * per), std::min(C, (t + 1) * per));
-    run(0, std::min(C, per));
-    for (std::thread &w : workers) w.join();
+    for (int c = c0; c < c1; ++c) kfbo::host::finalize(h->p, h->h_sums + (size_t)c * D * 4, &out[c]);
+}
+
+}  // namespace
+
+struct kfbo_assembly_pool {
+    static constexpr int kWorkers = 3;
+    std::thread th[kWorkers];
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t posted = 0;               // job generation (guarded by mu)
+    bool stop = false;
+    std::atomic<int> done{0};
+    const kfbo_handle *h = nullptr;    // the job
+    kfbo_result *out = nullptr;
+    int C = 0;
+
+    kfbo_assembly_pool()
+    {
+        for (int i = 0; i < kWorkers; ++i) th[i] = std::thread([this, i] { work(i + 1); });
+    }
+    ~kfbo_assembly_pool()
+    {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (std::thread &t : th) t.join();
+    }
+    static void slice(int C, int part, int *c0, int *c1)
+    {
+        const int per = (C + kWorkers) / (kWorkers + 1);
+        *c0 = std::min(C, part * per);
+        *c1 = std::min(C, (part + 1) * per);
+    }
+    void work(int part)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || posted != seen; });
+                if (stop) return;
+                seen = posted;
+            }
+            int c0, c1;
+            slice(C, part, &c0, &c1);
+            finalize_range(h, out, c0, c1);
+            done.fetch_add(1, std::memory_order_release);
+        }
+    }
+    void run(const kfbo_handle *hh, int CC, kfbo_result *o)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            h = hh; C = CC; out = o;
+            done.store(0, std::memory_order_relaxed);
+            ++posted;
+        }
+        cv.notify_all();
+        int c0, c1;
+        slice(CC, 0, &c0, &c1);
+        finalize_range(hh, o, c0, c1);
+        while (done.load(std::memory_order_acquire) != kWorkers) std::this_thread::yield();
+    }
+};
+
+namespace {
+
+void finalize_all(kfbo_handle *h, int C, kfbo_result *out)
+{
+    if (C < 1024) { finalize_range(h, out, 0, C); return; }
+    if (!h->pool) h->pool = new (std::nothrow) kfbo_assembly_pool;
+    if (!h->pool) { finalize_range(h, out, 0, C); return; }
+    h->pool->run(h, C, out);
 }
 
 int cases_per_launch(const kfbo_handle *h, int tiles)
@@ -277,6 +344,7 @@ const char *kfbo_last_error(const kfbo_handle *h) { return h ? h->err.c_str() : 
 void kfbo_destroy(kfbo_handle *h)
 {
     if (!h) return;
+    delete h->pool;
     cudaSetDevice(h->device);
     if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
