@@ -96,6 +96,10 @@ __device__ __forceinline__ void block_reduce_and_publish(const double out[4], in
 #ifndef KFBO_PHILOX_MIN_BLOCKS
 #define KFBO_PHILOX_MIN_BLOCKS 4
 #endif
+#ifndef KFBO_PHILOX_GROUP_UNROLL
+#define KFBO_PHILOX_GROUP_UNROLL 1
+#endif
+constexpr int KFBO_PHILOX_GROUP_UNROLL_V = KFBO_PHILOX_GROUP_UNROLL;
 
 __device__ __forceinline__ void load_noise_tables(math::LogTables *dst, const math::LogTables *__restrict__ src)
 {
@@ -138,6 +142,7 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
     // table lookups and the log/sqrt chains of one step's normals with the filter recursion of the previous step.
     const int nfull = T >> 2;
     GroupWords r = philox_group(trial, m.stream, 0u, key);
+#pragma unroll KFBO_PHILOX_GROUP_UNROLL_V
     for (int g = 0; g < nfull; ++g) {
         const GroupWords q = philox_group(trial, m.stream, (uint32_t)g + 1u, key, zero);
         const double2 *gs = gu + 4 * g;
