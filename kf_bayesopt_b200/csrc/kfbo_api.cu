@@ -540,7 +540,7 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
                 h->last_launches += 2;
             } else {
                 KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, st, h->d_gu, h->d_logtab, h->max_T, h->p.seed, (uint32_t)t0, ntrials,
-                                                         nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream));
+                                                         nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream, h->h_cases + first));
                 ++h->last_launches;
             }
         }

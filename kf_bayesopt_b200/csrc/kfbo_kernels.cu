@@ -109,6 +109,7 @@ __device__ __forceinline__ void load_noise_tables(math::LogTables *dst, const ma
     for (int i = threadIdx.x; i < (int)(sizeof(math::LogTables) / sizeof(double2)); i += kThreads) ld[i] = ls[i];
 }
 
+template <bool kUniformEst>
 __global__ void __launch_bounds__(kThreads, KFBO_PHILOX_MIN_BLOCKS)
 rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTimeConsts st,
                const double2 *__restrict__ gu_tables, const math::LogTables *__restrict__ logtab,
@@ -119,10 +120,13 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
     extern __shared__ __align__(16) unsigned char s_tables_raw[];
     math::LogTables &s_log = *reinterpret_cast<math::LogTables *>(s_tables_raw);
     const int case_idx = blockIdx.y * gridDim.z + blockIdx.z, tile = blockIdx.x;
-    const Case m = cases[case_idx];
+    Case m = cases[case_idx];
     const int T = m.T;
     const uint32_t zero = (uint32_t)T >> 30;  // 0 (T <= 2000), opaque to the compiler: KFBO_PHILOX_SPLIT_MUL experiment only
     const unsigned kk = st.k0 + blockIdx.z;   // == m.k, but provably uniform
+    if (kUniformEst) {                        // one candidate per launch: its Qd / R come by value, like f and the truth factor
+        m.q00 = pick4(st.q00, kk); m.q01 = pick4(st.q01, kk); m.q11 = pick4(st.q11, kk); m.r_est = pick4(st.r_est, kk);
+    }
     const double f = pick4(st.f, kk), l00 = pick4(st.l00, kk), l10 = pick4(st.l10, kk), l11 = pick4(st.l11, kk),
                  sr = pick4(st.sr, kk);
     const double2 *__restrict__ gu = gu_tables + (size_t)kk * kMaxSteps;
@@ -691,7 +695,7 @@ PhiloxKeys expand_philox_key(uint64_t seed)
 cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, int max_T,
                                   uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
                                   size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
-                                  cudaStream_t stream)
+                                  cudaStream_t stream, const Case *h_cases)
 {
     if (ncases <= 0 || ntrials == 0) return cudaSuccess;
     (void)max_T;
@@ -699,10 +703,18 @@ cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleT
     const size_t smem = sizeof(math::LogTables);
     const dim3 grid((unsigned)tiles, (unsigned)(ncases / st.nk), (unsigned)st.nk);   // ncases = candidates x nk
     // the noise tables (48.4 KB) pass the default 48 KB of shared memory: opt in (per device, a few microseconds)
-    const cudaError_t attr = cudaFuncSetAttribute(rollout_philox, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool uniform_est = h_cases != nullptr && ncases == st.nk;
+    auto *kernel = uniform_est ? rollout_philox<true> : rollout_philox<false>;
+    const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (attr != cudaSuccess) return attr;
-    rollout_philox<<<grid, kThreads, smem, stream>>>(
-        d_cases, st, d_gu, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0, ntrials, tiles,
+    SampleTimeConsts stc = st;
+    if (uniform_est)
+        for (int i = 0; i < st.nk; ++i) {
+            const int k = st.k0 + i;
+            stc.q00[k] = h_cases[i].q00; stc.q01[k] = h_cases[i].q01; stc.q11[k] = h_cases[i].q11; stc.r_est[k] = h_cases[i].r_est;
+        }
+    kernel<<<grid, kThreads, smem, stream>>>(
+        d_cases, stc, d_gu, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0, ntrials, tiles,
         d_per_trial, per_trial_ld, d_partials, d_tickets, d_sums);
     return cudaGetLastError();
 }

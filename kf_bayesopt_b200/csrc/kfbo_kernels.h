@@ -36,6 +36,10 @@ struct Case {
 struct SampleTimeConsts {
     double f[4], l00[4], l10[4], l11[4], sr[4];   // indexed by the sample-time index k < KFBO_MAX_SAMPLE_TIMES
     int32_t k0, nk;                               // a launch covers sample times [k0, k0+nk): grid.z = nk, cases laid out [candidate][k]
+    // A launch of ONE candidate (the "noise" -> "cost" evaluation) also carries that candidate's estimator constants
+    // per sample time, so that they too are uniform-register / parameter-bank operands instead of four doubles loaded
+    // into every thread's vector registers (the kernel sits at its 128-register cap).
+    double q00[4], q01[4], q11[4], r_est[4];
 };
 
 // The 10 Philox4x32 round keys (key + r*Weyl), expanded on the host so the kernel reads them from
@@ -48,10 +52,11 @@ PhiloxKeys expand_philox_key(uint64_t seed);
 // d_cases[ncases]; d_gu[D][kMaxSteps] = (g0*u, g1*u); d_logtab = math::LogTables on the device;
 // trials [trial0, trial0+ntrials).  d_per_trial (optional) is [slots][4][per_trial_ld];
 // d_partials [ncases][tiles][4]; d_tickets [ncases] zero-initialised once; d_sums [slots][4].
+// h_cases (optional): the host copy of d_cases; given, a single-candidate launch passes the estimator constants by value.
 cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, int max_T,
                                   uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
                                   size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
-                                  cudaStream_t stream);
+                                  cudaStream_t stream, const Case *h_cases = nullptr);
 
 // Reduced form (opt-in): per step of a case the gain K, 1/S and P^-1 = [[a, b/2], [b/2, c]], tabulated once
 // per case by riccati_gains; d_gains holds ncases x gain_stride_for(max_T) entries.
