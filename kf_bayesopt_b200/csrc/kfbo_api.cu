@@ -83,7 +83,7 @@ struct kfbo_handle {
     double truth_l[KFBO_MAX_SAMPLE_TIMES][3]{};
     double truth_sr[KFBO_MAX_SAMPLE_TIMES]{};
     double fd01[KFBO_MAX_SAMPLE_TIMES]{};
-    int max_T = 0;
+    int max_T = 0, min_T = kfbo::kMaxSteps;
     kfbo::SampleTimeConsts st{};       // per-sample-time constants, passed to the kernels by value
     // per-evaluation buffers (sized at create)
     Case *d_cases = nullptr, *h_cases = nullptr;
@@ -416,6 +416,7 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
         h->st.f[k] = Fd[1]; h->st.l00[k] = h->truth_l[k][0]; h->st.l10[k] = h->truth_l[k][1];
         h->st.l11[k] = h->truth_l[k][2]; h->st.sr[k] = h->truth_sr[k];
         h->max_T = std::max(h->max_T, p->max_iterations[k]);
+        h->min_T = std::min(h->min_T, p->max_iterations[k]);
     }
     if (cu(cudaMalloc(&h->d_gu, gu.size() * sizeof(double2)), "cudaMalloc(gu)")) return bail(KFBO_ECUDA);
     if (cu(cudaMemcpy(h->d_gu, gu.data(), gu.size() * sizeof(double2), cudaMemcpyHostToDevice), "cudaMemcpy(gu)")) return bail(KFBO_ECUDA);
@@ -539,7 +540,7 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
                                                                  ntrials, nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream));
                 h->last_launches += 2;
             } else {
-                KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, st, h->d_gu, h->d_logtab, h->max_T, h->p.seed, (uint32_t)t0, ntrials,
+                KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, st, h->d_gu, h->d_logtab, h->min_T, h->p.seed, (uint32_t)t0, ntrials,
                                                          nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream, h->h_cases + first));
                 ++h->last_launches;
             }
@@ -731,7 +732,7 @@ int kfbo_eval_philox_trials(kfbo_handle *h, int32_t k, double q_est, double r_es
         KFBO_CUDA(h, kfbo::launch_rollout_philox_reduced(d_case, 1, st, h->d_gains, h->d_logtab, h->max_T, h->p.seed, trial0, (uint32_t)ntrials,
                                                          h->d_scratch[4], (size_t)ntrials, d_partials, d_ticket, d_sums, h->stream));
     else
-        KFBO_CUDA(h, kfbo::launch_rollout_philox(d_case, 1, st, h->d_gu, h->d_logtab, h->max_T, h->p.seed, trial0, (uint32_t)ntrials, h->d_scratch[4],
+        KFBO_CUDA(h, kfbo::launch_rollout_philox(d_case, 1, st, h->d_gu, h->d_logtab, h->min_T, h->p.seed, trial0, (uint32_t)ntrials, h->d_scratch[4],
                                                  (size_t)ntrials, d_partials, d_ticket, d_sums, h->stream));
     KFBO_CUDA(h, cudaMemcpyAsync(per_trial, h->d_scratch[4], 4 * (size_t)ntrials * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     KFBO_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -115,6 +115,19 @@ __device__ __forceinline__ GroupWords philox_group(uint32_t trial, uint32_t stre
 #define KFBO_RCP(x) ::kfbo::math::rcp(x)
 #endif
 
+// The one-pass time variance of trial.cpp:84-98 is formed from SHIFTED sums, sum (v - k) and sum (v - k)^2; its cancellation
+// error is eps (1 + (mean - k)^2 / variance).  Two shift policies (template parameter kShiftFirst of filter_step):
+//   kShiftFirst = true : k = the trial's first sample -- within a few standard deviations of the mean whatever the
+//       samples are, exact for T = 2.  Costs two registers, two predicated multiplies per step group, and makes the shifted
+//       value a DFMA with three distinct vector-register sources (2.9 FP64-pipe cycles instead of 2.0, microbench/rf_ports.cu).
+//   kShiftFirst = false: k = the value a consistent filter averages to (trial.cpp:77,93 compare against exactly these:
+//       stateDOF = 2, observationDOF = 1) -- an immediate operand.  For chi-square-like samples (mean - k)^2 / variance is
+//       O(1) as soon as a trial has more than a handful of steps; only for very short trials can the samples of one
+//       trial coincide to many digits (T = 2: |a - b| << |a - k| with probability ~ that ratio), so the launchers take
+//       this policy only when every case of the launch has T >= kMinStepsConstShift.  Measured: 13.37 -> 13.10 ms (cfg3).
+constexpr int kMinStepsConstShift = 32;
+constexpr double kShiftNees = 2.0, kShiftNis = 1.0;
+
 // Per-trajectory register state.
 struct Traj {
     double x0, x1;               // truth state            (Simulator::x_)
@@ -123,17 +136,19 @@ struct Traj {
                                  // symmetrises; P(0,1) and P(1,0) are equal in exact arithmetic (Ppred is
                                  // symmetric and P = (I-KH)Ppred with K = Ppred H^T/S), they differ by
                                  // rounding only (~1e-16, contracting), far inside the 1e-9 parity bound.
-    double kn, ki;               // shift = first NEES / NIS sample of the trial
+    double kn, ki;               // the shift k of the sums below (constants unless KFBO_SHIFT_FIRST_SAMPLE)
     double sdn, sqn, sdi, sqi;   // sum (v-k), sum (v-k)^2 for NEES and NIS
 };
 
+template <bool kShiftFirst = true>
 __device__ __forceinline__ void traj_init(Traj &t, double x0n0, double x0n1)
 {
     t.x0 = 0.0 + x0n0;           // x0 = 0, P0 = I hard-coded (trial.cpp:31-32); simulator.cpp:12
     t.x1 = 0.0 + x0n1;
     t.xh0 = 0.0; t.xh1 = 0.0;    // kalman_filter.cpp:14-15
     t.p00 = 1.0; t.p01 = 0.0; t.p11 = 1.0;
-    t.kn = 0.0; t.ki = 0.0;
+    t.kn = kShiftFirst ? 0.0 : kShiftNees;
+    t.ki = kShiftFirst ? 0.0 : kShiftNis;
     t.sdn = 0.0; t.sqn = 0.0; t.sdi = 0.0; t.sqi = 0.0;
 }
 
@@ -149,7 +164,7 @@ struct StepProbe { double nees, nis; };
 // gu = g*u[step] = (0.5 dt^2 u, dt u), rounded products exactly as the reference forms them.
 // f = Fd(0,1) comes in as a uniform value (SampleTimeConsts), the candidate's Qd / R from the Case.
 // kFused: noise = standard normals (n0, n1, n2), l00/l10/l11/sr = the truth transform.
-template <bool kFirst, bool kFused>
+template <bool kFirst, bool kFused, bool kShiftFirst = true>
 __device__ __forceinline__ void filter_step(Traj &t, const Case &m, const double f, double2 gu, const StepNoise nz,
                                             const double l00 = 0.0, const double l10 = 0.0, const double l11 = 0.0,
                                             const double sr = 0.0, StepProbe *probe = nullptr, const bool first_rt = false)
@@ -202,9 +217,15 @@ __device__ __forceinline__ void filter_step(Traj &t, const Case &m, const double
     if (probe != nullptr) { probe->nees = num * invdet; probe->nis = nu_s * nu; }
     // first_rt: the same for callers that only know at run time whether this is the trial's first step (a uniform
     // predicate on two multiplies instead of a branch, so that a whole step group stays one basic block)
-    if (kFirst || first_rt) { t.kn = num * invdet; t.ki = nu_s * nu; }
-    const double dn = fma(num, invdet, -t.kn);
-    const double di = fma(nu_s, nu, -t.ki);
+    double dn, di;
+    if (kShiftFirst) {
+        if (kFirst || first_rt) { t.kn = num * invdet; t.ki = nu_s * nu; }
+        dn = fma(num, invdet, -t.kn);
+        di = fma(nu_s, nu, -t.ki);
+    } else {
+        dn = fma(num, invdet, -kShiftNees);
+        di = fma(nu_s, nu, -kShiftNis);
+    }
     t.sdn += dn; t.sqn = fma(dn, dn, t.sqn);
     t.sdi += di; t.sqi = fma(di, di, t.sqi);
 }

@@ -109,7 +109,7 @@ __device__ __forceinline__ void load_noise_tables(math::LogTables *dst, const ma
     for (int i = threadIdx.x; i < (int)(sizeof(math::LogTables) / sizeof(double2)); i += kThreads) ld[i] = ls[i];
 }
 
-template <bool kUniformEst>
+template <bool kUniformEst, bool kShiftFirst>
 __global__ void __launch_bounds__(kThreads, KFBO_PHILOX_MIN_BLOCKS)
 rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTimeConsts st,
                const double2 *__restrict__ gu_tables, const math::LogTables *__restrict__ logtab,
@@ -140,7 +140,7 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
         double a, b;
         const uint4 w = philox4x32_10(trial, m.stream, 0u, 0u, key);
         math::normal_pair(w.x, w.y, s_log, a, b);
-        traj_init(t, a, b);
+        traj_init<kShiftFirst>(t, a, b);
     }
     // Whole groups of four steps: ONE basic block per group (no branch inside), so the scheduler is free to overlap the
     // table lookups and the log/sqrt chains of one step's normals with the filter recursion of the previous step.
@@ -155,13 +155,13 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
         math::normal_pair(r.c.x, r.c.y, s_log, o0, o1);
         math::normal_pair(r.a.x, r.a.y, s_log, p0a, p0b);
         math::normal_pair(r.a.z, r.a.w, s_log, p1a, p1b);
-        filter_step<false, true>(t, m, f, g0, StepNoise{p0a, p0b, o0}, l00, l10, l11, sr, nullptr, g == 0);
+        filter_step<false, true, kShiftFirst>(t, m, f, g0, StepNoise{p0a, p0b, o0}, l00, l10, l11, sr, nullptr, g == 0);
         math::normal_pair(r.c.z, r.c.w, s_log, o2, o3);
         math::normal_pair(r.b.x, r.b.y, s_log, p2a, p2b);
-        filter_step<false, true>(t, m, f, g1, StepNoise{p1a, p1b, o1}, l00, l10, l11, sr);
+        filter_step<false, true, kShiftFirst>(t, m, f, g1, StepNoise{p1a, p1b, o1}, l00, l10, l11, sr);
         math::normal_pair(r.b.z, r.b.w, s_log, p3a, p3b);
-        filter_step<false, true>(t, m, f, g2, StepNoise{p2a, p2b, o2}, l00, l10, l11, sr);
-        filter_step<false, true>(t, m, f, g3, StepNoise{p3a, p3b, o3}, l00, l10, l11, sr);
+        filter_step<false, true, kShiftFirst>(t, m, f, g2, StepNoise{p2a, p2b, o2}, l00, l10, l11, sr);
+        filter_step<false, true, kShiftFirst>(t, m, f, g3, StepNoise{p3a, p3b, o3}, l00, l10, l11, sr);
         r = q;
     }
     // the partial last group (T mod 4 steps); its unused normals are never formed
@@ -170,15 +170,15 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
         double pa, pb, o0, o1;
         math::normal_pair(r.c.x, r.c.y, s_log, o0, o1);
         math::normal_pair(r.a.x, r.a.y, s_log, pa, pb);
-        filter_step<false, true>(t, m, f, __ldg(gu + sT), StepNoise{pa, pb, o0}, l00, l10, l11, sr, nullptr, nfull == 0);
+        filter_step<false, true, kShiftFirst>(t, m, f, __ldg(gu + sT), StepNoise{pa, pb, o0}, l00, l10, l11, sr, nullptr, nfull == 0);
         if (rem > 1) {
             math::normal_pair(r.a.z, r.a.w, s_log, pa, pb);
-            filter_step<false, true>(t, m, f, __ldg(gu + sT + 1), StepNoise{pa, pb, o1}, l00, l10, l11, sr);
+            filter_step<false, true, kShiftFirst>(t, m, f, __ldg(gu + sT + 1), StepNoise{pa, pb, o1}, l00, l10, l11, sr);
         }
         if (rem > 2) {
             math::normal_pair(r.c.z, r.c.w, s_log, o0, o1);
             math::normal_pair(r.b.x, r.b.y, s_log, pa, pb);
-            filter_step<false, true>(t, m, f, __ldg(gu + sT + 2), StepNoise{pa, pb, o0}, l00, l10, l11, sr);
+            filter_step<false, true, kShiftFirst>(t, m, f, __ldg(gu + sT + 2), StepNoise{pa, pb, o0}, l00, l10, l11, sr);
         }
     }
     double out[4] = {0.0, 0.0, 0.0, 0.0};
@@ -692,19 +692,21 @@ PhiloxKeys expand_philox_key(uint64_t seed)
     return k;
 }
 
-cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, int max_T,
+cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, int min_T,
                                   uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
                                   size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
                                   cudaStream_t stream, const Case *h_cases)
 {
     if (ncases <= 0 || ntrials == 0) return cudaSuccess;
-    (void)max_T;
     const int tiles = rollout_tiles(ntrials);
     const size_t smem = sizeof(math::LogTables);
     const dim3 grid((unsigned)tiles, (unsigned)(ncases / st.nk), (unsigned)st.nk);   // ncases = candidates x nk
     // the noise tables (48.4 KB) pass the default 48 KB of shared memory: opt in (per device, a few microseconds)
     const bool uniform_est = h_cases != nullptr && ncases == st.nk;
-    auto *kernel = uniform_est ? rollout_philox<true> : rollout_philox<false>;
+    // shift policy of the one-pass time variance (kfbo_device.cuh): the constant shift only when no trial is very short
+    const bool shift_first = min_T < kMinStepsConstShift;
+    auto *kernel = uniform_est ? (shift_first ? rollout_philox<true, true> : rollout_philox<true, false>)
+                               : (shift_first ? rollout_philox<false, true> : rollout_philox<false, false>);
     const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (attr != cudaSuccess) return attr;
     SampleTimeConsts stc = st;

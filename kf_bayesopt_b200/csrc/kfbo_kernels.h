@@ -53,7 +53,8 @@ PhiloxKeys expand_philox_key(uint64_t seed);
 // trials [trial0, trial0+ntrials).  d_per_trial (optional) is [slots][4][per_trial_ld];
 // d_partials [ncases][tiles][4]; d_tickets [ncases] zero-initialised once; d_sums [slots][4].
 // h_cases (optional): the host copy of d_cases; given, a single-candidate launch passes the estimator constants by value.
-cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, int max_T,
+// min_T: the smallest step count among the cases of the launch (selects the shift policy of the time variance, kfbo_device.cuh).
+cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, int min_T,
                                   uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
                                   size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
                                   cudaStream_t stream, const Case *h_cases = nullptr);

@@ -29,6 +29,18 @@
 #define KFBO_HD inline
 #endif
 
+// KFBO_SQRT_PRODUCT_FORM: the last step of sqrt_pos as g * (1 + r t) (1) or as g + (g r) t (0).  (1) has no DFMA with three
+//   distinct vector-register sources (2.9 pipe cycles instead of 2.0, tools/microbench/rf_ports.cu) and costs 1 ulp.
+// KFBO_LOG_DEGREE: 4 = the Taylor polynomial of -2 ln(1+r)/r to r^4 (<= 1.7 ulp); 30 = degree 3 with the r^4 term folded
+//   into the lower coefficients (one DFMA fewer per normal pair; <= 15 ulp of L, i.e. <= 3e-18 absolute where L is small).
+// Measured on the cfg3 evaluation together with KFBO_SHIFT_FIRST_SAMPLE = 0 (kfbo_device.cuh): 13.37 -> 12.99 ms.
+#ifndef KFBO_SQRT_PRODUCT_FORM
+#define KFBO_SQRT_PRODUCT_FORM 1
+#endif
+#ifndef KFBO_LOG_DEGREE
+#define KFBO_LOG_DEGREE 30
+#endif
+
 namespace kfbo {
 namespace math {
 
@@ -156,7 +168,7 @@ KFBO_HD double rcp(double x)
     return fma(y, t, y);
 }
 
-// sqrt(a) to <= 1 ulp for normal a > 0: g = a y0 = sqrt(a)(1 - e), r = 1/2 - g y0/2 = e - e^2/2, and
+// sqrt(a) to <= 2 ulp for normal a > 0: g = a y0 = sqrt(a)(1 - e), r = 1/2 - g y0/2 = e - e^2/2, and
 // sqrt(a) = g (1 - 2r)^(-1/2) = g (1 + r + 3/2 r^2 + O(r^3)): one third-order step on the 20-bit seed
 // (|r|^3 < 2^-57), 5 FP64 instructions instead of the 7 of two coupled Goldschmidt iterations.
 KFBO_HD double sqrt_pos(double a)
@@ -167,7 +179,11 @@ KFBO_HD double sqrt_pos(double a)
     const double g = a * y, h = make_double(hi_word(y) - 0x00100000u, lo_word(y));
     const double r = fma(-h, g, 0.5);
     const double t = fma(r, 1.5, 1.0);
+#if KFBO_SQRT_PRODUCT_FORM
+    return g * fma(r, t, 1.0);            // no DFMA with three distinct vector-register sources (3 pipe cycles); <= 2 ulp
+#else
     return fma(g * r, t, g);
+#endif
 }
 
 #if defined(__CUDACC__)
@@ -176,12 +192,18 @@ KFBO_HD double sqrt_pos(double a)
 #define KFBO_CONST static const
 #endif
 
-// -2 ln(1+r)/r = -2 + r - (2/3) r^2 + (2/4) r^3 - (2/5) r^4 + ... ; |r| <= 2^-11 (1024 sub-intervals): the first
+// -2 ln(1+r)/r = -2 + r - (2/3) r^2 + (2/4) r^3 - (2/5) r^4 + ... ; |r| <= h = 2^-11 (1024 sub-intervals): the first
 // dropped term (1/3) r^5 is < 5e-18 of the leading -2.
-// -2, 1, 1/2 are immediates, the hi32-rounded -2/5 too (its 4e-7 relative rounding is scaled by r^4 < 6e-14);
-// -2/3 needs full precision.
+// Degree 4 (KFBO_LOG_DEGREE 4): -2, 1, 1/2 are immediates, the hi32-rounded -2/5 too (its 4e-7 relative rounding is
+// scaled by r^4 < 6e-14); -2/3 needs full precision.
 KFBO_CONST double kLogPolyU[1] = {-2.0 / 3.0};
 #define KFBO_LOG_C4 -0x1.9999900000000p-2
+// Degree 3 (KFBO_LOG_DEGREE 30, the default): Chebyshev economisation of the r^4 term.  On |r| <= h,
+// r^4 = h^2 r^2 - h^4/8 + (h^4/8) T4(r/h), so -(2/5) r^4 ~ -(2/5) h^2 r^2 + (1/20) h^4 with |error| <= h^4/20 = 2.8e-15
+// of the leading -2 -- 1.4e-15 relative on r * poly, which is the whole of L only next to u = 1 (L < 2^-10).
+// What matters downstream is the ABSOLUTE error of a normal draw, rad * (cos, sin) with rad = sqrt(L): 3e-15 for |n| up
+// to 7.9 in either form (tests/native/math_check.cpp), unchanged.
+KFBO_CONST double kLogPolyE[2] = {-2.0 / 3.0 - 0.4 * 0x1p-22, -2.0 + 0.05 * 0x1p-44};
 // L = -2 ln(u) for u in [2^-52, 1): table-driven, no division, no branch.
 //   u = 2^k z, z in [0.6875, 1.375);  i = top 10 bits of (bits(z) - OFF);  r = z/c_i - 1, |r| <= 2^-11
 //   -2 ln u = 2 (-k) ln2 + 2 ln(invc_i) + r * (-2 ln(1+r)/r)
@@ -195,10 +217,18 @@ KFBO_HD double neg2_log(double u, const double (*tab)[2])
     const double z = make_double(hi - ((uint32_t)tmp & 0xFFF00000u), lo);
     const double invc = tab[i][0], logc2 = tab[i][1];
     const double r = fma(z, invc, -1.0);
+#if KFBO_LOG_DEGREE == 4
     double s = fma(KFBO_LOG_C4, r, 0.5);
     s = fma(s, r, kLogPolyU[0]);
+#else   // 30: degree 3 with the dropped r^4 term folded into the r^2 and constant coefficients (Chebyshev economisation)
+    double s = fma(0.5, r, kLogPolyE[0]);
+#endif
     s = fma(s, r, 1.0);
+#if KFBO_LOG_DEGREE == 30
+    s = fma(s, r, kLogPolyE[1]);
+#else
     s = fma(s, r, -2.0);
+#endif
     // the exponent's share -2 k ln 2 by one conversion + multiply-add (k in [-52, 0] is exact in FP64); a 53-entry table
     // would cost a shared-memory lookup, and shared-memory wavefronts are the scarcer resource (measured: 13.42 vs 13.59 ms)
 #if defined(__CUDA_ARCH__)

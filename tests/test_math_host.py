@@ -15,7 +15,8 @@ def test_custom_math_accuracy(tmp_path):
     # ulps against the correctly rounded result; the normals' absolute error (|n| <= 8.5)
     assert got["rcp_ulp"] <= 1.0
     assert got["sqrt_ulp"] <= 2.0
-    assert got["neg2log_ulp"] <= 2.5
+    # degree-3 economised polynomial (KFBO_LOG_DEGREE 30): <= 15 ulp of L, reached only where L < 2^-10
+    assert got["neg2log_ulp"] <= 15.0
     # sin/cos of the Box-Muller angle: absolute error in units of 2^-53 (half an ulp of 1)
     assert got["sin_ulp"] <= 3.0 and got["cos_ulp"] <= 3.0
     assert got["na_abs"] < 4e-15 and got["nb_abs"] < 4e-15

@@ -5,9 +5,10 @@
 template <int MODE>
 __global__ void __launch_bounds__(256) k(double *out, int iters, double a, double b)
 {
-    double x[8], y[8], z[8];
+    double x[8], y[8], z[8], w[8];
+    const double c = 1.0 - 1e-9 * threadIdx.x;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { x[j] = threadIdx.x + j; y[j] = 1.0 + 1e-9 * (threadIdx.x + j); z[j] = 1e-9 * j * threadIdx.x; }
+    for (int j = 0; j < 8; ++j) { x[j] = threadIdx.x + j; y[j] = 1.0 + 1e-9 * (threadIdx.x + j); z[j] = 1e-9 * j * threadIdx.x; w[j] = 0.5 * threadIdx.x - j; }
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int u = 0; u < 8; ++u)
@@ -19,11 +20,14 @@ __global__ void __launch_bounds__(256) k(double *out, int iters, double a, doubl
                 if (MODE == 3) x[j] = fma(x[j], y[j], x[j]);      // 3 slots, 2 distinct
                 if (MODE == 4) x[j] = x[j] * y[j];                // DMUL 2
                 if (MODE == 5) x[j] = x[j] + y[j];                // DADD 2
+                if (MODE == 6) x[j] = fma(c, x[j], z[j]);         // 3 distinct, one of them the same register in every instruction (.reuse)
+                if (MODE == 7) { x[j] = fma(x[j], y[j], z[j]); w[j] = fma(w[j], a, b); }   // 3 distinct interleaved with 1 source: do the register reads average out?
+                if (MODE == 8) { x[j] = fma(x[j], y[j], z[j]); w[j] = fma(w[j], y[j], b); } // 3 distinct + 2 sources, the second re-reading y[j] in the same slot
             }
     }
     double s = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += x[j] + y[j] + z[j];
+    for (int j = 0; j < 8; ++j) s += x[j] + y[j] + z[j] + w[j];
     if (s == 123.456) out[0] = s;
 }
 
@@ -43,7 +47,7 @@ void run(double *d, const char *name)
     cudaEventSynchronize(e1);
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
-    const double instr_per_smsp = (double)iters * 64 * (blocks * 256 / 32) / (p.multiProcessorCount * 4);
+    const double instr_per_smsp = (double)iters * (MODE >= 7 ? 128 : 64) * (blocks * 256 / 32) / (p.multiProcessorCount * 4);
     std::printf("%-40s %.2f cycles per instruction per SMSP\n", name, ms * 1e-3 * p.clockRate * 1e3 / instr_per_smsp);
 }
 
@@ -57,5 +61,8 @@ int main()
     run<3>(d, "DFMA x = fma(x, y, x)   2 distinct");
     run<4>(d, "DMUL x = x * y");
     run<5>(d, "DADD x = x + y");
+    run<6>(d, "DFMA x = fma(c, x, z)   3 distinct, c reused");
+    run<7>(d, "DFMA 3 distinct + DFMA 1 source, alternating");
+    run<8>(d, "DFMA 3 distinct + DFMA 2 sources (y re-read)");
     return 0;
 }
