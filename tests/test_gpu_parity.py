@@ -90,7 +90,9 @@ def test_philox_trials_match_oracle_draw_for_draw(kfbo, oracle):
     seed = 0x0123456789ABCDEF
     rv = kfbo.ReadParaVehicle(nsimruns_=300, cpu_core_number_=1)
     # step counts of every residue mod 4 (the noise comes in groups of four steps), including less than one group
-    for times in (CODE_TIMES, README_TIMES, [(0.1, 200), (0.5, 2)], [(0.1, 3), (0.5, 4), (1.0, 5), (0.2, 6)], [(0.1, 7), (0.5, 1999)]):
+    # ... and both sides of the 32-step bound below which the kernel shifts its variance sums by the first sample
+    for times in (CODE_TIMES, README_TIMES, [(0.1, 200), (0.5, 2)], [(0.1, 3), (0.5, 4), (1.0, 5), (0.2, 6)], [(0.1, 7), (0.5, 1999)],
+                  [(0.1, 31), (0.5, 40)], [(0.1, 32), (0.5, 33)]):
         with kfbo.CostEvaluator(rv, times, seed=seed) as ev:
             for k, (dt, T) in enumerate(times):
                 for qe, re, stream, trial0 in [(1.0, 0.1, 0, 0), (0.3, 0.7, 77, 1000), (4.0, 0.02, 0xFFFFFFFE, 0xFFFFFF00)]:
@@ -98,6 +100,35 @@ def test_philox_trials_match_oracle_draw_for_draw(kfbo, oracle):
                     got = ev.eval_philox_trials(k, qe, re, stream, trial0, n)
                     want = oracle.eval_philox(seed, stream, dt, T, Q_TRUTH, R_TRUTH, qe, re, trial0, n)
                     assert rel_err(got, want) < RTOL, (times, k, qe, stream)
+
+
+def test_random_configurations_match_oracle(kfbo, oracle):
+    # seeded sweep over what the fixed cases above hold constant: the TRUTH noise levels (pnoise_ / onoise_ of the
+    # simulator's ReadParaVehicle), the sample time, the step count, a ragged trial count and the candidate
+    rng = np.random.default_rng(20261020)
+    for case in range(16):
+        dt = float(rng.choice([0.05, 0.1, 0.2, 0.25, 0.5, 1.0]))
+        T = int(rng.integers(2, 400))
+        B = int(rng.integers(1, 300))
+        q_truth, r_truth = float(np.exp(rng.uniform(np.log(0.05), np.log(5.0)))), float(np.exp(rng.uniform(np.log(0.01), np.log(1.0))))
+        q_est, r_est = float(np.exp(rng.uniform(np.log(0.05), np.log(5.0)))), float(np.exp(rng.uniform(np.log(0.01), np.log(1.0))))
+        stream, trial0 = int(rng.integers(0, 2**32 - 1)), int(rng.integers(0, 2**32 - 512))
+        seed = int(rng.integers(0, 2**63))
+        rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1, pnoise_=[q_truth], onoise_=[r_truth])
+        with kfbo.CostEvaluator(rv, [(dt, T)], seed=seed) as ev:
+            got = ev.eval_philox_trials(0, q_est, r_est, stream, trial0, B)
+            want = oracle.eval_philox(seed, stream, dt, T, q_truth, r_truth, q_est, r_est, trial0, B)
+            assert rel_err(got, want) < RTOL, (case, dt, T, B, q_truth, r_truth, q_est, r_est)
+            # the same candidate against supplied draws of that truth model
+            _, Qd = oracle.discretize(q_truth, dt)
+            L = np.linalg.cholesky(Qd)
+            x0n = rng.standard_normal((2, B))
+            w = np.ascontiguousarray(np.einsum("ij,tjb->tib", L, rng.standard_normal((T, 2, B))))
+            v = np.sqrt(r_truth / dt) * rng.standard_normal((T, B))
+            pt, sm = ev.eval_supplied(0, q_est, r_est, x0n, w, v)
+            want = oracle.eval_supplied(dt, T, q_est, r_est, x0n, w, v)
+            assert rel_err(pt[0], want) < RTOL, (case, dt, T, B)
+            assert rel_err(sm[0], want.sum(axis=1)) < RTOL
 
 
 def test_eval_batch_sums_match_oracle_and_selection_is_identical(kfbo, oracle):
