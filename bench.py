@@ -64,19 +64,55 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons / power DURING the timed region (B200_PROFILING.md recipe).  Sampled through NVML
+    (the library nvidia-smi reads) every 10 ms from a thread of this process, so that a timed region of a few tens of
+    milliseconds (8 GPUs) still holds samples; the nvidia-smi loop of the recipe (100 ms) is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.source, self._stop = [], None, index, None, False
+
+    def _nvml_loop(self, nv, dev):
+        bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+        mx = str(nv.nvmlDeviceGetMaxClockInfo(dev, nv.NVML_CLOCK_SM))
+        while not self._stop:
+            try:
+                why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(dev)
+                row = [str(nv.nvmlDeviceGetClockInfo(dev, nv.NVML_CLOCK_SM)), mx, str(nv.nvmlDeviceGetPowerUsage(dev) / 1e3)]
+                row += ["Active" if why & b else "Not Active" for b in bits]
+                self.rows.append((time.perf_counter(), row))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            uuid = str(self.index)
+            if uuid.startswith("GPU-"):
+                try:
+                    dev = nv.nvmlDeviceGetHandleByUUID(uuid)
+                except TypeError:
+                    dev = nv.nvmlDeviceGetHandleByUUID(uuid.encode())
+            else:
+                dev = nv.nvmlDeviceGetHandleByIndex(int(uuid))
+            nv.nvmlDeviceGetClockInfo(dev, nv.NVML_CLOCK_SM)
+            self.source = "nvml, 10 ms"
+            self.t = threading.Thread(target=self._nvml_loop, args=(nv, dev), daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 100"
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -87,18 +123,23 @@ class ClockSampler:
             self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self, t0: float, t1: float):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1] or [r for _, r in self.rows]
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"]}
+        time.sleep(0.15 if self.proc is not None else 0.02)
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
+        window = "timed region"
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
+        if not rows:       # a region shorter than the sampling period: the samples right around it
+            rows, window = [r for t, r in self.rows if t0 - 0.15 <= t <= t1 + 0.15] or [r for _, r in self.rows], "around the timed region"
         sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows for n, v in zip(self.NAMES, r[3:7]) if v.lower().startswith("active")})
         power = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
                 "sm_max_mhz": float(rows[0][1]) if rows and rows[0][1].replace(".", "").isdigit() else None,
-                "power_w_max": max(power) if power else None, "samples": len(rows), "reasons": reasons}
+                "power_w_max": max(power) if power else None, "samples": len(rows), "reasons": reasons,
+                "source": self.source, "window": window}
 
 
 def cpu_reference_run(steps: int, warmup: int, budget_s: float, kind: str = "auto"):
@@ -248,6 +289,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-supplied", action="store_true", help="skip the supplied-noise (HBM roofline) leg")
     ap.add_argument("--no-reduced", action="store_true", help="skip the reduced-form leg")
+    ap.add_argument("--reduce", default="auto", choices=["auto", "nccl"],
+                    help="N > 1: how the cost sums of the ranks meet -- auto = the peer-memory exchange in the tail of the "
+                         "rollout kernel when the ranks can map each other's buffers, nccl = one ncclAllReduce")
+    ap.add_argument("--peer-fuse", default="auto", choices=["auto", "never", "always"],
+                    help="N > 1, peer-memory exchange: in the tail of the rollout kernel or as a kernel behind it (KFBO_OPT_PEER_FUSE)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "kfbo" else args.warmup
 
@@ -297,7 +343,9 @@ def main():
     stream = torch.cuda.Stream()           # the stream every kernel of the evaluator is launched on
     ev.set_cuda_stream(stream.cuda_stream)
     if world > 1:
-        init_comm(ev, shard)
+        init_comm(ev, shard, peer=(args.reduce == "auto"))
+        from kf_bayesopt_b200 import _lib as L0
+        ev.set_option(L0.OPT_PEER_FUSE, {"never": L0.PEER_FUSE_NEVER, "auto": L0.PEER_FUSE_AUTO, "always": L0.PEER_FUSE_ALWAYS}[args.peer_fuse])
     steps_per_eval = float(trials) * n_cand * sum(T for _, T in sample_times)
 
     class _First:   # the first candidate of a batch, shaped like Result where the JSON line reads it
@@ -332,6 +380,7 @@ def main():
     e1.record(stream)
     barrier()
     t1 = time.perf_counter()
+    reduce_path = ev.last_reduce_path()
     clocks = sampler.stop(t0, t1)
     elapsed_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -375,7 +424,9 @@ def main():
                                    "MEASURED_PEAKS.json has no FP64 figure",
                     "flops_per_filter_step": FLOPS_PER_STEP, "kernel_ms": k_ms,
                     "filter_steps_per_launch": local_steps,
-                    "note": "tensor cores do not apply (2x2 FP64 recursion); RNG flops are excluded from 'achieved'"}
+                    "note": "tensor cores do not apply (2x2 FP64 recursion); RNG flops are excluded from 'achieved'" +
+                            ("; kernel_ms at N > 1 includes the in-kernel wait for the other ranks' sums when the exchange is fused"
+                             if world > 1 else "")}
         line_extra["roofline"] = roofline
 
     # ---- the opt-in reduced form (KFBO_FORM_REDUCED) on the same workload and streams: reported on its own
@@ -442,8 +493,8 @@ def main():
                 "config": {"workload": workload, "trials": trials, "candidates": n_cand,
                            "sample_times": sample_times,
                            "candidate": "64 x 64 log grid over q in [0.1,5], r in [0.01,1]" if cfg4 else {"pnoise": CANDIDATE[0], "onoise": CANDIDATE[1]},
-                           "sharding": (f"{'candidates' if cfg4 else 'trials'} over {world} rank(s), one ncclAllReduce of "
-                                        f"{n_cand * D * 4} doubles") if world > 1 else "single GPU",
+                           "sharding": (f"{'candidates' if cfg4 else 'trials'} over {world} rank(s); the {n_cand * D * 4} doubles of "
+                                        f"cost sums meet by: {reduce_path}") if world > 1 else "single GPU",
                            "l2": "n/a for the Philox path: no HBM-resident inputs (noise is generated on the fly); "
                                  "the supplied-noise leg streams 25 GB >> L2"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

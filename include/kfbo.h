@@ -38,7 +38,8 @@ enum {
     KFBO_ENODEVICE = -3,   /* no usable CUDA device: there is no CPU fallback */
     KFBO_ESTATE = -4,      /* call not valid in this state (e.g. comm already initialised) */
     KFBO_ECUDA = 1,        /* a CUDA runtime call failed; see kfbo_last_error */
-    KFBO_ENCCL = 2         /* an NCCL call failed; see kfbo_last_error */
+    KFBO_ENCCL = 2,        /* an NCCL call failed; see kfbo_last_error */
+    KFBO_EPEER = 3         /* the peer-memory exchange of the cost sums timed out waiting for a rank */
 };
 
 /* how a multi-rank evaluation is partitioned (kfbo_comm_init) */
@@ -165,7 +166,10 @@ int kfbo_set_cuda_stream(kfbo_handle *h, void *cuda_stream);
  * streams are 16-byte aligned and B is even, else the per-thread-load kernel. */
 enum { KFBO_OPT_SUPPLIED_KERNEL = 1, KFBO_OPT_BULK_SMEM_PAD = 2 /* extra dynamic shared memory (bytes) per CTA of the
                                         bulk-copy kernel: lowers the CTAs resident per SM */,
-       KFBO_OPT_ROLLOUT_FORM = 3 };
+       KFBO_OPT_ROLLOUT_FORM = 3,
+       KFBO_OPT_REDUCE = 4 /* how the cost sums of a multi-GPU evaluation meet, KFBO_REDUCE_* below */,
+       KFBO_OPT_PEER_FUSE = 5 /* KFBO_PEER_FUSE_* below */,
+       KFBO_OPT_PEER_TIMEOUT_MS = 6 /* how long the exchange waits for a rank before KFBO_EPEER (default 10000) */ };
 /* KFBO_OPT_ROLLOUT_FORM, for the on-device-noise evaluations (kfbo_eval, kfbo_eval_batch, kfbo_eval_philox_trials):
  *   KFBO_FORM_REFERENCE (default): every trajectory carries truth state, estimate and covariance and runs
  *       simulator.cpp:15-19 + kalman_filter.cpp:18-38 + trial.cpp:53-60 step by step, as north_star prescribes.
@@ -175,20 +179,51 @@ enum { KFBO_OPT_SUPPLIED_KERNEL = 1, KFBO_OPT_BULK_SMEM_PAD = 2 /* extra dynamic
  *       instructions in the filter part.  The supplied-noise parity entry points always use the reference form. */
 enum { KFBO_FORM_REFERENCE = 0, KFBO_FORM_REDUCED = 1 };
 enum { KFBO_SUPPLIED_AUTO = 0, KFBO_SUPPLIED_LDG = 1, KFBO_SUPPLIED_BULK = 2 };
+/* KFBO_OPT_REDUCE (set it to the same value on every rank):
+ *   KFBO_REDUCE_AUTO (default): the peer-memory exchange (below) when the ranks are attached to each other, else NCCL;
+ *   KFBO_REDUCE_NCCL: always one ncclAllReduce.
+ * KFBO_OPT_PEER_FUSE: where the exchange runs -- KFBO_PEER_FUSE_AUTO (default) and KFBO_PEER_FUSE_NEVER: as a small
+ *   kernel launched behind the rollout on the same stream; KFBO_PEER_FUSE_ALWAYS: in the tail of the rollout kernel itself
+ *   (the CTA that finishes the evaluation's last case runs it).  The fused form is the slower one on B200 -- the rollout
+ *   loop is FP64-issue bound and ptxas schedules it differently when the exchange follows in the same kernel (+0.9 % /
+ *   +2.0 % kernel time for one candidate / a batch, against 2-3 us for the second launch; profiles/NOTES_r1.md) -- so
+ *   it stays an option, and the single-GPU kernel is the same machine code either way. */
+enum { KFBO_REDUCE_AUTO = 0, KFBO_REDUCE_NCCL = 1 };
+enum { KFBO_PEER_FUSE_NEVER = 0, KFBO_PEER_FUSE_AUTO = 1, KFBO_PEER_FUSE_ALWAYS = 2 };
 int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value);
 
-/* ---- multi-GPU: one process per GPU, one NCCL allreduce of the cost sums per evaluation ---- */
+/* ---- multi-GPU: one process per GPU; the cost sums of an evaluation meet in ONE exchange (peer memory or NCCL) ---- */
 #define KFBO_NCCL_ID_BYTES 128
 int kfbo_nccl_unique_id(void *id_bytes /*[KFBO_NCCL_ID_BYTES]*/);
 int kfbo_comm_init(kfbo_handle *h, const void *id_bytes, int32_t rank, int32_t nranks, int32_t shard_mode);
+/* The exchange of the cost sums over peer memory (NVLink / NVSwitch) instead of the NCCL call: behind the rollout, each
+ * rank stores its share of the [C][D][4] sums into an exchange buffer on every GPU of the box, raises a flag there,
+ * waits for the other ranks' flags and -- trials sharded -- adds the ranks' shares in rank order (the total is the same
+ * bit pattern on every rank and from run to run; candidates sharded: every slot has one owner and nothing is added).
+ * No NCCL launch, no host round trip; two generations of buffers, so consecutive evaluations need no barrier.
+ * Ranks on one box (at most KFBO_MAX_PEERS), after kfbo_comm_init:
+ *   kfbo_peer_export  allocates this rank's exchange buffer and returns its CUDA IPC handle;
+ *   kfbo_peer_attach  takes the handles of ALL ranks in rank order (exchanged by the caller, e.g. an all-gather over
+ *                     torch.distributed -- kf_bayesopt_b200/dist.py) and maps the peers' buffers.
+ * Every rank must make the same sequence of kfbo_eval* calls (as for NCCL); a rank that waits longer than
+ * KFBO_OPT_PEER_TIMEOUT_MS for another returns KFBO_EPEER instead of hanging.  A device group (below) attaches its
+ * devices by itself.  Trial-sharded evaluations of more than 1024 (candidate, sample time) pairs keep the NCCL call. */
+#define KFBO_MAX_PEERS 8
+#define KFBO_PEER_HANDLE_BYTES 64
+int kfbo_peer_export(kfbo_handle *h, void *handle_bytes /*[KFBO_PEER_HANDLE_BYTES]*/);
+int kfbo_peer_attach(kfbo_handle *h, const void *all_handle_bytes /*[nranks][KFBO_PEER_HANDLE_BYTES]*/);
+/* 0: the last kfbo_eval / kfbo_eval_batch ran on one rank; 1: its sums met in an ncclAllReduce; 2: in the peer-memory
+ * exchange as a kernel of its own; 3: in the peer-memory exchange fused into the rollout kernel. */
+int kfbo_last_reduce_path(const kfbo_handle *h);
 /* [begin,end) of n units owned by `rank` of `nranks` (contiguous, remainder to the low ranks). */
 int kfbo_shard_range(int64_t n, int32_t rank, int32_t nranks, int64_t *begin, int64_t *end);
 
 /* ---- multi-GPU from ONE process: a device group ----
  * What a single-process caller (the ROS node robot1d_kf, src/test_trial.cpp) needs to spread an evaluation over
  * several GPUs of the box: one host thread drives n_devices devices (devices[i], or 0..n_devices-1 when NULL); each
- * evaluation launches its shard on every device, then ONE grouped ncclAllReduce of the [C][D][4] cost sums, then the
- * costs are assembled from the first device's copy.  Sharding, Philox streams and therefore the results are those of
+ * evaluation launches its shard on every device; the [C][D][4] cost sums meet in the peer-memory exchange above (the
+ * devices are attached to each other at creation when they can access each other's memory) or in ONE grouped
+ * ncclAllReduce; then the costs are assembled from the first device's copy.  Sharding, Philox streams and therefore the results are those of
  * the one-process-per-GPU mode with n_devices ranks.  n_devices == 1 needs no NCCL. */
 typedef struct kfbo_group kfbo_group;
 int kfbo_group_create(const kfbo_params *p, int32_t n_devices, const int32_t *devices, int32_t shard_mode, kfbo_group **out);

@@ -18,6 +18,16 @@ SHARD_TRIALS, SHARD_CANDIDATES = 0, 1
 OPT_SUPPLIED_KERNEL = 1
 OPT_BULK_SMEM_PAD = 2
 OPT_ROLLOUT_FORM = 3
+OPT_REDUCE = 4
+OPT_PEER_FUSE = 5
+OPT_PEER_TIMEOUT_MS = 6
+REDUCE_AUTO, REDUCE_NCCL = 0, 1
+PEER_FUSE_NEVER, PEER_FUSE_AUTO, PEER_FUSE_ALWAYS = 0, 1, 2
+MAX_PEERS = 8
+PEER_HANDLE_BYTES = 64
+# kfbo_last_reduce_path
+REDUCE_PATHS = {0: "single rank", 1: "ncclAllReduce", 2: "peer-memory exchange (kernel behind the rollout)",
+                3: "peer-memory exchange fused into the rollout kernel"}
 FORM_REFERENCE, FORM_REDUCED = 0, 1
 SUPPLIED_AUTO, SUPPLIED_LDG, SUPPLIED_BULK = 0, 1, 2
 
@@ -84,6 +94,9 @@ SIGNATURES = {
     "kfbo_set_option": (C.c_int, [_vp, C.c_int32, C.c_int64]),
     "kfbo_nccl_unique_id": (C.c_int, [_vp]),
     "kfbo_comm_init": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32]),
+    "kfbo_peer_export": (C.c_int, [_vp, _vp]),
+    "kfbo_peer_attach": (C.c_int, [_vp, _vp]),
+    "kfbo_last_reduce_path": (C.c_int, [_vp]),
     "kfbo_group_create": (C.c_int, [C.POINTER(KfboParams), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(_vp)]),
     "kfbo_group_destroy": (None, [_vp]),
     "kfbo_group_last_error": (C.c_char_p, [_vp]),

@@ -67,6 +67,11 @@ NcclApi &nccl()
 
 constexpr size_t kPartialsBudgetBytes = 64u << 20;  // per-launch partial-sum scratch cap
 constexpr size_t kGainsBudgetBytes = 256u << 20;    // per-launch gain-table cap (reduced form)
+constexpr size_t kXchgFlagBytes = 256;              // flags [2][kMaxPeers] in front of the exchange slabs
+constexpr size_t kPeerMaxSummedDoubles = 4096;      // trials sharded: one CTA adds nranks slabs of this many doubles at most
+static_assert(KFBO_MAX_PEERS == kfbo::kMaxPeers, "kfbo.h and kfbo_kernels.h disagree on the peer count");
+static_assert(KFBO_PEER_HANDLE_BYTES == sizeof(cudaIpcMemHandle_t), "cudaIpcMemHandle_t size");
+static_assert(2 * kfbo::kMaxPeers * sizeof(unsigned) <= kXchgFlagBytes, "flag block");
 
 }  // namespace
 
@@ -85,7 +90,9 @@ struct kfbo_handle {
     double fd01[KFBO_MAX_SAMPLE_TIMES]{};
     int max_T = 0, min_T = kfbo::kMaxSteps;
     kfbo::SampleTimeConsts st{};       // per-sample-time constants, passed to the kernels by value
-    // per-evaluation buffers (sized at create)
+    // per-evaluation buffers (sized at create).  The case constants sit behind a kPeerCtxBytes header that carries the
+    // PeerCtx of a multi-GPU evaluation (one host-to-device copy brings both): d_cases = d_case_buf + kPeerCtxBytes
+    unsigned char *d_case_buf = nullptr, *h_case_buf = nullptr;
     Case *d_cases = nullptr, *h_cases = nullptr;
     int cases_cap = 0;
     double *d_partials = nullptr;
@@ -103,6 +110,19 @@ struct kfbo_handle {
     // NCCL
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1, shard_mode = KFBO_SHARD_TRIALS;
+    // peer-memory exchange of the cost sums (kfbo_peer_export / kfbo_peer_attach, or kfbo_group_create)
+    unsigned char *d_xchg = nullptr;       // [kXchgFlagBytes: flags [2][kMaxPeers]] [vals [2][nranks][xchg_cap] doubles]
+    size_t xchg_cap = 0;                   // doubles per slab = cases_cap * 4
+    unsigned char *peer_base[kfbo::kMaxPeers] = {};   // rank r's d_xchg as mapped in this process
+    bool peer_opened[kfbo::kMaxPeers] = {};           // mapped through cudaIpcOpenMemHandle (to be closed)
+    bool peer_ready = false;
+    unsigned *d_done = nullptr;            // cases finished in the launch that carries the exchange
+    int32_t *h_status = nullptr;           // pinned, written by the kernel: 1 + the rank whose flag did not arrive
+    uint32_t peer_epoch = 0;
+    int reduce_pref = KFBO_REDUCE_AUTO, peer_fuse = KFBO_PEER_FUSE_AUTO;
+    int64_t peer_timeout_ms = 10000;
+    int reduce_path = 0;                   // of the evaluation in flight / the last one: kfbo_last_reduce_path
+    const double *result_src = nullptr;    // where the evaluation in flight leaves the total sums on this device
     // Philox stream bookkeeping
     uint32_t stream_base = 0, eval_counter = 0;
     int supplied_kernel = kfbo::kSuppliedAuto;
@@ -352,8 +372,13 @@ void kfbo_destroy(kfbo_handle *h)
     if (h->d_gains) cudaFree(h->d_gains);
     if (h->d_gu) cudaFree(h->d_gu);
     if (h->d_logtab) cudaFree(h->d_logtab);
-    if (h->d_cases) cudaFree(h->d_cases);
-    if (h->h_cases) cudaFreeHost(h->h_cases);
+    for (int r = 0; r < kfbo::kMaxPeers; ++r)
+        if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    if (h->d_xchg) cudaFree(h->d_xchg);
+    if (h->d_done) cudaFree(h->d_done);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->d_case_buf) cudaFree(h->d_case_buf);
+    if (h->h_case_buf) cudaFreeHost(h->h_case_buf);
     if (h->d_partials) cudaFree(h->d_partials);
     if (h->d_tickets) cudaFree(h->d_tickets);
     if (h->d_sums) cudaFree(h->d_sums);
@@ -434,14 +459,18 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
     const size_t budget = kPartialsBudgetBytes / sizeof(double);
     if (part > budget) part = std::max(budget, (size_t)tiles * 4 * h->D);   // at least one whole candidate per launch
     h->partials_cap = part;
-    if (cu(cudaMalloc(&h->d_cases, h->cases_cap * sizeof(Case)), "cudaMalloc(cases)") ||
-        cu(cudaMallocHost(&h->h_cases, h->cases_cap * sizeof(Case)), "cudaMallocHost(cases)") ||
+    const size_t case_bytes = kfbo::kPeerCtxBytes + h->cases_cap * sizeof(Case);
+    if (cu(cudaMalloc(&h->d_case_buf, case_bytes), "cudaMalloc(cases)") ||
+        cu(cudaMallocHost(&h->h_case_buf, case_bytes), "cudaMallocHost(cases)") ||
         cu(cudaMalloc(&h->d_partials, h->partials_cap * sizeof(double)), "cudaMalloc(partials)") ||
         cu(cudaMalloc(&h->d_tickets, h->cases_cap * sizeof(unsigned)), "cudaMalloc(tickets)") ||
         cu(cudaMemset(h->d_tickets, 0, h->cases_cap * sizeof(unsigned)), "cudaMemset(tickets)") ||
         cu(cudaMalloc(&h->d_sums, (size_t)h->cases_cap * 4 * sizeof(double)), "cudaMalloc(sums)") ||
         cu(cudaMallocHost(&h->h_sums, (size_t)h->cases_cap * 4 * sizeof(double)), "cudaMallocHost(sums)"))
         return bail(KFBO_ECUDA);
+    std::memset(h->h_case_buf, 0, kfbo::kPeerCtxBytes);
+    h->d_cases = reinterpret_cast<Case *>(h->d_case_buf + kfbo::kPeerCtxBytes);
+    h->h_cases = reinterpret_cast<Case *>(h->h_case_buf + kfbo::kPeerCtxBytes);
     *out = h;
     return KFBO_OK;
 }
@@ -475,6 +504,18 @@ int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value)
     case KFBO_OPT_BULK_SMEM_PAD:
         if (value < 0 || value > (128 << 10)) return fail(h, KFBO_EINVAL, "kfbo_set_option: smem pad %lld", (long long)value);
         h->bulk_smem_pad = (int)value;
+        return KFBO_OK;
+    case KFBO_OPT_REDUCE:
+        if (value != KFBO_REDUCE_AUTO && value != KFBO_REDUCE_NCCL) return fail(h, KFBO_EINVAL, "kfbo_set_option: reduce %lld", (long long)value);
+        h->reduce_pref = (int)value;
+        return KFBO_OK;
+    case KFBO_OPT_PEER_FUSE:
+        if (value < KFBO_PEER_FUSE_NEVER || value > KFBO_PEER_FUSE_ALWAYS) return fail(h, KFBO_EINVAL, "kfbo_set_option: peer fuse %lld", (long long)value);
+        h->peer_fuse = (int)value;
+        return KFBO_OK;
+    case KFBO_OPT_PEER_TIMEOUT_MS:
+        if (value < 1 || value > 3600000) return fail(h, KFBO_EINVAL, "kfbo_set_option: peer timeout %lld ms", (long long)value);
+        h->peer_timeout_ms = value;
         return KFBO_OK;
     default:
         return fail(h, KFBO_EINVAL, "kfbo_set_option: unknown option %d", option);
@@ -518,35 +559,71 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
             if (rc) return rc;
         }
     const size_t nsums = (size_t)C * D * 4;
+    // ---- how the sums of the ranks will meet (the same decision on every rank: it depends on C, D and options only)
+    const bool gather = h->shard_mode == KFBO_SHARD_CANDIDATES;
+    const bool use_peer = h->comm && h->peer_ready && h->reduce_pref != KFBO_REDUCE_NCCL && nsums <= h->xchg_cap &&
+                          (gather || nsums <= kPeerMaxSummedDoubles);
+    const uint32_t ntrials = (uint32_t)(t1 - t0);
+    const bool reduced = h->rollout_form == KFBO_FORM_REDUCED;
+    const int tiles = reduced ? kfbo::rollout_tiles(ntrials) : kfbo::philox_tiles(ntrials);
+    int step = cases_per_launch(h, std::max(tiles, 1));
+    if (reduced) step = std::max(D, std::min(step, (int)h->gains_cap));
+    const bool has_work = ncases > 0 && ntrials > 0;
+    // Opt-in (KFBO_OPT_PEER_FUSE): the exchange rides in the tail of the rollout kernel when the evaluation is one launch.
+    // Off by default because it is slower, measured: the rollout loop is FP64-issue bound and ptxas schedules it
+    // differently when the exchange follows it in the same kernel (+0.9 % kernel time for one candidate, +2.0 % for a
+    // batch, i.e. 15-60 us), which is more than the 2-3 us a second launch on the same stream costs.
+    const bool fused = use_peer && has_work && ncases <= step && h->peer_fuse == KFBO_PEER_FUSE_ALWAYS;
+    h->reduce_path = !h->comm ? 0 : !use_peer ? 1 : fused ? 3 : 2;
+    h->result_src = h->d_sums;
+    if (use_peer) {
+        kfbo::PeerCtx *pc = reinterpret_cast<kfbo::PeerCtx *>(h->h_case_buf);
+        const uint32_t epoch = ++h->peer_epoch;
+        const size_t slabs = gather ? 1u : (size_t)h->nranks;
+        for (int r = 0; r < h->nranks; ++r) {
+            pc->flags[r] = reinterpret_cast<unsigned *>(h->peer_base[r]);
+            pc->vals[r] = reinterpret_cast<double *>(h->peer_base[r] + kXchgFlagBytes);
+            int64_t b = 0, e = C;
+            if (gather) kfbo::host::shard_range(C, r, h->nranks, &b, &e);
+            pc->begin[r] = (int32_t)(b * D * 4); pc->end[r] = (int32_t)(e * D * 4);
+        }
+        pc->nranks = h->nranks; pc->rank = h->rank; pc->gather = gather ? 1 : 0; pc->nsums = (int32_t)nsums;
+        pc->cap = (uint32_t)h->xchg_cap; pc->epoch = epoch; pc->ncases = (uint32_t)ncases;
+        pc->done = h->d_done; pc->status = h->h_status; pc->sums = h->d_sums;
+        pc->timeout_ns = (unsigned long long)h->peer_timeout_ms * 1000000ull;
+        if (gather) h->result_src = reinterpret_cast<const double *>(h->d_xchg + kXchgFlagBytes) + (size_t)(epoch & 1u) * slabs * h->xchg_cap;
+    }
     h->tp[1] = clk::now();
     // ranks that own no case of a slot (candidate sharding) or no trials contribute zeros
     KFBO_CUDA(h, cudaMemsetAsync(h->d_sums, 0, nsums * sizeof(double), h->stream));
-    if (ncases > 0)
+    if (use_peer)   // header (PeerCtx) and cases in one copy
+        KFBO_CUDA(h, cudaMemcpyAsync(h->d_case_buf, h->h_case_buf, kfbo::kPeerCtxBytes + (size_t)ncases * sizeof(Case), cudaMemcpyHostToDevice, h->stream));
+    else if (ncases > 0)
         KFBO_CUDA(h, cudaMemcpyAsync(h->d_cases, h->h_cases, (size_t)ncases * sizeof(Case), cudaMemcpyHostToDevice, h->stream));
     h->last_launches = 0;
     KFBO_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    const uint32_t ntrials = (uint32_t)(t1 - t0);
-    if (ncases > 0 && ntrials > 0) {
-        const bool reduced = h->rollout_form == KFBO_FORM_REDUCED;
-        const int tiles = reduced ? kfbo::rollout_tiles(ntrials) : kfbo::philox_tiles(ntrials);
-        int step = cases_per_launch(h, tiles);
-        if (reduced) step = std::max(D, std::min(step, (int)h->gains_cap));
+    if (has_work) {
         for (int first = 0; first < ncases; first += step) {
             const int n = std::min(step, ncases - first);
             kfbo::SampleTimeConsts st = h->st;
             st.k0 = 0; st.nk = D;   // cases are laid out [candidate][sample time]; chunks hold whole candidates
             if (reduced) {
                 KFBO_CUDA(h, kfbo::launch_rollout_philox_reduced(h->d_cases + first, n, st, h->d_gains, h->d_logtab, h->max_T, h->p.seed, (uint32_t)t0,
-                                                                 ntrials, nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream));
+                                                                 ntrials, nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream, fused));
                 h->last_launches += 2;
             } else {
                 KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, st, h->d_gu, h->d_logtab, h->min_T, h->p.seed, (uint32_t)t0, ntrials,
-                                                         nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream, h->h_cases + first));
+                                                         nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream, h->h_cases + first, fused));
                 ++h->last_launches;
             }
         }
     }
     KFBO_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    if (use_peer && !fused) {
+        const kfbo::PeerCtx *pc = reinterpret_cast<const kfbo::PeerCtx *>(h->h_case_buf);
+        KFBO_CUDA(h, kfbo::launch_peer_exchange(reinterpret_cast<const kfbo::PeerCtx *>(h->d_case_buf), pc->end[h->rank] - pc->begin[h->rank], h->stream));
+        ++h->last_launches;
+    }
     return KFBO_OK;
 }
 
@@ -556,6 +633,10 @@ static int eval_reduce(kfbo_handle *h, int32_t C, bool in_group)
 {
     if (!h->comm) return KFBO_OK;
     KFBO_CUDA(h, cudaSetDevice(h->device));
+    if (h->reduce_path >= 2) {   // the sums met in peer memory: in the rollout kernel itself, or in the kernel behind it
+        if (!in_group) KFBO_CUDA(h, cudaEventRecord(h->ev2, h->stream));
+        return KFBO_OK;
+    }
     const size_t nsums = (size_t)C * h->D * 4;
     KFBO_NCCL(h, nccl().AllReduce(h->d_sums, h->d_sums, nsums, ncclDouble, ncclSum, h->comm, h->stream));
     if (!in_group) KFBO_CUDA(h, cudaEventRecord(h->ev2, h->stream));
@@ -570,10 +651,16 @@ static int eval_collect(kfbo_handle *h, int32_t C, kfbo_result *out)
     KFBO_CUDA(h, cudaSetDevice(h->device));
     const int D = h->D;
     const size_t nsums = (size_t)C * D * 4;
-    if (out) KFBO_CUDA(h, cudaMemcpyAsync(h->h_sums, h->d_sums, nsums * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (out) KFBO_CUDA(h, cudaMemcpyAsync(h->h_sums, h->result_src, nsums * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     const clk::time_point w2 = clk::now();
     KFBO_CUDA(h, cudaStreamSynchronize(h->stream));
     const clk::time_point w3 = clk::now();
+    if (h->reduce_path >= 2 && *h->h_status != 0) {
+        const int who = *h->h_status - 1;
+        *h->h_status = 0;
+        return fail(h, KFBO_EPEER, "peer-memory exchange: rank %d waited %lld ms for the cost sums of rank %d (did every rank make this call?)",
+                    h->rank, (long long)h->peer_timeout_ms, who);
+    }
     float ms = 0.f;
     KFBO_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms;
@@ -790,6 +877,66 @@ int kfbo_comm_init(kfbo_handle *h, const void *id_bytes, int32_t rank, int32_t n
     return KFBO_OK;
 }
 
+// ---- peer-memory exchange: buffers and attachment ------------------------------------------------------------------
+static int peer_alloc(kfbo_handle *h)
+{
+    if (h->d_xchg) return KFBO_OK;
+    if (h->nranks > kfbo::kMaxPeers) return fail(h, KFBO_ERANGE, "peer exchange: %d ranks, at most %d (one box)", h->nranks, kfbo::kMaxPeers);
+    KFBO_CUDA(h, cudaSetDevice(h->device));
+    h->xchg_cap = (size_t)h->cases_cap * 4;
+    const size_t bytes = kXchgFlagBytes + 2 * (size_t)h->nranks * h->xchg_cap * sizeof(double);
+    KFBO_CUDA(h, cudaMalloc(&h->d_xchg, bytes));
+    KFBO_CUDA(h, cudaMemset(h->d_xchg, 0, bytes));
+    KFBO_CUDA(h, cudaMalloc(&h->d_done, sizeof(unsigned)));
+    KFBO_CUDA(h, cudaMemset(h->d_done, 0, sizeof(unsigned)));
+    KFBO_CUDA(h, cudaMallocHost(&h->h_status, sizeof(int32_t)));
+    *h->h_status = 0;
+    KFBO_CUDA(h, cudaDeviceSynchronize());   // zeroed before anyone can be told about the buffer
+    return KFBO_OK;
+}
+
+int kfbo_peer_export(kfbo_handle *h, void *handle_bytes)
+{
+    if (!h) return KFBO_EINVAL;
+    if (!handle_bytes) return fail(h, KFBO_EINVAL, "kfbo_peer_export: NULL argument");
+    if (!h->comm) return fail(h, KFBO_ESTATE, "kfbo_peer_export: call kfbo_comm_init first (rank and rank count come from it)");
+    if (h->peer_ready) return fail(h, KFBO_ESTATE, "kfbo_peer_export: peers already attached");
+    const int rc = peer_alloc(h);
+    if (rc) return rc;
+    cudaIpcMemHandle_t ipc;
+    KFBO_CUDA(h, cudaIpcGetMemHandle(&ipc, h->d_xchg));
+    std::memcpy(handle_bytes, &ipc, sizeof ipc);
+    return KFBO_OK;
+}
+
+int kfbo_peer_attach(kfbo_handle *h, const void *all_handle_bytes)
+{
+    if (!h) return KFBO_EINVAL;
+    if (!all_handle_bytes) return fail(h, KFBO_EINVAL, "kfbo_peer_attach: NULL argument");
+    if (!h->d_xchg) return fail(h, KFBO_ESTATE, "kfbo_peer_attach: call kfbo_peer_export first");
+    if (h->peer_ready) return fail(h, KFBO_ESTATE, "kfbo_peer_attach: peers already attached");
+    KFBO_CUDA(h, cudaSetDevice(h->device));
+    for (int r = 0; r < h->nranks; ++r) {
+        if (r == h->rank) { h->peer_base[r] = h->d_xchg; continue; }
+        cudaIpcMemHandle_t ipc;
+        std::memcpy(&ipc, static_cast<const unsigned char *>(all_handle_bytes) + (size_t)r * sizeof ipc, sizeof ipc);
+        void *base = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&base, ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int q = 0; q < r; ++q)
+                if (h->peer_opened[q]) { cudaIpcCloseMemHandle(h->peer_base[q]); h->peer_opened[q] = false; }
+            return fail(h, KFBO_ECUDA, "kfbo_peer_attach: cudaIpcOpenMemHandle of rank %d failed: %s", r, cudaGetErrorString(e));
+        }
+        h->peer_base[r] = static_cast<unsigned char *>(base);
+        h->peer_opened[r] = true;
+    }
+    h->peer_ready = true;
+    return KFBO_OK;
+}
+
+int kfbo_last_reduce_path(const kfbo_handle *h) { return h ? h->reduce_path : KFBO_EINVAL; }
+
 // ------------------------------------------------------------------------------------------------------------------
 // Device group: ONE host process (one thread) driving several GPUs of the box -- what a single-process caller such as
 // the ROS node needs to use more than one GPU.  A group is one handle per device, joined by ncclCommInitAll; an
@@ -850,6 +997,29 @@ int kfbo_group_create(const kfbo_params *p, int32_t n_devices, const int32_t *de
             g->hs[i]->comm = comms[i];
             g->hs[i]->rank = i; g->hs[i]->nranks = n_devices; g->hs[i]->shard_mode = shard_mode;
         }
+        // Peer-memory exchange between the devices of the group, when every device can map every other's memory
+        // (NVLink / NVSwitch boxes); otherwise the group keeps the NCCL call.  Same process: plain device pointers.
+        bool p2p = n_devices <= kfbo::kMaxPeers;
+        for (int i = 0; i < n_devices && p2p; ++i)
+            for (int j = 0; j < n_devices && p2p; ++j) {
+                int can = 0;
+                if (i != j && (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) != cudaSuccess || !can)) p2p = false;
+            }
+        for (int i = 0; i < n_devices && p2p; ++i) {
+            if (cudaSetDevice(devs[i]) != cudaSuccess) { p2p = false; break; }
+            for (int j = 0; j < n_devices && p2p; ++j) {
+                if (i == j) continue;
+                const cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess) { cudaGetLastError(); p2p = false; }
+            }
+            if (p2p && peer_alloc(g->hs[i]) != KFBO_OK) p2p = false;
+        }
+        if (p2p)
+            for (int i = 0; i < n_devices; ++i) {
+                for (int j = 0; j < n_devices; ++j) g->hs[i]->peer_base[j] = g->hs[j]->d_xchg;
+                g->hs[i]->peer_ready = true;
+            }
     }
     *out = g;
     return KFBO_OK;
@@ -874,7 +1044,10 @@ int kfbo_group_eval_batch(kfbo_group *g, int32_t C, const double *q_est, const d
     if (rc) return rc;
     for (kfbo_handle *h : g->hs)
         if ((rc = check(h, eval_launch(h, C, q_est, r_est)))) return rc;
-    if (g->hs.size() > 1) {
+    if (g->hs.size() > 1 && g->hs[0]->reduce_path >= 2) {   // the sums met in peer memory (every device took the same path)
+        for (kfbo_handle *h : g->hs)
+            if ((rc = check(h, eval_reduce(h, C, false)))) return rc;
+    } else if (g->hs.size() > 1) {
         ncclResult_t r = nccl().GroupStart();
         if (r != ncclSuccess) return group_fail(g, KFBO_ENCCL, std::string("ncclGroupStart: ") + nccl().GetErrorString(r));
         for (kfbo_handle *h : g->hs)

@@ -13,6 +13,8 @@
 // case and its sample-time constants are provably uniform (uniform registers / parameter bank).
 // Reduction: warp shuffle -> shared -> one [4] partial per CTA -> the LAST CTA of each case
 // (ticket counter) sums the partials in a fixed order, so sums are deterministic run to run.
+#include <algorithm>
+
 #include "kfbo_device.cuh"
 #include "kfbo_kernels.h"
 
@@ -31,12 +33,133 @@ __device__ __forceinline__ double pick4(const double (&a)[4], unsigned k)
     return __hiloint2double(hi, lo);
 }
 
+// -----------------------------------------------------------------------------------------
+// Cross-GPU exchange of the cost sums over peer memory (PeerCtx, kfbo_kernels.h).  One CTA runs it: the CTA that
+// finished the launch's last case (peer_tail), or the single CTA of peer_exchange_kernel.
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// part / nparts: the CTAs of peer_exchange_kernel share the stores of step 1; the last of them to finish goes on alone.
+__device__ __forceinline__ void peer_exchange(const PeerCtx *__restrict__ pc, int part, int nparts)
+{
+    __shared__ bool s_last_part;
+    const int tid = threadIdx.x, nranks = pc->nranks, me = pc->rank;
+    const unsigned epoch = pc->epoch, gen = epoch & 1u;
+    const bool gather = pc->gather != 0;
+    const size_t cap = pc->cap, slabs = gather ? 1u : (size_t)nranks;
+    const size_t my_off = ((size_t)gen * slabs + (gather ? 0u : (size_t)me)) * cap;
+    double *const sums = pc->sums;
+    // 1. this rank's share into the exchange buffer of every GPU (its own included: the total is formed from the
+    //    exchange buffers alone).  Slots are 4 doubles, so everything is 16-byte aligned; a value is read once and
+    //    stored nranks times, kPeerUnroll independent reads in flight per thread.
+    constexpr int kPeerUnroll = 4;
+    const int b2 = pc->begin[me] >> 1, e2 = pc->end[me] >> 1;
+    const double2 *src = reinterpret_cast<const double2 *>(sums);
+    for (int i0 = b2 + part * kThreads * kPeerUnroll + tid; i0 < e2; i0 += nparts * kThreads * kPeerUnroll) {
+        double2 v[kPeerUnroll];
+#pragma unroll
+        for (int u = 0; u < kPeerUnroll; ++u)
+            if (i0 + u * kThreads < e2) v[u] = __ldcg(src + i0 + u * kThreads);
+        for (int r = 0; r < nranks; ++r) {
+            int to = me + r;                  // own buffer first, then the peers staggered by rank
+            if (to >= nranks) to -= nranks;
+            double2 *dst = reinterpret_cast<double2 *>(pc->vals[to] + my_off);
+#pragma unroll
+            for (int u = 0; u < kPeerUnroll; ++u)
+                if (i0 + u * kThreads < e2) dst[i0 + u * kThreads] = v[u];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (nparts > 1) {
+        if (tid == 0) {
+            const unsigned t = atomicAdd(pc->done, 1u);
+            s_last_part = (t == (unsigned)nparts - 1u);
+            if (s_last_part) *pc->done = 0u;
+        }
+        __syncthreads();
+        if (!s_last_part) return;
+        __threadfence();
+    }
+    // 2. one flag per GPU: "evaluation `epoch` of rank `me` has landed";  3. wait for the same from every rank
+    if (tid < nranks) {
+        st_release_sys(pc->flags[tid] + gen * kMaxPeers + me, epoch);
+        const unsigned *f = pc->flags[me] + gen * kMaxPeers + tid;
+        const unsigned long long t0 = global_ns(), limit = pc->timeout_ns;
+        while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+            if (global_ns() - t0 > limit) { *pc->status = 1 + tid; break; }   // reported by the host as KFBO_EPEER
+            __nanosleep(20);
+        }
+    }
+    __syncthreads();
+    // 4. trials sharded: the slabs added in rank order (candidates sharded: the gathered block is the result as it is)
+    if (!gather) {
+        const double2 *slab0 = reinterpret_cast<const double2 *>(pc->vals[me] + (size_t)gen * slabs * cap);
+        const size_t cap2 = cap >> 1;
+        const int n2 = pc->nsums >> 1;
+        for (int i = tid; i < n2; i += kThreads) {
+            double2 v[kMaxPeers];
+#pragma unroll
+            for (int r = 0; r < kMaxPeers; ++r)
+                if (r < nranks) v[r] = __ldcg(slab0 + (size_t)r * cap2 + i);
+            double2 a = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int r = 0; r < kMaxPeers; ++r)
+                if (r < nranks) { a.x += v[r].x; a.y += v[r].y; }
+            reinterpret_cast<double2 *>(sums)[i] = a;
+        }
+    }
+}
+
+// Called by all threads of a CTA that has just published the sums of one case.
+__device__ __forceinline__ void peer_tail(const PeerCtx *__restrict__ pc)
+{
+    __shared__ bool s_final;
+    __syncthreads();                      // the four writers of this case's sums have fenced
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(pc->done, 1u);
+        s_final = (t == pc->ncases - 1u);
+        if (s_final) *pc->done = 0u;      // ready for the next launch
+    }
+    __syncthreads();
+    if (!s_final) return;
+    __threadfence();
+    peer_exchange(pc, 0, 1);
+}
+
+// the PeerCtx of a launch sits in the kPeerCtxBytes in front of its case constants
+__device__ __forceinline__ const PeerCtx *peer_ctx_of(const Case *cases)
+{
+    return reinterpret_cast<const PeerCtx *>(reinterpret_cast<const char *>(cases) - kPeerCtxBytes);
+}
+
+__global__ void __launch_bounds__(kThreads) peer_exchange_kernel(const PeerCtx *__restrict__ pc)
+{
+    peer_exchange(pc, (int)blockIdx.x, (int)gridDim.x);
+}
+
 // CTA partial -> global; last CTA of the case reduces all partials of the case in fixed order.
 // s_red: kThreads x 4 doubles of shared memory the caller no longer needs (or a static array).
+// peer (optional, uniform): the CTA that finishes the launch's last case goes on to the cross-GPU exchange.
 __device__ __forceinline__ void block_reduce_and_publish(const double out[4], int case_idx, int tile, int tiles,
                                                          int out_slot, double *__restrict__ partials,
                                                          unsigned *__restrict__ tickets, double *__restrict__ sums,
-                                                         double (*s_red)[4])
+                                                         double (*s_red)[4], const PeerCtx *__restrict__ peer = nullptr)
 {
     __shared__ double s_part[kThreads / 32][4];
     __shared__ bool s_last;
@@ -83,6 +206,10 @@ __device__ __forceinline__ void block_reduce_and_publish(const double out[4], in
     }
     if (threadIdx.x < 4) sums[(size_t)out_slot * 4 + threadIdx.x] = s_red[0][threadIdx.x];
     if (threadIdx.x == 0) tickets[case_idx] = 0u;  // ready for the next launch
+    if (peer != nullptr) {
+        if (threadIdx.x < 4) __threadfence();
+        peer_tail(peer);
+    }
 }
 
 // -----------------------------------------------------------------------------------------
@@ -109,7 +236,7 @@ __device__ __forceinline__ void load_noise_tables(math::LogTables *dst, const ma
     for (int i = threadIdx.x; i < (int)(sizeof(math::LogTables) / sizeof(double2)); i += kThreads) ld[i] = ls[i];
 }
 
-template <bool kUniformEst, bool kShiftFirst>
+template <bool kUniformEst, bool kShiftFirst, bool kPeer>
 __global__ void __launch_bounds__(kThreads, KFBO_PHILOX_MIN_BLOCKS)
 rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTimeConsts st,
                const double2 *__restrict__ gu_tables, const math::LogTables *__restrict__ logtab,
@@ -197,7 +324,10 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
     // every thread is past its last table lookup: the table space doubles as the reduction scratch
     static_assert(sizeof(math::LogTables) >= sizeof(double) * 4 * kThreads, "tables too small for the reduction scratch");
     __syncthreads();
-    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, reinterpret_cast<double (*)[4]>(s_tables_raw));
+    // kPeer: a compile-time switch and not a run-time test, so that the single-GPU kernel is the same machine code with
+    // or without the exchange (ptxas' schedule of the rollout loop moves with what follows it)
+    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, reinterpret_cast<double (*)[4]>(s_tables_raw),
+                             kPeer ? peer_ctx_of(cases) : nullptr);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -503,6 +633,7 @@ __device__ __forceinline__ void reduced_step(double &e0, double &e1, double &kn,
     sdi += di; sqi = fma(di, di, sqi);
 }
 
+template <bool kPeer>
 __global__ void __launch_bounds__(kThreads)
 rollout_philox_reduced(const Case *__restrict__ cases, const __grid_constant__ SampleTimeConsts st,
                        const GainStep *__restrict__ gains, int gain_stride, const math::LogTables *__restrict__ logtab,
@@ -617,7 +748,8 @@ rollout_philox_reduced(const Case *__restrict__ cases, const __grid_constant__ S
         }
     }
     __syncthreads();
-    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, reinterpret_cast<double (*)[4]>(s_tables_raw));
+    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, reinterpret_cast<double (*)[4]>(s_tables_raw),
+                             kPeer ? peer_ctx_of(cases) : nullptr);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -695,7 +827,7 @@ PhiloxKeys expand_philox_key(uint64_t seed)
 cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, int min_T,
                                   uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
                                   size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
-                                  cudaStream_t stream, const Case *h_cases)
+                                  cudaStream_t stream, const Case *h_cases, bool with_peer)
 {
     if (ncases <= 0 || ntrials == 0) return cudaSuccess;
     const int tiles = rollout_tiles(ntrials);
@@ -705,8 +837,11 @@ cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleT
     const bool uniform_est = h_cases != nullptr && ncases == st.nk;
     // shift policy of the one-pass time variance (kfbo_device.cuh): the constant shift only when no trial is very short
     const bool shift_first = min_T < kMinStepsConstShift;
-    auto *kernel = uniform_est ? (shift_first ? rollout_philox<true, true> : rollout_philox<true, false>)
-                               : (shift_first ? rollout_philox<false, true> : rollout_philox<false, false>);
+    auto *kernel = with_peer
+                       ? (uniform_est ? (shift_first ? rollout_philox<true, true, true> : rollout_philox<true, false, true>)
+                                      : (shift_first ? rollout_philox<false, true, true> : rollout_philox<false, false, true>))
+                       : (uniform_est ? (shift_first ? rollout_philox<true, true, false> : rollout_philox<true, false, false>)
+                                      : (shift_first ? rollout_philox<false, true, false> : rollout_philox<false, false, false>));
     const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (attr != cudaSuccess) return attr;
     SampleTimeConsts stc = st;
@@ -718,6 +853,14 @@ cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleT
     kernel<<<grid, kThreads, smem, stream>>>(
         d_cases, stc, d_gu, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0, ntrials, tiles,
         d_per_trial, per_trial_ld, d_partials, d_tickets, d_sums);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_exchange(const PeerCtx *d_peer, int own_doubles, cudaStream_t stream)
+{
+    // one CTA per 8 KB of this rank's share (1024 doubles), at most 32
+    const int nparts = std::max(1, std::min(32, (own_doubles + 1023) / 1024));
+    peer_exchange_kernel<<<nparts, kThreads, 0, stream>>>(d_peer);
     return cudaGetLastError();
 }
 
@@ -733,7 +876,7 @@ int gain_stride_for(int max_T) { return (max_T + kGainChunk - 1) / kGainChunk * 
 cudaError_t launch_rollout_philox_reduced(const Case *d_cases, int ncases, const SampleTimeConsts &st, GainStep *d_gains, const void *d_logtab,
                                           int max_T, uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
                                           size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
-                                          cudaStream_t stream)
+                                          cudaStream_t stream, bool with_peer)
 {
     if (ncases <= 0 || ntrials == 0) return cudaSuccess;
     const int stride = gain_stride_for(max_T);
@@ -743,9 +886,10 @@ cudaError_t launch_rollout_philox_reduced(const Case *d_cases, int ncases, const
     const int tiles = rollout_tiles(ntrials);
     const dim3 grid((unsigned)tiles, (unsigned)(ncases / st.nk), (unsigned)st.nk);
     const size_t smem = sizeof(math::LogTables);
-    e = cudaFuncSetAttribute(rollout_philox_reduced, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(with_peer ? rollout_philox_reduced<true> : rollout_philox_reduced<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rollout_philox_reduced<<<grid, kThreads, smem, stream>>>(
+    auto *kernel = with_peer ? rollout_philox_reduced<true> : rollout_philox_reduced<false>;
+    kernel<<<grid, kThreads, smem, stream>>>(
         d_cases, st, d_gains, stride, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0, ntrials, tiles,
         d_per_trial, per_trial_ld, d_partials, d_tickets, d_sums);
     return cudaGetLastError();

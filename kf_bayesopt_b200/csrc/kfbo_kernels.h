@@ -49,15 +49,52 @@ struct PhiloxKeys {
 };
 PhiloxKeys expand_philox_key(uint64_t seed);
 
+// Cross-GPU exchange of the cost sums through peer memory (NVLink / NVSwitch): this GPU's share of the [C][D][4] sums
+// is stored into an exchange buffer on every GPU of the job, one flag per peer is raised, the peers' flags are awaited
+// and the total formed -- no NCCL launch and no host round trip between the rollout and the all-reduce.  It runs as
+// peer_exchange_kernel behind the rollout, or (opt-in, slower: see KFBO_OPT_PEER_FUSE in kfbo.h) in the tail of the
+// rollout kernel, by the CTA that finishes the launch's last case.  One PeerCtx per evaluation sits in front of the
+// case constants in device memory (one host-to-device copy brings both).
+//   trials sharded     every rank owns every slot; rank r's values land in slab r of each peer, and every rank adds the
+//                      slabs in rank order: the total is the same bit pattern on all ranks and from run to run.
+//   candidates sharded every slot has one owner, who stores it straight into its place of each peer's gathered block;
+//                      nothing is added.
+// Two generations (parity of the evaluation number) of slabs and flags: a rank that is one evaluation ahead of a peer
+// writes the other generation, and it cannot get two ahead (it needs that peer's flag of the evaluation between).
+constexpr int kMaxPeers = 8;              // the GPUs of one NVSwitch box
+struct PeerCtx {
+    double *vals[kMaxPeers];              // rank r's exchange buffer as mapped HERE: [2 generations][slabs][cap] doubles
+    unsigned *flags[kMaxPeers];           // rank r's flags as mapped here: [2 generations][kMaxPeers], value = evaluation number
+    int32_t begin[kMaxPeers], end[kMaxPeers];   // the doubles of the sums that rank r owns
+    int32_t nranks, rank;
+    int32_t gather;                       // 1: candidates sharded (one owner per slot), 0: trials sharded (slabs, summed)
+    int32_t nsums;                        // C * D * 4
+    uint32_t cap;                         // doubles per slab
+    uint32_t epoch;                       // evaluation number, from 1
+    uint32_t ncases;                      // cases of the launch that carries the exchange (its last case's CTA runs it)
+    uint32_t pad0;
+    unsigned *done;                       // local: cases finished in this launch
+    int32_t *status;                      // local: set to 1 when a peer's flag did not arrive within timeout_ns
+    double *sums;                         // local: this rank's sums in (kernel output), the total out (trials sharded)
+    unsigned long long timeout_ns;
+};
+static_assert(sizeof(PeerCtx) <= 256, "PeerCtx shares a 256-byte header with the case constants");
+constexpr size_t kPeerCtxBytes = 256;
+// the same exchange as a kernel of its own, launched behind the rollout (own_doubles: the size of this rank's share; the
+// stores are spread over a few CTAs, the last of which raises the flags and waits)
+cudaError_t launch_peer_exchange(const PeerCtx *d_peer, int own_doubles, cudaStream_t stream);
+
 // d_cases[ncases]; d_gu[D][kMaxSteps] = (g0*u, g1*u); d_logtab = math::LogTables on the device;
 // trials [trial0, trial0+ntrials).  d_per_trial (optional) is [slots][4][per_trial_ld];
 // d_partials [ncases][tiles][4]; d_tickets [ncases] zero-initialised once; d_sums [slots][4].
+// with_peer: the launch ends with the cross-GPU exchange of the sums; its PeerCtx sits in the kPeerCtxBytes in front of
+// d_cases (no kernel parameter of its own: one more parameter changes ptxas' schedule of the rollout loop).
 // h_cases (optional): the host copy of d_cases; given, a single-candidate launch passes the estimator constants by value.
 // min_T: the smallest step count among the cases of the launch (selects the shift policy of the time variance, kfbo_device.cuh).
 cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, int min_T,
                                   uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
                                   size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
-                                  cudaStream_t stream, const Case *h_cases = nullptr);
+                                  cudaStream_t stream, const Case *h_cases = nullptr, bool with_peer = false);
 
 // Reduced form (opt-in): per step of a case the gain K, 1/S and P^-1 = [[a, b/2], [b/2, c]], tabulated once
 // per case by riccati_gains; d_gains holds ncases x gain_stride_for(max_T) entries.
@@ -66,7 +103,7 @@ int gain_stride_for(int max_T);
 cudaError_t launch_rollout_philox_reduced(const Case *d_cases, int ncases, const SampleTimeConsts &st, GainStep *d_gains, const void *d_logtab,
                                           int max_T, uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
                                           size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
-                                          cudaStream_t stream);
+                                          cudaStream_t stream, bool with_peer = false);
 
 cudaError_t launch_rollout_supplied(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, int max_T, const double *d_x0noise,
                                     const double *d_w, const double *d_v, size_t B, double *d_per_trial,

@@ -300,6 +300,23 @@ class CostEvaluator:
         buf = C.create_string_buffer(bytes(id_bytes), _lib.NCCL_ID_BYTES)
         self._check(self._lib.kfbo_comm_init(self._h, buf, rank, nranks, shard_mode))
 
+    # -- peer-memory exchange of the cost sums (kfbo_peer_export / kfbo_peer_attach in include/kfbo.h)
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        self._check(self._lib.kfbo_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_attach(self, handles) -> None:
+        """handles: the peer_export() bytes of ALL ranks, in rank order."""
+        blob = b"".join(bytes(x) for x in handles)
+        if len(blob) % _lib.PEER_HANDLE_BYTES:
+            raise ValueError("peer handles are PEER_HANDLE_BYTES each")
+        buf = C.create_string_buffer(blob, len(blob))
+        self._check(self._lib.kfbo_peer_attach(self._h, buf))
+
+    def last_reduce_path(self) -> str:
+        return _lib.REDUCE_PATHS.get(self._lib.kfbo_last_reduce_path(self._h), "?")
+
 
 class CostEvaluatorGroup:
     """Owns one kfbo_group: ONE process driving `n_gpus` devices of the box (kfbo_group_* in include/kfbo.h) -- the
@@ -367,6 +384,9 @@ class CostEvaluatorGroup:
 
     def set_option(self, option: int, value: int) -> None:
         self._check(self._lib.kfbo_group_set_option(self._g, option, value))
+
+    def last_reduce_path(self) -> str:
+        return _lib.REDUCE_PATHS.get(self._lib.kfbo_last_reduce_path(self._lib.kfbo_group_handle(self._g, 0)), "?")
 
     def set_stream_base(self, base: int) -> None:
         self._check(self._lib.kfbo_group_set_stream_base(self._g, base))

@@ -70,3 +70,52 @@ def test_two_rank_sharding_matches_unsharded(tmp_path, kfbo, oracle, mode):
         a, b = kfbo.finalize(params, total[c]), kfbo.finalize(params, full[c])
         np.testing.assert_allclose(a.cost, b.cost, rtol=1e-12)
         assert a.index_max == b.index_max
+
+
+# ---------------------------------------------------------------------------------------------
+# The attach protocol of the peer-memory exchange (dist.attach_peers): export -> all-gather -> attach -> agree.
+# The CUDA side needs GPUs (tests/test_gpu_multi.py); here two gloo ranks run the protocol on a stand-in evaluator.
+# ---------------------------------------------------------------------------------------------
+class _FakeEvaluator:
+    def __init__(self, rank, fail_export=False, fail_attach=False):
+        self.rank, self.fail_export, self.fail_attach = rank, fail_export, fail_attach
+        self.attached, self.options = None, []
+
+    def peer_export(self):
+        from kf_bayesopt_b200 import KfboError
+        if self.fail_export:
+            raise KfboError(1, "no IPC here")
+        return bytes([self.rank]) * 64
+
+    def peer_attach(self, handles):
+        from kf_bayesopt_b200 import KfboError
+        if self.fail_attach:
+            raise KfboError(1, "cannot map the peer")
+        self.attached = list(handles)
+
+    def set_option(self, option, value):
+        self.options.append((option, value))
+
+
+def _attach_worker(rank, world, port, scenario, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kf_bayesopt_b200 import _lib
+    from kf_bayesopt_b200.dist import attach_peers
+    ev = _FakeEvaluator(rank, fail_export=(scenario == "export" and rank == 1), fail_attach=(scenario == "attach" and rank == 0))
+    ok = attach_peers(ev, world)
+    if scenario == "ok":
+        assert ok and ev.attached == [bytes([r]) * 64 for r in range(world)] and ev.options == []
+    else:       # one rank failed: EVERY rank falls back to the NCCL call
+        assert not ok and ev.options == [(_lib.OPT_REDUCE, _lib.REDUCE_NCCL)]
+    open(os.path.join(out_dir, f"done{rank}"), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("scenario", ["ok", "export", "attach"])
+def test_peer_attach_protocol_agrees_across_ranks(tmp_path, scenario):
+    mp.spawn(_attach_worker, args=(2, _free_port(), scenario, str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["done0", "done1"]

@@ -62,7 +62,28 @@ def test_device_group_matches_single_device(kfbo):
             sums = gr.last_sums(C)
             one = gr.eval([1.0], [0.1]).cost                            # a second evaluation on the same communicators
             ms, launches = gr.last_kernel_ms()
-            assert ms > 0 and 1 <= launches <= G                        # one candidate, candidate-sharded: one device has work
+            assert ms > 0 and 1 <= launches <= 2 * G                    # one candidate, candidate-sharded: one device has work
+            path = gr.last_reduce_path()
+            # the same two evaluations with the sums meeting in an ncclAllReduce instead of peer memory (or again in
+            # NCCL on a box without peer access): the same numbers -- bit for bit where the sum has one order
+            from kf_bayesopt_b200 import _lib
+            gr.set_option(_lib.OPT_REDUCE, _lib.REDUCE_NCCL)
+            gr.set_eval_counter(0)
+            got_nccl = gr.eval_batch_raw(q, r)
+            sums_nccl = gr.last_sums(C)
+            assert gr.last_reduce_path() == "ncclAllReduce"
+            if mode == kfbo.SHARD_CANDIDATES or G == 2:
+                assert np.array_equal(sums, sums_nccl) and np.array_equal(got["cost"], got_nccl["cost"]), path
+            else:
+                np.testing.assert_allclose(sums, sums_nccl, rtol=1e-12)
+            # back to the default path for a run of single-candidate evaluations (both generations of the exchange buffers)
+            gr.set_option(_lib.OPT_REDUCE, _lib.REDUCE_AUTO)
+            gr.set_eval_counter(50)
+            run_a = [gr.eval([0.4 + 0.05 * i], [0.1]).cost.copy() for i in range(12)]
+            gr.set_option(_lib.OPT_REDUCE, _lib.REDUCE_NCCL)
+            gr.set_eval_counter(50)
+            run_b = [gr.eval([0.4 + 0.05 * i], [0.1]).cost.copy() for i in range(12)]
+            np.testing.assert_allclose(np.stack(run_a), np.stack(run_b), rtol=1e-10, atol=1e-13)
         if mode == kfbo.SHARD_CANDIDATES:                               # every slot written by one device, the others add 0.0
             assert np.array_equal(sums, want_sums) and np.array_equal(got["cost"], want["cost"])
         else:                                                           # the same trials, summed in another order

@@ -3,6 +3,10 @@
   * SHARD_TRIALS: the all-reduced cost sums of G ranks equal the single-GPU sums (Philox counters use
     the global trial index, so the draws do not depend on G) to 1e-12, costs to 1e-12, argmax identical;
   * SHARD_CANDIDATES: bit-identical (every slot is written by one rank, the others add 0.0).
+  * the cost sums meet over peer memory (fused into the rollout kernel / as a kernel behind it) or in an
+    ncclAllReduce: the three give the same numbers (bit for bit between the two peer-memory forms, and against NCCL
+    where the sum has one order: candidates sharded, or two ranks), also over a run of back-to-back evaluations
+    (both generations of the exchange buffers) and for batches with fewer candidates than ranks.
 Prints 'multi_gpu_check ok' on rank 0."""
 import os
 import sys
@@ -13,6 +17,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import kf_bayesopt_b200 as kf
+from kf_bayesopt_b200 import _lib
 from kf_bayesopt_b200.dist import init_comm
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -24,14 +29,55 @@ rv = kf.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
 q = np.linspace(0.1, 5.0, C)
 r = np.linspace(0.01, 1.0, C)
 seed = 77
-res = {}
+res, paths = {}, {}
 for mode in (kf.SHARD_TRIALS, kf.SHARD_CANDIDATES):
     with kf.CostEvaluator(rv, times, seed=seed, max_candidates=C, device=local) as ev:
-        init_comm(ev, mode)
+        peer = init_comm(ev, mode)
         out = ev.eval_batch(q, r)
         res[mode] = (ev.last_sums(C).copy(), np.stack([o.cost for o in out]), [o.index_max for o in out])
+        paths[mode] = [ev.last_reduce_path()]
         one = ev.eval([1.0], [0.1])     # a second evaluation on the same communicator
         res[mode] += (one.cost.copy(),)
+        paths[mode].append(ev.last_reduce_path())
+        # the same two evaluations again (same Philox streams) with every way the sums can meet
+        variants = {}
+        settings = [("nccl", _lib.REDUCE_NCCL, _lib.PEER_FUSE_AUTO)]
+        if peer:
+            settings += [("peer", _lib.REDUCE_AUTO, _lib.PEER_FUSE_AUTO), ("peer-never-fused", _lib.REDUCE_AUTO, _lib.PEER_FUSE_NEVER),
+                         ("peer-always-fused", _lib.REDUCE_AUTO, _lib.PEER_FUSE_ALWAYS)]
+        for name, red, fuse in settings:
+            ev.set_option(_lib.OPT_REDUCE, red)
+            ev.set_option(_lib.OPT_PEER_FUSE, fuse)
+            ev.set_eval_counter(0)
+            ev.eval_batch(q, r)
+            a = ev.last_sums(C).copy()
+            pa = ev.last_reduce_path()
+            ev.eval([1.0], [0.1])
+            variants[name] = (a, ev.last_sums(1).copy(), pa, ev.last_reduce_path())
+        for name, (a, b, pa, pb) in variants.items():
+            np.testing.assert_allclose(a, res[mode][0], rtol=1e-12, err_msg=name)
+            if name.startswith("peer"):
+                assert np.array_equal(a, variants["peer"][0]) and np.array_equal(b, variants["peer"][1]), name
+                assert "peer" in pa and "peer" in pb, (name, pa, pb)
+            if mode == kf.SHARD_CANDIDATES or world == 2:
+                assert np.array_equal(a, variants["nccl"][0]) and np.array_equal(b, variants["nccl"][1]), name
+        if peer:
+            if mode == kf.SHARD_TRIALS:   # every rank has work in every evaluation, so the path is the option's
+                assert "fused" in variants["peer-always-fused"][2] and "fused" in variants["peer-always-fused"][3]
+                assert "behind" in variants["peer-never-fused"][3] and "behind" in variants["peer"][2] and "behind" in variants["peer"][3]
+            # a run of back-to-back single-candidate evaluations: both generations of the buffers, no host barrier between
+            ev.set_option(_lib.OPT_REDUCE, _lib.REDUCE_AUTO)
+            ev.set_option(_lib.OPT_PEER_FUSE, _lib.PEER_FUSE_AUTO)
+            ev.set_eval_counter(100)
+            run_peer = [ev.eval([0.5 + 0.01 * i], [0.1]).cost.copy() for i in range(40)]
+            # fewer candidates than ranks: ranks without a candidate (or with one) still take part in the exchange
+            few_peer = ev.eval_batch_raw(q[:1], r[:1])["cost"].copy()
+            ev.set_option(_lib.OPT_REDUCE, _lib.REDUCE_NCCL)
+            ev.set_eval_counter(100)
+            run_nccl = [ev.eval([0.5 + 0.01 * i], [0.1]).cost.copy() for i in range(40)]
+            few_nccl = ev.eval_batch_raw(q[:1], r[:1])["cost"].copy()
+            np.testing.assert_allclose(np.stack(run_peer), np.stack(run_nccl), rtol=1e-10, atol=1e-13)
+            np.testing.assert_allclose(few_peer, few_nccl, rtol=1e-10, atol=1e-13)
 if rank == 0:
     with kf.CostEvaluator(rv, times, seed=seed, max_candidates=C, device=local) as ev:
         out = ev.eval_batch(q, r)
@@ -45,6 +91,6 @@ if rank == 0:
     s_c, c_c, i_c, o_c = res[kf.SHARD_CANDIDATES]
     assert np.array_equal(s_c, sums) and np.array_equal(c_c, cost) and i_c == idx and np.array_equal(o_c, one)
     print(f"multi_gpu_check ok: {world} ranks, trials-sharded max rel diff "
-          f"{np.max(np.abs(s_t - sums) / np.abs(sums)):.2e}, candidates-sharded bit-identical", flush=True)
+          f"{np.max(np.abs(s_t - sums) / np.abs(sums)):.2e}, candidates-sharded bit-identical; the sums met by: {paths}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
