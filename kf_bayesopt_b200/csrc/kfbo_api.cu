@@ -68,6 +68,7 @@ NcclApi &nccl()
 constexpr size_t kPartialsBudgetBytes = 64u << 20;  // per-launch partial-sum scratch cap
 constexpr size_t kGainsBudgetBytes = 256u << 20;    // per-launch gain-table cap (reduced form)
 constexpr size_t kXchgFlagBytes = 256;              // flags [2][kMaxPeers] in front of the exchange slabs
+constexpr size_t kZeroCopyMaxDoubles = 1024;        // results up to this size are stored straight into mapped host memory by the kernel
 constexpr size_t kPeerMaxSummedDoubles = 4096;      // trials sharded: one CTA adds nranks slabs of this many doubles at most
 static_assert(KFBO_MAX_PEERS == kfbo::kMaxPeers, "kfbo.h and kfbo_kernels.h disagree on the peer count");
 static_assert(KFBO_PEER_HANDLE_BYTES == sizeof(cudaIpcMemHandle_t), "cudaIpcMemHandle_t size");
@@ -99,6 +100,7 @@ struct kfbo_handle {
     size_t partials_cap = 0;          // doubles
     unsigned *d_tickets = nullptr;
     double *d_sums = nullptr, *h_sums = nullptr;
+    double *h_sums_dev = nullptr;     // h_sums as the device sees it (mapped pinned memory): small results are stored there by the kernel
     // grow-only scratch for the supplied-noise / per-trial entry points
     double *d_scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_cap[5] = {0, 0, 0, 0, 0};
@@ -468,6 +470,7 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
         cu(cudaMalloc(&h->d_sums, (size_t)h->cases_cap * 4 * sizeof(double)), "cudaMalloc(sums)") ||
         cu(cudaMallocHost(&h->h_sums, (size_t)h->cases_cap * 4 * sizeof(double)), "cudaMallocHost(sums)"))
         return bail(KFBO_ECUDA);
+    if (cu(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->h_sums_dev), h->h_sums, 0), "cudaHostGetDevicePointer(sums)")) return bail(KFBO_ECUDA);
     std::memset(h->h_case_buf, 0, kfbo::kPeerCtxBytes);
     h->d_cases = reinterpret_cast<Case *>(h->d_case_buf + kfbo::kPeerCtxBytes);
     h->h_cases = reinterpret_cast<Case *>(h->h_case_buf + kfbo::kPeerCtxBytes);
@@ -575,7 +578,13 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
     // batch, i.e. 15-60 us), which is more than the 2-3 us a second launch on the same stream costs.
     const bool fused = use_peer && has_work && ncases <= step && h->peer_fuse == KFBO_PEER_FUSE_ALWAYS;
     h->reduce_path = !h->comm ? 0 : !use_peer ? 1 : fused ? 3 : 2;
-    h->result_src = h->d_sums;
+    // Where the total lands.  A small result is stored by the kernel straight into the mapped pinned buffer the costs are
+    // assembled from (no device-to-host copy on the critical path of a "noise" -> "cost" evaluation): by the rollout
+    // itself on a single rank, by the exchange when the trials are sharded.  Otherwise it stays on the device (the
+    // all-reduce buffer d_sums, or the gathered block of the exchange buffer) and one copy brings it over.
+    const bool zero_copy = nsums <= kZeroCopyMaxDoubles && (!h->comm || (use_peer && !gather));
+    double *const rollout_sums = (!h->comm && zero_copy) ? h->h_sums_dev : h->d_sums;
+    h->result_src = zero_copy ? nullptr : h->d_sums;
     if (use_peer) {
         kfbo::PeerCtx *pc = reinterpret_cast<kfbo::PeerCtx *>(h->h_case_buf);
         const uint32_t epoch = ++h->peer_epoch;
@@ -590,12 +599,15 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
         pc->nranks = h->nranks; pc->rank = h->rank; pc->gather = gather ? 1 : 0; pc->nsums = (int32_t)nsums;
         pc->cap = (uint32_t)h->xchg_cap; pc->epoch = epoch; pc->ncases = (uint32_t)ncases;
         pc->done = h->d_done; pc->status = h->h_status; pc->sums = h->d_sums;
+        pc->out = zero_copy ? h->h_sums_dev : h->d_sums;
         pc->timeout_ns = (unsigned long long)h->peer_timeout_ms * 1000000ull;
         if (gather) h->result_src = reinterpret_cast<const double *>(h->d_xchg + kXchgFlagBytes) + (size_t)(epoch & 1u) * slabs * h->xchg_cap;
     }
     h->tp[1] = clk::now();
-    // ranks that own no case of a slot (candidate sharding) or no trials contribute zeros
-    KFBO_CUDA(h, cudaMemsetAsync(h->d_sums, 0, nsums * sizeof(double), h->stream));
+    // Zeros only where the rollout does not write every slot that is read afterwards: a rank without work, and the slots
+    // of other ranks' candidates under the NCCL all-reduce (the exchange moves only what a rank owns).
+    if (!has_work || (h->comm && !use_peer && gather))
+        KFBO_CUDA(h, cudaMemsetAsync(h->d_sums, 0, nsums * sizeof(double), h->stream));
     if (use_peer)   // header (PeerCtx) and cases in one copy
         KFBO_CUDA(h, cudaMemcpyAsync(h->d_case_buf, h->h_case_buf, kfbo::kPeerCtxBytes + (size_t)ncases * sizeof(Case), cudaMemcpyHostToDevice, h->stream));
     else if (ncases > 0)
@@ -609,11 +621,11 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
             st.k0 = 0; st.nk = D;   // cases are laid out [candidate][sample time]; chunks hold whole candidates
             if (reduced) {
                 KFBO_CUDA(h, kfbo::launch_rollout_philox_reduced(h->d_cases + first, n, st, h->d_gains, h->d_logtab, h->max_T, h->p.seed, (uint32_t)t0,
-                                                                 ntrials, nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream, fused));
+                                                                 ntrials, nullptr, 0, h->d_partials, h->d_tickets, rollout_sums, h->stream, fused));
                 h->last_launches += 2;
             } else {
                 KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, st, h->d_gu, h->d_logtab, h->min_T, h->p.seed, (uint32_t)t0, ntrials,
-                                                         nullptr, 0, h->d_partials, h->d_tickets, h->d_sums, h->stream, h->h_cases + first, fused));
+                                                         nullptr, 0, h->d_partials, h->d_tickets, rollout_sums, h->stream, h->h_cases + first, fused));
                 ++h->last_launches;
             }
         }
@@ -651,7 +663,8 @@ static int eval_collect(kfbo_handle *h, int32_t C, kfbo_result *out)
     KFBO_CUDA(h, cudaSetDevice(h->device));
     const int D = h->D;
     const size_t nsums = (size_t)C * D * 4;
-    if (out) KFBO_CUDA(h, cudaMemcpyAsync(h->h_sums, h->result_src, nsums * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (out && h->result_src)   // NULL: the kernel has stored the result in h_sums itself
+        KFBO_CUDA(h, cudaMemcpyAsync(h->h_sums, h->result_src, nsums * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     const clk::time_point w2 = clk::now();
     KFBO_CUDA(h, cudaStreamSynchronize(h->stream));
     const clk::time_point w3 = clk::now();

@@ -14,6 +14,7 @@
 // Reduction: warp shuffle -> shared -> one [4] partial per CTA -> the LAST CTA of each case
 // (ticket counter) sums the partials in a fixed order, so sums are deterministic run to run.
 #include <algorithm>
+#include <atomic>
 
 #include "kfbo_device.cuh"
 #include "kfbo_kernels.h"
@@ -121,7 +122,7 @@ __device__ __forceinline__ void peer_exchange(const PeerCtx *__restrict__ pc, in
 #pragma unroll
             for (int r = 0; r < kMaxPeers; ++r)
                 if (r < nranks) { a.x += v[r].x; a.y += v[r].y; }
-            reinterpret_cast<double2 *>(sums)[i] = a;
+            reinterpret_cast<double2 *>(pc->out)[i] = a;
         }
     }
 }
@@ -813,6 +814,22 @@ __global__ void __launch_bounds__(256) dfma_chain(double *out, int iters, double
 }
 
 // ------------------------------- launchers (host) -------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel) instead of once per launch (1-2 us each).
+// The attribute lives in the device's context; a race between two threads sets it twice to the same value.
+static cudaError_t ensure_dynamic_smem(const void *kernel, int slot, size_t smem)
+{
+    constexpr int kDevs = 64, kSlots = 16;
+    static std::atomic<size_t> have[kDevs][kSlots];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const bool cached = dev < kDevs && slot < kSlots;
+    if (cached && have[dev][slot].load(std::memory_order_acquire) >= smem) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && cached) have[dev][slot].store(smem, std::memory_order_release);
+    return e;
+}
+
 PhiloxKeys expand_philox_key(uint64_t seed)
 {
     PhiloxKeys k;
@@ -842,7 +859,7 @@ cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleT
                                       : (shift_first ? rollout_philox<false, true, true> : rollout_philox<false, false, true>))
                        : (uniform_est ? (shift_first ? rollout_philox<true, true, false> : rollout_philox<true, false, false>)
                                       : (shift_first ? rollout_philox<false, true, false> : rollout_philox<false, false, false>));
-    const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const cudaError_t attr = ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), (with_peer ? 4 : 0) + (uniform_est ? 2 : 0) + (shift_first ? 1 : 0), smem);
     if (attr != cudaSuccess) return attr;
     SampleTimeConsts stc = st;
     if (uniform_est)
@@ -886,9 +903,9 @@ cudaError_t launch_rollout_philox_reduced(const Case *d_cases, int ncases, const
     const int tiles = rollout_tiles(ntrials);
     const dim3 grid((unsigned)tiles, (unsigned)(ncases / st.nk), (unsigned)st.nk);
     const size_t smem = sizeof(math::LogTables);
-    e = cudaFuncSetAttribute(with_peer ? rollout_philox_reduced<true> : rollout_philox_reduced<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     auto *kernel = with_peer ? rollout_philox_reduced<true> : rollout_philox_reduced<false>;
+    e = ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), with_peer ? 9 : 8, smem);
+    if (e != cudaSuccess) return e;
     kernel<<<grid, kThreads, smem, stream>>>(
         d_cases, st, d_gains, stride, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0, ntrials, tiles,
         d_per_trial, per_trial_ld, d_partials, d_tickets, d_sums);

@@ -75,11 +75,12 @@ struct PeerCtx {
     uint32_t pad0;
     unsigned *done;                       // local: cases finished in this launch
     int32_t *status;                      // local: set to 1 when a peer's flag did not arrive within timeout_ns
-    double *sums;                         // local: this rank's sums in (kernel output), the total out (trials sharded)
+    double *sums;                         // local: this rank's sums (the rollout's output)
+    double *out;                          // trials sharded: where the total goes (device memory or mapped host memory)
     unsigned long long timeout_ns;
 };
-static_assert(sizeof(PeerCtx) <= 256, "PeerCtx shares a 256-byte header with the case constants");
-constexpr size_t kPeerCtxBytes = 256;
+constexpr size_t kPeerCtxBytes = 512;     // the header in front of the case constants
+static_assert(sizeof(PeerCtx) <= kPeerCtxBytes, "PeerCtx must fit the header in front of the case constants");
 // the same exchange as a kernel of its own, launched behind the rollout (own_doubles: the size of this rank's share; the
 // stores are spread over a few CTAs, the last of which raises the flags and waits)
 cudaError_t launch_peer_exchange(const PeerCtx *d_peer, int own_doubles, cudaStream_t stream);
