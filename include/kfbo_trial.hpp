@@ -21,6 +21,7 @@
 #define KFBO_TRIAL_HPP_
 
 #include <atomic>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <fstream>
@@ -275,6 +276,21 @@ public:
         if (g_) throw Error(KFBO_ESTATE, "CommInit: this evaluator already drives a device group");
         Check(kfbo_comm_init(h_, nccl_id, rank, nranks, shard_mode));
     }
+    // ... and, on one NVLink box, let the cost sums meet in the peers' memory instead of the NCCL call: every rank exports
+    // the handle of its exchange buffer, the caller all-gathers the KFBO_PEER_HANDLE_BYTES of each (MPI_Allgather, ...),
+    // every rank attaches to all of them (rank order).  kfbo.h: kfbo_peer_export / kfbo_peer_attach.
+    std::array<unsigned char, KFBO_PEER_HANDLE_BYTES> PeerExport()
+    {
+        std::array<unsigned char, KFBO_PEER_HANDLE_BYTES> hb{};
+        Check(kfbo_peer_export(h_, hb.data()));
+        return hb;
+    }
+    void PeerAttach(const std::vector<std::array<unsigned char, KFBO_PEER_HANDLE_BYTES>> &all_ranks)
+    {
+        Check(kfbo_peer_attach(h_, all_ranks.data()));
+    }
+    // how the sums of the last evaluation met: 0 one rank, 1 ncclAllReduce, 2 / 3 peer memory (behind / inside the rollout kernel)
+    int LastReducePath() const { return kfbo_last_reduce_path(g_ ? kfbo_group_handle(g_, 0) : h_); }
     const kfbo_params &params() const { return p_; }
     kfbo_handle *handle() { return h_; }          // of a group: its first device
     int n_gpus() const { return g_ ? (int)kfbo_group_size(g_) : 1; }
