@@ -206,7 +206,8 @@ int kfbo_comm_init(kfbo_handle *h, const void *id_bytes, int32_t rank, int32_t n
  *   kfbo_peer_attach  takes the handles of ALL ranks in rank order (exchanged by the caller, e.g. an all-gather over
  *                     torch.distributed -- kf_bayesopt_b200/dist.py) and maps the peers' buffers.
  * Every rank must make the same sequence of kfbo_eval* calls (as for NCCL); a rank that waits longer than
- * KFBO_OPT_PEER_TIMEOUT_MS for another returns KFBO_EPEER instead of hanging.  A device group (below) attaches its
+ * KFBO_OPT_PEER_TIMEOUT_MS for another returns KFBO_EPEER instead of hanging (the ranks are then out of step with each
+ * other: destroy the handles and start over, as after an NCCL failure).  A device group (below) attaches its
  * devices by itself.  Trial-sharded evaluations of more than 1024 (candidate, sample time) pairs keep the NCCL call. */
 #define KFBO_MAX_PEERS 8
 #define KFBO_PEER_HANDLE_BYTES 64

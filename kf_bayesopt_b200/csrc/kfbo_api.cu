@@ -4,6 +4,7 @@
 // launcher over trials x candidates x sample times.  No CPU fallback: every evaluation runs the
 // sm_100a kernels of kfbo_kernels.cu or fails with an error code.
 #include <dlfcn.h>
+#include <sched.h>
 #include <nccl.h>
 
 #include <atomic>
@@ -112,6 +113,7 @@ struct kfbo_handle {
     // NCCL
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1, shard_mode = KFBO_SHARD_TRIALS;
+    int host_procs = 1;                    // processes that share this box's host cores with this one (kfbo_comm_init: nranks; a group: 1)
     // peer-memory exchange of the cost sums (kfbo_peer_export / kfbo_peer_attach, or kfbo_group_create)
     unsigned char *d_xchg = nullptr;       // [kXchgFlagBytes: flags [2][kMaxPeers]] [vals [2][nranks][xchg_cap] doubles]
     size_t xchg_cap = 0;                   // doubles per slab = cases_cap * 4
@@ -219,8 +221,9 @@ void finalize_range(const kfbo_handle *h, kfbo_result *out, int c0, int c1)
 }  // namespace
 
 struct kfbo_assembly_pool {
-    static constexpr int kWorkers = 3;
-    std::thread th[kWorkers];
+    static constexpr int kMaxWorkers = 3;
+    const int nworkers;
+    std::thread th[kMaxWorkers];
     std::mutex mu;
     std::condition_variable cv;
     uint64_t posted = 0;               // job generation (guarded by mu)
@@ -230,21 +233,21 @@ struct kfbo_assembly_pool {
     kfbo_result *out = nullptr;
     int C = 0;
 
-    kfbo_assembly_pool()
+    explicit kfbo_assembly_pool(int n) : nworkers(std::max(0, std::min(n, (int)kMaxWorkers)))
     {
-        for (int i = 0; i < kWorkers; ++i) th[i] = std::thread([this, i] { work(i + 1); });
+        for (int i = 0; i < nworkers; ++i) th[i] = std::thread([this, i] { work(i + 1); });
     }
     ~kfbo_assembly_pool()
     {
         { std::lock_guard<std::mutex> lk(mu); stop = true; }
         cv.notify_all();
-        for (std::thread &t : th) t.join();
+        for (int i = 0; i < nworkers; ++i) th[i].join();
     }
-    static void slice(int C, int part, int *c0, int *c1)
+    void slice(int CC, int part, int *c0, int *c1) const
     {
-        const int per = (C + kWorkers) / (kWorkers + 1);
-        *c0 = std::min(C, part * per);
-        *c1 = std::min(C, (part + 1) * per);
+        const int per = (CC + nworkers) / (nworkers + 1);
+        *c0 = std::min(CC, part * per);
+        *c1 = std::min(CC, (part + 1) * per);
     }
     void work(int part)
     {
@@ -274,7 +277,7 @@ struct kfbo_assembly_pool {
         int c0, c1;
         slice(CC, 0, &c0, &c1);
         finalize_range(hh, o, c0, c1);
-        while (done.load(std::memory_order_acquire) != kWorkers) std::this_thread::yield();
+        while (done.load(std::memory_order_acquire) != nworkers) std::this_thread::yield();
     }
 };
 
@@ -283,8 +286,17 @@ namespace {
 void finalize_all(kfbo_handle *h, int C, kfbo_result *out)
 {
     if (C < 1024) { finalize_range(h, out, 0, C); return; }
-    if (!h->pool) h->pool = new (std::nothrow) kfbo_assembly_pool;
-    if (!h->pool) { finalize_range(h, out, 0, C); return; }
+    if (!h->pool) {
+        // Workers beside the calling thread: what this process' share of the host cores allows.  One process per GPU
+        // means that many processes assemble at the same moment (the exchange ends on all of them together): on a
+        // 16-core box with 8 ranks four threads each would be 32 runnable threads, the callers among them spinning.
+        cpu_set_t set;
+        int cores = (int)std::thread::hardware_concurrency();
+        if (sched_getaffinity(0, sizeof set, &set) == 0) cores = CPU_COUNT(&set);
+        const int share = std::max(1, cores / std::max(1, h->host_procs));
+        h->pool = new (std::nothrow) kfbo_assembly_pool(share - 1);
+    }
+    if (!h->pool || h->pool->nworkers == 0) { finalize_range(h, out, 0, C); return; }
     h->pool->run(h, C, out);
 }
 
@@ -887,6 +899,7 @@ int kfbo_comm_init(kfbo_handle *h, const void *id_bytes, int32_t rank, int32_t n
     std::memcpy(&id, id_bytes, sizeof id);
     KFBO_NCCL(h, nccl().CommInitRank(&h->comm, nranks, id, rank));
     h->rank = rank; h->nranks = nranks; h->shard_mode = shard_mode;
+    h->host_procs = nranks;               // one process per GPU of the box
     return KFBO_OK;
 }
 
