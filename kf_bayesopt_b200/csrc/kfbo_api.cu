@@ -1,4 +1,5 @@
-// kfbo_api.cu -- the C ABI (include/kfbo.h): handle, host orchestration, NCCL reduction.
+// kfbo_api.cu -- the C ABI (include/kfbo.h): handle, host orchestration, the cross-GPU exchange of the cost sums
+// (peer memory over NVLink / NVSwitch: kfbo_peer_*, kfbo_group_create; NCCL all-reduce as the fallback).
 //
 // Replaces the CPUcoreNumber std::thread pool of trial_node.cpp:54-67 with a device-side batch
 // launcher over trials x candidates x sample times.  No CPU fallback: every evaluation runs the

@@ -8,6 +8,8 @@
 //   riccati_gains +
 //   rollout_philox_reduced  opt-in reduced form: gain table once per case, error-state trajectories
 //   trace_philox            one trajectory replayed step by step (the Nsimruns == 1 record)
+//   peer_exchange_kernel    multi-GPU: the ranks' cost sums meet in each other's memory (stores + flags over NVLink),
+//                           launched behind the rollout; the same code can run in the rollout's tail (kPeer, opt-in)
 //
 // Grid: (tiles, candidates, sample times): blockIdx.y/z give the case without any division, so the
 // case and its sample-time constants are provably uniform (uniform registers / parameter bank).
