@@ -86,7 +86,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 }
 
 // Noise stream layout (restated draw for draw by oracle/kfbo_oracle.c):
-//   key = (seed_lo, seed_hi); counter = (trial, case.stream, block, sub)
+//   key = (seed_lo, seed_hi); counter = (trial, block, case.stream, sub)   [KFBO_PHILOX_LAYOUT below]
 //   block 0, sub 0         -> words (x, y): the N(0,P0) draw added to x0
 //   block g+1, sub 0, 1, 2 -> calls A, B, C of the STEP GROUP g = steps 4g .. 4g+3; a call (x, y, z, w) holds the two
 //                             normal pairs (x, y) and (z, w) of math::normal_pair:
@@ -97,12 +97,31 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 //   3 calls per 4 steps: all 12 x 32 = 384 bits are used, none is shared between two normals.
 struct GroupWords { uint4 a, b, c; };
 
+// KFBO_PHILOX_LAYOUT: where (trial, stream, block, sub) sit in the counter (c0, c1, c2, c3).  A Philox round multiplies c0
+// and c2 and only XORs c1 and c3 in, so what the counter holds THERE decides how many of the 20 multiplies of a call are
+// loop-invariant or shared by the three calls of a step group (the compiler hoists / merges them):
+//   1 (the spec, which the CPU checker restates): (trial, block, stream, sub) -- both multiplied words are loop-invariant, block
+//      and sub enter through the XORs: rounds 1-3 cost 2 multiplies per group, 44 per group in all;
+//   0 (the layout until r1o, kept as a timing knob only -- the parity tests fail with it): (trial, stream, block, sub) --
+//      block is multiplied in round 1 and the three calls diverge one round earlier: 48 per group.
+#ifndef KFBO_PHILOX_LAYOUT
+#define KFBO_PHILOX_LAYOUT 1
+#endif
+__device__ __forceinline__ uint4 philox_at(uint32_t trial, uint32_t stream, uint32_t block, uint32_t sub, const PhiloxKeys &key, uint32_t zero = 0u)
+{
+#if KFBO_PHILOX_LAYOUT == 1
+    return philox4x32_10(trial, block, stream, sub, key, zero);
+#else
+    return philox4x32_10(trial, stream, block, sub, key, zero);
+#endif
+}
+
 __device__ __forceinline__ GroupWords philox_group(uint32_t trial, uint32_t stream, uint32_t group, const PhiloxKeys &key, uint32_t zero = 0u)
 {
     GroupWords w;
-    w.a = philox4x32_10(trial, stream, group + 1u, 0u, key, zero);
-    w.b = philox4x32_10(trial, stream, group + 1u, 1u, key, zero);
-    w.c = philox4x32_10(trial, stream, group + 1u, 2u, key, zero);
+    w.a = philox_at(trial, stream, group + 1u, 0u, key, zero);
+    w.b = philox_at(trial, stream, group + 1u, 1u, key, zero);
+    w.c = philox_at(trial, stream, group + 1u, 2u, key, zero);
     return w;
 }
 

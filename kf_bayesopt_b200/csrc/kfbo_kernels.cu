@@ -268,7 +268,7 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
     Traj t;
     {
         double a, b;
-        const uint4 w = philox4x32_10(trial, m.stream, 0u, 0u, key);
+        const uint4 w = philox_at(trial, m.stream, 0u, 0u, key);
         math::normal_pair(w.x, w.y, s_log, a, b);
         traj_init<kShiftFirst>(t, a, b);
     }
@@ -679,7 +679,7 @@ rollout_philox_reduced(const Case *__restrict__ cases, const __grid_constant__ S
     const uint32_t trial = trial0 + local;    // past-the-end trajectories of the last tile are computed and discarded
     double e0, e1, kn = 0.0, ki = 0.0, sdn = 0.0, sqn = 0.0, sdi = 0.0, sqi = 0.0;
     {
-        const uint4 w = philox4x32_10(trial, m.stream, 0u, 0u, key);
+        const uint4 w = philox_at(trial, m.stream, 0u, 0u, key);
         math::normal_pair(w.x, w.y, s_log, e0, e1);    // e = x0 + N(0,P0) - xhat0 = the draw itself
     }
     static_assert(kGainChunk % 4 == 0, "a gain chunk holds whole step groups");
@@ -774,7 +774,7 @@ __global__ void trace_philox(const Case *__restrict__ cases, const __grid_consta
     Traj t;
     {
         double a, b;
-        const uint4 w = philox4x32_10(trial, m.stream, 0u, 0u, key);
+        const uint4 w = philox_at(trial, m.stream, 0u, 0u, key);
         math::normal_pair(w.x, w.y, tab, a, b);
         traj_init(t, a, b);
     }

@@ -361,7 +361,7 @@ static void philox_noise(void *p, int step, double *w0, double *w1, double *v)
     if (group != c->cached_group) {
         uint32_t out[3][4];
         for (uint32_t j = 0; j < 3; ++j) {
-            const uint32_t ctr[4] = {c->trial, c->stream, (uint32_t)group + 1u, j};
+            const uint32_t ctr[4] = {c->trial, (uint32_t)group + 1u, c->stream, j};   /* (trial, block, stream, sub) */
             ko_philox4x32_10(ctr, c->key, out[j]);
         }
         ko_normals_of_group(out[0], out[1], out[2], c->pn, c->on);
@@ -390,7 +390,7 @@ int ko_eval_philox(uint64_t seed, uint32_t stream, double dt, int T, double q_tr
     for (long i = 0; i < ntrials; ++i) {
         c.trial = trial0 + (uint32_t)i;
         c.cached_group = -1;
-        const uint32_t ctr[4] = {c.trial, c.stream, 0u, 0u};
+        const uint32_t ctr[4] = {c.trial, 0u, c.stream, 0u};                      /* block 0: the x0 draw */
         uint32_t o[4];
         double x0n[2], out[4];
         ko_philox4x32_10(ctr, c.key, o);
