@@ -41,6 +41,18 @@
 #define KFBO_LOG_DEGREE 30
 #endif
 
+// KFBO_EXPERIMENT_NO_BANK_CONFLICTS (timing experiment only -- the results are WRONG): the low three bits of every table
+// index are replaced by the lane number, so the 8 lanes of a quarter-warp read 8 different 16-byte bank groups and a
+// lookup is 4 shared-memory wavefronts instead of ~10.  Measures what conflict-free tables could buy before building them.
+#ifndef KFBO_EXPERIMENT_NO_BANK_CONFLICTS
+#define KFBO_EXPERIMENT_NO_BANK_CONFLICTS 0
+#endif
+#if defined(__CUDA_ARCH__) && KFBO_EXPERIMENT_NO_BANK_CONFLICTS
+#define KFBO_TABLE_INDEX(i) (((i) & ~7) | (int)(threadIdx.x & 7u))
+#else
+#define KFBO_TABLE_INDEX(i) (i)
+#endif
+
 namespace kfbo {
 namespace math {
 
@@ -215,7 +227,7 @@ KFBO_HD double neg2_log(double u, const double (*tab)[2])
     const int i = (tmp >> (20 - kLogTableBits)) & (kLogTableSize - 1);
     const int k = tmp >> 20;                                   // arithmetic: k in [-52, 0]
     const double z = make_double(hi - ((uint32_t)tmp & 0xFFF00000u), lo);
-    const double invc = tab[i][0], logc2 = tab[i][1];
+    const double invc = tab[KFBO_TABLE_INDEX(i)][0], logc2 = tab[KFBO_TABLE_INDEX(i)][1];
     const double r = fma(z, invc, -1.0);
 #if KFBO_LOG_DEGREE == 4
     double s = fma(KFBO_LOG_C4, r, 0.5);
@@ -245,8 +257,8 @@ KFBO_HD double neg2_log(double u, const double (*tab)[2])
 KFBO_HD void rad_direction(double rad, uint32_t dir, const LogTables &tab, double &c, double &s)
 {
     const uint32_t i = (dir >> kDirTableBits) & (kDirTableSize - 1u), j = dir & (kDirTableSize - 1u);
-    const double a = rad * tab.dir_coarse[i][0], b = rad * tab.dir_coarse[i][1];
-    const double c2 = tab.dir_fine[j][0], s2 = tab.dir_fine[j][1];
+    const double a = rad * tab.dir_coarse[KFBO_TABLE_INDEX(i)][0], b = rad * tab.dir_coarse[KFBO_TABLE_INDEX(i)][1];
+    const double c2 = tab.dir_fine[KFBO_TABLE_INDEX(j)][0], s2 = tab.dir_fine[KFBO_TABLE_INDEX(j)][1];
     c = fma(a, c2, -(b * s2));
     s = fma(b, c2, a * s2);
 }
