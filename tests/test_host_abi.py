@@ -167,3 +167,40 @@ def test_read_para_vehicle_yaml_roundtrip(kfbo, tmp_path):
     assert kfbo.sample_times_from(rv) == [(0.1, 201), (1.0, 201)]
     assert kfbo.sample_times_from(rv, kfbo.README_SECOND_SAMPLE_TIME) == [(0.1, 201), (0.5, 211)]
     assert kfbo.sample_times_from(rv, None) == [(0.1, 201)]
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(kfbo, tmp_path):
+    # the boundary is a C ABI: include/kfbo.h compiles as C99 (-pedantic) and a C program links against libkfbo.so and
+    # calls host-only entry points (no device needed: defaults, sharding arithmetic, the no-fallback error of kfbo_create)
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "kfbo.h"
+int main(void)
+{
+    kfbo_params p;
+    kfbo_handle *h = 0;
+    int64_t b = -1, e = -1;
+    kfbo_default_params(&p);
+    if (p.n_sample_times != 2 || p.nsimruns != 200 || p.cpu_core_number != 10) return 1;
+    if (kfbo_shard_range(10, 1, 4, &b, &e) != KFBO_OK || b != 3 || e != 6) return 2;
+    if (kfbo_effective_trials(&p) != 200) return 3;
+    printf("%s rc=%d\n", kfbo_version(), kfbo_create(&p, &h));
+    if (h) kfbo_destroy(h);
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(kfbo.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-o", str(exe), "-L", libdir, "-lkfbo", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "sm_100a" in out.stdout
+    import torch
+    if not torch.cuda.is_available():
+        assert f"rc={-3}" in out.stdout                          # KFBO_ENODEVICE: no CPU fallback
