@@ -381,6 +381,7 @@ def main():
     barrier()
     t1 = time.perf_counter()
     reduce_path = ev.last_reduce_path()
+    host_us = ev.last_host_us()              # phases of the last timed evaluation on this rank (kfbo_last_host_us)
     clocks = sampler.stop(t0, t1)
     elapsed_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -498,6 +499,7 @@ def main():
                            "l2": "n/a for the Philox path: no HBM-resident inputs (noise is generated on the fly); "
                                  "the supplied-noise leg streams 25 GB >> L2"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "host_phases_us": {k: round(v, 1) for k, v in host_us.items()},
                 "result": {"J_NEES": [float(c) for c in res.cost], "cost": float(res.max_cost), "index_max": res.index_max}}
         line.update(line_extra)
         emit(line)

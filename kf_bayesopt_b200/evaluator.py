@@ -163,6 +163,8 @@ def _ptr(a: np.ndarray):
 def _small(a):
     """A short host sequence as a ctypes double array (0.6 us; numpy conversion + pointer cast are 5 us, which shows
     in the 'noise' -> 'cost' call of the default workload, 80 us in all)."""
+    if not hasattr(a, "__len__") or getattr(a, "ndim", 1) == 0:     # a bare number / 0-d array, as the numpy path accepted
+        a = (float(a),)
     return (C.c_double * len(a))(*a)
 
 
@@ -212,7 +214,8 @@ class CostEvaluator:
     # -- the "noise" -> "cost" evaluation
     def eval(self, pn: Sequence[float], on: Sequence[float]) -> Result:
         r = KfboResult()
-        rc = self._lib.kfbo_eval(self._h, _small(pn), len(pn), _small(on), len(on), r)
+        cpn, con = _small(pn), _small(on)
+        rc = self._lib.kfbo_eval(self._h, cpn, len(cpn), con, len(con), r)
         if rc:
             self._check(rc)
         return Result.from_c(r, self.D)
@@ -254,7 +257,7 @@ class CostEvaluator:
         """Host wall time (us) of the phases of the last eval / eval_batch on this rank."""
         us = np.empty(5)
         self._check(self._lib.kfbo_last_host_us(self._h, _ptr(us)))
-        return dict(zip(("build_cases", "enqueue", "device_wait", "cost_assembly", "allreduce_device"), us.tolist()))
+        return dict(zip(("build_cases", "enqueue", "device_wait", "cost_assembly", "exchange_device"), us.tolist()))
 
     # -- exact-parity entry points
     def eval_supplied(self, k: int, q_est, r_est, x0noise, w, v, per_trial: bool = True):
@@ -367,7 +370,8 @@ class CostEvaluatorGroup:
 
     def eval(self, pn: Sequence[float], on: Sequence[float]) -> Result:
         r = KfboResult()
-        rc = self._lib.kfbo_group_eval(self._g, _small(pn), len(pn), _small(on), len(on), r)
+        cpn, con = _small(pn), _small(on)
+        rc = self._lib.kfbo_group_eval(self._g, cpn, len(cpn), con, len(con), r)
         if rc:
             self._check(rc)
         return Result.from_c(r, self.D)
