@@ -277,6 +277,190 @@ _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# Legs of the default line besides the headline workload (every BASELINE.json config in a driver-run record)
+# --------------------------------------------------------------------------------------------------------------------
+DEFAULT_YAML = {"CPUcoreNumber": 10, "stateDOF": 2, "observationDOF": 1, "t_start": 0.0, "t_end": 20.1, "dt": 0.1, "xi0": 0.0,
+                "xidot0": 0.0, "Nsimruns": 200, "pnoise": [Q_TRUTH], "onoise": [R_TRUTH], "optimizationChoice": "processNoise",
+                "costChoice": "JNEES", "n_init_samples": 20}     # config/vehicleParams.yaml, config/bayesParams.yaml:10
+CODE_TIMES = [(0.1, 201), (1.0, 201)]        # trial_node.cpp:105-114 (what the code runs)
+README_TIMES = [(0.1, 201), (0.5, 211)]      # README.md:96 / BASELINE.json configs[1] ("0.1/0.5")
+
+
+def timed_evals(torch, stream, ev, call, steps, warmup):
+    """K evaluations timed with CUDA events on the launching stream -> (ms per evaluation, mean kernel ms, launches, last result)."""
+    for _ in range(warmup):
+        res = call()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms, launches = [], 0
+    e0.record(stream)
+    for _ in range(steps):
+        res = call()
+        ms, n = ev.last_kernel_ms()
+        kms.append(ms)
+        launches += n
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, float(sum(kms) / len(kms)), launches, res
+
+
+def wall_evals(call, steps, warmup):
+    for _ in range(warmup):
+        call()
+    t = time.perf_counter()
+    for _ in range(steps):
+        call()
+    return (time.perf_counter() - t) / steps * 1e3
+
+
+def oracle_slice_parity(kf, ev_factory, sample_times, q, r, seed, ntrials=300):
+    """A <= 300-trial evaluation on the CUDA path against the CPU oracle on the SAME Philox streams (checker only):
+    max relative error of the [D][4] cost sums."""
+    import numpy as np
+    from oracle import oracle as o
+    with ev_factory(ntrials) as ev:
+        ev.eval([q], [r])
+        got = ev.last_sums(1)[0]
+    want = np.stack([o.eval_philox(seed, k, dt, T, Q_TRUTH, R_TRUTH, q, r, 0, ntrials).sum(axis=1) for k, (dt, T) in enumerate(sample_times)])
+    return float(np.max(np.abs(got - want) / np.abs(want)))
+
+
+def leg_default_workload(kf, torch, stream, device, with_cpu):
+    """BASELINE.json configs[0] and configs[1]: ONE "noise" -> "cost" evaluation of the default vehicleParams.yaml workload
+    (200 trials x 201 steps x 2 sample times), as latency.  cfg1: optimizationChoice=processNoise (1-D candidate, onoise
+    fixed at the yaml value), J_NEES, the code's sample-time pair, beside the REFERENCE NODE's own callback on the host
+    cores (trial_node.cpp compiled into oracle/_ref, CPUcoreNumber = 10 threads).  cfg2: optimizationChoice=all (2-D
+    candidate), the README pair 0.1/0.5, J_NEES and J_NIS out of the same pass."""
+    import numpy as np
+    out = {}
+    seed = 0x4B46424F00002026
+    for name, times, cand, choice in (("cfg1", CODE_TIMES, (0.7, R_TRUTH), "JNEES"), ("cfg2", README_TIMES, (0.7, 0.2), "JNEES")):
+        rv = kf.ReadParaVehicle(nsimruns_=200, cpu_core_number_=10, pnoise_=[Q_TRUTH], onoise_=[R_TRUTH], cost_choice_=choice)
+        with kf.CostEvaluator(rv, times, seed=seed, device=device) as ev:
+            ev.set_cuda_stream(stream.cuda_stream)
+            rt = kf.RunTrial(rv, evaluator=ev)
+            msg = kf.Float64MultiArray.noise([cand[0]], [cand[1]])
+            ms, kms, _, _ = timed_evals(torch, stream, ev, lambda: ev.eval([cand[0]], [cand[1]]), 200, 20)
+            wall = wall_evals(lambda: rt.ProcessNoiseCallback(msg), 200, 20)
+            res, phases = rt.last_result, ev.last_host_us()
+            sums = ev.last_sums(1)[0]
+            leg = {"workload": f"200 trials x 201 steps x 2 sample times {times}, candidate pnoise {cand[0]} onoise {cand[1]}",
+                   "latency_ms": wall, "device_ms": ms, "kernel_ms": kms, "filter_steps_per_s": 200.0 * sum(T for _, T in times) / (wall * 1e-3),
+                   "api": "RunTrial.ProcessNoiseCallback ('noise' -> 'cost') over the C ABI kfbo_eval, host buffers",
+                   "host_phases_us": {k: round(v, 1) for k, v in phases.items()},
+                   "J_NEES": [float(abs(np.log(a / 2.0))) for a in res.average_nees],
+                   "J_NIS": [float(abs(np.log(a / 1.0))) for a in res.average_nis], "cost": float(res.max_cost), "index_max": int(res.index_max)}
+        # the same workload's sums against the oracle on the same Philox streams (B = 200: the oracle needs milliseconds)
+        leg["parity_vs_oracle_max_rel"] = oracle_slice_parity(
+            kf, lambda n: kf.CostEvaluator(kf.ReadParaVehicle(nsimruns_=n, cpu_core_number_=10, pnoise_=[Q_TRUTH], onoise_=[R_TRUTH]), times,
+                                           seed=seed, device=device), times, cand[0], cand[1], seed, ntrials=200)
+        del sums
+        out[name] = leg
+    if with_cpu:
+        from oracle import oracle as o
+        from oracle import ref
+        cand, n = (0.7, R_TRUTH), 20
+        if ref.available():
+            ref.set_params(dict(DEFAULT_YAML))
+            msgs = [([cand[0]], [cand[1]])] * n
+            ref.node_run(msgs[:4], clock0=1)
+            t = time.perf_counter()
+            costs, _ = ref.node_run(msgs, clock0=1)
+            cpu_ms = (time.perf_counter() - t) / n * 1e3
+            kind = "reference"
+            how = (f"{n} 'noise' messages through the reference's own RunTrial::ProcessNoiseCallback (trial_node.cpp compiled into "
+                   f"oracle/_ref with stand-ins for Eigen3 / ROS): 10 Trial objects + std::threads per pass, two passes")
+        else:
+            t = time.perf_counter()
+            for _ in range(n):
+                for dt, T in CODE_TIMES:
+                    o.eval_mt(dt, T, Q_TRUTH, R_TRUTH, cand[0], cand[1], 200, 10, seed=1)
+            cpu_ms = (time.perf_counter() - t) / n * 1e3
+            kind, how = "port", f"{n} evaluations by the oracle's threaded restatement, 10 threads"
+        out["cfg1"]["cpu_baseline"] = {"value": 200.0 * 402 / (cpu_ms * 1e-3), "unit": UNIT, "latency_ms": cpu_ms, "cores": min(10, os.cpu_count() or 1),
+                                       "kind": kind, "sample": how}
+    return out
+
+
+def leg_cfg4(kf, torch, dist, stream, device, world, rank, steps=10, warmup=3):
+    """BASELINE.json configs[3]: 4096 candidates x 1024 trials x 2 sample times, candidates sharded over the ranks, the
+    [4096][2][4] sums gathered in one exchange.  Device-timed and end to end (host candidate arrays -> host costs)."""
+    import numpy as np
+    from kf_bayesopt_b200.dist import init_comm
+    qq = np.repeat(np.geomspace(*CFG4_BOUNDS[0], CFG4_GRID), CFG4_GRID)
+    rr = np.tile(np.geomspace(*CFG4_BOUNDS[1], CFG4_GRID), CFG4_GRID)
+    rv = kf.ReadParaVehicle(nsimruns_=CFG4_TRIALS, cpu_core_number_=1, pnoise_=[Q_TRUTH], onoise_=[R_TRUTH])
+    steps_per_eval = float(CFG4_TRIALS) * qq.size * sum(T for _, T in CFG4_SAMPLE_TIMES)
+    with kf.CostEvaluator(rv, CFG4_SAMPLE_TIMES, seed=0x4B46424F00002026, device=device, max_candidates=qq.size) as ev:
+        ev.set_cuda_stream(stream.cuda_stream)
+        if world > 1:
+            init_comm(ev, kf.SHARD_CANDIDATES)
+            dist.barrier()
+        ms, kms, launches, _ = timed_evals(torch, stream, ev, lambda: ev.eval_batch_costs(qq, rr), steps, warmup)
+        if world > 1:
+            dist.barrier()
+        wall = wall_evals(lambda: ev.eval_batch_costs(qq, rr), steps, 1)
+        t = torch.tensor([ms, wall, kms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall, kms = (float(x) for x in t.tolist())
+        phases, path = ev.last_host_us(), ev.last_reduce_path()
+    return {"workload": "cfg4: %d candidates (64 x 64 log grid over the yaml bounds) x %d trials x sample times %s" % (qq.size, CFG4_TRIALS, CFG4_SAMPLE_TIMES),
+            "value": steps_per_eval / (ms * 1e-3), "unit": UNIT, "ms_per_sweep": ms, "kernel_ms": kms, "e2e_ms_per_sweep": wall,
+            "e2e_value": steps_per_eval / (wall * 1e-3), "sharding": f"candidates over {world} rank(s); sums meet by: {path}",
+            "api": "CostEvaluator.eval_batch_costs (host candidate arrays -> host cost arrays) over the C ABI",
+            "host_phases_us": {k: round(v, 1) for k, v in phases.items()}, "gpu_launches_per_sweep": launches / steps}
+
+
+def parity_self_check(kf, torch, dist, device, world, rank):
+    """N > 1, before anything is timed, on every rank: trial-sharded and candidate-sharded cost sums -- through the
+    peer-memory exchange and through ncclAllReduce -- against THIS rank's own unsharded evaluation of the same Philox
+    streams, plus a 300-trial sharded evaluation against the CPU oracle.  Returns the dict for the JSON line; the caller
+    exits non-zero when "ok" is false."""
+    import numpy as np
+    from kf_bayesopt_b200 import _lib as L
+    from kf_bayesopt_b200.dist import init_comm
+    times, B, C, seed = README_TIMES, 4099, 13, 77                        # neither B nor C divides by the rank count
+    rv = kf.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
+    q, r = np.linspace(0.1, 5.0, C), np.linspace(0.01, 1.0, C)
+    with kf.CostEvaluator(rv, times, seed=seed, max_candidates=C, device=device) as ev1:
+        want = ev1.eval_batch_raw(q, r)
+        want_sums = ev1.last_sums(C).copy()
+    out = {"ranks": world, "paths": [], "max_rel": 0.0, "bit_identical_candidates": True, "selection_identical": True}
+    for mode, name in ((kf.SHARD_TRIALS, "trials"), (kf.SHARD_CANDIDATES, "candidates")):
+        with kf.CostEvaluator(rv, times, seed=seed, max_candidates=C, device=device) as ev:
+            peer = init_comm(ev, mode)
+            for red in (["peer"] if peer else []) + ["nccl"]:
+                ev.set_option(L.OPT_REDUCE, L.REDUCE_AUTO if red == "peer" else L.REDUCE_NCCL)
+                ev.set_eval_counter(0)
+                got = ev.eval_batch_raw(q, r)
+                sums = ev.last_sums(C)
+                rel = float(np.max(np.abs(sums - want_sums) / np.abs(want_sums)))
+                rec = {"sharded": name, "met_by": ev.last_reduce_path(), "max_rel": rel}
+                if mode == kf.SHARD_CANDIDATES:
+                    rec["bit_identical"] = bool(np.array_equal(sums, want_sums) and np.array_equal(got["cost"], want["cost"]))
+                    out["bit_identical_candidates"] &= rec["bit_identical"]
+                out["selection_identical"] &= bool(np.array_equal(got["index_max"], want["index_max"]))
+                out["max_rel"] = max(out["max_rel"], rel)
+                out["paths"].append(rec)
+    # a 300-trial evaluation, trials sharded over the ranks, against the oracle's restatement of the same streams
+    def factory(n):
+        ev = kf.CostEvaluator(kf.ReadParaVehicle(nsimruns_=n, cpu_core_number_=1), times, seed=seed, device=device)
+        init_comm(ev, kf.SHARD_TRIALS)
+        return ev
+    out["oracle_max_rel"] = oracle_slice_parity(kf, factory, times, 0.7, 0.2, seed, ntrials=300)
+    ok = out["max_rel"] <= 1e-12 and out["bit_identical_candidates"] and out["selection_identical"] and out["oracle_max_rel"] <= 1e-9
+    flag = torch.tensor([1.0 if ok else 0.0, out["max_rel"], out["oracle_max_rel"]], dtype=torch.float64, device="cuda")
+    worst = flag.clone()
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    out["ok"] = bool(flag[0].item() == 1.0)                               # every rank agrees
+    out["max_rel"], out["oracle_max_rel"] = float(worst[1].item()), float(worst[2].item())
+    out["tolerance"] = {"trials_sharded_vs_unsharded": 1e-12, "candidates_sharded": "bit-identical", "vs_oracle": 1e-9}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -284,14 +468,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kfbo", choices=["kfbo", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4", "cfg5"],
-                    help="cfg3 (default, the configuration the metric is quoted on), the cfg4 candidate sweep, or the "
-                         "cfg5 Bayesian-optimisation loop over the noise/cost topic contract (N=1 only)")
+                    help="cfg3 (default, the configuration the metric is quoted on; its line also carries the other configs as "
+                         "`extra` legs), the cfg4 candidate sweep as the headline, or the cfg5 Bayesian-optimisation loop (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-supplied", action="store_true", help="skip the supplied-noise (HBM roofline) leg")
     ap.add_argument("--no-reduced", action="store_true", help="skip the reduced-form leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (cfg1/cfg2 latency, cfg4 sweep, NCCL path) and the N>1 parity self-check")
     ap.add_argument("--reduce", default="auto", choices=["auto", "nccl"],
-                    help="N > 1: how the cost sums of the ranks meet -- auto = the peer-memory exchange in the tail of the "
-                         "rollout kernel when the ranks can map each other's buffers, nccl = one ncclAllReduce")
+                    help="N > 1: how the cost sums of the ranks meet -- auto = the peer-memory exchange behind the rollout "
+                         "kernel when the ranks can map each other's buffers, nccl = one ncclAllReduce")
     ap.add_argument("--peer-fuse", default="auto", choices=["auto", "never", "always"],
                     help="N > 1, peer-memory exchange: in the tail of the rollout kernel or as a kernel behind it (KFBO_OPT_PEER_FUSE)")
     args = ap.parse_args()
@@ -312,6 +497,7 @@ def main():
     import torch
     import torch.distributed as dist
     import kf_bayesopt_b200 as kf
+    from kf_bayesopt_b200 import _lib as L
     from kf_bayesopt_b200.dist import init_comm
 
     if not torch.cuda.is_available():
@@ -327,6 +513,19 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    line_extra = {}
+    # ---- N > 1: multi-GPU correctness first, in the record the driver keeps (a failure ends the run non-zero)
+    if world > 1 and not args.no_extra:
+        pn = parity_self_check(kf, torch, dist, local_rank, world, rank)
+        line_extra["parity_n"] = pn
+        if not pn["ok"]:
+            if rank == 0:
+                emit({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "parity_n": pn,
+                      "error": "multi-GPU parity self-check failed; nothing was timed"})
+            dist.barrier()
+            dist.destroy_process_group()
+            raise SystemExit(3)
 
     cfg4 = args.workload == "cfg4"
     if cfg4:
@@ -344,8 +543,7 @@ def main():
     ev.set_cuda_stream(stream.cuda_stream)
     if world > 1:
         init_comm(ev, shard, peer=(args.reduce == "auto"))
-        from kf_bayesopt_b200 import _lib as L0
-        ev.set_option(L0.OPT_PEER_FUSE, {"never": L0.PEER_FUSE_NEVER, "auto": L0.PEER_FUSE_AUTO, "always": L0.PEER_FUSE_ALWAYS}[args.peer_fuse])
+        ev.set_option(L.OPT_PEER_FUSE, {"never": L.PEER_FUSE_NEVER, "auto": L.PEER_FUSE_AUTO, "always": L.PEER_FUSE_ALWAYS}[args.peer_fuse])
     steps_per_eval = float(trials) * n_cand * sum(T for _, T in sample_times)
 
     class _First:   # the first candidate of a batch, shaped like Result where the JSON line reads it
@@ -406,26 +604,41 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = steps_per_eval * args.steps / float(e2e_s.item())
     D = len(sample_times)
-    # per evaluation: H2D = the (candidate, sample time) constants (struct Case, 96 B each), D2H = the [C][D][4] sums
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 96 * D * n_cand, "d2h_bytes_per_step": 32 * D * n_cand,
+    h2d, d2h = ev.last_transfer_bytes()
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_eval": float(e2e_s.item()) / args.steps * 1e3,
-           "api": ("CostEvaluator.eval_batch_costs (host candidate arrays -> host costs) over the C ABI kfbo_eval_batch" if cfg4 else
+           "api": ("CostEvaluator.eval_batch_costs (host candidate arrays -> host costs) over the C ABI kfbo_eval_batch_costs" if cfg4 else
                    "RunTrial.ProcessNoiseCallback (Float64MultiArray 'noise' -> Float64 'cost') over the C ABI kfbo_eval")}
+
+    # ---- N > 1: the same evaluations with the sums meeting in ONE ncclAllReduce (north_star's wording) instead of the
+    # peer-memory exchange -- device-timed like `value`
+    if world > 1 and not args.no_extra and args.reduce == "auto":
+        ev.set_option(L.OPT_REDUCE, L.REDUCE_NCCL)
+        barrier()
+        nms, _, _, _ = timed_evals(torch, stream, ev, evaluate, min(args.steps, 10), 3)
+        nccl_path = ev.last_reduce_path()
+        ev.set_option(L.OPT_REDUCE, L.REDUCE_AUTO)
+        t = torch.tensor([nms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        line_extra["nccl_ms"] = float(t.item())
+        line_extra["nccl"] = {"ms_per_step": float(t.item()), "value": steps_per_eval / (float(t.item()) * 1e-3), "unit": UNIT, "met_by": nccl_path,
+                              "note": "same workload, KFBO_OPT_REDUCE = KFBO_REDUCE_NCCL; the default line's sums met by: " + reduce_path}
 
     # ---- roofline of the dominant kernel (rollout_philox): FP64 pipe
     k_ms = float(np.mean(kernel_ms))
     local_steps = steps_per_eval / world
-    line_extra = {}
     if rank == 0:
-        fp64_peak = kf.measure_fp64_peak(local_rank, 400.0)
+        fp64_peak, fp64_uniform = kf.measure_fp64_peak(local_rank, 400.0, both=True)
         achieved = FLOPS_PER_STEP * local_steps / (k_ms * 1e-3) / 1e12
         roofline = {"bound": "fp64", "kernel": "rollout_philox", "achieved": achieved, "peak": fp64_peak,
                     "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": profiled_traffic("rollout_philox", args.workload),
-                    "peak_source": "measured live on this GPU: DFMA-chain microbenchmark (kfbo_measure_fp64_peak); "
-                                   "MEASURED_PEAKS.json has no FP64 figure",
+                    "peak_source": "measured live on this GPU: DFMA-chain microbenchmark x = fma(x, y, U), the 2.0-cycle operand form "
+                                   "(kfbo_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+                    "peak_uniform_operands": fp64_uniform,
                     "flops_per_filter_step": FLOPS_PER_STEP, "kernel_ms": k_ms,
                     "filter_steps_per_launch": local_steps,
-                    "note": "tensor cores do not apply (2x2 FP64 recursion); RNG flops are excluded from 'achieved'" +
+                    "note": "tensor cores do not apply (2x2 FP64 recursion); RNG flops are excluded from 'achieved'; peak_uniform_operands "
+                            "is the chain x = fma(x, U, U) round 1 divided by (2.2 cycles per instruction: not the pipe's peak)" +
                             ("; kernel_ms at N > 1 includes the in-kernel wait for the other ranks' sums when the exchange is fused"
                              if world > 1 else "")}
         line_extra["roofline"] = roofline
@@ -433,7 +646,6 @@ def main():
     # ---- the opt-in reduced form (KFBO_FORM_REDUCED) on the same workload and streams: reported on its own
     # line with its own instruction count -- it is not the per-thread-covariance formulation north_star names
     if not args.no_reduced:
-        from kf_bayesopt_b200 import _lib as L
         ev.set_option(L.OPT_ROLLOUT_FORM, L.FORM_REDUCED)
         red_ms = []
         for i in range(3 + 5):
@@ -478,6 +690,22 @@ def main():
             "kernel_ms": float(np.mean(ms_s)),
             "filter_steps_per_s": Bs * Ts / (float(np.mean(ms_s)) * 1e-3),
             "workload": f"{Bs} trials x {Ts} steps, supplied noise resident in HBM ({byts / 1e9:.2f} GB > L2)"}
+
+    # ---- the other BASELINE.json configs as legs of this line (cfg3 is the headline)
+    if not args.no_extra and not cfg4:
+        extra = {}
+        if world > 1:
+            dist.barrier()
+        extra["cfg4"] = leg_cfg4(kf, torch, dist, stream, local_rank, world, rank)
+        if rank == 0:
+            extra.update(leg_default_workload(kf, torch, stream, local_rank, with_cpu=(world == 1 and not args.no_cpu_baseline)))
+            if world == 1:     # single GPU: the CUDA path against the oracle on a 300-trial slice of the headline workload's streams
+                seed = 0x4B46424F00002026
+                extra["parity_vs_oracle"] = {
+                    "max_rel": oracle_slice_parity(kf, lambda n: kf.CostEvaluator(kf.ReadParaVehicle(nsimruns_=n, cpu_core_number_=1), sample_times,
+                                                                                  seed=seed, device=local_rank), sample_times, 1.0, 0.1, seed),
+                    "what": "cost sums of 300 trials x 1000 steps x 2 sample times, CUDA path vs CPU oracle on the same Philox streams", "tolerance": 1e-9}
+        line_extra["extra"] = extra
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle's threaded path on a bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not cfg4:

@@ -8,7 +8,7 @@
 // Each Trial::Run is one thread's share of the Monte Carlo batch (nsimruns_/cpu_core_number_ trials, trial.cpp:28)
 // as one kernel launch with its own Philox stream; evaluator handles are pooled across Trial objects
 // (kfbo::detail::EvaluatorPool), so the CPUcoreNumber x 2 Trials a callback creates cost launches, not allocations.
-// tests/native/dropin builds the reference's trial_node.cpp this way and tests/test_gpu_dropin.py runs it on the GPU.
+// tests/native/dropin builds the reference's trial_node.cpp this way and tests/test_dropin.py runs it on the GPU.
 //
 // kfbo::RunTrial (kfbo_trial.hpp) is the faster way in -- one launch for all threads' shares and both sample
 // times -- when the caller can change.

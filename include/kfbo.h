@@ -12,6 +12,9 @@
  * that drives RunTrial::ProcessNoiseCallback, trial_node.cpp:154).
  *
  * There is NO CPU fallback: without a CUDA device kfbo_create fails.
+ *
+ * The CUDA device that is current on the calling thread is PRESERVED by every entry point (a handle may live on another
+ * device than the caller's other CUDA work, e.g. torch's).
  */
 #ifndef KFBO_H_
 #define KFBO_H_
@@ -36,7 +39,8 @@ enum {
     KFBO_EINVAL = -1,      /* bad argument (NULL pointer, size mismatch, ...) */
     KFBO_ERANGE = -2,      /* max_iterations outside [2, 2000], too many sample times ... */
     KFBO_ENODEVICE = -3,   /* no usable CUDA device: there is no CPU fallback */
-    KFBO_ESTATE = -4,      /* call not valid in this state (e.g. comm already initialised) */
+    KFBO_ESTATE = -4,      /* call not valid in this state (comm already initialised; a multi-GPU handle / group after a
+                              failed evaluation: its ranks are out of step, destroy it and start over) */
     KFBO_ECUDA = 1,        /* a CUDA runtime call failed; see kfbo_last_error */
     KFBO_ENCCL = 2,        /* an NCCL call failed; see kfbo_last_error */
     KFBO_EPEER = 3         /* the peer-memory exchange of the cost sums timed out waiting for a rank */
@@ -99,7 +103,11 @@ const char *kfbo_last_error(const kfbo_handle *h);
 
 /* One "noise" message -> one "cost": replaces the body of RunTrial::ProcessNoiseCallback
  * (trial_node.cpp:29-119).  pn[npn], on[non] are the message halves (only [0] is read, like
- * system_models.hpp:39,143).  On-device Philox noise; each call draws fresh streams. */
+ * system_models.hpp:39,143).  On-device Philox noise; each call draws fresh streams.
+ * Domain of a candidate (pn[0], on[0]): finite and > 0.  Outside it (NaN, inf, <= 0) the call still SUCCEEDS and the
+ * result is all NaN (max_cost NaN, index_max 0) -- what the reference observably does: its filter degenerates and
+ * std::abs(std::log(.)) (trial_node.cpp:77,93) publishes a NaN "cost", which ends the optimiser's wait loop
+ * (robot1d_bayesopt.cpp:107).  Positive values outside [1e-100, 1e100] return KFBO_ERANGE. */
 int kfbo_eval(kfbo_handle *h, const double *pn, int32_t npn, const double *on, int32_t non,
               kfbo_result *out);
 
@@ -107,6 +115,15 @@ int kfbo_eval(kfbo_handle *h, const double *pn, int32_t npn, const double *on, i
  * are pnoise_[0], onoise_[0] of candidate c; out[n_candidates]. */
 int kfbo_eval_batch(kfbo_handle *h, int32_t n_candidates, const double *q_est, const double *r_est,
                     kfbo_result *out);
+
+/* The same batch with the COST ASSEMBLY ON THE DEVICE (trial_node.cpp:70-119 per candidate: averages, the configured
+ * cost per sample time, max_element and its first index) and a compact answer: cost[n_candidates][D], max_cost and
+ * index_max[n_candidates] (host arrays).  What a cost-surface sweep wants: per candidate 16 bytes go to the device and
+ * 8 (D + 1) + 4 come back, and the host does no per-candidate arithmetic.  Same divisions as kfbo_finalize in the same
+ * order; log() is CUDA's (within 1 ulp of libm's), so costs agree with kfbo_eval_batch's to ~1e-15 relative and the
+ * selection is the same unless two sample times' costs tie to the last bit.  kfbo_last_sums is not available after it. */
+int kfbo_eval_batch_costs(kfbo_handle *h, int32_t n_candidates, const double *q_est, const double *r_est,
+                          double *cost, double *max_cost, int32_t *index_max);
 
 /* Exact-parity entry: sample time `k`, n_candidates estimators against ONE set of supplied
  * post-transform noise draws (host pointers, trial index fastest):
@@ -128,19 +145,24 @@ int kfbo_eval_supplied_dev(kfbo_handle *h, int32_t k, int32_t n_candidates, cons
 
 /* Philox-mode per-trial outputs for draw-for-draw checks: trials [trial0, trial0+ntrials) of
  * sample time k on Philox stream `stream`; per_trial[4][ntrials] (host). */
-int kfbo_eval_philox_trials(kfbo_handle *h, int32_t k, double q_est, double r_est, uint32_t stream,
+int kfbo_eval_philox_trials(kfbo_handle *h, int32_t k, double q_est, double r_est, uint64_t stream,
                             uint32_t trial0, int64_t ntrials, double *per_trial);
 
 /* The Nsimruns == 1 path of Trial::Run (trial.cpp:69-78,116-129: the error inside its 95 % band): trajectory
  * `trial` of Philox stream `stream` at sample time k, replayed step by step.
  * trace[T][9] (host) = {time, e1, e2, lb1, ub1, lb2, ub2, nees, nis}, lb/ub = -/+ 2 sqrt(P_ii) of the posterior. */
 #define KFBO_TRACE_COLUMNS 9
-int kfbo_trace_trial(kfbo_handle *h, int32_t k, double q_est, double r_est, uint32_t stream, uint32_t trial, double *trace);
+int kfbo_trace_trial(kfbo_handle *h, int32_t k, double q_est, double r_est, uint64_t stream, uint32_t trial, double *trace);
 
 /* Philox stream bookkeeping: evaluation e of candidate c at sample time k uses stream
- * base + (e*max_candidates + c)*n_sample_times + k.  kfbo_eval* advance e by one per call. */
-int kfbo_set_stream_base(kfbo_handle *h, uint32_t base);
-int kfbo_set_eval_counter(kfbo_handle *h, uint32_t e);
+ * base + (e*max_candidates + c)*n_sample_times + k, a KFBO_STREAM_BITS-bit id (modulo 2^62): it never wraps in
+ * practice (a 4096-candidate handle could run 5e14 evaluations).  kfbo_eval* advance e by one per call.
+ * Callers that hand out stream bases themselves keep them apart by the top bits: the Trial adapters of
+ * include/kfbo_trial.hpp start at KFBO_TRIAL_STREAM_BASE, RunTrial / kfbo_eval at 0. */
+#define KFBO_STREAM_BITS 62
+#define KFBO_TRIAL_STREAM_BASE (1ull << 61)
+int kfbo_set_stream_base(kfbo_handle *h, uint64_t base);
+int kfbo_set_eval_counter(kfbo_handle *h, uint64_t e);
 
 /* Raw cost sums of the last kfbo_eval / kfbo_eval_batch: sums[n_candidates][D][4] =
  * {sum row_nees, sum row_nis, sum var_nees, sum var_nis} over the trials (all ranks). */
@@ -149,6 +171,10 @@ int kfbo_last_sums(const kfbo_handle *h, double *sums, int32_t n_candidates);
 /* Device time (ms, CUDA events on the handle's stream) of the last rollout kernel launch(es)
  * and how many kernels the last evaluation launched. */
 int kfbo_last_kernel_ms(const kfbo_handle *h, double *ms, int32_t *launches);
+
+/* Bytes the last kfbo_eval* moved host -> device (candidate constants, exchange header) and device -> host (sums or
+ * compact costs; sums the kernel stores straight into mapped host memory count too). */
+int kfbo_last_transfer_bytes(const kfbo_handle *h, int64_t *h2d, int64_t *d2h);
 
 /* Host wall time (microseconds) of the phases of the last kfbo_eval / kfbo_eval_batch on this rank:
  * us[0] building the per-(candidate, sample time) constants, us[1] enqueueing copies and launches,
@@ -169,7 +195,10 @@ enum { KFBO_OPT_SUPPLIED_KERNEL = 1, KFBO_OPT_BULK_SMEM_PAD = 2 /* extra dynamic
        KFBO_OPT_ROLLOUT_FORM = 3,
        KFBO_OPT_REDUCE = 4 /* how the cost sums of a multi-GPU evaluation meet, KFBO_REDUCE_* below */,
        KFBO_OPT_PEER_FUSE = 5 /* KFBO_PEER_FUSE_* below */,
-       KFBO_OPT_PEER_TIMEOUT_MS = 6 /* how long the exchange waits for a rank before KFBO_EPEER (default 10000) */ };
+       KFBO_OPT_PEER_TIMEOUT_MS = 6 /* how long the exchange waits for a rank before KFBO_EPEER (default 10000) */,
+       KFBO_OPT_RESERVE_SUPPLIED_TRIALS = 7 /* pre-size the scratch of the parity entry points (kfbo_eval_supplied,
+                                        kfbo_eval_philox_trials, kfbo_trace_trial) for this many trials x max_candidates
+                                        candidates: after it they allocate nothing, like kfbo_eval* */ };
 /* KFBO_OPT_ROLLOUT_FORM, for the on-device-noise evaluations (kfbo_eval, kfbo_eval_batch, kfbo_eval_philox_trials):
  *   KFBO_FORM_REFERENCE (default): every trajectory carries truth state, estimate and covariance and runs
  *       simulator.cpp:15-19 + kalman_filter.cpp:18-38 + trial.cpp:53-60 step by step, as north_star prescribes.
@@ -207,12 +236,14 @@ int kfbo_comm_init(kfbo_handle *h, const void *id_bytes, int32_t rank, int32_t n
  *                     torch.distributed -- kf_bayesopt_b200/dist.py) and maps the peers' buffers.
  * Every rank must make the same sequence of kfbo_eval* calls (as for NCCL); a rank that waits longer than
  * KFBO_OPT_PEER_TIMEOUT_MS for another returns KFBO_EPEER instead of hanging (the ranks are then out of step with each
- * other: destroy the handles and start over, as after an NCCL failure).  A device group (below) attaches its
+ * other: the handle -- or the whole device group, after every device has been drained -- refuses further evaluations
+ * with KFBO_ESTATE; destroy it and start over, as after an NCCL failure).  A device group (below) attaches its
  * devices by itself.  Trial-sharded evaluations of more than 1024 (candidate, sample time) pairs keep the NCCL call. */
 #define KFBO_MAX_PEERS 8
 #define KFBO_PEER_HANDLE_BYTES 64
 int kfbo_peer_export(kfbo_handle *h, void *handle_bytes /*[KFBO_PEER_HANDLE_BYTES]*/);
-int kfbo_peer_attach(kfbo_handle *h, const void *all_handle_bytes /*[nranks][KFBO_PEER_HANDLE_BYTES]*/);
+int kfbo_peer_attach(kfbo_handle *h, const void *all_handle_bytes /*[n_handles][KFBO_PEER_HANDLE_BYTES]*/,
+                     int32_t n_handles /* must equal the rank count given to kfbo_comm_init */);
 /* 0: the last kfbo_eval / kfbo_eval_batch ran on one rank; 1: its sums met in an ncclAllReduce; 2: in the peer-memory
  * exchange as a kernel of its own; 3: in the peer-memory exchange fused into the rollout kernel. */
 int kfbo_last_reduce_path(const kfbo_handle *h);
@@ -237,8 +268,8 @@ int kfbo_group_eval_batch(kfbo_group *g, int32_t n_candidates, const double *q_e
 int kfbo_group_last_sums(const kfbo_group *g, double *sums, int32_t n_candidates);
 int kfbo_group_last_kernel_ms(const kfbo_group *g, double *ms_max /* slowest device */, int32_t *launches /* all devices */);
 int kfbo_group_set_option(kfbo_group *g, int32_t option, int64_t value);
-int kfbo_group_set_stream_base(kfbo_group *g, uint32_t base);
-int kfbo_group_set_eval_counter(kfbo_group *g, uint32_t e);
+int kfbo_group_set_stream_base(kfbo_group *g, uint64_t base);
+int kfbo_group_set_eval_counter(kfbo_group *g, uint64_t e);
 
 /* ---- host-side pieces of the path, exported so they can be tested without a GPU ---- */
 /* continuousToDiscrete for the robot1d model (continuous2discrete.hpp:8-32, system_models.hpp:33-39,58). */
@@ -252,8 +283,10 @@ int kfbo_finalize(const kfbo_params *p, const double *sums, kfbo_result *out);
 int64_t kfbo_effective_trials(const kfbo_params *p);
 
 /* DFMA-chain microbenchmark: sustained FP64 FMA throughput of `device` in TFLOP/s (2 flops per FMA)
- * over about `millis` ms -- the roofline denominator for the Philox path. */
-int kfbo_measure_fp64_peak(int32_t device, double millis, double *tflops, double *sm_clock_mhz_unused);
+ * over about `millis` ms -- the roofline denominator for the Philox path.  *tflops: chains x = fma(x, y, U) with the
+ * multiplier in a register (the full-rate operand form, 2.0 pipe cycles per warp instruction); *tflops_uniform_operands
+ * (optional): x = fma(x, U, U), both other operands in the parameter bank, which the pipe runs ~10 % slower. */
+int kfbo_measure_fp64_peak(int32_t device, double millis, double *tflops, double *tflops_uniform_operands);
 
 const char *kfbo_version(void);
 

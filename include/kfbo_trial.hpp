@@ -261,15 +261,15 @@ public:
         return ms;
     }
     // The Nsimruns == 1 record of trial.cpp:69-78: rows {time, e1, e2, lb1, ub1, lb2, ub2, nees, nis} of one trajectory.
-    std::vector<double> TraceTrial(int k, double q_est, double r_est, uint32_t stream, uint32_t trial)
+    std::vector<double> TraceTrial(int k, double q_est, double r_est, uint64_t stream, uint32_t trial)
     {
         std::vector<double> t((size_t)p_.max_iterations[k] * KFBO_TRACE_COLUMNS);
         Check(kfbo_trace_trial(h_, k, q_est, r_est, stream, trial, t.data()));
         return t;
     }
     void SetOption(int option, long long value) { Check(g_ ? kfbo_group_set_option(g_, option, value) : kfbo_set_option(h_, option, value)); }
-    void SetStreamBase(uint32_t base) { Check(g_ ? kfbo_group_set_stream_base(g_, base) : kfbo_set_stream_base(h_, base)); }
-    void SetEvalCounter(uint32_t e) { Check(g_ ? kfbo_group_set_eval_counter(g_, e) : kfbo_set_eval_counter(h_, e)); }
+    void SetStreamBase(uint64_t base) { Check(g_ ? kfbo_group_set_stream_base(g_, base) : kfbo_set_stream_base(h_, base)); }
+    void SetEvalCounter(uint64_t e) { Check(g_ ? kfbo_group_set_eval_counter(g_, e) : kfbo_set_eval_counter(h_, e)); }
     // one process per GPU instead (MPI / torchrun style): join the NCCL communicator of the ranks
     void CommInit(const void *nccl_id, int rank, int nranks, int shard_mode)
     {
@@ -287,7 +287,7 @@ public:
     }
     void PeerAttach(const std::vector<std::array<unsigned char, KFBO_PEER_HANDLE_BYTES>> &all_ranks)
     {
-        Check(kfbo_peer_attach(h_, all_ranks.data()));
+        Check(kfbo_peer_attach(h_, all_ranks.data(), (int32_t)all_ranks.size()));
     }
     // how the sums of the last evaluation met: 0 one rank, 1 ncclAllReduce, 2 / 3 peer memory (behind / inside the rollout kernel)
     int LastReducePath() const { return kfbo_last_reduce_path(g_ ? kfbo_group_handle(g_, 0) : h_); }
@@ -342,9 +342,9 @@ inline std::vector<std::pair<double, int>> SampleTimesFrom(const ReadParaVehicle
 constexpr uint64_t kDefaultSeed = 0x4B46424F20260101ull;
 
 namespace detail {
-inline std::atomic<uint32_t> &TrialStreamCounter()
+inline std::atomic<uint64_t> &TrialStreamCounter()
 {
-    static std::atomic<uint32_t> c{0x40000000u};
+    static std::atomic<uint64_t> c{KFBO_TRIAL_STREAM_BASE};   // the Trial adapters' own range of the 62-bit stream ids (kfbo.h)
     return c;
 }
 

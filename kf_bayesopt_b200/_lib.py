@@ -21,6 +21,9 @@ OPT_ROLLOUT_FORM = 3
 OPT_REDUCE = 4
 OPT_PEER_FUSE = 5
 OPT_PEER_TIMEOUT_MS = 6
+OPT_RESERVE_SUPPLIED_TRIALS = 7
+STREAM_BITS = 62
+TRIAL_STREAM_BASE = 1 << 61
 REDUCE_AUTO, REDUCE_NCCL = 0, 1
 PEER_FUSE_NEVER, PEER_FUSE_AUTO, PEER_FUSE_ALWAYS = 0, 1, 2
 MAX_PEERS = 8
@@ -81,12 +84,14 @@ SIGNATURES = {
     "kfbo_last_error": (C.c_char_p, [_vp]),
     "kfbo_eval": (C.c_int, [_vp, _dp, C.c_int32, _dp, C.c_int32, C.POINTER(KfboResult)]),
     "kfbo_eval_batch": (C.c_int, [_vp, C.c_int32, _dp, _dp, C.POINTER(KfboResult)]),
+    "kfbo_eval_batch_costs": (C.c_int, [_vp, C.c_int32, _dp, _dp, _dp, _dp, C.POINTER(C.c_int32)]),
+    "kfbo_last_transfer_bytes": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "kfbo_eval_supplied": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
     "kfbo_eval_supplied_dev": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp, _dp, C.c_int64, _vp, _vp, _vp, _vp, _dp]),
-    "kfbo_eval_philox_trials": (C.c_int, [_vp, C.c_int32, C.c_double, C.c_double, C.c_uint32, C.c_uint32, C.c_int64, _dp]),
-    "kfbo_trace_trial": (C.c_int, [_vp, C.c_int32, C.c_double, C.c_double, C.c_uint32, C.c_uint32, _dp]),
-    "kfbo_set_stream_base": (C.c_int, [_vp, C.c_uint32]),
-    "kfbo_set_eval_counter": (C.c_int, [_vp, C.c_uint32]),
+    "kfbo_eval_philox_trials": (C.c_int, [_vp, C.c_int32, C.c_double, C.c_double, C.c_uint64, C.c_uint32, C.c_int64, _dp]),
+    "kfbo_trace_trial": (C.c_int, [_vp, C.c_int32, C.c_double, C.c_double, C.c_uint64, C.c_uint32, _dp]),
+    "kfbo_set_stream_base": (C.c_int, [_vp, C.c_uint64]),
+    "kfbo_set_eval_counter": (C.c_int, [_vp, C.c_uint64]),
     "kfbo_last_sums": (C.c_int, [_vp, _dp, C.c_int32]),
     "kfbo_last_kernel_ms": (C.c_int, [_vp, _dp, C.POINTER(C.c_int32)]),
     "kfbo_last_host_us": (C.c_int, [_vp, _dp]),
@@ -95,7 +100,7 @@ SIGNATURES = {
     "kfbo_nccl_unique_id": (C.c_int, [_vp]),
     "kfbo_comm_init": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32]),
     "kfbo_peer_export": (C.c_int, [_vp, _vp]),
-    "kfbo_peer_attach": (C.c_int, [_vp, _vp]),
+    "kfbo_peer_attach": (C.c_int, [_vp, _vp, C.c_int32]),
     "kfbo_last_reduce_path": (C.c_int, [_vp]),
     "kfbo_group_create": (C.c_int, [C.POINTER(KfboParams), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(_vp)]),
     "kfbo_group_destroy": (None, [_vp]),
@@ -107,8 +112,8 @@ SIGNATURES = {
     "kfbo_group_last_sums": (C.c_int, [_vp, _dp, C.c_int32]),
     "kfbo_group_last_kernel_ms": (C.c_int, [_vp, _dp, C.POINTER(C.c_int32)]),
     "kfbo_group_set_option": (C.c_int, [_vp, C.c_int32, C.c_int64]),
-    "kfbo_group_set_stream_base": (C.c_int, [_vp, C.c_uint32]),
-    "kfbo_group_set_eval_counter": (C.c_int, [_vp, C.c_uint32]),
+    "kfbo_group_set_stream_base": (C.c_int, [_vp, C.c_uint64]),
+    "kfbo_group_set_eval_counter": (C.c_int, [_vp, C.c_uint64]),
     "kfbo_shard_range": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "kfbo_discretize": (C.c_int, [C.c_double, C.c_double, _dp, _dp]),
     "kfbo_control_table": (C.c_int, [C.c_double, C.c_int32, _dp]),

@@ -86,7 +86,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 }
 
 // Noise stream layout (restated draw for draw by oracle/kfbo_oracle.c):
-//   key = (seed_lo, seed_hi); counter = (trial, block, case.stream, sub)   [KFBO_PHILOX_LAYOUT below]
+//   key = (seed_lo, seed_hi); counter = (trial, block, stream[31:0], sub ^ (stream[61:32] << 2))   [KFBO_PHILOX_LAYOUT below]
+//   (the stream id is 62 bits: sub < 4 leaves the upper 30 bits of its word free for the id's upper half, which enters the
+//   first round through an XOR with a loop-invariant word -- no instruction in the step loop)
 //   block 0, sub 0         -> words (x, y): the N(0,P0) draw added to x0
 //   block g+1, sub 0, 1, 2 -> calls A, B, C of the STEP GROUP g = steps 4g .. 4g+3; a call (x, y, z, w) holds the two
 //                             normal pairs (x, y) and (z, w) of math::normal_pair:
@@ -107,21 +109,22 @@ struct GroupWords { uint4 a, b, c; };
 #ifndef KFBO_PHILOX_LAYOUT
 #define KFBO_PHILOX_LAYOUT 1
 #endif
-__device__ __forceinline__ uint4 philox_at(uint32_t trial, uint32_t stream, uint32_t block, uint32_t sub, const PhiloxKeys &key, uint32_t zero = 0u)
+// stream: bits 0..31 of the stream id; stream_x: its bits 32..61 shifted left by 2 (Case::stream_x)
+__device__ __forceinline__ uint4 philox_at(uint32_t trial, uint32_t stream, uint32_t stream_x, uint32_t block, uint32_t sub, const PhiloxKeys &key, uint32_t zero = 0u)
 {
 #if KFBO_PHILOX_LAYOUT == 1
-    return philox4x32_10(trial, block, stream, sub, key, zero);
+    return philox4x32_10(trial, block, stream, sub ^ stream_x, key, zero);
 #else
-    return philox4x32_10(trial, stream, block, sub, key, zero);
+    return philox4x32_10(trial, stream, block, sub ^ stream_x, key, zero);
 #endif
 }
 
-__device__ __forceinline__ GroupWords philox_group(uint32_t trial, uint32_t stream, uint32_t group, const PhiloxKeys &key, uint32_t zero = 0u)
+__device__ __forceinline__ GroupWords philox_group(uint32_t trial, uint32_t stream, uint32_t stream_x, uint32_t group, const PhiloxKeys &key, uint32_t zero = 0u)
 {
     GroupWords w;
-    w.a = philox_at(trial, stream, group + 1u, 0u, key, zero);
-    w.b = philox_at(trial, stream, group + 1u, 1u, key, zero);
-    w.c = philox_at(trial, stream, group + 1u, 2u, key, zero);
+    w.a = philox_at(trial, stream, stream_x, group + 1u, 0u, key, zero);
+    w.b = philox_at(trial, stream, stream_x, group + 1u, 1u, key, zero);
+    w.c = philox_at(trial, stream, stream_x, group + 1u, 2u, key, zero);
     return w;
 }
 

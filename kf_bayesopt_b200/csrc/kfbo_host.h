@@ -15,20 +15,58 @@
 namespace kfbo {
 namespace host {
 
+#if defined(__CUDACC__)
+#define KFBO_HOST_DEVICE __host__ __device__
+#else
+#define KFBO_HOST_DEVICE
+#endif
+
+// The arithmetic of the discretisation as separately rounded IEEE operations.  On the host that is what the compiler
+// emits anyway (no FMA contraction on baseline x86-64); on the device the rounding intrinsics keep nvcc from fusing a
+// multiply into the following add, so that the device-built constants (build_cases_kernel, kfbo_kernels.cu) are BIT
+// FOR BIT those of this host code.
+struct RoundedOps {
+    KFBO_HOST_DEVICE static double mul(double a, double b)
+    {
+#if defined(__CUDA_ARCH__)
+        return __dmul_rn(a, b);
+#else
+        return a * b;
+#endif
+    }
+    KFBO_HOST_DEVICE static double add(double a, double b)
+    {
+#if defined(__CUDA_ARCH__)
+        return __dadd_rn(a, b);
+#else
+        return a + b;
+#endif
+    }
+    KFBO_HOST_DEVICE static double div(double a, double b)
+    {
+#if defined(__CUDA_ARCH__)
+        return __ddiv_rn(a, b);
+#else
+        return a / b;
+#endif
+    }
+};
+
 // exp(A) for the 4x4 Van Loan matrix of the robot1d model.  With Fc = [[0,1],[0,0]] the matrix
 // [[-Fc dt, Qc dt],[0, Fc^T dt]] is nilpotent (A^4 = 0), so exp(A) = I + A + A^2/2 + A^3/6 is the
 // complete series; evaluated in Horner form  I + A (I + A/2 (I + A/3)).
-inline void expm_nilpotent4(const double A[4][4], double E[4][4])
+KFBO_HOST_DEVICE inline void expm_nilpotent4(const double A[4][4], double E[4][4])
 {
+    using R = RoundedOps;
     double M[4][4], N[4][4];
     for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) M[i][j] = (i == j ? 1.0 : 0.0) + A[i][j] / 3.0;
+        for (int j = 0; j < 4; ++j) M[i][j] = R::add(i == j ? 1.0 : 0.0, R::div(A[i][j], 3.0));
     for (int pass = 2; pass >= 1; --pass) {
         for (int i = 0; i < 4; ++i)
             for (int j = 0; j < 4; ++j) {
                 double s = 0.0;
-                for (int k = 0; k < 4; ++k) s += A[i][k] * M[k][j];
-                N[i][j] = (i == j ? 1.0 : 0.0) + s / (double)pass;
+                for (int k = 0; k < 4; ++k) s = R::add(s, R::mul(A[i][k], M[k][j]));
+                N[i][j] = R::add(i == j ? 1.0 : 0.0, R::div(s, (double)pass));
             }
         for (int i = 0; i < 4; ++i)
             for (int j = 0; j < 4; ++j) M[i][j] = N[i][j];
@@ -39,17 +77,18 @@ inline void expm_nilpotent4(const double A[4][4], double E[4][4])
 
 // continuousToDiscrete(fd_, qd_, fc, qc, dt) with fc(0,1) = 1, qc(1,1) = pnoise_[0], all other
 // entries 0 (the reference leaves three entries of qc uninitialised; 0 is the intended model).
-inline void discretize(double pnoise0, double dt, double Fd[4], double Qd[4])
+KFBO_HOST_DEVICE inline void discretize(double pnoise0, double dt, double Fd[4], double Qd[4])
 {
+    using R = RoundedOps;
     double A[4][4] = {{0}}, E[4][4];
-    A[0][1] = -1.0 * dt;      // topLeft   = -Fc*dt
-    A[1][3] = pnoise0 * dt;   // topRight  =  Qc*dt   (only Qc(1,1) is non-zero)
-    A[3][2] = 1.0 * dt;       // botRight  =  Fc^T*dt
+    A[0][1] = R::mul(-1.0, dt);      // topLeft   = -Fc*dt
+    A[1][3] = R::mul(pnoise0, dt);   // topRight  =  Qc*dt   (only Qc(1,1) is non-zero)
+    A[3][2] = R::mul(1.0, dt);       // botRight  =  Fc^T*dt
     expm_nilpotent4(A, E);
     // Fd = bottomRight^T ; Qd = Fd * topRight
     Fd[0] = E[2][2]; Fd[1] = E[3][2]; Fd[2] = E[2][3]; Fd[3] = E[3][3];
     for (int i = 0; i < 2; ++i)
-        for (int j = 0; j < 2; ++j) Qd[2 * i + j] = Fd[2 * i] * E[0][2 + j] + Fd[2 * i + 1] * E[1][2 + j];
+        for (int j = 0; j < 2; ++j) Qd[2 * i + j] = R::add(R::mul(Fd[2 * i], E[0][2 + j]), R::mul(Fd[2 * i + 1], E[1][2 + j]));
 }
 
 inline void control_table(double dt, int n, double *u)
@@ -70,26 +109,30 @@ inline int64_t effective_trials(const kfbo_params &p)
 // Thread t of `cores` reports all_nees_t / k_average etc.; the callback adds getter/cores over t.
 // With the per-thread sums unknown individually, the mean over threads is formed from the total:
 // mathematically identical, rounding differs at the 1e-16 level.
-inline void averages(const kfbo_params &p, int k, const double sums[4], double avg[4])
+// (The same two functions run on the device for the compact cost output of kfbo_eval_batch_costs: every operation is a
+// separately rounded IEEE operation there too; only log() differs -- CUDA's is within 1 ulp of libm's.)
+KFBO_HOST_DEVICE inline void averages(const kfbo_params &p, int k, const double sums[4], double avg[4])
 {
+    using R = RoundedOps;
     const int64_t T = p.max_iterations[k];
     const double cores = (double)p.cpu_core_number;
     const double k_average = (double)(T * (int64_t)p.nsimruns / p.cpu_core_number);  // trial.cpp:19
-    avg[0] = sums[0] / k_average / cores;                                             // trial.cpp:112, trial_node.cpp:74
-    avg[1] = sums[1] / k_average / cores;                                             // trial.cpp:113, trial_node.cpp:90
-    avg[2] = sums[2] * cores / (double)p.nsimruns / cores;                            // trial.cpp:110, trial_node.cpp:75
-    avg[3] = sums[3] * cores / (double)p.nsimruns / cores;                            // trial.cpp:111, trial_node.cpp:91
+    avg[0] = R::div(R::div(sums[0], k_average), cores);                               // trial.cpp:112, trial_node.cpp:74
+    avg[1] = R::div(R::div(sums[1], k_average), cores);                               // trial.cpp:113, trial_node.cpp:90
+    avg[2] = R::div(R::div(R::mul(sums[2], cores), (double)p.nsimruns), cores);       // trial.cpp:110, trial_node.cpp:75
+    avg[3] = R::div(R::div(R::mul(sums[3], cores), (double)p.nsimruns), cores);       // trial.cpp:111, trial_node.cpp:91
 }
 
-inline double cost_of(const kfbo_params &p, const double avg[4])
+KFBO_HOST_DEVICE inline double cost_of(const kfbo_params &p, const double avg[4])
 {
+    using R = RoundedOps;
     switch (p.cost_choice) {
-    case KFBO_JNEES: return std::abs(std::log(avg[0] / p.state_dof));                                   // trial_node.cpp:77
-    case KFBO_CNEES: return std::abs(std::log(avg[0] / p.state_dof)) +
-                            std::abs(std::log(0.5 * avg[2] / p.state_dof));                             // :78-81
-    case KFBO_JNIS:  return std::abs(std::log(avg[1] / p.observation_dof));                             // :93
-    default:         return std::abs(std::log(avg[1] / p.observation_dof)) +
-                            std::abs(std::log(0.5 * avg[3] / p.observation_dof));                       // :94-97
+    case KFBO_JNEES: return fabs(log(R::div(avg[0], p.state_dof)));                                     // trial_node.cpp:77
+    case KFBO_CNEES: return R::add(fabs(log(R::div(avg[0], p.state_dof))),
+                                   fabs(log(R::div(R::mul(0.5, avg[2]), p.state_dof))));                // :78-81
+    case KFBO_JNIS:  return fabs(log(R::div(avg[1], p.observation_dof)));                               // :93
+    default:         return R::add(fabs(log(R::div(avg[1], p.observation_dof))),
+                                   fabs(log(R::div(R::mul(0.5, avg[3]), p.observation_dof))));          // :94-97
     }
 }
 

@@ -19,6 +19,7 @@
 #include <atomic>
 
 #include "kfbo_device.cuh"
+#include "kfbo_host.h"
 #include "kfbo_kernels.h"
 
 namespace kfbo {
@@ -268,17 +269,17 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
     Traj t;
     {
         double a, b;
-        const uint4 w = philox_at(trial, m.stream, 0u, 0u, key);
+        const uint4 w = philox_at(trial, m.stream, m.stream_x, 0u, 0u, key);
         math::normal_pair(w.x, w.y, s_log, a, b);
         traj_init<kShiftFirst>(t, a, b);
     }
     // Whole groups of four steps: ONE basic block per group (no branch inside), so the scheduler is free to overlap the
     // table lookups and the log/sqrt chains of one step's normals with the filter recursion of the previous step.
     const int nfull = T >> 2;
-    GroupWords r = philox_group(trial, m.stream, 0u, key);
+    GroupWords r = philox_group(trial, m.stream, m.stream_x, 0u, key);
 #pragma unroll KFBO_PHILOX_GROUP_UNROLL_V
     for (int g = 0; g < nfull; ++g) {
-        const GroupWords q = philox_group(trial, m.stream, (uint32_t)g + 1u, key, zero);
+        const GroupWords q = philox_group(trial, m.stream, m.stream_x, (uint32_t)g + 1u, key, zero);
         const double2 *gs = gu + 4 * g;
         const double2 g0 = __ldg(gs), g1 = __ldg(gs + 1), g2 = __ldg(gs + 2), g3 = __ldg(gs + 3);
         double p0a, p0b, p1a, p1b, p2a, p2b, p3a, p3b, o0, o1, o2, o3;
@@ -679,11 +680,11 @@ rollout_philox_reduced(const Case *__restrict__ cases, const __grid_constant__ S
     const uint32_t trial = trial0 + local;    // past-the-end trajectories of the last tile are computed and discarded
     double e0, e1, kn = 0.0, ki = 0.0, sdn = 0.0, sqn = 0.0, sdi = 0.0, sqi = 0.0;
     {
-        const uint4 w = philox_at(trial, m.stream, 0u, 0u, key);
+        const uint4 w = philox_at(trial, m.stream, m.stream_x, 0u, 0u, key);
         math::normal_pair(w.x, w.y, s_log, e0, e1);    // e = x0 + N(0,P0) - xhat0 = the draw itself
     }
     static_assert(kGainChunk % 4 == 0, "a gain chunk holds whole step groups");
-    GroupWords r = philox_group(trial, m.stream, 0u, key);
+    GroupWords r = philox_group(trial, m.stream, m.stream_x, 0u, key);
     for (int c = 0; c < nchunks; ++c) {
         if (threadIdx.x == 0) {
             const int nx = c + kGainStages - 1;
@@ -701,7 +702,7 @@ rollout_philox_reduced(const Case *__restrict__ cases, const __grid_constant__ S
 #pragma unroll kReducedUnroll
         for (int gi = 0; gi < nfull; ++gi) {                              // whole groups: one basic block each
             const int j = 4 * gi, s0 = c0 + j;
-            const GroupWords q = philox_group(trial, m.stream, (uint32_t)(s0 >> 2) + 1u, key);
+            const GroupWords q = philox_group(trial, m.stream, m.stream_x, (uint32_t)(s0 >> 2) + 1u, key);
             double p0a, p0b, p1a, p1b, p2a, p2b, p3a, p3b, o0, o1, o2, o3;
             math::normal_pair(r.c.x, r.c.y, s_log, o0, o1);
             math::normal_pair(r.a.x, r.a.y, s_log, p0a, p0b);
@@ -774,13 +775,13 @@ __global__ void trace_philox(const Case *__restrict__ cases, const __grid_consta
     Traj t;
     {
         double a, b;
-        const uint4 w = philox_at(trial, m.stream, 0u, 0u, key);
+        const uint4 w = philox_at(trial, m.stream, m.stream_x, 0u, 0u, key);
         math::normal_pair(w.x, w.y, tab, a, b);
         traj_init(t, a, b);
     }
     for (int s = 0; s < m.T; ++s) {
         // the normals of step s out of its group's words (kfbo_device.cuh: philox_group), formed anew every step
-        const GroupWords w = philox_group(trial, m.stream, (uint32_t)(s >> 2), key);
+        const GroupWords w = philox_group(trial, m.stream, m.stream_x, (uint32_t)(s >> 2), key);
         const int q = s & 3;
         const uint4 pw = q < 2 ? w.a : w.b;
         double pa, pb, oa, ob;
@@ -799,19 +800,99 @@ __global__ void trace_philox(const Case *__restrict__ cases, const __grid_consta
 }
 
 // -----------------------------------------------------------------------------------------
-// DFMA-chain microbenchmark: 8 independent FMA chains per thread.
+// A candidate batch without the host on its critical path.
+//   build_cases_kernel     16 bytes per candidate in -> the Case of every (candidate, sample time): continuousToDiscrete
+//                          (continuous2discrete.hpp:8-32) and R = onoise/dt (system_models.hpp:143) with the HOST's
+//                          arithmetic, operation for operation (kfbo_host.h: RoundedOps): bit-identical constants
+//   assemble_costs_kernel  trial_node.cpp:70-119 per candidate: the four averages, the configured cost per sample time,
+//                          max_element and its (first) index
 // -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) build_cases_kernel(const double2 *__restrict__ cand, int ncand, const __grid_constant__ CaseBuildConsts cb,
+                                                          Case *__restrict__ cases)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= ncand * cb.D) return;
+    const int c = i / cb.D, k = i - c * cb.D;
+    const double2 qr = cand[c];
+    double Fd[4], Qd[4];
+    host::discretize(qr.x, cb.dt[k], Fd, Qd);
+    Case m;
+    m.f = Fd[1];
+    m.q00 = Qd[0]; m.q01 = Qd[1]; m.q10 = Qd[2]; m.q11 = Qd[3];
+    m.r_est = __ddiv_rn(qr.y, cb.dt[k]);
+    m.l00 = cb.l00[k]; m.l10 = cb.l10[k]; m.l11 = cb.l11[k]; m.sr = cb.sr[k];
+    m.T = cb.T[k];
+    const uint64_t stream = cb.stream0 + (uint64_t)(cb.c0 + c) * (uint64_t)cb.D + (uint64_t)k;
+    m.stream = (uint32_t)stream;
+    m.stream_x = (uint32_t)((stream >> 32) & 0x3FFFFFFFull) << 2;
+    m.out_slot = (cb.c0 + c) * cb.D + k;
+    cases[i] = m;
+}
+
+cudaError_t launch_build_cases(const double2 *d_cand, int ncand, const CaseBuildConsts &cb, Case *d_cases, cudaStream_t stream)
+{
+    if (ncand <= 0) return cudaSuccess;
+    build_cases_kernel<<<(ncand * cb.D + 127) / 128, 128, 0, stream>>>(d_cand, ncand, cb, d_cases);
+    return cudaGetLastError();
+}
+
+size_t compact_costs_bytes(int C, int D) { return (size_t)C * ((size_t)D + 1) * sizeof(double) + (size_t)C * sizeof(int32_t); }
+
+__global__ void __launch_bounds__(128) assemble_costs_kernel(const double *__restrict__ sums, int C, const __grid_constant__ kfbo_params p,
+                                                             double *__restrict__ cost, double *__restrict__ max_cost, int32_t *__restrict__ index_max)
+{
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= C) return;
+    const int D = p.n_sample_times;
+    double best = 0.0;
+    int arg = 0;
+    for (int k = 0; k < D; ++k) {
+        const double4 s4 = *reinterpret_cast<const double4 *>(sums + ((size_t)c * D + k) * 4);
+        const double s[4] = {s4.x, s4.y, s4.z, s4.w};
+        double avg[4];
+        host::averages(p, k, s, avg);
+        const double j = host::cost_of(p, avg);
+        cost[(size_t)c * D + k] = j;
+        // std::max_element (trial_node.cpp:118-119): the FIRST maximal element; a later one replaces it only if the
+        // current best compares less than it (NaN never does)
+        if (k == 0 || best < j) { best = j; arg = k; }
+    }
+    max_cost[c] = best;
+    index_max[c] = arg;
+}
+
+cudaError_t launch_assemble_costs(const double *d_sums, int C, const void *params, void *d_out, cudaStream_t stream)
+{
+    const kfbo_params &p = *static_cast<const kfbo_params *>(params);
+    double *cost = static_cast<double *>(d_out), *mx = cost + (size_t)C * p.n_sample_times;
+    int32_t *idx = reinterpret_cast<int32_t *>(mx + C);
+    assemble_costs_kernel<<<(C + 127) / 128, 128, 0, stream>>>(d_sums, C, p, cost, mx, idx);
+    return cudaGetLastError();
+}
+
+// -----------------------------------------------------------------------------------------
+// DFMA-chain microbenchmark: 8 independent FMA chains per thread -- the FP64 roofline denominator.
+//   kRegMultiplier = true  (the peak): x = fma(x, y, U), the multiplier y in a vector register of its own per chain and the
+//       addend a uniform / parameter-bank operand: 2.01 cycles per warp instruction on an SMSP (tools/microbench/rf_ports.cu,
+//       profiles/rf_ports_r1k.txt) = the pipe's 16 lanes x 2 passes;
+//   kRegMultiplier = false: x = fma(x, U, U), both other operands uniform -- 2.22 cycles: the form round 1 reported its
+//       fraction against (which flattered it by 10 %); kept as `peak_uniform_operands` for comparison.
+// -----------------------------------------------------------------------------------------
+template <bool kRegMultiplier>
 __global__ void __launch_bounds__(256) dfma_chain(double *out, int iters, double a, double b)
 {
-    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    double x[8], y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { x[j] = threadIdx.x + j; y[j] = a - 1e-12 * (threadIdx.x + j); }
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
-        }
+        for (int u = 0; u < 16; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = kRegMultiplier ? fma(x[j], y[j], b) : fma(x[j], a, b);
     }
-    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += x[j] + y[j];
     if (s == 123.456) out[0] = s;  // keep the chains alive
 }
 
@@ -945,13 +1026,13 @@ int supplied_variant_for(int requested, const double *d_w, const double *d_v, si
     return kSuppliedBulk;
 }
 
-cudaError_t launch_dfma_chain(double *d_out, int blocks, int iters, cudaStream_t stream)
+cudaError_t launch_dfma_chain(double *d_out, int blocks, int iters, bool reg_multiplier, cudaStream_t stream)
 {
-    dfma_chain<<<blocks, 256, 0, stream>>>(d_out, iters, 0.999999, 1e-9);
+    if (reg_multiplier) dfma_chain<true><<<blocks, 256, 0, stream>>>(d_out, iters, 0.999999, 1e-9);
+    else                dfma_chain<false><<<blocks, 256, 0, stream>>>(d_out, iters, 0.999999, 1e-9);
     return cudaGetLastError();
 }
 
 int rollout_tiles(size_t ntrials) { return (int)((ntrials + kThreads - 1) / kThreads); }
-int philox_tiles(size_t ntrials) { return rollout_tiles(ntrials); }
 
 }  // namespace kfbo

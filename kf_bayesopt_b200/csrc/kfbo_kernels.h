@@ -24,8 +24,9 @@ struct Case {
     double l00, l10, l11;        // Cholesky factor of the truth Qd  (replaces eigenmvn.h:126-130)
     double sr;                   // sqrt(truth R)
     int32_t T;                   // max_iterations_
-    int32_t k;                   // sample-time index (selects the g*u table)
-    uint32_t stream;             // Philox stream of this (evaluation, candidate, sample time)
+    uint32_t stream_x;           // bits 32..61 of the Philox stream id, shifted left by 2: XORed into the counter word that
+                                 // holds the call index `sub` (0..2) -- kfbo_device.cuh: philox_at
+    uint32_t stream;             // bits 0..31 of the Philox stream id of this (evaluation, candidate, sample time)
     int32_t out_slot;            // row of the [n][4] sums / per-trial output this case writes
 };
 
@@ -120,9 +121,35 @@ int supplied_variant_for(int requested, const double *d_w, const double *d_v, si
 cudaError_t launch_trace_philox(const Case *d_case, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, uint64_t seed,
                                 uint32_t trial, double dt, double *d_trace, cudaStream_t stream);
 
-cudaError_t launch_dfma_chain(double *d_out, int blocks, int iters, cudaStream_t stream);
+// reg_multiplier: x = fma(x, y, U) (the full-rate operand form, the peak) or x = fma(x, U, U) (10 % slower; see kfbo_kernels.cu)
+// ---- a candidate batch without the host on the critical path (kfbo_eval_batch with more than one candidate, kfbo_eval_batch_costs)
+// build_cases_kernel: the per-(candidate, sample time) constants from 16 bytes per candidate, on the device, with the
+// host's arithmetic operation for operation (kfbo_host.h: RoundedOps) -- the Case table is bit for bit what
+// build_case (kfbo_api.cu) makes on the host.
+struct CaseBuildConsts {
+    double dt[4], l00[4], l10[4], l11[4], sr[4];   // per sample time: dt and the truth noise transform
+    int32_t T[4];
+    int32_t D;                                     // sample times per candidate
+    int32_t c0;                                    // index of the first candidate of d_cand in the whole batch (out_slot, stream)
+    uint64_t stream0;                              // stream id of candidate 0, sample time 0 of this evaluation
+};
+cudaError_t launch_build_cases(const double2 *d_cand /* (pnoise, onoise) */, int ncand, const CaseBuildConsts &cb, Case *d_cases, cudaStream_t stream);
 
-int rollout_tiles(size_t ntrials);   // CTAs per case of the supplied-noise kernel (upper bound for the Philox one)
-int philox_tiles(size_t ntrials);    // CTAs per case of the Philox kernel
+// assemble_costs_kernel: trial_node.cpp:70-119 per candidate on the device -- averages, the configured cost per sample
+// time, the first-max selection -- from the [C][D][4] sums; out = cost[C][D] doubles, then max_cost[C] doubles, then
+// index_max[C] int32 (one contiguous block, copied to the host in one piece).
+size_t compact_costs_bytes(int C, int D);
+cudaError_t launch_assemble_costs(const double *d_sums, int C, const void *params /* const kfbo_params* (host) */, void *d_out, cudaStream_t stream);
+
+cudaError_t launch_dfma_chain(double *d_out, int blocks, int iters, bool reg_multiplier, cudaStream_t stream);
+
+int rollout_tiles(size_t ntrials);   // CTAs per case of the rollout kernels
+
+// The Philox stream id is 62 bits wide (kfbo.h: KFBO_STREAM_BITS): where its halves go in a Case.
+inline void set_case_stream(Case *c, uint64_t stream)
+{
+    c->stream = (uint32_t)stream;
+    c->stream_x = (uint32_t)((stream >> 32) & 0x3FFFFFFFull) << 2;
+}
 
 }  // namespace kfbo

@@ -238,10 +238,22 @@ class CostEvaluator:
         self._check(self._lib.kfbo_eval_batch(self._h, q.size, _ptr(q), _ptr(r), res.ctypes.data_as(C.POINTER(KfboResult))))
         return res
 
-    def eval_batch_costs(self, q_est, r_est) -> Tuple[np.ndarray, np.ndarray]:
-        """(cost[C][D], max_cost[C]) of a candidate batch."""
-        res = self.eval_batch_raw(q_est, r_est)
-        return res["cost"][:, :self.D].copy(), res["max_cost"].copy()
+    def eval_batch_costs(self, q_est, r_est, with_index: bool = False):
+        """(cost[C][D], max_cost[C]) of a candidate batch (with_index: also index_max[C]), assembled on the device
+        (kfbo_eval_batch_costs): 16 bytes per candidate in, 8 (D + 1) + 4 out, no per-candidate host work."""
+        q, r = _f64(q_est), _f64(r_est)
+        if q.shape != r.shape or q.ndim != 1:
+            raise ValueError("q_est and r_est must be 1-D arrays of equal length")
+        cost, mx, idx = np.empty((q.size, self.D)), np.empty(q.size), np.empty(q.size, dtype=np.int32)
+        self._check(self._lib.kfbo_eval_batch_costs(self._h, q.size, _ptr(q), _ptr(r), _ptr(cost), _ptr(mx),
+                                                    idx.ctypes.data_as(C.POINTER(C.c_int32))))
+        return (cost, mx, idx) if with_index else (cost, mx)
+
+    def last_transfer_bytes(self) -> Tuple[int, int]:
+        """(host -> device, device -> host) bytes of the last evaluation."""
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self._lib.kfbo_last_transfer_bytes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def last_sums(self, n_candidates: int = 1) -> np.ndarray:
         out = np.empty((n_candidates, self.D, 4))
@@ -318,11 +330,12 @@ class CostEvaluator:
 
     def peer_attach(self, handles) -> None:
         """handles: the peer_export() bytes of ALL ranks, in rank order."""
-        blob = b"".join(bytes(x) for x in handles)
-        if len(blob) % _lib.PEER_HANDLE_BYTES:
+        handles = [bytes(x) for x in handles]
+        if any(len(x) != _lib.PEER_HANDLE_BYTES for x in handles):
             raise ValueError("peer handles are PEER_HANDLE_BYTES each")
+        blob = b"".join(handles)
         buf = C.create_string_buffer(blob, len(blob))
-        self._check(self._lib.kfbo_peer_attach(self._h, buf))
+        self._check(self._lib.kfbo_peer_attach(self._h, buf, len(handles)))   # the library checks the count against its ranks
 
     def last_reduce_path(self) -> str:
         return _lib.REDUCE_PATHS.get(self._lib.kfbo_last_reduce_path(self._h), "?")
@@ -445,18 +458,20 @@ def control_table(dt: float, n: int = 2000) -> np.ndarray:
     return u
 
 
-def measure_fp64_peak(device: int = -1, millis: float = 200.0) -> float:
-    t = C.c_double()
-    rc = _lib.load().kfbo_measure_fp64_peak(device, millis, C.byref(t), None)
+def measure_fp64_peak(device: int = -1, millis: float = 200.0, both: bool = False):
+    """Sustained DFMA throughput (TFLOP/s) of the register-multiplier chain x = fma(x, y, U) -- the FP64 roofline
+    denominator; both=True: (that, the same with both other operands uniform: x = fma(x, U, U), ~10 % slower)."""
+    t, u = C.c_double(), C.c_double()
+    rc = _lib.load().kfbo_measure_fp64_peak(device, millis, C.byref(t), C.byref(u) if both else None)
     if rc:
         raise KfboError(rc, (_lib.load().kfbo_last_error(None) or b"").decode())
-    return t.value
+    return (t.value, u.value) if both else t.value
 
 
 # -------------------------------------------------------------------------------------------
 # Reference-shaped interface
 # -------------------------------------------------------------------------------------------
-_trial_streams = itertools.count(0x40000000)
+_trial_streams = itertools.count(_lib.TRIAL_STREAM_BASE)   # the Trial adapters' own range of the 62-bit stream ids
 
 
 class Trial:

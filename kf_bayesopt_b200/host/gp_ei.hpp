@@ -123,13 +123,13 @@ private:
         const double r = std::sqrt(3.0 * r2);
         return (1.0 + r) * std::exp(-r);
     }
-    // Cholesky of K + noise I for length-scales ell; returns false if not positive definite
-    bool Factor(const Vec &ell, std::vector<double> *L) const
+    // Cholesky of K + (noise + jitter) I for length-scales ell; returns false if not positive definite
+    bool Factor(const Vec &ell, std::vector<double> *L, double jitter = 1e-10) const
     {
         const size_t n = X_.size();
         L->assign(n * n, 0.0);
         for (size_t i = 0; i < n; ++i)
-            for (size_t j = 0; j <= i; ++j) (*L)[i * n + j] = Kernel(X_[i], X_[j], ell) + (i == j ? rb_.noise_ + 1e-10 : 0.0);
+            for (size_t j = 0; j <= i; ++j) (*L)[i * n + j] = Kernel(X_[i], X_[j], ell) + (i == j ? rb_.noise_ + jitter : 0.0);
         for (size_t j = 0; j < n; ++j) {
             double s = (*L)[j * n + j];
             for (size_t k = 0; k < j; ++k) s -= (*L)[j * n + k] * (*L)[j * n + k];
@@ -198,7 +198,13 @@ private:
     void Fit()
     {
         Standardise();
-        if (!Factor(ell_, &L_)) throw Error(KFBO_EINVAL, "GP covariance is not positive definite");
+        // near-duplicate samples (the optimiser converging) make K numerically singular: escalate the diagonal jitter
+        // instead of giving the whole loop up
+        double jitter = 1e-10;
+        while (!Factor(ell_, &L_, jitter)) {
+            jitter *= 100.0;
+            if (jitter > 1e-2) throw Error(KFBO_EINVAL, "GP covariance is not positive definite even with a jitter of 1e-2");
+        }
         alpha_ = ys_;
         SolveLower(L_, X_.size(), &alpha_);
         SolveUpper(L_, X_.size(), &alpha_);

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <iomanip>
+#include <limits>
 #include <sstream>
 
 #include "kfbo_trial.hpp"
@@ -54,7 +55,18 @@ int main(int nargs, char *args[])
         ros::Publisher pub_cost = n.advertise<std_msgs::Float64>("cost", 10);                     // trial_node.cpp:17
         kfbo::RunTrial rT(rv, sec, n_init, [&](const std_msgs::Float64 &c) { pub_cost.publish(c); }, verbose, device, seed, max_cand, gpus);
         boost::function<void(const std_msgs::Float64MultiArray::ConstPtr &)> cb =
-            [&](const std_msgs::Float64MultiArray::ConstPtr &m) { rT.ProcessNoiseCallback(*m); };
+            [&](const std_msgs::Float64MultiArray::ConstPtr &m) {
+                // a malformed message or a failed evaluation must not escape ros::spin() and kill the node: log it and
+                // answer with a NaN cost, which ends the optimiser's wait loop (robot1d_bayesopt.cpp:107)
+                try {
+                    rT.ProcessNoiseCallback(*m);
+                } catch (const std::exception &e) {
+                    ROS_ERROR("robot_1d_kf: noise message dropped: %s", e.what());
+                    std_msgs::Float64 c;
+                    c.data = std::numeric_limits<double>::quiet_NaN();
+                    pub_cost.publish(c);
+                }
+            };
         ros::Subscriber sub = n.subscribe<std_msgs::Float64MultiArray>("noise", 10, cb);           // trial_node.cpp:150
         ros::spin();
 #else

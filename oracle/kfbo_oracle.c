@@ -348,7 +348,7 @@ void ko_noise_transform(const double *Qd, double R, double *L /*[3]: L00,L10,L11
 }
 
 typedef struct {
-    uint32_t key[2], trial, stream;
+    uint32_t key[2], trial, stream, stream_x;   /* stream id bits 0..31; bits 32..61 shifted left by 2 */
     double L[3], sr;
     int cached_group;  /* index of the step group whose 12 normals are in pn[], on[] */
     double pn[8], on[4];
@@ -361,7 +361,7 @@ static void philox_noise(void *p, int step, double *w0, double *w1, double *v)
     if (group != c->cached_group) {
         uint32_t out[3][4];
         for (uint32_t j = 0; j < 3; ++j) {
-            const uint32_t ctr[4] = {c->trial, (uint32_t)group + 1u, c->stream, j};   /* (trial, block, stream, sub) */
+            const uint32_t ctr[4] = {c->trial, (uint32_t)group + 1u, c->stream, j ^ c->stream_x};   /* (trial, block, stream lo, sub ^ stream hi << 2) */
             ko_philox4x32_10(ctr, c->key, out[j]);
         }
         ko_normals_of_group(out[0], out[1], out[2], c->pn, c->on);
@@ -375,7 +375,7 @@ static void philox_noise(void *p, int step, double *w0, double *w1, double *v)
 
 /* Philox-stream evaluation of trials [trial0, trial0+ntrials) of one
  * (candidate, sample time).  per_trial[4][ntrials]. */
-int ko_eval_philox(uint64_t seed, uint32_t stream, double dt, int T, double q_truth, double r_truth,
+int ko_eval_philox(uint64_t seed, uint64_t stream /* 62-bit id */, double dt, int T, double q_truth, double r_truth,
                    double q_est, double r_est, uint32_t trial0, long ntrials, double *per_trial)
 {
     if (T < 2 || T > KO_U_TABLE || ntrials < 0) return -1;
@@ -385,12 +385,13 @@ int ko_eval_philox(uint64_t seed, uint32_t stream, double dt, int T, double q_tr
     ko_model_init(est, q_est, r_est, dt);
     philox_ctx c;
     c.key[0] = (uint32_t)seed; c.key[1] = (uint32_t)(seed >> 32);
-    c.stream = stream;
+    c.stream = (uint32_t)stream;
+    c.stream_x = (uint32_t)((stream >> 32) & 0x3FFFFFFFu) << 2;
     ko_noise_transform(truth->Qd, truth->R, c.L, &c.sr);
     for (long i = 0; i < ntrials; ++i) {
         c.trial = trial0 + (uint32_t)i;
         c.cached_group = -1;
-        const uint32_t ctr[4] = {c.trial, 0u, c.stream, 0u};                      /* block 0: the x0 draw */
+        const uint32_t ctr[4] = {c.trial, 0u, c.stream, c.stream_x};              /* block 0, sub 0: the x0 draw */
         uint32_t o[4];
         double x0n[2], out[4];
         ko_philox4x32_10(ctr, c.key, o);

@@ -40,7 +40,7 @@ def lib() -> C.CDLL:
         L.ko_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
         L.ko_normal_pair.argtypes = [C.c_uint32, C.c_uint32, _dp, _dp]
         L.ko_noise_transform.argtypes = [_dp, C.c_double, _dp, _dp]
-        L.ko_eval_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_double, C.c_int, C.c_double, C.c_double,
+        L.ko_eval_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_double, C.c_double,
                                      C.c_double, C.c_double, C.c_uint32, C.c_long, _dp]
         L.ko_eval_philox.restype = C.c_int
         L.ko_thread_averages.argtypes = [_dp, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, _dp]

@@ -105,6 +105,15 @@ def test_reference_node_unmodified_runs_on_the_gpu(dropin, kfbo):
 
 
 @pytest.mark.gpu
+def test_reference_node_answers_an_impossible_candidate_with_nan(dropin):
+    # pnoise <= 0 / NaN: the reference's own arithmetic publishes NaN for such a message (the optimiser's wait loop ends on
+    # it, robot1d_bayesopt.cpp:107); through the drop-in the unmodified node does the same, and goes on to the next message
+    set_params(dropin, Nsimruns=2000)
+    costs, _ = node_run(dropin, [([-1.0], [0.1]), ([1.0], [0.0]), ([1.0], [0.1])])
+    assert len(costs) == 3 and np.isnan(costs[0]) and np.isnan(costs[1]) and 0 <= costs[2] < 0.05
+
+
+@pytest.mark.gpu
 def test_reference_node_cost_choices_and_thread_counts(dropin):
     for choice, lo, hi in [("JNIS", 0.0, 0.01), ("CNEES", 0.0, 0.1), ("CNIS", 0.0, 0.05)]:
         for cores in (1, 4, 10):

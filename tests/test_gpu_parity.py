@@ -95,11 +95,102 @@ def test_philox_trials_match_oracle_draw_for_draw(kfbo, oracle):
                   [(0.1, 31), (0.5, 40)], [(0.1, 32), (0.5, 33)]):
         with kfbo.CostEvaluator(rv, times, seed=seed) as ev:
             for k, (dt, T) in enumerate(times):
-                for qe, re, stream, trial0 in [(1.0, 0.1, 0, 0), (0.3, 0.7, 77, 1000), (4.0, 0.02, 0xFFFFFFFE, 0xFFFFFF00)]:
+                # stream ids are 62 bits wide (kfbo.h: KFBO_STREAM_BITS): the upper 30 bits ride in the counter word of the call index
+                for qe, re, stream, trial0 in [(1.0, 0.1, 0, 0), (0.3, 0.7, 77, 1000), (4.0, 0.02, 0xFFFFFFFE, 0xFFFFFF00),
+                                               (1.0, 0.1, (1 << 32) + 77, 0), (2.0, 0.3, (1 << 62) - 1, 5), (0.5, 0.05, kfbo_trial_base() + 3, 9)]:
                     n = 255 if trial0 else 300
                     got = ev.eval_philox_trials(k, qe, re, stream, trial0, n)
                     want = oracle.eval_philox(seed, stream, dt, T, Q_TRUTH, R_TRUTH, qe, re, trial0, n)
                     assert rel_err(got, want) < RTOL, (times, k, qe, stream)
+
+
+def kfbo_trial_base():
+    from kf_bayesopt_b200 import _lib
+    return _lib.TRIAL_STREAM_BASE
+
+
+def test_stream_id_upper_bits_select_other_streams(kfbo):
+    rv = kfbo.ReadParaVehicle(nsimruns_=64, cpu_core_number_=1)
+    with kfbo.CostEvaluator(rv, [(0.1, 21)], seed=3) as ev:
+        a = ev.eval_philox_trials(0, 1.0, 0.1, 9, 0, 64)
+        b = ev.eval_philox_trials(0, 1.0, 0.1, 9 + (1 << 32), 0, 64)
+        assert not np.array_equal(a, b)
+        # the evaluation counter no longer wraps the stream id at 2^32: evaluation 2^32 is not evaluation 0 again
+        ev.set_eval_counter(0)
+        s0 = (ev.eval([1.0], [0.1]), ev.last_sums(1).copy())[1]
+        ev.set_eval_counter(1 << 32)
+        s1 = (ev.eval([1.0], [0.1]), ev.last_sums(1).copy())[1]
+        ev.set_eval_counter(0)
+        s2 = (ev.eval([1.0], [0.1]), ev.last_sums(1).copy())[1]
+        assert np.array_equal(s0, s2) and not np.array_equal(s0, s1)
+
+
+def test_parity_envelope(kfbo, oracle):
+    """The corners the reference can reach beyond the yaml bounds (tests/envelope_model.py: CASES).  Inside the envelope the
+    CUDA path matches the oracle's reference arithmetic to 1e-9; where r_est -> 0 pushes the REFERENCE's (I - K H) P-
+    past 1e-9 of its own exact value, the CUDA path (P = R K) is checked against the long-double evaluation instead.
+    The measured errors are recorded in DESIGN.md section 6."""
+    import envelope_model as em
+    rng = np.random.default_rng(20261021)
+    B = 48
+    for name, dt, T, qt, rt, qe, re_, inside in em.CASES:
+        x0n, w, v = em.noise(oracle, rng, dt, T, B, qt, rt)
+        rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1, pnoise_=[qt], onoise_=[rt])
+        with kfbo.CostEvaluator(rv, [(dt, T)]) as ev:
+            pt, _ = ev.eval_supplied(0, qe, re_, x0n, w, v)
+        want = oracle.eval_supplied(dt, T, qe, re_, x0n, w, v)
+        exact = em.run(oracle, "reference", dt, T, qe, re_, x0n, w, v, em.LD)
+        vs_oracle, vs_exact, oracle_vs_exact = rel_err(pt[0], want), em.rel(pt[0], exact), em.rel(want, exact)
+        print(f"envelope {name}: cuda-vs-oracle {vs_oracle:.1e}, cuda-vs-long-double {vs_exact:.1e}, oracle-vs-long-double {oracle_vs_exact:.1e}")
+        assert vs_exact < 1e-10, (name, vs_exact)                  # the CUDA path itself is at rounding level everywhere
+        if inside:
+            assert vs_oracle < RTOL, (name, vs_oracle)
+        else:
+            assert oracle_vs_exact > RTOL                          # the reference formulas are the inaccurate side here
+
+
+def test_candidates_outside_the_domain_give_a_nan_cost_like_the_reference(kfbo):
+    """Non-finite or <= 0 pnoise / onoise: the reference's filter degenerates and it publishes a NaN "cost"
+    (trial_node.cpp:77,127-129), which ends the optimiser's wait loop (robot1d_bayesopt.cpp:107).  Same here: the call
+    succeeds, that candidate's result is NaN with index_max 0, its neighbours in a batch are untouched."""
+    rv = kfbo.ReadParaVehicle(nsimruns_=256, cpu_core_number_=1)
+    with kfbo.CostEvaluator(rv, seed=11, max_candidates=6) as ev:
+        for pn, on in [([0.0], [0.1]), ([-1.0], [0.1]), ([1.0], [0.0]), ([float("nan")], [0.1]), ([1.0], [float("inf")])]:
+            r = ev.eval(pn, on)
+            assert np.isnan(r.max_cost) and r.index_max == 0 and np.all(np.isnan(r.cost)), (pn, on)
+            assert np.all(np.isnan(ev.last_sums(1)))
+        ev.set_eval_counter(0)
+        good = ev.eval_batch_raw([0.5, 1.0, 2.0, 3.0, 4.0, 5.0], [0.1] * 6)
+        ev.set_eval_counter(0)
+        mixed = ev.eval_batch_raw([0.5, -1.0, 2.0, float("nan"), 4.0, 5.0], [0.1, 0.1, 0.0, 0.1, 0.1, 0.1])
+        for c in (0, 4, 5):
+            assert np.array_equal(mixed["cost"][c], good["cost"][c]) and mixed["index_max"][c] == good["index_max"][c]
+        for c in (1, 2, 3):
+            assert np.isnan(mixed["max_cost"][c]) and mixed["index_max"][c] == 0
+        with pytest.raises(kfbo.KfboError) as e:                   # positive but absurd: refused, not guessed at
+            ev.eval([1e-200], [0.1])
+        assert e.value.code == -2
+        with pytest.raises(kfbo.KfboError):
+            ev.eval_philox_trials(0, -1.0, 0.1, 0, 0, 10)          # the parity entry points have no "cost" message to fill
+        assert ev.eval([1.0], [0.1]).max_cost >= 0                 # the handle stays usable
+
+
+def test_reserved_scratch_makes_the_parity_entry_points_allocation_free(kfbo, oracle):
+    import torch
+    from kf_bayesopt_b200 import _lib
+    rng = np.random.default_rng(2)
+    B, T = 300, 201
+    rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
+    x0n, w, v = _noise(rng, oracle, 0.1, T, B)
+    with kfbo.CostEvaluator(rv, [(0.1, T)], max_candidates=3) as ev:
+        ev.set_option(_lib.OPT_RESERVE_SUPPLIED_TRIALS, B)
+        torch.cuda.synchronize()
+        free0 = torch.cuda.mem_get_info()[0]
+        pt, _ = ev.eval_supplied(0, [0.5, 1.0, 2.0], [0.1, 0.1, 0.2], x0n, w, v)
+        ev.eval_philox_trials(0, 1.0, 0.1, 0, 0, B)
+        ev.trace_trial(0, 1.0, 0.1, 0, 0)
+        assert torch.cuda.mem_get_info()[0] == free0               # nothing was allocated on the device by the calls
+        assert rel_err(pt[1], oracle.eval_supplied(0.1, T, 1.0, 0.1, x0n, w, v)) < RTOL
 
 
 def test_random_configurations_match_oracle(kfbo, oracle):
@@ -162,6 +253,56 @@ def test_eval_batch_sums_match_oracle_and_selection_is_identical(kfbo, oracle):
             ev.set_eval_counter(0)
             res3 = ev.eval_batch(q, r)
             assert all(np.array_equal(a.cost, b.cost) for a, b in zip(res, res3))
+
+
+def test_device_built_cases_are_bit_identical_to_host_built(kfbo):
+    """A batch of more than one candidate sends (pnoise, onoise) to the device and build_cases_kernel makes Fd, Qd, R and the
+    Philox stream ids there; one candidate is built on the host (kfbo_api.cu: build_case).  Same arithmetic operation for
+    operation (kfbo_host.h: RoundedOps), so candidate c of a batch and a single evaluation on the same streams are the
+    same bits -- over awkward values of pnoise / dt too."""
+    rng = np.random.default_rng(9)
+    q = np.concatenate([[1.0, 0.1, 5.0, 1.0 / 3.0, 0.7], np.exp(rng.uniform(np.log(1e-3), np.log(1e3), 11))])
+    r = np.concatenate([[0.1, 0.1, 1.0, 0.01, 0.3], np.exp(rng.uniform(np.log(1e-4), np.log(10.0), 11))])
+    times = [(0.1, 201), (0.5, 211), (1.0 / 3.0, 37), (0.07, 64)]
+    C, D = len(q), len(times)
+    rv = kfbo.ReadParaVehicle(nsimruns_=300, cpu_core_number_=1)
+    with kfbo.CostEvaluator(rv, times, seed=5, max_candidates=C) as ev:
+        ev.set_stream_base((1 << 40) + 17)                         # the device forms the 62-bit stream ids too
+        batch = ev.eval_batch_raw(q, r)
+        sums = ev.last_sums(C)
+        assert ev.last_transfer_bytes() == (16 * C, 32 * D * C)   # 16 bytes per candidate in, the [C][D][4] sums out
+        for c in range(C):
+            ev.set_stream_base((1 << 40) + 17 + c * D)            # candidate c's streams as candidate 0 of a single evaluation
+            ev.set_eval_counter(0)
+            one = ev.eval([q[c]], [r[c]])
+            assert np.array_equal(ev.last_sums(1)[0], sums[c]), c
+            assert np.array_equal(one.cost, batch["cost"][c, :D]) and one.index_max == batch["index_max"][c]
+
+
+def test_device_side_cost_assembly_matches_the_host(kfbo):
+    """kfbo_eval_batch_costs: trial_node.cpp:70-119 per candidate on the device.  Same divisions in the same order as
+    kfbo_finalize; log() is CUDA's, within 1 ulp of libm's -- costs to 1e-9 (observed ~1e-16), selection identical."""
+    rng = np.random.default_rng(4)
+    C = 700
+    q, r = np.exp(rng.uniform(np.log(0.1), np.log(5.0), C)), np.exp(rng.uniform(np.log(0.01), np.log(1.0), C))
+    rv = kfbo.ReadParaVehicle(nsimruns_=130, cpu_core_number_=10)
+    for choice in ("JNEES", "CNEES", "JNIS", "CNIS"):
+        with kfbo.CostEvaluator(rv, README_TIMES, seed=21, max_candidates=C, cost_choice=choice) as ev:
+            full = ev.eval_batch_raw(q, r)
+            ev.set_eval_counter(0)
+            cost, mx, idx = ev.eval_batch_costs(q, r, with_index=True)
+            h2d, d2h = ev.last_transfer_bytes()
+            assert (h2d, d2h) == (16 * C, C * (8 * 3 + 4))
+            assert rel_err(cost, full["cost"][:, :2]) < RTOL and rel_err(mx, full["max_cost"]) < RTOL, choice
+            assert np.array_equal(idx, full["index_max"]), choice
+            # a candidate outside the domain in the middle of the batch: NaN there, its neighbours untouched
+            q2 = q.copy()
+            q2[5] = -1.0
+            ev.set_eval_counter(0)
+            cost2, mx2, idx2 = ev.eval_batch_costs(q2, r, with_index=True)
+            assert np.isnan(mx2[5]) and np.all(np.isnan(cost2[5])) and idx2[5] == 0
+            keep = np.arange(C) != 5
+            assert np.array_equal(cost2[keep], cost[keep]) and np.array_equal(idx2[keep], idx[keep])
 
 
 def test_eval_single_candidate_equals_batch_of_one(kfbo):

@@ -211,3 +211,40 @@ def test_statistical_anchors_threaded_mt(oracle):
     assert out[4] == pytest.approx(abs(np.log(out[1] / 1)), rel=1e-14)
     with pytest.raises(ValueError):
         oracle.eval_mt(0.1, 2001, 1.0, 0.1, 1.0, 0.1, 80, 8)   # T > 2000: control table limit
+
+
+# ---------------------------------------------------------------------------------------------
+# The parity envelope: how far outside the yaml bounds the 1e-9 bound can hold at all.
+# ---------------------------------------------------------------------------------------------
+def test_envelope_reference_formulas_lose_accuracy_as_r_est_goes_to_zero(oracle):
+    import envelope_model as em
+    rng = np.random.default_rng(20261021)
+    B = 48
+    worst = {}
+    for name, dt, T, qt, rt, qe, re_, inside in em.CASES:
+        x0n, w, v = em.noise(oracle, rng, dt, T, B, qt, rt)
+        want = oracle.eval_supplied(dt, T, qe, re_, x0n, w, v)
+        # the numpy restatement in float64 IS the oracle, bit for bit -- so its long-double run is "the reference's
+        # formulas without rounding error"
+        assert np.array_equal(em.run(oracle, "reference", dt, T, qe, re_, x0n, w, v), want), name
+        exact = em.run(oracle, "reference", dt, T, qe, re_, x0n, w, v, em.LD)
+        dev64 = em.run(oracle, "device", dt, T, qe, re_, x0n, w, v)
+        worst[name] = (em.rel(want, exact), em.rel(dev64, exact), em.rel(dev64, want))
+        # the device's formulation (P = R K: no 1 - k0 cancellation) stays at rounding level everywhere ...
+        assert worst[name][1] < 1e-10, (name, worst[name])
+        # ... and agrees with the reference arithmetic to 1e-9 wherever the reference itself is that accurate
+        if inside:
+            assert worst[name][2] < 1e-9, (name, worst[name])
+    # r_est -> 0: (I - K H) P- cancels (1 - k0 = R/S ~ 1e-9 of k0), the REFERENCE side drifts past 1e-9
+    assert worst["r_est 1e-10"][0] > 1e-9 > worst["r_est 1e-10"][1]
+    assert worst["r_est 1e-8"][0] > 100 * worst["r_est 1e-8"][1]
+
+
+def test_philox_stream_ids_are_62_bits_wide(oracle):
+    seed, T = 0xABCDEF, 9
+    a = oracle.eval_philox(seed, 5, 0.1, T, 1.0, 0.1, 1.0, 0.1, 0, 8)
+    b = oracle.eval_philox(seed, 5 + (1 << 32), 0.1, T, 1.0, 0.1, 1.0, 0.1, 0, 8)      # same low word, other stream
+    c = oracle.eval_philox(seed, 5 + (1 << 61), 0.1, T, 1.0, 0.1, 1.0, 0.1, 0, 8)
+    d = oracle.eval_philox(seed, 5 + (1 << 62), 0.1, T, 1.0, 0.1, 1.0, 0.1, 0, 8)      # bit 62 is outside the id
+    assert not np.array_equal(a, b) and not np.array_equal(a, c) and not np.array_equal(b, c)
+    assert np.array_equal(a, d)
