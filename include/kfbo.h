@@ -72,7 +72,14 @@ typedef struct kfbo_params {
     uint64_t seed;                                   /* Philox key; replaces the wall-clock seeds
                                                         (system_models.hpp:74,147, simulator.cpp:9) */
     int32_t max_candidates;                          /* capacity of kfbo_eval_batch (>= 1) */
-    int32_t reserved;
+    int32_t state_dim;                               /* 0 or 2: the reference's model (#define N 2, system_models.hpp:11).
+                                                        3 or 4: the STATE-AUGMENTED variant north_star names -- the same
+                                                        recursion on a chain of 3 / 4 integrators (position, velocity,
+                                                        acceleration [, jerk]; noise and control drive the highest
+                                                        derivative; H = [1 0 ..]).  The reference has no such variant:
+                                                        oracle/kfbo_oracle_aug.c states it.  Set state_dof to match.
+                                                        Noise arrays of the parity entry points then have state_dim rows
+                                                        where the text below says 2. */
 } kfbo_params;
 
 /* What RunTrial::ProcessNoiseCallback computes per "noise" message (trial_node.cpp:70-119). */
@@ -199,14 +206,11 @@ enum { KFBO_OPT_SUPPLIED_KERNEL = 1, KFBO_OPT_BULK_SMEM_PAD = 2 /* extra dynamic
        KFBO_OPT_RESERVE_SUPPLIED_TRIALS = 7 /* pre-size the scratch of the parity entry points (kfbo_eval_supplied,
                                         kfbo_eval_philox_trials, kfbo_trace_trial) for this many trials x max_candidates
                                         candidates: after it they allocate nothing, like kfbo_eval* */ };
-/* KFBO_OPT_ROLLOUT_FORM, for the on-device-noise evaluations (kfbo_eval, kfbo_eval_batch, kfbo_eval_philox_trials):
- *   KFBO_FORM_REFERENCE (default): every trajectory carries truth state, estimate and covariance and runs
- *       simulator.cpp:15-19 + kalman_filter.cpp:18-38 + trial.cpp:53-60 step by step, as north_star prescribes.
- *   KFBO_FORM_REDUCED: the data-independent covariance / gain recursion is tabulated once per (candidate,
- *       sample time) and each trajectory propagates only the error e = x - xhat (the control and the truth
- *       state cancel in it).  Same per-trial NEES/NIS to rounding (tests: 1e-9 relative), ~2.5x fewer FP64
- *       instructions in the filter part.  The supplied-noise parity entry points always use the reference form. */
-enum { KFBO_FORM_REFERENCE = 0, KFBO_FORM_REDUCED = 1 };
+/* KFBO_OPT_ROLLOUT_FORM: only KFBO_FORM_REFERENCE exists -- every trajectory carries truth state, estimate and covariance and
+ * runs simulator.cpp:15-19 + kalman_filter.cpp:18-38 + trial.cpp:53-60 step by step, as north_star prescribes.  (Round 1 also
+ * had a "reduced" form -- gain recursion tabulated once per case, error-state trajectories; it was never more than 6 % faster
+ * and was removed: DESIGN.md section 4a.  The option number stays reserved.) */
+enum { KFBO_FORM_REFERENCE = 0 };
 enum { KFBO_SUPPLIED_AUTO = 0, KFBO_SUPPLIED_LDG = 1, KFBO_SUPPLIED_BULK = 2 };
 /* KFBO_OPT_REDUCE (set it to the same value on every rank):
  *   KFBO_REDUCE_AUTO (default): the peer-memory exchange (below) when the ranks are attached to each other, else NCCL;

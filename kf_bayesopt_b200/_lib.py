@@ -31,7 +31,7 @@ PEER_HANDLE_BYTES = 64
 # kfbo_last_reduce_path
 REDUCE_PATHS = {0: "single rank", 1: "ncclAllReduce", 2: "peer-memory exchange (kernel behind the rollout)",
                 3: "peer-memory exchange fused into the rollout kernel"}
-FORM_REFERENCE, FORM_REDUCED = 0, 1
+FORM_REFERENCE = 0
 SUPPLIED_AUTO, SUPPLIED_LDG, SUPPLIED_BULK = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -55,7 +55,7 @@ class KfboParams(C.Structure):
         ("device", C.c_int32),
         ("seed", C.c_uint64),
         ("max_candidates", C.c_int32),
-        ("reserved", C.c_int32),
+        ("state_dim", C.c_int32),
     ]
 
 

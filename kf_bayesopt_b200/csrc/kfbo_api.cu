@@ -69,7 +69,6 @@ NcclApi &nccl()
 }
 
 constexpr size_t kPartialsBudgetBytes = 64u << 20;  // per-launch partial-sum scratch cap
-constexpr size_t kGainsBudgetBytes = 256u << 20;    // per-launch gain-table cap (reduced form)
 constexpr size_t kXchgFlagBytes = 256;              // flags [2][kMaxPeers] in front of the exchange slabs
 constexpr size_t kZeroCopyMaxDoubles = 1024;        // results up to this size are stored straight into mapped host memory by the kernel
 constexpr size_t kPeerMaxSummedDoubles = 4096;      // trials sharded: one CTA adds nranks slabs of this many doubles at most
@@ -120,6 +119,13 @@ struct kfbo_handle {
     // non-trivial host work per case
     struct DiscMemo { uint64_t qbits = 0; int k = -1; double f = 0, Qd[4] = {0, 0, 0, 0}; };
     DiscMemo disc_memo[256];
+    // the state-augmented variants (kfbo_params.state_dim = 3, 4; kfbo_aug.cuh): their own case / table types
+    int N = 2;                                   // state dimension
+    kfbo::AugSampleTime h_aug_st[KFBO_MAX_SAMPLE_TIMES]{};
+    kfbo::AugSampleTime *d_aug_st = nullptr;     // [D]
+    double *d_u = nullptr;                       // [D][kMaxSteps] control table u_[i] per sample time
+    kfbo::AugCase *d_aug_cases = nullptr, *h_aug_cases = nullptr;   // [cases_cap]
+    std::vector<kfbo::AugCase> sup_aug_cases;
     // NCCL
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1, shard_mode = KFBO_SHARD_TRIALS;
@@ -150,9 +156,6 @@ struct kfbo_handle {
     std::vector<Case> sup_cases;           // host scratch of the supplied-noise entry points (grow-only)
     std::vector<double> sup_sums;
     int supplied_kernel = kfbo::kSuppliedAuto;
-    int rollout_form = KFBO_FORM_REFERENCE;
-    kfbo::GainStep *d_gains = nullptr;   // reduced form only: [cases per launch][gain stride]
-    size_t gains_cap = 0;                // entries
     int bulk_smem_pad = 0;
     // last evaluation
     int last_ncand = 0, last_launches = 0;
@@ -226,9 +229,23 @@ int ensure_scratch(kfbo_handle *h, int slot, size_t doubles)
 }
 
 // scratch slot 3 of the supplied-noise entry points: partials, sums, cases, tickets of C candidates
+constexpr size_t kCaseDoubles = (std::max(sizeof(Case), sizeof(kfbo::AugCase)) + 7) / 8;   // room for either case type
 size_t supplied_scratch3_doubles(int C, int tiles)
 {
-    return (size_t)C * tiles * 4 + (size_t)C * 4 + (size_t)C * ((sizeof(Case) + 7) / 8) + C;
+    return (size_t)C * tiles * 4 + (size_t)C * 4 + (size_t)C * kCaseDoubles + C;
+}
+
+// The constants of (candidate, sample time k) of a state-augmented evaluation.
+int build_aug_case(kfbo_handle *h, int k, double q_est, double r_est, uint64_t stream, int out_slot, kfbo::AugCase *c)
+{
+    double Fd[16];
+    kfbo::host::discretize_chain(h->N, q_est, h->p.dt[k], Fd, c->qd);
+    c->r_est = r_est / h->p.dt[k];
+    c->T = h->p.max_iterations[k];
+    c->stream = (uint32_t)stream;
+    c->stream_x = (uint32_t)((stream >> 32) & 0x3FFFFFFFull) << 2;
+    c->out_slot = out_slot;
+    return KFBO_OK;
 }
 
 // Constants of (candidate q_est/r_est, sample time k): ProcessModel / ObservationModel of the
@@ -445,7 +462,6 @@ void kfbo_destroy(kfbo_handle *h)
     if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (int i = 0; i < 5; ++i) if (h->d_scratch[i]) cudaFree(h->d_scratch[i]);
-    if (h->d_gains) cudaFree(h->d_gains);
     if (h->d_gu) cudaFree(h->d_gu);
     if (h->d_logtab) cudaFree(h->d_logtab);
     for (int r = 0; r < kfbo::kMaxPeers; ++r)
@@ -455,6 +471,10 @@ void kfbo_destroy(kfbo_handle *h)
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->d_case_buf) cudaFree(h->d_case_buf);
     if (h->h_case_buf) cudaFreeHost(h->h_case_buf);
+    if (h->d_aug_st) cudaFree(h->d_aug_st);
+    if (h->d_u) cudaFree(h->d_u);
+    if (h->d_aug_cases) cudaFree(h->d_aug_cases);
+    if (h->h_aug_cases) cudaFreeHost(h->h_aug_cases);
     if (h->d_compact) cudaFree(h->d_compact);
     if (h->h_compact) cudaFreeHost(h->h_compact);
     if (h->d_partials) cudaFree(h->d_partials);
@@ -534,7 +554,28 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
     // ---- evaluation buffers
     h->cases_cap = p->max_candidates * h->D;
     h->cand_bad.assign((size_t)p->max_candidates, 0);
-    const int tiles = kfbo::rollout_tiles((size_t)h->b_eff);
+    h->N = p->state_dim >= 2 ? p->state_dim : 2;
+    if (h->N > 2) {
+        // the chain-of-integrators model per sample time (kfbo_host.h: discretize_chain)
+        std::vector<double> ut((size_t)h->D * kfbo::kMaxSteps);
+        for (int k = 0; k < h->D; ++k) {
+            kfbo::AugSampleTime &a = h->h_aug_st[k];
+            double Qd[16];
+            kfbo::host::discretize_chain(h->N, p->pnoise_truth, p->dt[k], a.F, Qd);
+            kfbo::host::control_vector_chain(h->N, p->dt[k], a.g);
+            if (!kfbo::host::cholesky_chain(h->N, Qd, a.L)) { fail(h, KFBO_EINVAL, "kfbo_create: the truth Qd is not positive definite"); return bail(KFBO_EINVAL); }
+            a.sr = std::sqrt(p->onoise_truth / p->dt[k]);
+            kfbo::host::control_table(p->dt[k], kfbo::kMaxSteps, ut.data() + (size_t)k * kfbo::kMaxSteps);
+        }
+        if (cu(cudaMalloc(&h->d_aug_st, sizeof h->h_aug_st), "cudaMalloc(aug tables)") ||
+            cu(cudaMemcpy(h->d_aug_st, h->h_aug_st, sizeof h->h_aug_st, cudaMemcpyHostToDevice), "cudaMemcpy(aug tables)") ||
+            cu(cudaMalloc(&h->d_u, ut.size() * sizeof(double)), "cudaMalloc(u)") ||
+            cu(cudaMemcpy(h->d_u, ut.data(), ut.size() * sizeof(double), cudaMemcpyHostToDevice), "cudaMemcpy(u)") ||
+            cu(cudaMalloc(&h->d_aug_cases, (size_t)h->cases_cap * sizeof(kfbo::AugCase)), "cudaMalloc(aug cases)") ||
+            cu(cudaMallocHost(&h->h_aug_cases, (size_t)h->cases_cap * sizeof(kfbo::AugCase)), "cudaMallocHost(aug cases)"))
+            return bail(KFBO_ECUDA);
+    }
+    const int tiles = h->N > 2 ? kfbo::aug_tiles((size_t)h->b_eff) : kfbo::rollout_tiles((size_t)h->b_eff);
     size_t part = (size_t)h->cases_cap * tiles * 4;
     const size_t budget = kPartialsBudgetBytes / sizeof(double);
     if (part > budget) part = std::max(budget, (size_t)tiles * 4 * h->D);   // at least one whole candidate per launch
@@ -573,21 +614,11 @@ int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value)
         if (value < KFBO_SUPPLIED_AUTO || value > KFBO_SUPPLIED_BULK) return fail(h, KFBO_EINVAL, "kfbo_set_option: supplied kernel %lld", (long long)value);
         h->supplied_kernel = (int)value;
         return KFBO_OK;
-    case KFBO_OPT_ROLLOUT_FORM: {
-        if (value != KFBO_FORM_REFERENCE && value != KFBO_FORM_REDUCED) return fail(h, KFBO_EINVAL, "kfbo_set_option: rollout form %lld", (long long)value);
-        if (value == KFBO_FORM_REDUCED && !h->d_gains) {
-            // gain table for as many cases as one launch may hold (whole candidates), at most kGainsBudgetBytes
-            KFBO_ON_DEVICE(h);
-            const size_t stride = (size_t)kfbo::gain_stride_for(h->max_T);
-            size_t ncases = kGainsBudgetBytes / (stride * sizeof(kfbo::GainStep));
-            ncases = std::max<size_t>(ncases / h->D * h->D, (size_t)h->D);
-            ncases = std::min<size_t>(ncases, (size_t)h->cases_cap);
-            KFBO_CUDA(h, cudaMalloc(&h->d_gains, ncases * stride * sizeof(kfbo::GainStep)));
-            h->gains_cap = ncases;
-        }
-        h->rollout_form = (int)value;
+    case KFBO_OPT_ROLLOUT_FORM:
+        // the reduced (tabulated-gain, error-state) form was removed in round 2: it never beat the reference form by more
+        // than 6 % (bound by shared-memory wavefronts of the noise tables, profiles/variants_reduced_r2a.txt)
+        if (value != KFBO_FORM_REFERENCE) return fail(h, KFBO_EINVAL, "kfbo_set_option: only KFBO_FORM_REFERENCE exists (the reduced form was removed)");
         return KFBO_OK;
-    }
     case KFBO_OPT_BULK_SMEM_PAD:
         if (value < 0 || value > (128 << 10)) return fail(h, KFBO_EINVAL, "kfbo_set_option: smem pad %lld", (long long)value);
         h->bulk_smem_pad = (int)value;
@@ -605,13 +636,14 @@ int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value)
         // for up to `value` trials, max_candidates candidates and the longest sample time
         if (value < 1 || value > 0x7fffffff) return fail(h, KFBO_EINVAL, "kfbo_set_option: reserve %lld trials", (long long)value);
         KFBO_ON_DEVICE(h);
-        const size_t B = (size_t)value, T = (size_t)h->max_T, C = (size_t)h->p.max_candidates;
+        const size_t B = (size_t)value, T = (size_t)h->max_T, C = (size_t)h->p.max_candidates, NS = (size_t)h->N;
         int rc;
-        if ((rc = ensure_scratch(h, 0, 2 * B)) || (rc = ensure_scratch(h, 1, 2 * T * B)) || (rc = ensure_scratch(h, 2, T * B)) ||
-            (rc = ensure_scratch(h, 3, supplied_scratch3_doubles((int)C, kfbo::rollout_tiles(B)))) ||
+        if ((rc = ensure_scratch(h, 0, NS * B)) || (rc = ensure_scratch(h, 1, NS * T * B)) || (rc = ensure_scratch(h, 2, T * B)) ||
+            (rc = ensure_scratch(h, 3, supplied_scratch3_doubles((int)C, h->N > 2 ? kfbo::aug_tiles(B) : kfbo::rollout_tiles(B)))) ||
             (rc = ensure_scratch(h, 4, std::max(C * 4 * B, (size_t)KFBO_TRACE_COLUMNS * T))))
             return rc;
         h->sup_cases.resize(C);
+        if (h->N > 2) h->sup_aug_cases.resize(C);
         h->sup_sums.resize(C * 4);
         return KFBO_OK;
     }
@@ -706,7 +738,8 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
     // The per-(candidate, sample time) constants.  One candidate (the "noise" -> "cost" call): built here, they also ride
     // in the kernel's parameter bank.  A batch: 16 bytes per candidate go to the device and build_cases_kernel makes
     // the same constants there, bit for bit (kfbo_host.h: RoundedOps) -- no per-candidate host work, a sixth of the bytes.
-    const bool device_build = C > 1;
+    const bool aug = h->N > 2;             // state-augmented variant: its own case type, built here for any batch size
+    const bool device_build = C > 1 && !aug;
     const uint64_t stream0 = h->stream_base + h->eval_counter * (uint64_t)h->p.max_candidates * (uint64_t)D;
     double2 *const h_cand = reinterpret_cast<double2 *>(h->h_hdr) - ncand;      // right-aligned against the header
     if (device_build) {
@@ -715,8 +748,9 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
     } else {
         for (int64_t c = c0; c < c1; ++c)
             for (int k = 0; k < D; ++k) {
-                const int rc = build_case(h, k, bad[c] ? 1.0 : q_est[c], bad[c] ? 1.0 : r_est[c], stream0 + (uint64_t)c * D + k, (int)(c * D + k),
-                                          &h->h_cases[(c - c0) * D + k]);
+                const double q = bad[c] ? 1.0 : q_est[c], r = bad[c] ? 1.0 : r_est[c];
+                const int rc = aug ? build_aug_case(h, k, q, r, stream0 + (uint64_t)c * D + k, (int)(c * D + k), &h->h_aug_cases[(c - c0) * D + k])
+                                   : build_case(h, k, q, r, stream0 + (uint64_t)c * D + k, (int)(c * D + k), &h->h_cases[(c - c0) * D + k]);
                 if (rc) return rc;
             }
     }
@@ -726,16 +760,14 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
     const bool use_peer = h->comm && h->peer_ready && h->reduce_pref != KFBO_REDUCE_NCCL && nsums <= h->xchg_cap &&
                           (gather || nsums <= kPeerMaxSummedDoubles);
     const uint32_t ntrials = (uint32_t)(t1 - t0);
-    const bool reduced = h->rollout_form == KFBO_FORM_REDUCED;
-    const int tiles = kfbo::rollout_tiles(ntrials);
+    const int tiles = aug ? kfbo::aug_tiles(ntrials) : kfbo::rollout_tiles(ntrials);
     int step = cases_per_launch(h, std::max(tiles, 1));
-    if (reduced) step = std::max(D, std::min(step, (int)h->gains_cap));
     const bool has_work = ncases > 0 && ntrials > 0;
     // Opt-in (KFBO_OPT_PEER_FUSE): the exchange rides in the tail of the rollout kernel when the evaluation is one launch.
     // Off by default because it is slower, measured: the rollout loop is FP64-issue bound and ptxas schedules it
     // differently when the exchange follows it in the same kernel (+0.9 % kernel time for one candidate, +2.0 % for a
     // batch, i.e. 15-60 us), which is more than the 2-3 us a second launch on the same stream costs.
-    const bool fused = use_peer && has_work && ncases <= step && h->peer_fuse == KFBO_PEER_FUSE_ALWAYS;
+    const bool fused = use_peer && has_work && ncases <= step && h->peer_fuse == KFBO_PEER_FUSE_ALWAYS && !aug;
     h->reduce_path = !h->comm ? 0 : !use_peer ? 1 : fused ? 3 : 2;
     // Where the total lands.  A small result is stored by the kernel straight into the mapped pinned buffer the costs are
     // assembled from (no device-to-host copy on the critical path of a "noise" -> "cost" evaluation): by the rollout
@@ -784,6 +816,11 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
             cb.D = D; cb.c0 = (int32_t)c0; cb.stream0 = stream0;
             KFBO_CUDA(h, kfbo::launch_build_cases(reinterpret_cast<const double2 *>(h->d_hdr) - ncand, ncand, cb, h->d_cases, h->stream));
         }
+    } else if (aug) {
+        if (use_peer) KFBO_CUDA(h, cudaMemcpyAsync(h->d_hdr, h->h_hdr, kfbo::kPeerCtxBytes, cudaMemcpyHostToDevice, h->stream));
+        if (ncases > 0)
+            KFBO_CUDA(h, cudaMemcpyAsync(h->d_aug_cases, h->h_aug_cases, (size_t)ncases * sizeof(kfbo::AugCase), cudaMemcpyHostToDevice, h->stream));
+        h->last_h2d = (int64_t)((size_t)ncases * sizeof(kfbo::AugCase) + (use_peer ? kfbo::kPeerCtxBytes : 0));
     } else {
         const size_t bytes = (size_t)ncases * sizeof(Case) + (use_peer ? kfbo::kPeerCtxBytes : 0);
         if (use_peer) KFBO_CUDA(h, cudaMemcpyAsync(h->d_hdr, h->h_hdr, bytes, cudaMemcpyHostToDevice, h->stream));
@@ -797,10 +834,10 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
             const int n = std::min(step, ncases - first);
             kfbo::SampleTimeConsts st = h->st;
             st.k0 = 0; st.nk = D;   // cases are laid out [candidate][sample time]; chunks hold whole candidates
-            if (reduced) {
-                KFBO_CUDA(h, kfbo::launch_rollout_philox_reduced(h->d_cases + first, n, st, h->d_gains, h->d_logtab, h->max_T, h->p.seed, (uint32_t)t0,
-                                                                 ntrials, nullptr, 0, h->d_partials, h->d_tickets, rollout_sums, h->stream, fused));
-                h->last_launches += 2;
+            if (aug) {
+                KFBO_CUDA(h, kfbo::launch_rollout_aug(h->N, false, h->d_aug_cases + first, n, D, 0, h->d_aug_st, h->d_u, h->d_logtab, h->p.seed, (uint32_t)t0,
+                                                      ntrials, nullptr, nullptr, nullptr, 0, nullptr, 0, h->d_partials, h->d_tickets, rollout_sums, h->stream));
+                ++h->last_launches;
             } else {
                 KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, st, h->d_gu, h->d_logtab, h->min_T, h->p.seed, (uint32_t)t0, ntrials,
                                                          nullptr, 0, h->d_partials, h->d_tickets, rollout_sums, h->stream,
@@ -969,28 +1006,35 @@ static int supplied_impl(kfbo_handle *h, int32_t k, int32_t C, const double *q_e
                          const double *d_x0, const double *d_w, const double *d_v, double *d_per_trial,
                          double *h_per_trial, double *sums)
 {
-    const int tiles = kfbo::rollout_tiles((size_t)B);
+    const bool aug = h->N > 2;
+    const int tiles = aug ? kfbo::aug_tiles((size_t)B) : kfbo::rollout_tiles((size_t)B);
     if (C > 65535) return fail(h, KFBO_ERANGE, "kfbo_eval_supplied: at most 65535 candidates per call");
     if (h->sup_cases.size() < (size_t)C) h->sup_cases.resize((size_t)C);   // grow-only (pre-sized by KFBO_OPT_RESERVE_SUPPLIED_TRIALS)
+    if (aug && h->sup_aug_cases.size() < (size_t)C) h->sup_aug_cases.resize((size_t)C);
     if (h->sup_sums.size() < (size_t)C * 4) h->sup_sums.resize((size_t)C * 4);
-    std::vector<Case> &cases = h->sup_cases;
     for (int c = 0; c < C; ++c) {
-        const int rc = build_case(h, k, q_est[c], r_est[c], 0u, c, &cases[c]);
+        const int rc = aug ? build_aug_case(h, k, q_est[c], r_est[c], 0u, c, &h->sup_aug_cases[c]) : build_case(h, k, q_est[c], r_est[c], 0u, c, &h->sup_cases[c]);
         if (rc) return rc;
     }
     int rc = ensure_scratch(h, 3, supplied_scratch3_doubles(C, tiles));
     if (rc) return rc;
     double *d_partials = h->d_scratch[3];
     double *d_sums = d_partials + (size_t)C * tiles * 4;
-    Case *d_cases = reinterpret_cast<Case *>(d_sums + (size_t)C * 4);
-    unsigned *d_tickets = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(d_cases) + (size_t)C * ((sizeof(Case) + 7) / 8) * 8);
-    KFBO_CUDA(h, cudaMemcpyAsync(d_cases, cases.data(), (size_t)C * sizeof(Case), cudaMemcpyHostToDevice, h->stream));
+    void *d_cases = d_sums + (size_t)C * 4;
+    unsigned *d_tickets = reinterpret_cast<unsigned *>(reinterpret_cast<double *>(d_cases) + (size_t)C * kCaseDoubles);
+    if (aug) KFBO_CUDA(h, cudaMemcpyAsync(d_cases, h->sup_aug_cases.data(), (size_t)C * sizeof(kfbo::AugCase), cudaMemcpyHostToDevice, h->stream));
+    else     KFBO_CUDA(h, cudaMemcpyAsync(d_cases, h->sup_cases.data(), (size_t)C * sizeof(Case), cudaMemcpyHostToDevice, h->stream));
     KFBO_CUDA(h, cudaMemsetAsync(d_tickets, 0, (size_t)C * sizeof(unsigned), h->stream));
     KFBO_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    kfbo::SampleTimeConsts st = h->st;
-    st.k0 = k; st.nk = 1;
-    KFBO_CUDA(h, kfbo::launch_rollout_supplied(d_cases, C, st, h->d_gu, h->p.max_iterations[k], d_x0, d_w, d_v, (size_t)B, d_per_trial,
-                                               d_partials, d_tickets, d_sums, h->supplied_kernel, h->bulk_smem_pad, h->stream));
+    if (aug) {
+        KFBO_CUDA(h, kfbo::launch_rollout_aug(h->N, true, static_cast<const kfbo::AugCase *>(d_cases), C, 1, k, h->d_aug_st, h->d_u, h->d_logtab, h->p.seed,
+                                              0u, (uint32_t)B, d_x0, d_w, d_v, (size_t)B, d_per_trial, (size_t)B, d_partials, d_tickets, d_sums, h->stream));
+    } else {
+        kfbo::SampleTimeConsts st = h->st;
+        st.k0 = k; st.nk = 1;
+        KFBO_CUDA(h, kfbo::launch_rollout_supplied(static_cast<const Case *>(d_cases), C, st, h->d_gu, h->p.max_iterations[k], d_x0, d_w, d_v, (size_t)B, d_per_trial,
+                                                   d_partials, d_tickets, d_sums, h->supplied_kernel, h->bulk_smem_pad, h->stream));
+    }
     KFBO_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     h->last_launches = 1;
     std::vector<double> &hs = h->sup_sums;
@@ -1025,13 +1069,13 @@ int kfbo_eval_supplied(kfbo_handle *h, int32_t k, int32_t C, const double *q_est
     int rc = supplied_check(h, k, C, q_est, r_est, B, x0noise, w, v);
     if (rc) return rc;
     KFBO_ON_DEVICE(h);
-    const size_t T = (size_t)h->p.max_iterations[k];
-    if ((rc = ensure_scratch(h, 0, 2 * (size_t)B))) return rc;
-    if ((rc = ensure_scratch(h, 1, 2 * T * (size_t)B))) return rc;
+    const size_t T = (size_t)h->p.max_iterations[k], NS = (size_t)h->N;      // noise rows per step = the state dimension
+    if ((rc = ensure_scratch(h, 0, NS * (size_t)B))) return rc;
+    if ((rc = ensure_scratch(h, 1, NS * T * (size_t)B))) return rc;
     if ((rc = ensure_scratch(h, 2, T * (size_t)B))) return rc;
     if (per_trial && (rc = ensure_scratch(h, 4, (size_t)C * 4 * (size_t)B))) return rc;
-    KFBO_CUDA(h, cudaMemcpyAsync(h->d_scratch[0], x0noise, 2 * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    KFBO_CUDA(h, cudaMemcpyAsync(h->d_scratch[1], w, 2 * T * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    KFBO_CUDA(h, cudaMemcpyAsync(h->d_scratch[0], x0noise, NS * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    KFBO_CUDA(h, cudaMemcpyAsync(h->d_scratch[1], w, NS * T * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     KFBO_CUDA(h, cudaMemcpyAsync(h->d_scratch[2], v, T * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     return supplied_impl(h, k, C, q_est, r_est, B, h->d_scratch[0], h->d_scratch[1], h->d_scratch[2],
                          per_trial ? h->d_scratch[4] : nullptr, per_trial, sums);
@@ -1055,26 +1099,31 @@ int kfbo_eval_philox_trials(kfbo_handle *h, int32_t k, double q_est, double r_es
     int rc = check_point_candidate(h, "kfbo_eval_philox_trials", q_est, r_est);
     if (rc) return rc;
     KFBO_ON_DEVICE(h);
+    const bool aug = h->N > 2;
     Case c;
-    rc = build_case(h, k, q_est, r_est, stream, 0, &c);
+    kfbo::AugCase ca;
+    rc = aug ? build_aug_case(h, k, q_est, r_est, stream, 0, &ca) : build_case(h, k, q_est, r_est, stream, 0, &c);
     if (rc) return rc;
-    const int tiles = kfbo::rollout_tiles((size_t)ntrials);
-    if ((rc = ensure_scratch(h, 3, (size_t)tiles * 4 + 4 + (sizeof(Case) + 7) / 8 + 1))) return rc;
+    const int tiles = aug ? kfbo::aug_tiles((size_t)ntrials) : kfbo::rollout_tiles((size_t)ntrials);
+    if ((rc = ensure_scratch(h, 3, supplied_scratch3_doubles(1, tiles)))) return rc;
     if ((rc = ensure_scratch(h, 4, 4 * (size_t)ntrials))) return rc;
     double *d_partials = h->d_scratch[3];
     double *d_sums = d_partials + (size_t)tiles * 4;
-    Case *d_case = reinterpret_cast<Case *>(d_sums + 4);
-    unsigned *d_ticket = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(d_case) + ((sizeof(Case) + 7) / 8) * 8);
-    KFBO_CUDA(h, cudaMemcpyAsync(d_case, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
+    void *d_case = d_sums + 4;
+    unsigned *d_ticket = reinterpret_cast<unsigned *>(reinterpret_cast<double *>(d_case) + kCaseDoubles);
+    if (aug) KFBO_CUDA(h, cudaMemcpyAsync(d_case, &ca, sizeof ca, cudaMemcpyHostToDevice, h->stream));
+    else     KFBO_CUDA(h, cudaMemcpyAsync(d_case, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     KFBO_CUDA(h, cudaMemsetAsync(d_ticket, 0, sizeof(unsigned), h->stream));
-    kfbo::SampleTimeConsts st = h->st;
-    st.k0 = k; st.nk = 1;
-    if (h->rollout_form == KFBO_FORM_REDUCED)
-        KFBO_CUDA(h, kfbo::launch_rollout_philox_reduced(d_case, 1, st, h->d_gains, h->d_logtab, h->max_T, h->p.seed, trial0, (uint32_t)ntrials,
-                                                         h->d_scratch[4], (size_t)ntrials, d_partials, d_ticket, d_sums, h->stream));
-    else
-        KFBO_CUDA(h, kfbo::launch_rollout_philox(d_case, 1, st, h->d_gu, h->d_logtab, h->min_T, h->p.seed, trial0, (uint32_t)ntrials, h->d_scratch[4],
-                                                 (size_t)ntrials, d_partials, d_ticket, d_sums, h->stream));
+    if (aug) {
+        KFBO_CUDA(h, kfbo::launch_rollout_aug(h->N, false, static_cast<const kfbo::AugCase *>(d_case), 1, 1, k, h->d_aug_st, h->d_u, h->d_logtab, h->p.seed,
+                                              trial0, (uint32_t)ntrials, nullptr, nullptr, nullptr, 0, h->d_scratch[4], (size_t)ntrials, d_partials, d_ticket,
+                                              d_sums, h->stream));
+    } else {
+        kfbo::SampleTimeConsts st = h->st;
+        st.k0 = k; st.nk = 1;
+        KFBO_CUDA(h, kfbo::launch_rollout_philox(static_cast<const Case *>(d_case), 1, st, h->d_gu, h->d_logtab, h->min_T, h->p.seed, trial0, (uint32_t)ntrials,
+                                                 h->d_scratch[4], (size_t)ntrials, d_partials, d_ticket, d_sums, h->stream));
+    }
     KFBO_CUDA(h, cudaMemcpyAsync(per_trial, h->d_scratch[4], 4 * (size_t)ntrials * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     KFBO_CUDA(h, cudaStreamSynchronize(h->stream));
     h->last_launches = 1;
@@ -1085,6 +1134,7 @@ int kfbo_trace_trial(kfbo_handle *h, int32_t k, double q_est, double r_est, uint
 {
     if (!h) return KFBO_EINVAL;
     if (!trace || k < 0 || k >= h->D) return fail(h, KFBO_EINVAL, "kfbo_trace_trial: bad argument");
+    if (h->N > 2) return fail(h, KFBO_EINVAL, "kfbo_trace_trial: the single-trial trace exists for state_dim = 2 only (trial.cpp:69-78 plots two states)");
     int rc = check_point_candidate(h, "kfbo_trace_trial", q_est, r_est);
     if (rc) return rc;
     KFBO_ON_DEVICE(h);
@@ -1092,7 +1142,7 @@ int kfbo_trace_trial(kfbo_handle *h, int32_t k, double q_est, double r_est, uint
     rc = build_case(h, k, q_est, r_est, stream, 0, &c);
     if (rc) return rc;
     const size_t T = (size_t)h->p.max_iterations[k];
-    if ((rc = ensure_scratch(h, 3, (sizeof(Case) + 7) / 8 + 1))) return rc;
+    if ((rc = ensure_scratch(h, 3, kCaseDoubles + 1))) return rc;
     if ((rc = ensure_scratch(h, 4, 9 * T))) return rc;
     Case *d_case = reinterpret_cast<Case *>(h->d_scratch[3]);
     KFBO_CUDA(h, cudaMemcpyAsync(d_case, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));

@@ -91,6 +91,68 @@ KFBO_HOST_DEVICE inline void discretize(double pnoise0, double dt, double Fd[4],
         for (int j = 0; j < 2; ++j) Qd[2 * i + j] = R::add(R::mul(Fd[2 * i], E[0][2 + j]), R::mul(Fd[2 * i + 1], E[1][2 + j]));
 }
 
+// ---- the state-augmented variants: a chain of N integrators (N = 3, 4), everything else as above.  The reference has no
+// such model (system_models.hpp:11-12: N = 2); the tests' CPU checker for the augmented variants spells the generalisation out
+//  and is what these are pinned against.  Fc = ones on the superdiagonal, Qc(N-1,N-1) = pnoise; the Van Loan matrix of size 2N is
+// nilpotent, so exp() is the finite series, in Horner form like expm_nilpotent4.  Matrices row-major with stride 4.
+inline void discretize_chain(int N, double pnoise0, double dt, double Fd[16], double Qd[16])
+{
+    const int n = 2 * N;
+    double A[8][8] = {{0}}, M[8][8], W[8][8];
+    for (int i = 0; i + 1 < N; ++i) { A[i][i + 1] = -dt; A[N + i + 1][N + i] = dt; }   // -Fc dt (top left), Fc^T dt (bottom right)
+    A[N - 1][2 * N - 1] = pnoise0 * dt;                                                   // Qc dt (top right)
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) M[i][j] = (i == j ? 1.0 : 0.0) + A[i][j] / (double)(n - 1);
+    for (int pass = n - 2; pass >= 1; --pass) {
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                double s = 0.0;
+                for (int k = 0; k < n; ++k) s += A[i][k] * M[k][j];
+                W[i][j] = (i == j ? 1.0 : 0.0) + s / (double)pass;
+            }
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) M[i][j] = W[i][j];
+    }
+    for (int i = 0; i < 16; ++i) Fd[i] = Qd[i] = 0.0;
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) Fd[4 * i + j] = M[N + j][N + i];                      // Fd = bottomRight^T
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < N; ++k) s += Fd[4 * i + k] * M[k][N + j];                 // Qd = Fd * topRight
+            Qd[4 * i + j] = s;
+        }
+}
+
+// g_i = dt^(N-i)/(N-i)! (system_models.hpp:46-47 for N = 2: dt^2/2, dt)
+inline void control_vector_chain(int N, double dt, double g[4])
+{
+    for (int i = 0; i < 4; ++i) g[i] = 0.0;
+    for (int i = 0; i < N; ++i) {
+        double p = 1.0, f = 1.0;
+        for (int k = 1; k <= N - i; ++k) { p *= dt; f *= (double)k; }
+        g[i] = p / f;
+    }
+}
+
+// lower Cholesky factor (stride 4) of an N x N symmetric positive definite matrix; false if it is not
+inline bool cholesky_chain(int N, const double A[16], double L[16])
+{
+    for (int i = 0; i < 16; ++i) L[i] = 0.0;
+    for (int j = 0; j < N; ++j) {
+        double s = A[4 * j + j];
+        for (int k = 0; k < j; ++k) s -= L[4 * j + k] * L[4 * j + k];
+        if (!(s > 0.0)) return false;
+        L[4 * j + j] = std::sqrt(s);
+        for (int i = j + 1; i < N; ++i) {
+            double t = A[4 * i + j];
+            for (int k = 0; k < j; ++k) t -= L[4 * i + k] * L[4 * j + k];
+            L[4 * i + j] = t / L[4 * j + j];
+        }
+    }
+    return true;
+}
+
 inline void control_table(double dt, int n, double *u)
 {
     double j = 0.0;
@@ -166,6 +228,7 @@ inline int validate(const kfbo_params &p)
     if (!(p.pnoise_truth > 0.0) || !(p.onoise_truth > 0.0)) return KFBO_EINVAL;
     if (p.cost_choice < KFBO_JNEES || p.cost_choice > KFBO_CNIS) return KFBO_EINVAL;
     if (p.max_candidates < 1) return KFBO_EINVAL;
+    if (p.state_dim != 0 && (p.state_dim < 2 || p.state_dim > 4)) return KFBO_ERANGE;
     return KFBO_OK;
 }
 

@@ -5,8 +5,6 @@
 //   rollout_supplied_bulk   noise streamed from HBM, SoA [step][component][trial], staged through
 //                           shared memory by cp.async.bulk + mbarriers (HBM bound)
 //   rollout_supplied        the same with per-thread loads (streams that are not 16-byte aligned)
-//   riccati_gains +
-//   rollout_philox_reduced  opt-in reduced form: gain table once per case, error-state trajectories
 //   trace_philox            one trajectory replayed step by step (the Nsimruns == 1 record)
 //   peer_exchange_kernel    multi-GPU: the ranks' cost sums meet in each other's memory (stores + flags over NVLink),
 //                           launched behind the rollout; the same code can run in the rollout's tail (kPeer, opt-in)
@@ -74,18 +72,19 @@ __device__ __forceinline__ void peer_exchange(const PeerCtx *__restrict__ pc, in
     constexpr int kPeerUnroll = 4;
     const int b2 = pc->begin[me] >> 1, e2 = pc->end[me] >> 1;
     const double2 *src = reinterpret_cast<const double2 *>(sums);
-    for (int i0 = b2 + part * kThreads * kPeerUnroll + tid; i0 < e2; i0 += nparts * kThreads * kPeerUnroll) {
+    const int nthreads = (int)blockDim.x;
+    for (int i0 = b2 + part * nthreads * kPeerUnroll + tid; i0 < e2; i0 += nparts * nthreads * kPeerUnroll) {
         double2 v[kPeerUnroll];
 #pragma unroll
         for (int u = 0; u < kPeerUnroll; ++u)
-            if (i0 + u * kThreads < e2) v[u] = __ldcg(src + i0 + u * kThreads);
+            if (i0 + u * nthreads < e2) v[u] = __ldcg(src + i0 + u * nthreads);
         for (int r = 0; r < nranks; ++r) {
             int to = me + r;                  // own buffer first, then the peers staggered by rank
             if (to >= nranks) to -= nranks;
             double2 *dst = reinterpret_cast<double2 *>(pc->vals[to] + my_off);
 #pragma unroll
             for (int u = 0; u < kPeerUnroll; ++u)
-                if (i0 + u * kThreads < e2) dst[i0 + u * kThreads] = v[u];
+                if (i0 + u * nthreads < e2) dst[i0 + u * nthreads] = v[u];
         }
     }
     __threadfence_system();
@@ -116,7 +115,7 @@ __device__ __forceinline__ void peer_exchange(const PeerCtx *__restrict__ pc, in
         const double2 *slab0 = reinterpret_cast<const double2 *>(pc->vals[me] + (size_t)gen * slabs * cap);
         const size_t cap2 = cap >> 1;
         const int n2 = pc->nsums >> 1;
-        for (int i = tid; i < n2; i += kThreads) {
+        for (int i = tid; i < n2; i += nthreads) {
             double2 v[kMaxPeers];
 #pragma unroll
             for (int r = 0; r < kMaxPeers; ++r)
@@ -160,12 +159,13 @@ __global__ void __launch_bounds__(kThreads) peer_exchange_kernel(const PeerCtx *
 // CTA partial -> global; last CTA of the case reduces all partials of the case in fixed order.
 // s_red: kThreads x 4 doubles of shared memory the caller no longer needs (or a static array).
 // peer (optional, uniform): the CTA that finishes the launch's last case goes on to the cross-GPU exchange.
+template <int kT = kThreads>
 __device__ __forceinline__ void block_reduce_and_publish(const double out[4], int case_idx, int tile, int tiles,
                                                          int out_slot, double *__restrict__ partials,
                                                          unsigned *__restrict__ tickets, double *__restrict__ sums,
                                                          double (*s_red)[4], const PeerCtx *__restrict__ peer = nullptr)
 {
-    __shared__ double s_part[kThreads / 32][4];
+    __shared__ double s_part[kT / 32][4];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double r[4];
@@ -179,7 +179,7 @@ __device__ __forceinline__ void block_reduce_and_publish(const double out[4], in
     if (threadIdx.x < 4) {
         double a = 0.0;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) a += s_part[w][threadIdx.x];
+        for (int w = 0; w < kT / 32; ++w) a += s_part[w][threadIdx.x];
         partials[((size_t)case_idx * tiles + tile) * 4 + threadIdx.x] = a;
         __threadfence();
     }
@@ -191,9 +191,9 @@ __device__ __forceinline__ void block_reduce_and_publish(const double out[4], in
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // fixed-order: thread j takes tiles j, j+kThreads, ...; then a fixed shared-memory tree
+    // fixed-order: thread j takes tiles j, j+kT, ...; then a fixed shared-memory tree
     double a[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int tt = threadIdx.x; tt < tiles; tt += kThreads) {
+    for (int tt = threadIdx.x; tt < tiles; tt += kT) {
         const double *p = partials + ((size_t)case_idx * tiles + tt) * 4;
 #pragma unroll
         for (int m = 0; m < 4; ++m) a[m] += __ldcg(p + m);
@@ -201,7 +201,7 @@ __device__ __forceinline__ void block_reduce_and_publish(const double out[4], in
 #pragma unroll
     for (int m = 0; m < 4; ++m) s_red[threadIdx.x][m] = a[m];
     __syncthreads();
-    for (int o = kThreads / 2; o > 0; o >>= 1) {
+    for (int o = kT / 2; o > 0; o >>= 1) {
         if (threadIdx.x < o) {
 #pragma unroll
             for (int m = 0; m < 4; ++m) s_red[threadIdx.x][m] += s_red[threadIdx.x + o][m];
@@ -232,12 +232,13 @@ __device__ __forceinline__ void block_reduce_and_publish(const double out[4], in
 #endif
 constexpr int KFBO_PHILOX_GROUP_UNROLL_V = KFBO_PHILOX_GROUP_UNROLL;
 
+template <int kT = kThreads>
 __device__ __forceinline__ void load_noise_tables(math::LogTables *dst, const math::LogTables *__restrict__ src)
 {
     const double2 *ls = reinterpret_cast<const double2 *>(src);
     double2 *ld = reinterpret_cast<double2 *>(dst);
     static_assert(sizeof(math::LogTables) % sizeof(double2) == 0, "tables are copied 16 bytes at a time");
-    for (int i = threadIdx.x; i < (int)(sizeof(math::LogTables) / sizeof(double2)); i += kThreads) ld[i] = ls[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(math::LogTables) / sizeof(double2)); i += kT) ld[i] = ls[i];
 }
 
 template <bool kUniformEst, bool kShiftFirst, bool kPeer>
@@ -566,197 +567,6 @@ rollout_supplied_bulk(const Case *__restrict__ cases, const __grid_constant__ Sa
 }
 
 // -----------------------------------------------------------------------------------------
-// REDUCED FORM of the Philox rollout (opt-in: KFBO_OPT_ROLLOUT_FORM = KFBO_FORM_REDUCED).
-//
-// Two exact identities of the reference recursion remove work that every trajectory of a case
-// repeats identically:
-//   1. the covariance recursion P, S, K (kalman_filter.cpp:23-37) does not depend on the data: it is
-//      the same for all trials of a (candidate, sample time).  riccati_gains runs it ONCE per case
-//      and tabulates, per step, the gain K, 1/S and P^-1 (what NEES / NIS need);
-//   2. the error e = x - xhat obeys e- = Fd e + w, nu = H e- + v, e = e- - K nu: the control g u and
-//      the truth state itself cancel (trial.cpp:53 only ever uses x - xhat).
-// Per trajectory that leaves 19 FP64 instructions per filter-step instead of 48 (plus the noise).
-// The per-trial NEES/NIS agree with the reference form to rounding (no x - xhat cancellation here,
-// so this form is the more accurate one); tests bound the difference by 1e-9 relative like every other
-// parity check.  It is NOT the formulation north_star prescribes (covariance per thread), so it is
-// off by default and bench.py reports it on its own line with its own instruction count.
-// -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) riccati_gains(const Case *__restrict__ cases, int ncases, GainStep *__restrict__ table, int stride)
-{
-    const int i = blockIdx.x * 32 + threadIdx.x;
-    if (i >= ncases) return;
-    const Case m = cases[i];
-    const double f = m.f;
-    double p00 = 1.0, p01 = 0.0, p11 = 1.0;                       // P0 = I (trial.cpp:32)
-    GainStep *out = table + (size_t)i * stride;
-    for (int s = 0; s < m.T; ++s) {
-        const double fp01 = fma(f, p11, p01);                     // same operations as filter_step
-        const double pp00 = fma(fp01, f, fma(f, p01, p00)) + m.q00;
-        const double pp01 = fp01 + m.q01;
-        const double pp11 = p11 + m.q11;
-        const double sv = pp00 + m.r_est;
-        const double sinv = KFBO_RCP(sv);
-        const double k0 = pp00 * sinv, k1 = pp01 * sinv;
-        p00 = m.r_est * k0;
-        p01 = m.r_est * k1;
-        p11 = fma(-k1, pp01, pp11);
-        const double det = fma(p00, p11, -(p01 * p01));
-        const double invdet = KFBO_RCP(det);
-        GainStep g;
-        g.k0 = k0; g.k1 = k1; g.sinv = sinv;
-        g.a = p11 * invdet; g.b = -2.0 * (p01 * invdet); g.c = p00 * invdet;   // P^-1 = [[a, b/2], [b/2, c]]
-        out[s] = g;
-    }
-}
-
-#ifndef KFBO_REDUCED_UNROLL
-#define KFBO_REDUCED_UNROLL 1
-#endif
-constexpr int kReducedUnroll = KFBO_REDUCED_UNROLL;   // groups of the chunk loop unrolled (constant offsets into the stage)
-constexpr int kGainChunk = 16;    // steps per stage of the gain ring (768 B)
-constexpr int kGainStages = 3;
-
-// first: whether this is the trial's first step (run-time, uniform: a predicate on two instructions, no branch)
-__device__ __forceinline__ void reduced_step(double &e0, double &e1, double &kn, double &ki, double &sdn, double &sqn,
-                                             double &sdi, double &sqi, const GainStep &g, const double f, const double l00,
-                                             const double l10, const double l11, const double sr, const double n0,
-                                             const double n1, const double n2, const bool first)
-{
-    const double em0 = fma(l00, n0, fma(f, e1, e0));            // e- = Fd e + w,  w = L n
-    const double em1 = fma(l11, n1, fma(l10, n0, e1));
-    const double nu = fma(sr, n2, em0);                          // nu = H e- + v
-    e0 = fma(-g.k0, nu, em0);                                    // e = e- - K nu
-    e1 = fma(-g.k1, nu, em1);
-    const double t2 = fma(g.b, e1, g.a * e0);                    // NEES = a e0^2 + b e0 e1 + c e1^2
-    const double q = (g.c * e1) * e1;
-    const double nu_s = nu * g.sinv;
-    if (first) { kn = fma(e0, t2, q); ki = nu_s * nu; }
-    const double dn = fma(e0, t2, q - kn);
-    const double di = fma(nu_s, nu, -ki);
-    sdn += dn; sqn = fma(dn, dn, sqn);
-    sdi += di; sqi = fma(di, di, sqi);
-}
-
-template <bool kPeer>
-__global__ void __launch_bounds__(kThreads)
-rollout_philox_reduced(const Case *__restrict__ cases, const __grid_constant__ SampleTimeConsts st,
-                       const GainStep *__restrict__ gains, int gain_stride, const math::LogTables *__restrict__ logtab,
-                       const __grid_constant__ PhiloxKeys key, uint32_t trial0, uint32_t ntrials, int tiles,
-                       double *__restrict__ per_trial, size_t per_trial_ld, double *__restrict__ partials,
-                       unsigned *__restrict__ tickets, double *__restrict__ sums)
-{
-    extern __shared__ __align__(16) unsigned char s_tables_raw[];
-    math::LogTables &s_log = *reinterpret_cast<math::LogTables *>(s_tables_raw);
-    __shared__ __align__(128) GainStep s_gain[kGainStages][kGainChunk];
-    __shared__ __align__(8) uint64_t s_full[kGainStages], s_empty[kGainStages];
-    const int case_idx = blockIdx.y * gridDim.z + blockIdx.z, tile = blockIdx.x;
-    const Case m = cases[case_idx];
-    const int T = m.T;
-    const unsigned kk = st.k0 + blockIdx.z;
-    const double f = pick4(st.f, kk), l00 = pick4(st.l00, kk), l10 = pick4(st.l10, kk), l11 = pick4(st.l11, kk),
-                 sr = pick4(st.sr, kk);
-    const int lane = threadIdx.x & 31;
-    load_noise_tables(&s_log, logtab);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < kGainStages; ++s) { mbar_init(&s_full[s], 1u); mbar_init(&s_empty[s], kThreads / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int nchunks = (T + kGainChunk - 1) / kGainChunk;
-    const GainStep *gsrc = gains + (size_t)case_idx * gain_stride;      // stride is a multiple of kGainChunk
-    uint64_t policy = 0;
-    auto issue = [&](int chunk) {
-        uint64_t *bar = &s_full[chunk % kGainStages];
-        mbar_arrive_expect_tx(bar, (uint32_t)sizeof(s_gain[0]));
-        bulk_g2s(&s_gain[chunk % kGainStages][0], gsrc + (size_t)chunk * kGainChunk, (uint32_t)sizeof(s_gain[0]), bar, policy);
-    };
-    if (threadIdx.x == 0) {
-        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));   // every CTA of the case re-reads it
-        for (int c = 0; c < kGainStages - 1 && c < nchunks; ++c) issue(c);
-    }
-
-    const uint32_t local = (uint32_t)tile * kThreads + threadIdx.x;
-    const uint32_t trial = trial0 + local;    // past-the-end trajectories of the last tile are computed and discarded
-    double e0, e1, kn = 0.0, ki = 0.0, sdn = 0.0, sqn = 0.0, sdi = 0.0, sqi = 0.0;
-    {
-        const uint4 w = philox_at(trial, m.stream, m.stream_x, 0u, 0u, key);
-        math::normal_pair(w.x, w.y, s_log, e0, e1);    // e = x0 + N(0,P0) - xhat0 = the draw itself
-    }
-    static_assert(kGainChunk % 4 == 0, "a gain chunk holds whole step groups");
-    GroupWords r = philox_group(trial, m.stream, m.stream_x, 0u, key);
-    for (int c = 0; c < nchunks; ++c) {
-        if (threadIdx.x == 0) {
-            const int nx = c + kGainStages - 1;
-            if (nx < nchunks) {
-                if (nx >= kGainStages) mbar_wait(&s_empty[nx % kGainStages], (uint32_t)((nx / kGainStages - 1) & 1));
-                issue(nx);
-            }
-        }
-        const int sidx = c % kGainStages;
-        mbar_wait(&s_full[sidx], (uint32_t)((c / kGainStages) & 1));
-        const GainStep *g = s_gain[sidx];
-        const int c0 = c * kGainChunk;
-        const int nsteps = T - c0 < kGainChunk ? T - c0 : kGainChunk;     // steps of this chunk that exist
-        const int nfull = nsteps >> 2;
-#pragma unroll kReducedUnroll
-        for (int gi = 0; gi < nfull; ++gi) {                              // whole groups: one basic block each
-            const int j = 4 * gi, s0 = c0 + j;
-            const GroupWords q = philox_group(trial, m.stream, m.stream_x, (uint32_t)(s0 >> 2) + 1u, key);
-            double p0a, p0b, p1a, p1b, p2a, p2b, p3a, p3b, o0, o1, o2, o3;
-            math::normal_pair(r.c.x, r.c.y, s_log, o0, o1);
-            math::normal_pair(r.a.x, r.a.y, s_log, p0a, p0b);
-            math::normal_pair(r.a.z, r.a.w, s_log, p1a, p1b);
-            reduced_step(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j], f, l00, l10, l11, sr, p0a, p0b, o0, s0 == 0);
-            math::normal_pair(r.c.z, r.c.w, s_log, o2, o3);
-            math::normal_pair(r.b.x, r.b.y, s_log, p2a, p2b);
-            reduced_step(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j + 1], f, l00, l10, l11, sr, p1a, p1b, o1, false);
-            math::normal_pair(r.b.z, r.b.w, s_log, p3a, p3b);
-            reduced_step(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j + 2], f, l00, l10, l11, sr, p2a, p2b, o2, false);
-            reduced_step(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j + 3], f, l00, l10, l11, sr, p3a, p3b, o3, false);
-            r = q;
-        }
-        const int rem = nsteps & 3;                                       // only the last chunk can end in a partial group
-        if (rem > 0) {
-            const int j = 4 * nfull, s0 = c0 + j;
-            double pa, pb, o0, o1;
-            math::normal_pair(r.c.x, r.c.y, s_log, o0, o1);
-            math::normal_pair(r.a.x, r.a.y, s_log, pa, pb);
-            reduced_step(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j], f, l00, l10, l11, sr, pa, pb, o0, s0 == 0);
-            if (rem > 1) {
-                math::normal_pair(r.a.z, r.a.w, s_log, pa, pb);
-                reduced_step(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j + 1], f, l00, l10, l11, sr, pa, pb, o1, false);
-            }
-            if (rem > 2) {
-                math::normal_pair(r.c.z, r.c.w, s_log, o0, o1);
-                math::normal_pair(r.b.x, r.b.y, s_log, pa, pb);
-                reduced_step(e0, e1, kn, ki, sdn, sqn, sdi, sqi, g[j + 2], f, l00, l10, l11, sr, pa, pb, o0, false);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[sidx]);
-    }
-    double out[4] = {0.0, 0.0, 0.0, 0.0};
-    {
-        Traj t;
-        t.kn = kn; t.ki = ki; t.sdn = sdn; t.sqn = sqn; t.sdi = sdi; t.sqi = sqi;
-        double o[4];
-        traj_finish(t, T, o);
-        if (local < ntrials) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) out[k] = o[k];
-            if (per_trial != nullptr) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) per_trial[((size_t)m.out_slot * 4 + k) * per_trial_ld + local] = o[k];
-            }
-        }
-    }
-    __syncthreads();
-    block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, reinterpret_cast<double (*)[4]>(s_tables_raw),
-                             kPeer ? peer_ctx_of(cases) : nullptr);
-}
-
-// -----------------------------------------------------------------------------------------
 // Single-trial trace (the Nsimruns == 1 path of trial.cpp:69-78,116-129, which plots the estimation
 // error inside its +-2 sigma band): one thread replays ONE trajectory of the Philox rollout -- same
 // streams, same filter_step -- and records per step
@@ -971,30 +781,6 @@ cudaError_t launch_trace_philox(const Case *d_case, const SampleTimeConsts &st, 
     return cudaGetLastError();
 }
 
-int gain_stride_for(int max_T) { return (max_T + kGainChunk - 1) / kGainChunk * kGainChunk; }
-
-cudaError_t launch_rollout_philox_reduced(const Case *d_cases, int ncases, const SampleTimeConsts &st, GainStep *d_gains, const void *d_logtab,
-                                          int max_T, uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
-                                          size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
-                                          cudaStream_t stream, bool with_peer)
-{
-    if (ncases <= 0 || ntrials == 0) return cudaSuccess;
-    const int stride = gain_stride_for(max_T);
-    riccati_gains<<<(ncases + 31) / 32, 32, 0, stream>>>(d_cases, ncases, d_gains, stride);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    const int tiles = rollout_tiles(ntrials);
-    const dim3 grid((unsigned)tiles, (unsigned)(ncases / st.nk), (unsigned)st.nk);
-    const size_t smem = sizeof(math::LogTables);
-    auto *kernel = with_peer ? rollout_philox_reduced<true> : rollout_philox_reduced<false>;
-    e = ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), with_peer ? 9 : 8, smem);
-    if (e != cudaSuccess) return e;
-    kernel<<<grid, kThreads, smem, stream>>>(
-        d_cases, st, d_gains, stride, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0, ntrials, tiles,
-        d_per_trial, per_trial_ld, d_partials, d_tickets, d_sums);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_rollout_supplied(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, int max_T, const double *d_x0noise,
                                     const double *d_w, const double *d_v, size_t B, double *d_per_trial,
                                     double *d_partials, unsigned *d_tickets, double *d_sums, int variant, int smem_pad,
@@ -1036,3 +822,5 @@ cudaError_t launch_dfma_chain(double *d_out, int blocks, int iters, bool reg_mul
 int rollout_tiles(size_t ntrials) { return (int)((ntrials + kThreads - 1) / kThreads); }
 
 }  // namespace kfbo
+
+#include "kfbo_aug.cuh"

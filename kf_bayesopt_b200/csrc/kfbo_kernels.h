@@ -98,15 +98,6 @@ cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleT
                                   size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
                                   cudaStream_t stream, const Case *h_cases = nullptr, bool with_peer = false);
 
-// Reduced form (opt-in): per step of a case the gain K, 1/S and P^-1 = [[a, b/2], [b/2, c]], tabulated once
-// per case by riccati_gains; d_gains holds ncases x gain_stride_for(max_T) entries.
-struct GainStep { double k0, k1, sinv, a, b, c; };
-int gain_stride_for(int max_T);
-cudaError_t launch_rollout_philox_reduced(const Case *d_cases, int ncases, const SampleTimeConsts &st, GainStep *d_gains, const void *d_logtab,
-                                          int max_T, uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
-                                          size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
-                                          cudaStream_t stream, bool with_peer = false);
-
 cudaError_t launch_rollout_supplied(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, int max_T, const double *d_x0noise,
                                     const double *d_w, const double *d_v, size_t B, double *d_per_trial,
                                     double *d_partials, unsigned *d_tickets, double *d_sums, int variant, int smem_pad,
@@ -141,9 +132,32 @@ cudaError_t launch_build_cases(const double2 *d_cand /* (pnoise, onoise) */, int
 size_t compact_costs_bytes(int C, int D);
 cudaError_t launch_assemble_costs(const double *d_sums, int C, const void *params /* const kfbo_params* (host) */, void *d_out, cudaStream_t stream);
 
+// ---- the state-augmented variants (N = 3, 4 states; kfbo_aug.cuh): one covariance row per lane of a 4-lane group ----
+constexpr int kAugGroup = 4;          // lanes per trajectory = the largest supported state dimension
+struct AugCase {                      // per (candidate, sample time); matrices row-major 4 x 4, zero-padded beyond N
+    double qd[16];                    // estimator Qd
+    double r_est;                     // estimator R = onoise_est/dt
+    int32_t T;
+    uint32_t stream_x, stream;        // Philox stream id, as in Case
+    int32_t out_slot;
+};
+struct AugSampleTime {                // per sample time: depends on dt and the truth side only
+    double F[16];                     // Fd
+    double g[4];                      // g_i = dt^(N-i)/(N-i)!
+    double L[16];                     // lower Cholesky factor of the truth Qd
+    double sr;                        // sqrt(truth R)
+};
+int aug_tiles(size_t ntrials);        // CTAs per case: 32 trajectories per 128-thread CTA
+// supplied: x0noise[N][B], w[T][N][B], v[T][B] (device), trials [0, ntrials) of them; else on-device Philox noise.
+// d_u[D][kMaxSteps]: the control table per sample time; cases laid out [candidate][sample time k0 .. k0+nk).
+cudaError_t launch_rollout_aug(int N, bool supplied, const AugCase *d_cases, int ncases, int nk, int k0, const AugSampleTime *d_sts,
+                               const double *d_u, const void *d_logtab, uint64_t seed, uint32_t trial0, uint32_t ntrials,
+                               const double *d_x0noise, const double *d_w, const double *d_v, size_t B, double *d_per_trial,
+                               size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums, cudaStream_t stream);
+
 cudaError_t launch_dfma_chain(double *d_out, int blocks, int iters, bool reg_multiplier, cudaStream_t stream);
 
-int rollout_tiles(size_t ntrials);   // CTAs per case of the rollout kernels
+int rollout_tiles(size_t ntrials);   // CTAs per case of the rollout kernels (128-thread CTAs)
 
 // The Philox stream id is 62 bits wide (kfbo.h: KFBO_STREAM_BITS): where its halves go in a Case.
 inline void set_case_stream(Case *c, uint64_t stream)

@@ -135,7 +135,7 @@ def sample_times_from(rv: ReadParaVehicle, second: Optional[Tuple[float, float]]
 
 
 def make_params(rv_gt: ReadParaVehicle, sample_times: Sequence[Tuple[float, int]], seed: int = 0x4B46424F20260101,
-                max_candidates: int = 1, device: int = -1, cost_choice: Optional[str] = None) -> KfboParams:
+                max_candidates: int = 1, device: int = -1, cost_choice: Optional[str] = None, state_dim: int = 0) -> KfboParams:
     if not 1 <= len(sample_times) <= MAX_SAMPLE_TIMES:
         raise ValueError(f"1..{MAX_SAMPLE_TIMES} sample times, got {len(sample_times)}")
     p = KfboParams()
@@ -149,6 +149,7 @@ def make_params(rv_gt: ReadParaVehicle, sample_times: Sequence[Tuple[float, int]
     p.pnoise_truth, p.onoise_truth = float(rv_gt.pnoise_[0]), float(rv_gt.onoise_[0])
     p.cost_choice = COST_CHOICES[cost_choice or rv_gt.cost_choice_]
     p.device, p.seed, p.max_candidates = device, seed & 0xFFFFFFFFFFFFFFFF, max_candidates
+    p.state_dim = state_dim        # 0 / 2: the reference's model; 3, 4: the state-augmented variants (kfbo.h)
     return p
 
 
@@ -174,12 +175,13 @@ class CostEvaluator:
 
     def __init__(self, rv_gt: Optional[ReadParaVehicle] = None, sample_times: Optional[Sequence[Tuple[float, int]]] = None,
                  seed: int = 0x4B46424F20260101, max_candidates: int = 1, device: int = -1,
-                 cost_choice: Optional[str] = None):
+                 cost_choice: Optional[str] = None, state_dim: int = 0):
         self._lib = _lib.load()
         self.rv_gt = rv_gt or ReadParaVehicle()
         self.sample_times = list(sample_times) if sample_times is not None else sample_times_from(self.rv_gt)
-        self.params = make_params(self.rv_gt, self.sample_times, seed, max_candidates, device, cost_choice)
+        self.params = make_params(self.rv_gt, self.sample_times, seed, max_candidates, device, cost_choice, state_dim)
         self.D = len(self.sample_times)
+        self.N = state_dim if state_dim >= 2 else 2      # state dimension: rows of the supplied noise arrays
         self._h = C.c_void_p()
         rc = self._lib.kfbo_create(C.byref(self.params), C.byref(self._h))
         if rc:
@@ -273,13 +275,13 @@ class CostEvaluator:
 
     # -- exact-parity entry points
     def eval_supplied(self, k: int, q_est, r_est, x0noise, w, v, per_trial: bool = True):
-        """Returns (per_trial[C][4][B] or None, sums[C][4]); x0noise[2][B], w[T][2][B], v[T][B]."""
+        """Returns (per_trial[C][4][B] or None, sums[C][4]); x0noise[N][B], w[T][N][B], v[T][B] (N = 2 unless state_dim says otherwise)."""
         q, r = np.atleast_1d(_f64(q_est)), np.atleast_1d(_f64(r_est))
         x0noise, w, v = _f64(x0noise), _f64(w), _f64(v)
         T = self.sample_times[k][1]
         B = x0noise.shape[-1]
-        if x0noise.shape != (2, B) or w.shape != (T, 2, B) or v.shape != (T, B):
-            raise ValueError(f"expected x0noise[2][{B}], w[{T}][2][{B}], v[{T}][{B}]")
+        if x0noise.shape != (self.N, B) or w.shape != (T, self.N, B) or v.shape != (T, B):
+            raise ValueError(f"expected x0noise[{self.N}][{B}], w[{T}][{self.N}][{B}], v[{T}][{B}]")
         pt = np.empty((q.size, 4, B)) if per_trial else None
         sums = np.empty((q.size, 4))
         self._check(self._lib.kfbo_eval_supplied(self._h, k, q.size, _ptr(q), _ptr(r), B, _ptr(x0noise), _ptr(w), _ptr(v),

@@ -135,7 +135,10 @@ int main(int nargs, char *args[])
         for (double r : result) std::cout << r << ",";
         std::cout << std::endl;
         std::cout << std::setprecision(10) << "{\"workload\": \"bo_loop\", \"iterations\": " << sc.it_counter()
-                  << ", \"n_init_samples\": " << rb.n_init_samples_ << ", \"nsimruns\": " << rv.nsimruns_
+                  << ", \"n_init_samples\": " << rb.n_init_samples_ << ", \"n_iterations\": " << rb.n_iterations_
+                  << ", \"lower_bound\": [" << rb.lower_bound_[0] << (rb.lower_bound_.size() > 1 ? ", " + std::to_string(rb.lower_bound_[1]) : "")
+                  << "], \"upper_bound\": [" << rb.upper_bound_[0] << (rb.upper_bound_.size() > 1 ? ", " + std::to_string(rb.upper_bound_[1]) : "")
+                  << "], \"optimization_choice\": \"" << rv.optimization_choice_ << "\", \"nsimruns\": " << rv.nsimruns_
                   << ", \"sample_times\": " << rT.evaluator().params().n_sample_times << ", \"reference_sleeps\": " << (sleeps ? "true" : "false")
                   << ", \"wall_s\": " << wall << ", \"evaluator_s\": " << eval_s << ", \"evaluator_ms_per_iteration\": " << eval_s / std::max(evals, 1) * 1e3
                   << ", \"optimiser_s\": " << wall - eval_s - (sleeps ? 0.5 * sc.it_counter() : 0.0) << ", \"best_cost\": " << opt.best_value() << ", \"best_x\": [";

@@ -19,8 +19,8 @@ COST_CHOICES = {"JNEES": 0, "CNEES": 1, "JNIS": 2, "CNIS": 3}
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "kfbo_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "kfbo_oracle.c"), os.path.join(_HERE, "kfbo_oracle_aug.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libkfbo_oracle.so"])
     return _SO
 
@@ -61,6 +61,18 @@ def lib() -> C.CDLL:
         L.ko_kf_run.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, _dp, _dp]
         L.ko_kf_run.restype = C.c_int
         L.ko_gu_table.argtypes = [C.c_double, C.c_int, _dp]
+        # the state-augmented variants (kfbo_oracle_aug.c)
+        L.koa_expm.argtypes = [C.c_int, _dp, _dp]
+        L.koa_discretize.argtypes = [C.c_int, C.c_double, C.c_double, _dp, _dp]
+        L.koa_discretize.restype = C.c_int
+        L.koa_gvector.argtypes = [C.c_int, C.c_double, _dp]
+        L.koa_cholesky.argtypes = [C.c_int, _dp, _dp]
+        L.koa_cholesky.restype = C.c_int
+        L.koa_eval_supplied.argtypes = [C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_long, _dp, _dp, _dp, _dp]
+        L.koa_eval_supplied.restype = C.c_int
+        L.koa_eval_philox.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double,
+                                      C.c_double, C.c_uint32, C.c_long, _dp]
+        L.koa_eval_philox.restype = C.c_int
         _lib = L
     return _lib
 
@@ -214,3 +226,52 @@ def refclock_draws(dt, T, q_truth, r_truth, clock0, i=0):
     if rc:
         raise ValueError(f"ko_refclock_draws rc={rc}")
     return x0n, w, v
+
+
+# ---- the state-augmented variants, N = 3, 4 (oracle/kfbo_oracle_aug.c; N = 2 reproduces the functions above) ----
+def aug_expm(A) -> np.ndarray:
+    A = _f64(A)
+    E = np.empty_like(A)
+    lib().koa_expm(A.shape[0], _p(A), _p(E))
+    return E
+
+
+def aug_discretize(N: int, q: float, dt: float):
+    Fd, Qd = np.empty((N, N)), np.empty((N, N))
+    if lib().koa_discretize(N, q, dt, _p(Fd), _p(Qd)):
+        raise ValueError("koa_discretize: N outside [2, 4]")
+    return Fd, Qd
+
+
+def aug_gvector(N: int, dt: float) -> np.ndarray:
+    g = np.empty(N)
+    lib().koa_gvector(N, dt, _p(g))
+    return g
+
+
+def aug_cholesky(A) -> np.ndarray:
+    A = _f64(A)
+    L = np.empty_like(A)
+    if lib().koa_cholesky(A.shape[0], _p(A), _p(L)):
+        raise ValueError("koa_cholesky: not positive definite")
+    return L
+
+
+def aug_eval_supplied(N, dt, T, q_est, r_est, x0noise, w, v) -> np.ndarray:
+    """x0noise[N][B], w[T][N][B], v[T][B] -> per_trial[4][B]."""
+    x0noise, w, v = _f64(x0noise), _f64(w), _f64(v)
+    B = x0noise.shape[1]
+    assert x0noise.shape == (N, B) and w.shape == (T, N, B) and v.shape == (T, B)
+    out = np.empty((4, B))
+    rc = lib().koa_eval_supplied(N, dt, T, q_est, r_est, B, _p(x0noise), _p(w), _p(v), _p(out))
+    if rc:
+        raise ValueError(f"koa_eval_supplied rc={rc}")
+    return out
+
+
+def aug_eval_philox(N, seed, stream, dt, T, q_truth, r_truth, q_est, r_est, trial0, ntrials) -> np.ndarray:
+    out = np.empty((4, ntrials))
+    rc = lib().koa_eval_philox(N, seed, stream, dt, T, q_truth, r_truth, q_est, r_est, trial0, ntrials, _p(out))
+    if rc:
+        raise ValueError(f"koa_eval_philox rc={rc}")
+    return out

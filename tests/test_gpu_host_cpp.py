@@ -66,6 +66,36 @@ def test_bo_loop_runs_the_topic_contract_end_to_end(host_bins, yamls):
     assert line["evaluator_s"] <= line["wall_s"]
 
 
+def test_bo_loop_consumes_the_settings_of_bayes_params_yaml(host_bins, yamls, tmp_path):
+    """The stand-in optimiser honours config/bayesParams.yaml the way the reference's node does
+    (robot1d_bayesopt.cpp:242-249 copies n_init_samples, n_iterations, ...; :251-262 the bounds): the number of
+    evaluations is n_init_samples + n_iterations FROM THE FILE, every sample lies inside the file's bounds, and
+    optimizationChoice of vehicleParams.yaml decides which half of the "noise" message the sample fills."""
+    import re
+    bayes = tmp_path / "bayesParams.yaml"
+    text = open(yamls[1]).read()
+    text = re.sub(r"n_init_samples: *\d+", "n_init_samples: 7", text)
+    text = re.sub(r"n_iterations: *\d+", "n_iterations: 9", text)
+    text = re.sub(r"lower_bound: *\[[^\]]*\]", "lower_bound: [0.5, 0.05]", text)
+    text = re.sub(r"upper_bound: *\[[^\]]*\]", "upper_bound: [2.0, 0.5]", text)
+    bayes.write_text(text)
+    out = _run("kfbo_bo_loop", "--vehicle", yamls[0], "--bayes", bayes, "--nsimruns", 1000)
+    line = json.loads(next(l for l in out.splitlines() if l.startswith("{")))
+    assert (line["n_init_samples"], line["n_iterations"], line["iterations"]) == (7, 9, 16)
+    assert line["lower_bound"] == [0.5, 0.05] and line["upper_bound"] == [2.0, 0.5]
+    xs = np.array([[float(v) for v in re.match(r"iteration \d+ x (\S+) (\S+) cost", l).groups()] for l in out.splitlines() if l.startswith("iteration ")])
+    assert xs.shape == (16, 2)
+    assert np.all(xs[:, 0] >= 0.5) and np.all(xs[:, 0] <= 2.0) and np.all(xs[:, 1] >= 0.05) and np.all(xs[:, 1] <= 0.5)
+    assert line["dt0_count"] + line["dt1_count"] == 16 - 7    # trial_node.cpp:121-126 counts after the initial samples
+    # optimizationChoice = processNoise: a 1-D search over pnoise inside the FIRST bound pair, onoise stays at the yaml value
+    vehicle = tmp_path / "vehicleParams.yaml"
+    vehicle.write_text(open(yamls[0]).read().replace("optimizationChoice: all", "optimizationChoice: processNoise"))
+    out = _run("kfbo_bo_loop", "--vehicle", vehicle, "--bayes", bayes, "--nsimruns", 1000)
+    line = json.loads(next(l for l in out.splitlines() if l.startswith("{")))
+    assert line["optimization_choice"] == "processNoise" and len(line["best_x"]) == 1 and 0.5 <= line["best_x"][0] <= 2.0
+    assert line["iterations"] == 16
+
+
 def test_trace_csv_and_cost_surface_cli(host_bins, yamls, tmp_path):
     trace = tmp_path / "trace.csv"
     out = _run("kfbo_test_trial", "--vehicle", yamls[0], "--nsimruns", 10, "--fused", "--trace", trace)

@@ -52,7 +52,7 @@ def test_cost_choices(kfbo):
 
 @pytest.mark.gpu
 def test_every_kernel_runs_on_small_ragged_shapes():
-    # tools/all_kernels_small.py: Philox (both forms, batch, per-trial), both supplied-noise kernels on whole + ragged tiles,
+    # tools/all_kernels_small.py: Philox (one candidate, batch, per-trial), the state-augmented kernels, both supplied-noise kernels on whole + ragged tiles,
     # odd trial counts, the gain recursion and the trace, with finite outputs everywhere
     import os
     import subprocess

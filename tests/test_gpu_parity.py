@@ -387,9 +387,12 @@ def test_full_size_cfg4_sweep_shape(kfbo, oracle):
     r = np.tile(np.geomspace(0.01, 1.0, n), n)
     rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
     with kfbo.CostEvaluator(rv, README_TIMES, seed=seed, max_candidates=n * n) as ev:
-        cost, mx = ev.eval_batch_costs(q, r)
+        full = ev.eval_batch_raw(q, r)
         sums = ev.last_sums(n * n)
+        ev.set_eval_counter(0)
+        cost, mx, idx = ev.eval_batch_costs(q, r, with_index=True)      # the same sweep, costs assembled on the device
     assert cost.shape == (n * n, 2) and np.all(np.isfinite(cost)) and np.all(mx == cost.max(axis=1))
+    assert rel_err(cost, full["cost"][:, :2]) < RTOL and np.array_equal(idx, full["index_max"])
     for c in (0, 777, 2049, 4095):
         for k, (dt, T) in enumerate(README_TIMES):
             pt = oracle.eval_philox(seed, c * 2 + k, dt, T, Q_TRUTH, R_TRUTH, q[c], r[c], 0, B)
@@ -434,64 +437,6 @@ def test_supplied_kernels_ldg_and_bulk_agree_bit_for_bit(kfbo, oracle):
         assert np.array_equal(out["ldg"][1], out["bulk"][1]), (B, T)
         want = oracle.eval_supplied(dt, T, 0.8, 0.15, x0n, w, v)
         assert rel_err(out["bulk"][0][0], want) < RTOL, (B, T)
-
-
-def test_reduced_form_matches_reference_form_and_oracle(kfbo, oracle):
-    # KFBO_FORM_REDUCED (gain table once per case + error-state trajectories) against the reference form
-    # (covariance per thread) and against the oracle, draw for draw: same Philox streams, same per-trial outputs
-    from kf_bayesopt_b200 import _lib
-    seed = 0xFEEDFACE12345678
-    rv = kfbo.ReadParaVehicle(nsimruns_=700, cpu_core_number_=1)
-    for times in (CODE_TIMES, README_TIMES, [(0.1, 2000), (0.5, 2)], [(1.0, 17), (0.1, 33)], [(0.2, 18), (0.5, 19), (0.1, 3)]):
-        with kfbo.CostEvaluator(rv, times, seed=seed, max_candidates=5) as ev:
-            for k, (dt, T) in enumerate(times):
-                for qe, re, stream, trial0, n in [(1.0, 0.1, 3, 0, 700), (0.2, 0.9, 9, 123456, 129), (4.5, 0.02, 0xFFFFFFF0, 7, 1)]:
-                    ev.set_option(_lib.OPT_ROLLOUT_FORM, _lib.FORM_REFERENCE)
-                    ref = ev.eval_philox_trials(k, qe, re, stream, trial0, n)
-                    ev.set_option(_lib.OPT_ROLLOUT_FORM, _lib.FORM_REDUCED)
-                    red = ev.eval_philox_trials(k, qe, re, stream, trial0, n)
-                    assert rel_err(red, ref) < RTOL, (times, k, qe)
-                    if T <= 211:
-                        want = oracle.eval_philox(seed, stream, dt, T, Q_TRUTH, R_TRUTH, qe, re, trial0, n)
-                        assert rel_err(red, want) < RTOL, (times, k, qe)
-            # the batched evaluation: same sums, same costs, same selection
-            q, r = np.array([1.0, 0.1, 5.0, 0.5, 2.0]), np.array([0.1, 0.1, 1.0, 0.01, 0.3])
-            out = {}
-            for form in (_lib.FORM_REFERENCE, _lib.FORM_REDUCED):
-                ev.set_option(_lib.OPT_ROLLOUT_FORM, form)
-                ev.set_eval_counter(5)
-                res = ev.eval_batch(q, r)
-                out[form] = (ev.last_sums(5).copy(), np.stack([x.cost for x in res]), [x.index_max for x in res])
-            assert rel_err(out[1][0], out[0][0]) < RTOL
-            np.testing.assert_allclose(out[1][1], out[0][1], rtol=1e-9, atol=1e-12)
-            assert out[1][2] == out[0][2]
-
-
-def test_reduced_form_full_size_and_chunked_gain_table(kfbo):
-    from kf_bayesopt_b200 import _lib
-    # cfg3 shape: chi-square consistency and agreement with the reference form on the same streams
-    B, T = 1 << 18, 1000
-    rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
-    with kfbo.CostEvaluator(rv, [(0.1, T), (0.5, T)], seed=11) as ev:
-        a = ev.eval([1.0], [0.1])
-        s_ref = ev.last_sums(1).copy()
-        ev.set_option(_lib.OPT_ROLLOUT_FORM, _lib.FORM_REDUCED)
-        ev.set_eval_counter(0)
-        b = ev.eval([1.0], [0.1])
-        assert rel_err(ev.last_sums(1), s_ref) < 1e-11
-        assert abs(b.average_nees[0] - 2.0) < 5 * 0.4 / 512 and b.index_max == a.index_max
-    # many candidates with the longest table (T = 2000): the gain table is filled in several launches
-    n = 3000
-    q, r = np.geomspace(0.1, 5.0, n), np.geomspace(0.01, 1.0, n)[::-1].copy()
-    rv = kfbo.ReadParaVehicle(nsimruns_=128, cpu_core_number_=1)
-    with kfbo.CostEvaluator(rv, [(0.1, 2000), (0.5, 400)], seed=3, max_candidates=n) as ev:
-        c_ref, _ = ev.eval_batch_costs(q, r)
-        launches_ref = ev.last_kernel_ms()[1]
-        ev.set_option(_lib.OPT_ROLLOUT_FORM, _lib.FORM_REDUCED)
-        ev.set_eval_counter(0)
-        c_red, _ = ev.eval_batch_costs(q, r)
-        assert ev.last_kernel_ms()[1] > 2 * launches_ref          # 256 MB of gains hold 2796 cases of 2000 steps
-    np.testing.assert_allclose(c_red, c_ref, rtol=1e-9, atol=1e-12)
 
 
 def test_single_trial_trace_matches_rollout_and_oracle_covariance(kfbo, oracle):

@@ -11,8 +11,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 rv = kf.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
 with kf.CostEvaluator(rv, [(0.1, T), (0.5, T)], seed=1) as ev:
-    form = int(os.environ.get("KFBO_FORM", "0"))        # 1 = the reduced form
-    ev.set_option(3, form)
+    form = 0
     ms = []
     for i in range(6):
         r = ev.eval([1.0], [0.1])
