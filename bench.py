@@ -579,17 +579,18 @@ def main():
     time.sleep(0.25)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, launches = [], 0
+    launches_per_eval = ev.last_kernel_ms()[1]
+    ev.kernel_ms_total(reset=True)           # the kernel times of the loop are accumulated inside the library and read once, after it
     t0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
         res = evaluate()
-        ms, n = ev.last_kernel_ms()
-        kernel_ms.append(ms)
-        launches += n
     e1.record(stream)
     barrier()
     t1 = time.perf_counter()
+    kms_total, kms_n = ev.kernel_ms_total()
+    assert kms_n == args.steps, (kms_n, args.steps)
+    kernel_ms, launches = [kms_total / kms_n], launches_per_eval * args.steps
     reduce_path = ev.last_reduce_path()
     host_us = ev.last_host_us()              # phases of the last timed evaluation on this rank (kfbo_last_host_us)
     clocks = sampler.stop(t0, t1)

@@ -183,6 +183,11 @@ int kfbo_last_kernel_ms(const kfbo_handle *h, double *ms, int32_t *launches);
  * compact costs; sums the kernel stores straight into mapped host memory count too). */
 int kfbo_last_transfer_bytes(const kfbo_handle *h, int64_t *h2d, int64_t *d2h);
 
+/* Sum of the rollout-kernel device times of the evaluations since the last reset, and how many (a benchmark loop reads
+ * this once at its end instead of calling kfbo_last_kernel_ms between evaluations).  The first call switches the
+ * handle to accumulating. */
+int kfbo_kernel_ms_total(kfbo_handle *h, double *ms_total, int64_t *evaluations, int32_t reset);
+
 /* Host wall time (microseconds) of the phases of the last kfbo_eval / kfbo_eval_batch on this rank:
  * us[0] building the per-(candidate, sample time) constants, us[1] enqueueing copies and launches,
  * us[2] waiting for the device (kernels, all-reduce, result copy), us[3] cost assembly (trial_node.cpp:70-119);
@@ -203,6 +208,10 @@ enum { KFBO_OPT_SUPPLIED_KERNEL = 1, KFBO_OPT_BULK_SMEM_PAD = 2 /* extra dynamic
        KFBO_OPT_REDUCE = 4 /* how the cost sums of a multi-GPU evaluation meet, KFBO_REDUCE_* below */,
        KFBO_OPT_PEER_FUSE = 5 /* KFBO_PEER_FUSE_* below */,
        KFBO_OPT_PEER_TIMEOUT_MS = 6 /* how long the exchange waits for a rank before KFBO_EPEER (default 10000) */,
+       KFBO_OPT_CUDA_GRAPH = 8 /* 1 (default): a single-candidate evaluation -- constants copy, rollout, exchange, timing events --
+                                        is replayed as ONE CUDA graph launch; 0: enqueued call by call */,
+       KFBO_OPT_HOST_POLL = 9 /* 1 (default): where the kernel stores the total into mapped host memory (multi-GPU, trials
+                                        sharded) the host polls that memory for it; 0: cudaStreamSynchronize */,
        KFBO_OPT_RESERVE_SUPPLIED_TRIALS = 7 /* pre-size the scratch of the parity entry points (kfbo_eval_supplied,
                                         kfbo_eval_philox_trials, kfbo_trace_trial) for this many trials x max_candidates
                                         candidates: after it they allocate nothing, like kfbo_eval* */ };

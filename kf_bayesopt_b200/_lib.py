@@ -22,6 +22,8 @@ OPT_REDUCE = 4
 OPT_PEER_FUSE = 5
 OPT_PEER_TIMEOUT_MS = 6
 OPT_RESERVE_SUPPLIED_TRIALS = 7
+OPT_CUDA_GRAPH = 8
+OPT_HOST_POLL = 9
 STREAM_BITS = 62
 TRIAL_STREAM_BASE = 1 << 61
 REDUCE_AUTO, REDUCE_NCCL = 0, 1
@@ -93,6 +95,7 @@ SIGNATURES = {
     "kfbo_set_stream_base": (C.c_int, [_vp, C.c_uint64]),
     "kfbo_set_eval_counter": (C.c_int, [_vp, C.c_uint64]),
     "kfbo_last_sums": (C.c_int, [_vp, _dp, C.c_int32]),
+    "kfbo_kernel_ms_total": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64), C.c_int32]),
     "kfbo_last_kernel_ms": (C.c_int, [_vp, _dp, C.POINTER(C.c_int32)]),
     "kfbo_last_host_us": (C.c_int, [_vp, _dp]),
     "kfbo_set_cuda_stream": (C.c_int, [_vp, _vp]),

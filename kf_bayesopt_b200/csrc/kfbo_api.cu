@@ -157,6 +157,28 @@ struct kfbo_handle {
     std::vector<double> sup_sums;
     int supplied_kernel = kfbo::kSuppliedAuto;
     int bulk_smem_pad = 0;
+    // The single-candidate evaluation ("noise" -> "cost") replayed from a CUDA graph: constants copy, rollout, exchange and the
+    // three timing events are ONE cudaGraphLaunch; between replays only the by-value estimator constants of the rollout
+    // kernel node change (cudaGraphExecKernelNodeSetParams).  Rebuilt when anything else about the launch changes (gsig).
+    bool use_graph = true, capturing = false, graph_used = false;
+    cudaGraphExec_t gexec = nullptr;
+    cudaGraphNode_t gnode = nullptr;           // the rollout kernel node
+    kfbo::PhiloxLaunchRecord grec;
+    struct GraphSig {
+        cudaStream_t stream = nullptr; const void *sums = nullptr; int ncases = -1; uint32_t ntrials = 0, t0 = 0; bool peer = false, zero_copy = false;
+        bool operator==(const GraphSig &o) const
+        {
+            return stream == o.stream && sums == o.sums && ncases == o.ncases && ntrials == o.ntrials && t0 == o.t0 && peer == o.peer && zero_copy == o.zero_copy;
+        }
+    } gsig;
+    // the host polls this word of mapped pinned memory for the exchange kernel's "total stored" instead of synchronising the stream
+    unsigned *h_flag = nullptr, *h_flag_dev = nullptr;
+    uint32_t flag_expect = 0;
+    bool flag_armed = false, use_poll = true;
+    // kernel timing is read back lazily (cudaEventElapsedTime costs a microsecond each): on query, or -- accumulating -- at the next launch
+    bool timing_pending = false, timing_accumulate = false;
+    double kernel_ms_total = 0.0;
+    int64_t kernel_ms_evals = 0;
     // last evaluation
     int last_ncand = 0, last_launches = 0;
     double last_ms = 0.0;
@@ -477,6 +499,8 @@ void kfbo_destroy(kfbo_handle *h)
     if (h->h_aug_cases) cudaFreeHost(h->h_aug_cases);
     if (h->d_compact) cudaFree(h->d_compact);
     if (h->h_compact) cudaFreeHost(h->h_compact);
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->d_partials) cudaFree(h->d_partials);
     if (h->d_tickets) cudaFree(h->d_tickets);
     if (h->d_sums) cudaFree(h->d_sums);
@@ -594,6 +618,9 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
         cu(cudaMallocHost(&h->h_sums, (size_t)h->cases_cap * 4 * sizeof(double)), "cudaMallocHost(sums)"))
         return bail(KFBO_ECUDA);
     if (cu(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->h_sums_dev), h->h_sums, 0), "cudaHostGetDevicePointer(sums)")) return bail(KFBO_ECUDA);
+    if (cu(cudaMallocHost(&h->h_flag, 64), "cudaMallocHost(flag)") ||
+        cu(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->h_flag_dev), h->h_flag, 0), "cudaHostGetDevicePointer(flag)")) return bail(KFBO_ECUDA);
+    *h->h_flag = 0;
     h->d_hdr = h->d_case_buf + cand_bytes;
     h->h_hdr = h->h_case_buf + cand_bytes;
     std::memset(h->h_hdr, 0, kfbo::kPeerCtxBytes);
@@ -647,6 +674,13 @@ int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value)
         h->sup_sums.resize(C * 4);
         return KFBO_OK;
     }
+    case KFBO_OPT_CUDA_GRAPH:
+        h->use_graph = value != 0;
+        if (!h->use_graph && h->gexec) { KFBO_ON_DEVICE(h); cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+        return KFBO_OK;
+    case KFBO_OPT_HOST_POLL:
+        h->use_poll = value != 0;
+        return KFBO_OK;
     case KFBO_OPT_PEER_TIMEOUT_MS:
         if (value < 1 || value > 3600000) return fail(h, KFBO_EINVAL, "kfbo_set_option: peer timeout %lld ms", (long long)value);
         h->peer_timeout_ms = value;
@@ -720,6 +754,29 @@ static void poison(kfbo_handle *h)
     h->poisoned = true;
 }
 
+// Timing of the last evaluation, read back lazily: ev0..ev1 around the rollout, ev1..ev2 around the exchange of the sums.
+static void resolve_timing(kfbo_handle *h)
+{
+    if (!h->timing_pending) return;
+    h->timing_pending = false;
+    DeviceGuard dg(h->device);
+    float ms = 0.f, ar = 0.f;
+    cudaEvent_t last = h->comm ? h->ev2 : h->ev1;
+    if (cudaEventSynchronize(last) != cudaSuccess || cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) { cudaGetLastError(); return; }
+    h->last_ms = ms;
+    h->kernel_ms_total += ms;
+    ++h->kernel_ms_evals;
+    h->last_host_us[4] = 0.0;
+    if (h->comm && cudaEventElapsedTime(&ar, h->ev1, h->ev2) == cudaSuccess) h->last_host_us[4] = 1e3 * ar;
+    cudaGetLastError();
+}
+
+static cudaError_t record_event(kfbo_handle *h, cudaEvent_t ev)
+{
+    // inside a stream capture an event that is to be read with cudaEventElapsedTime must be recorded as an "external" node
+    return cudaEventRecordWithFlags(ev, h->stream, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+
 // bad: the classification of the candidates by eval_check (of this handle, or of a group's first handle)
 // compact: the evaluation ends in the device-side cost assembly (kfbo_eval_batch_costs) instead of the host's
 static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const double *r_est, const uint8_t *bad, bool compact = false)
@@ -734,6 +791,8 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
     }
     const int ncand = (int)(c1 - c0), ncases = ncand * D;
     h->compact = compact;
+    if (h->timing_accumulate) resolve_timing(h);   // the previous evaluation's events are about to be recorded again
+    h->timing_pending = false;
     h->tp[0] = clk::now();
     // The per-(candidate, sample time) constants.  One candidate (the "noise" -> "cost" call): built here, they also ride
     // in the kernel's parameter bank.  A batch: 16 bytes per candidate go to the device and build_cases_kernel makes
@@ -792,10 +851,63 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
         pc->cap = (uint32_t)h->xchg_cap; pc->epoch = epoch; pc->ncases = (uint32_t)ncases;
         pc->done = h->d_done; pc->status = h->h_status; pc->sums = h->d_sums;
         pc->out = zero_copy ? h->h_sums_dev : h->d_sums;
+        // a total that lands in mapped host memory is announced there too: the host polls for it (eval_collect)
+        h->flag_armed = zero_copy && !fused && h->use_poll;
+        pc->host_flag = h->flag_armed ? h->h_flag_dev : nullptr;
+        h->flag_expect = epoch;
         pc->timeout_ns = (unsigned long long)h->peer_timeout_ms * 1000000ull;
         if (gather) h->result_src = reinterpret_cast<const double *>(h->d_xchg + kXchgFlagBytes) + (size_t)(epoch & 1u) * slabs * h->xchg_cap;
     }
+    if (!use_peer) h->flag_armed = false;
     h->tp[1] = clk::now();
+    // ---- the single-candidate evaluation as ONE graph launch (see kfbo_handle::gexec)
+    h->graph_used = false;
+    const bool graphable = h->use_graph && C == 1 && !aug && has_work && ncases <= step && !fused && (!h->comm || use_peer);
+    if (graphable) {
+        kfbo_handle::GraphSig sig;
+        sig.stream = h->stream; sig.sums = rollout_sums; sig.ncases = ncases; sig.ntrials = ntrials; sig.t0 = (uint32_t)t0; sig.peer = use_peer; sig.zero_copy = zero_copy;
+        if (h->gexec && sig == h->gsig) {
+            h->grec.st = h->st;
+            h->grec.st.k0 = 0; h->grec.st.nk = D;
+            kfbo::set_uniform_estimator(&h->grec.st, h->h_cases);
+            cudaKernelNodeParams kp{};
+            kp.func = const_cast<void *>(h->grec.func); kp.gridDim = h->grec.grid; kp.blockDim = dim3(h->grec.block);
+            kp.sharedMemBytes = (unsigned)h->grec.smem; kp.kernelParams = h->grec.argv; kp.extra = nullptr;
+            if (cudaGraphExecKernelNodeSetParams(h->gexec, h->gnode, &kp) == cudaSuccess && cudaGraphLaunch(h->gexec, h->stream) == cudaSuccess) {
+                h->last_h2d = (int64_t)((size_t)ncases * sizeof(Case) + (use_peer ? kfbo::kPeerCtxBytes : 0));
+                h->last_launches = use_peer ? 2 : 1;
+                h->graph_used = true;
+                return KFBO_OK;
+            }
+            cudaGetLastError();                 // the replay failed: drop the graph, enqueue directly from now on
+            cudaGraphExecDestroy(h->gexec);
+            h->gexec = nullptr;
+            h->use_graph = false;
+        } else {
+            if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+            if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                h->capturing = true;
+                h->gsig = sig;
+            } else {
+                cudaGetLastError();
+                h->use_graph = false;
+            }
+        }
+    }
+    // whatever happens below, a capture that was begun is ended (a failed enqueue must not leave the stream capturing)
+    struct CaptureEnd {
+        kfbo_handle *h;
+        ~CaptureEnd()
+        {
+            if (!h->capturing) return;
+            cudaGraph_t g = nullptr;
+            cudaStreamEndCapture(h->stream, &g);
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            h->capturing = false;
+            h->use_graph = false;
+        }
+    } capture_end{h};
     // Zeros only where the rollout does not write every slot that is read afterwards: a rank without work, and the slots
     // of other ranks' candidates under the NCCL all-reduce (the exchange moves only what a rank owns).
     if (!has_work || (h->comm && !use_peer && gather))
@@ -828,7 +940,7 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
         h->last_h2d = (int64_t)bytes;
     }
     h->last_launches = (device_build && ncand > 0) ? 1 : 0;
-    KFBO_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    KFBO_CUDA(h, record_event(h, h->ev0));
     if (has_work) {
         for (int first = 0; first < ncases; first += step) {
             const int n = std::min(step, ncases - first);
@@ -841,16 +953,47 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
             } else {
                 KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, st, h->d_gu, h->d_logtab, h->min_T, h->p.seed, (uint32_t)t0, ntrials,
                                                          nullptr, 0, h->d_partials, h->d_tickets, rollout_sums, h->stream,
-                                                         device_build ? nullptr : h->h_cases + first, fused));
+                                                         device_build ? nullptr : h->h_cases + first, fused, h->capturing ? &h->grec : nullptr));
                 ++h->last_launches;
             }
         }
     }
-    KFBO_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    KFBO_CUDA(h, record_event(h, h->ev1));
     if (use_peer && !fused) {
         const kfbo::PeerCtx *pc = reinterpret_cast<const kfbo::PeerCtx *>(h->h_hdr);
         KFBO_CUDA(h, kfbo::launch_peer_exchange(reinterpret_cast<const kfbo::PeerCtx *>(h->d_hdr), pc->end[h->rank] - pc->begin[h->rank], h->stream));
         ++h->last_launches;
+    }
+    if (h->capturing) {
+        // close the capture (the exchange's closing event belongs to it), instantiate, find the rollout's node, launch
+        if (use_peer) KFBO_CUDA(h, record_event(h, h->ev2));
+        cudaGraph_t g = nullptr;
+        h->capturing = false;
+        cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&h->gexec, g, 0);
+        if (e == cudaSuccess) {
+            size_t n = 0;
+            cudaGraphGetNodes(g, nullptr, &n);
+            std::vector<cudaGraphNode_t> nodes(n);
+            cudaGraphGetNodes(g, nodes.data(), &n);
+            h->gnode = nullptr;
+            for (cudaGraphNode_t nd : nodes) {
+                cudaGraphNodeType ty;
+                cudaKernelNodeParams kp{};
+                if (cudaGraphNodeGetType(nd, &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel &&
+                    cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess && kp.func == h->grec.func) h->gnode = nd;
+            }
+            if (!h->gnode) e = cudaErrorUnknown;
+        }
+        if (g) cudaGraphDestroy(g);       // the executable graph keeps what it needs (node handles stay valid for ExecKernelNodeSetParams)
+        if (e == cudaSuccess) e = cudaGraphLaunch(h->gexec, h->stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+            h->use_graph = false;
+            return fail(h, KFBO_ECUDA, "building the evaluation's CUDA graph failed: %s", cudaGetErrorString(e));
+        }
+        h->graph_used = true;
     }
     return KFBO_OK;
 }
@@ -862,7 +1005,7 @@ static int eval_reduce(kfbo_handle *h, int32_t C, bool in_group)
     if (!h->comm) return KFBO_OK;
     KFBO_ON_DEVICE(h);
     if (h->reduce_path >= 2) {   // the sums met in peer memory: in the rollout kernel itself, or in the kernel behind it
-        if (!in_group) KFBO_CUDA(h, cudaEventRecord(h->ev2, h->stream));
+        if (!in_group && !h->graph_used) KFBO_CUDA(h, cudaEventRecord(h->ev2, h->stream));   // a graph replay records it itself
         return KFBO_OK;
     }
     const size_t nsums = (size_t)C * h->D * 4;
@@ -894,7 +1037,17 @@ static int eval_collect(kfbo_handle *h, int32_t C, kfbo_result *out, double *cos
         h->last_d2h = (int64_t)(nsums * sizeof(double));   // stored over PCIe by the kernel (mapped pinned memory)
     }
     const clk::time_point w2 = clk::now();
-    KFBO_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->flag_armed && !h->compact && !(out && h->result_src)) {
+        // the exchange kernel stores the total into mapped host memory and then this word: poll for it (what a stream
+        // synchronisation does inside the driver, minus the driver); every so often make sure the stream is still alive
+        volatile unsigned *flag = h->h_flag;
+        for (unsigned spins = 1; (int)(*flag - h->flag_expect) < 0; ++spins)
+            if ((spins & 0x3FFFu) == 0 && cudaStreamQuery(h->stream) != cudaErrorNotReady) break;
+        std::atomic_thread_fence(std::memory_order_acquire);
+        if ((int)(*flag - h->flag_expect) < 0) KFBO_CUDA(h, cudaStreamSynchronize(h->stream));   // the stream ended without the flag: an error
+    } else {
+        KFBO_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
     const clk::time_point w3 = clk::now();
     if (h->reduce_path >= 2 && *h->h_status != 0) {
         const int who = *h->h_status - 1;
@@ -902,9 +1055,7 @@ static int eval_collect(kfbo_handle *h, int32_t C, kfbo_result *out, double *cos
         return fail(h, KFBO_EPEER, "peer-memory exchange: rank %d waited %lld ms for the cost sums of rank %d (did every rank make this call?)",
                     h->rank, (long long)h->peer_timeout_ms, who);
     }
-    float ms = 0.f;
-    KFBO_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    h->last_ms = ms;
+    h->timing_pending = true;            // read back on query (kfbo_last_kernel_ms, kfbo_last_host_us) or, accumulating, at the next launch
     h->last_ncand = (out && !h->compact) ? C : 0;
     if (h->compact) {
         const double *hc = static_cast<const double *>(h->h_compact), *hm = hc + (size_t)C * D;
@@ -925,12 +1076,6 @@ static int eval_collect(kfbo_handle *h, int32_t C, kfbo_result *out, double *cos
     const clk::time_point w4 = clk::now();
     const clk::time_point w[5] = {h->tp[0], h->tp[1], w2, w3, w4};
     for (int i = 0; i < 4; ++i) h->last_host_us[i] = std::chrono::duration<double, std::micro>(w[i + 1] - w[i]).count();
-    h->last_host_us[4] = 0.0;
-    if (h->comm) {
-        float ar = 0.f;
-        KFBO_CUDA(h, cudaEventElapsedTime(&ar, h->ev1, h->ev2));
-        h->last_host_us[4] = 1e3 * ar;
-    }
     ++h->eval_counter;
     return KFBO_OK;
 }
@@ -987,16 +1132,31 @@ int kfbo_last_sums(const kfbo_handle *h, double *sums, int32_t n_candidates)
     return KFBO_OK;
 }
 
-int kfbo_last_host_us(const kfbo_handle *h, double us[KFBO_HOST_PHASES])
+int kfbo_last_host_us(const kfbo_handle *hc, double us[KFBO_HOST_PHASES])
 {
-    if (!h || !us) return KFBO_EINVAL;
+    if (!hc || !us) return KFBO_EINVAL;
+    kfbo_handle *h = const_cast<kfbo_handle *>(hc);
+    resolve_timing(h);
     for (int i = 0; i < KFBO_HOST_PHASES; ++i) us[i] = h->last_host_us[i];
     return KFBO_OK;
 }
 
-int kfbo_last_kernel_ms(const kfbo_handle *h, double *ms, int32_t *launches)
+int kfbo_kernel_ms_total(kfbo_handle *h, double *ms_total, int64_t *evaluations, int32_t reset)
 {
     if (!h) return KFBO_EINVAL;
+    resolve_timing(h);
+    if (ms_total) *ms_total = h->kernel_ms_total;
+    if (evaluations) *evaluations = h->kernel_ms_evals;
+    if (reset) { h->kernel_ms_total = 0.0; h->kernel_ms_evals = 0; }
+    h->timing_accumulate = true;         // from now on every evaluation's time is read back (at the next launch at the latest)
+    return KFBO_OK;
+}
+
+int kfbo_last_kernel_ms(const kfbo_handle *hc, double *ms, int32_t *launches)
+{
+    if (!hc) return KFBO_EINVAL;
+    kfbo_handle *h = const_cast<kfbo_handle *>(hc);
+    resolve_timing(h);
     if (ms) *ms = h->last_ms;
     if (launches) *launches = h->last_launches;
     return KFBO_OK;
@@ -1045,6 +1205,7 @@ static int supplied_impl(kfbo_handle *h, int32_t k, int32_t C, const double *q_e
     float ms = 0.f;
     KFBO_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms;
+    h->timing_pending = false;
     if (sums) std::memcpy(sums, hs.data(), (size_t)C * 4 * sizeof(double));
     return KFBO_OK;
 }

@@ -127,6 +127,12 @@ __device__ __forceinline__ void peer_exchange(const PeerCtx *__restrict__ pc, in
             reinterpret_cast<double2 *>(pc->out)[i] = a;
         }
     }
+    // 5. tell the host (it may be polling mapped memory for exactly this instead of synchronising the stream)
+    if (pc->host_flag != nullptr) {
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) st_release_sys(pc->host_flag, epoch);
+    }
 }
 
 // Called by all threads of a CTA that has just published the sums of one case.
@@ -737,7 +743,7 @@ PhiloxKeys expand_philox_key(uint64_t seed)
 cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, int min_T,
                                   uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
                                   size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
-                                  cudaStream_t stream, const Case *h_cases, bool with_peer)
+                                  cudaStream_t stream, const Case *h_cases, bool with_peer, PhiloxLaunchRecord *rec)
 {
     if (ncases <= 0 || ntrials == 0) return cudaSuccess;
     const int tiles = rollout_tiles(ntrials);
@@ -755,15 +761,22 @@ cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleT
     const cudaError_t attr = ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), (with_peer ? 4 : 0) + (uniform_est ? 2 : 0) + (shift_first ? 1 : 0), smem);
     if (attr != cudaSuccess) return attr;
     SampleTimeConsts stc = st;
-    if (uniform_est)
-        for (int i = 0; i < st.nk; ++i) {
-            const int k = st.k0 + i;
-            stc.q00[k] = h_cases[i].q00; stc.q01[k] = h_cases[i].q01; stc.q11[k] = h_cases[i].q11; stc.r_est[k] = h_cases[i].r_est;
-        }
-    kernel<<<grid, kThreads, smem, stream>>>(
-        d_cases, stc, d_gu, static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0, ntrials, tiles,
-        d_per_trial, per_trial_ld, d_partials, d_tickets, d_sums);
-    return cudaGetLastError();
+    if (uniform_est) set_uniform_estimator(&stc, h_cases);
+    PhiloxLaunchRecord local;
+    PhiloxLaunchRecord &r = rec ? *rec : local;
+    r.func = reinterpret_cast<const void *>(kernel); r.grid = grid; r.block = kThreads; r.smem = smem;
+    r.cases = d_cases; r.st = stc; r.gu = d_gu; r.logtab = d_logtab; r.key = expand_philox_key(seed); r.trial0 = trial0; r.ntrials = ntrials;
+    r.tiles = tiles; r.per_trial = d_per_trial; r.per_trial_ld = per_trial_ld; r.partials = d_partials; r.tickets = d_tickets; r.sums = d_sums;
+    r.bind();
+    return cudaLaunchKernel(r.func, r.grid, dim3(r.block), r.argv, r.smem, stream);
+}
+
+void set_uniform_estimator(SampleTimeConsts *st, const Case *h_cases)
+{
+    for (int i = 0; i < st->nk; ++i) {
+        const int k = st->k0 + i;
+        st->q00[k] = h_cases[i].q00; st->q01[k] = h_cases[i].q01; st->q11[k] = h_cases[i].q11; st->r_est[k] = h_cases[i].r_est;
+    }
 }
 
 cudaError_t launch_peer_exchange(const PeerCtx *d_peer, int own_doubles, cudaStream_t stream)

@@ -75,6 +75,8 @@ struct PeerCtx {
     uint32_t ncases;                      // cases of the launch that carries the exchange (its last case's CTA runs it)
     uint32_t pad0;
     unsigned *done;                       // local: cases finished in this launch
+    unsigned *host_flag;                  // local, mapped host memory (or NULL): set to `epoch` once the total has been stored, so
+                                          // that the host can poll for the result instead of synchronising the stream
     int32_t *status;                      // local: set to 1 when a peer's flag did not arrive within timeout_ns
     double *sums;                         // local: this rank's sums (the rollout's output)
     double *out;                          // trials sharded: where the total goes (device memory or mapped host memory)
@@ -93,10 +95,29 @@ cudaError_t launch_peer_exchange(const PeerCtx *d_peer, int own_doubles, cudaStr
 // d_cases (no kernel parameter of its own: one more parameter changes ptxas' schedule of the rollout loop).
 // h_cases (optional): the host copy of d_cases; given, a single-candidate launch passes the estimator constants by value.
 // min_T: the smallest step count among the cases of the launch (selects the shift policy of the time variance, kfbo_device.cuh).
+// rec (optional): a copy of the launch -- function, grid, argument values -- for a caller that replays it from a CUDA graph
+// and only swaps argument values between replays (kfbo_api.cu: the single-candidate evaluation).
+struct PhiloxLaunchRecord {
+    const void *func = nullptr;
+    dim3 grid;
+    unsigned block = 0;
+    size_t smem = 0;
+    // the argument list of rollout_philox, in order
+    const Case *cases; SampleTimeConsts st; const double2 *gu; const void *logtab; PhiloxKeys key; uint32_t trial0, ntrials; int tiles;
+    double *per_trial; size_t per_trial_ld; double *partials; unsigned *tickets; double *sums;
+    void *argv[13];
+    void bind()
+    {
+        void *a[13] = {&cases, &st, &gu, &logtab, &key, &trial0, &ntrials, &tiles, &per_trial, &per_trial_ld, &partials, &tickets, &sums};
+        for (int i = 0; i < 13; ++i) argv[i] = a[i];
+    }
+};
+// The by-value estimator constants of a single-candidate launch (SampleTimeConsts::q00 ...), refreshed from its cases.
+void set_uniform_estimator(SampleTimeConsts *st, const Case *h_cases);
 cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, int min_T,
                                   uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
                                   size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
-                                  cudaStream_t stream, const Case *h_cases = nullptr, bool with_peer = false);
+                                  cudaStream_t stream, const Case *h_cases = nullptr, bool with_peer = false, PhiloxLaunchRecord *rec = nullptr);
 
 cudaError_t launch_rollout_supplied(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, int max_T, const double *d_x0noise,
                                     const double *d_w, const double *d_v, size_t B, double *d_per_trial,

@@ -105,22 +105,40 @@ class ReadParaVehicle:
         return copy.deepcopy(self)
 
 
-@dataclass
 class Result:
-    """struct kfbo_result as plain Python."""
-    average_nees: np.ndarray
-    average_nis: np.ndarray
-    average_var_nees: np.ndarray
-    average_var_nis: np.ndarray
-    cost: np.ndarray          # pic_max of trial_node.cpp:50
-    max_cost: float
-    index_max: int
+    """struct kfbo_result as plain Python.  The arrays are cut out of the C struct on first use: the 'noise' -> 'cost' call
+    itself only needs max_cost (a 70 us evaluation should not spend 8 of them building arrays nobody reads)."""
+    __slots__ = ("_c", "_D", "_rows", "max_cost", "index_max")
+
+    def __init__(self, average_nees=None, average_nis=None, average_var_nees=None, average_var_nis=None, cost=None,
+                 max_cost=float("nan"), index_max=0):
+        self._c, self._D = None, 0
+        self._rows = None if average_nees is None else [np.asarray(a, dtype=np.float64) for a in
+                                                         (average_nees, average_nis, average_var_nees, average_var_nis, cost)]
+        self.max_cost, self.index_max = float(max_cost), int(index_max)
 
     @classmethod
     def from_c(cls, r: KfboResult, D: int) -> "Result":
-        # one copy of the five [MAX_SAMPLE_TIMES] arrays at the head of the struct; the fields are its rows
-        a = np.frombuffer(r, dtype=np.float64, count=5 * MAX_SAMPLE_TIMES).reshape(5, MAX_SAMPLE_TIMES)[:, :D].copy()
-        return cls(a[0], a[1], a[2], a[3], a[4], float(r.max_cost), int(r.index_max))
+        self = cls.__new__(cls)
+        self._c, self._D, self._rows = r, D, None
+        self.max_cost, self.index_max = r.max_cost, r.index_max
+        return self
+
+    def _get(self, i):
+        if self._rows is None:
+            # one copy of the five [MAX_SAMPLE_TIMES] arrays at the head of the struct; the fields are its rows
+            a = np.frombuffer(self._c, dtype=np.float64, count=5 * MAX_SAMPLE_TIMES).reshape(5, MAX_SAMPLE_TIMES)[:, :self._D].copy()
+            self._rows = [a[0], a[1], a[2], a[3], a[4]]
+        return self._rows[i]
+
+    average_nees = property(lambda self: self._get(0))
+    average_nis = property(lambda self: self._get(1))
+    average_var_nees = property(lambda self: self._get(2))
+    average_var_nis = property(lambda self: self._get(3))
+    cost = property(lambda self: self._get(4))          # pic_max of trial_node.cpp:50
+
+    def __repr__(self):
+        return f"Result(cost={self.cost}, max_cost={self.max_cost}, index_max={self.index_max})"
 
 
 def sample_times_from(rv: ReadParaVehicle, second: Optional[Tuple[float, float]] = CODE_SECOND_SAMPLE_TIME):
@@ -265,6 +283,13 @@ class CostEvaluator:
     def last_kernel_ms(self) -> Tuple[float, int]:
         ms, n = C.c_double(), C.c_int32()
         self._check(self._lib.kfbo_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def kernel_ms_total(self, reset: bool = False) -> Tuple[float, int]:
+        """(sum of the rollout-kernel device times, number of evaluations) since the last reset -- what a benchmark loop reads
+        once at its end instead of last_kernel_ms() between evaluations.  The first call switches the handle to accumulating."""
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self._lib.kfbo_kernel_ms_total(self._h, C.byref(ms), C.byref(n), int(reset)))
         return ms.value, n.value
 
     def last_host_us(self) -> dict:

@@ -305,6 +305,36 @@ def test_device_side_cost_assembly_matches_the_host(kfbo):
             assert np.array_equal(cost2[keep], cost[keep]) and np.array_equal(idx2[keep], idx[keep])
 
 
+def test_graph_replay_gives_the_same_bits_as_call_by_call_enqueueing(kfbo):
+    """A single-candidate evaluation is replayed from a CUDA graph (constants copy + rollout + timing events in one launch;
+    only the by-value estimator constants of the kernel node change between replays).  Same kernels, same arguments:
+    the results are the same bits as with KFBO_OPT_CUDA_GRAPH = 0 -- across changing candidates, a batch in between,
+    a change of the CUDA stream (the graph is rebuilt) and the lazily read kernel time."""
+    import torch
+    from kf_bayesopt_b200 import _lib
+    rv = kfbo.ReadParaVehicle(nsimruns_=3000, cpu_core_number_=10)
+    cands = [(0.7, 0.2), (1.0, 0.1), (3.0, 0.05), (0.7, 0.2), (0.2, 0.9)]
+    with kfbo.CostEvaluator(rv, seed=3, max_candidates=4) as a, kfbo.CostEvaluator(rv, seed=3, max_candidates=4) as b:
+        b.set_option(_lib.OPT_CUDA_GRAPH, 0)
+        stream = torch.cuda.Stream()
+        for i, (q, r) in enumerate(cands):
+            if i == 2:        # a batch between two replays ...
+                assert np.array_equal(a.eval_batch_raw([0.5, 1.5], [0.1, 0.2])["cost"], b.eval_batch_raw([0.5, 1.5], [0.1, 0.2])["cost"])
+            if i == 3:        # ... and another stream: the graph is captured anew on it
+                a.set_cuda_stream(stream.cuda_stream)
+                b.set_cuda_stream(stream.cuda_stream)
+            ra, rb = a.eval([q], [r]), b.eval([q], [r])
+            assert np.array_equal(a.last_sums(1), b.last_sums(1)), i
+            assert np.array_equal(ra.cost, rb.cost) and ra.max_cost == rb.max_cost and ra.index_max == rb.index_max
+            (ms_a, n_a), (ms_b, n_b) = a.last_kernel_ms(), b.last_kernel_ms()
+            assert n_a == n_b == 1 and 0 < ms_a < 50 and 0 < ms_b < 50
+        a.kernel_ms_total(reset=True)
+        for q, r in cands:
+            a.eval([q], [r])
+        total, n = a.kernel_ms_total()
+        assert n == len(cands) and 0 < total < 50 * n
+
+
 def test_eval_single_candidate_equals_batch_of_one(kfbo):
     rv = kfbo.ReadParaVehicle()                                   # yaml defaults: B=200, 10 "cores"
     with kfbo.CostEvaluator(rv, seed=11) as a, kfbo.CostEvaluator(rv, seed=11, max_candidates=1) as b:
