@@ -425,6 +425,46 @@ def leg_cfg4(kf, torch, dist, stream, device, world, rank, steps=10, warmup=3):
             "host_phases_us": {k: round(v, 1) for k, v in phases.items()}, "gpu_launches_per_sweep": launches / steps}
 
 
+def dense_flops_per_step(N: int) -> int:
+    """The reference-faithful dense flop count of one filter-step for an N-state, 1-observation model -- SURVEY.md 8(d)'s
+    convention (every mul / add / sub / div of the N x N and 1 x 1 products counts 1, RNG excluded), which gives 137 for N = 2:
+    simulator N(2N-1) + 2N + [N(2N-1) + 2N] + (2N-1) + 3; filter [N(2N-1) + 2N] + 2 N^2 (2N-1) + N^2 + N(2N-1) + 2N + (1+N) + 2N
+    + 2N + 2N^2 + N^2 (2N-1); metrics N + inverse(N) + N(2N-1) + (2N-1) + 3 + 2 + 8, inverse by cofactors = 8 / 42 / 140."""
+    inv = {2: 8, 3: 42, 4: 140}[N]
+    sim = N * (2 * N - 1) + 2 * N + (N * (2 * N - 1) + 2 * N) + (2 * N - 1) + 3
+    kf_ = (N * (2 * N - 1) + 2 * N) + 2 * N * N * (2 * N - 1) + N * N + N * (2 * N - 1) + 2 * N + (1 + N) + 2 * N + 2 * N + 2 * N * N + N * N * (2 * N - 1)
+    met = N + inv + N * (2 * N - 1) + (2 * N - 1) + 3 + 2 + 8
+    return sim + kf_ + met
+
+
+def leg_augmented(kf, torch, stream, device, fp64_peak):
+    """SURVEY.md 8 row f4, north_star's "state-augmented variants": the same evaluation on a chain of N = 3 / 4 integrators,
+    one covariance row per lane of a 4-lane group (kfbo_aug.cuh).  The reference has no such variant; reported on its own,
+    with its own flop count, never against the N = 2 figures."""
+    import numpy as np
+    from oracle import oracle as o
+    out = {}
+    trials, T, times = 1 << 18, 1000, [(0.1, 1000), (0.5, 1000)]
+    for N in (3, 4):
+        rv = kf.ReadParaVehicle(nsimruns_=trials, cpu_core_number_=1, pnoise_=[Q_TRUTH], onoise_=[R_TRUTH], state_dof_=N)
+        with kf.CostEvaluator(rv, times, seed=0x4B46424F00002026, device=device, state_dim=N) as ev:
+            ev.set_cuda_stream(stream.cuda_stream)
+            ms, kms, launches, res = timed_evals(torch, stream, ev, lambda: ev.eval(*CANDIDATE), 5, 3)
+            small = ev.eval_philox_trials(0, 0.7, 0.2, 5, 0, 64)
+        steps = float(trials) * T * len(times)
+        flops = dense_flops_per_step(N)
+        want = o.aug_eval_philox(N, 0x4B46424F00002026, 5, 0.1, T, Q_TRUTH, R_TRUTH, 0.7, 0.2, 0, 64)
+        ach = flops * steps / (kms * 1e-3) / 1e12
+        out[f"N{N}"] = {"state_dim": N, "workload": f"{trials} trials x {T} steps x {len(times)} sample times, on-device Philox noise",
+                        "value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_eval": ms, "kernel_ms": kms, "kernel": f"rollout_aug<{N}>",
+                        "flops_per_filter_step": flops, "achieved_tflops": ach, "frac_of_fp64_peak": ach / fp64_peak if fp64_peak else None,
+                        "J_NEES": [float(c) for c in res.cost],
+                        "parity_vs_oracle_max_rel": float(np.max(np.abs(small - want) / np.abs(want)))}
+    out["note"] = ("builder extension named by north_star, not in the reference (system_models.hpp:11-12 fixes N = 2); parity is against "
+                   "oracle/kfbo_oracle_aug.c, which tests/test_oracle_aug.py pins with scipy / closed forms; flop counts by dense_flops_per_step")
+    return out
+
+
 def parity_self_check(kf, torch, dist, device, world, rank):
     """N > 1, before anything is timed, on every rank: trial-sharded and candidate-sharded cost sums -- through the
     peer-memory exchange and through ncclAllReduce -- against THIS rank's own unsharded evaluation of the same Philox
@@ -690,6 +730,7 @@ def main():
         extra["cfg4"] = leg_cfg4(kf, torch, dist, stream, local_rank, world, rank)
         if rank == 0:
             extra.update(leg_default_workload(kf, torch, stream, local_rank, with_cpu=(world == 1 and not args.no_cpu_baseline)))
+            extra["state_augmented"] = leg_augmented(kf, torch, stream, local_rank, line_extra.get("roofline", {}).get("peak"))
             if world == 1:     # single GPU: the CUDA path against the oracle on a 300-trial slice of the headline workload's streams
                 seed = 0x4B46424F00002026
                 extra["parity_vs_oracle"] = {

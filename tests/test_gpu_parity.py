@@ -139,7 +139,7 @@ def test_parity_envelope(kfbo, oracle):
         with kfbo.CostEvaluator(rv, [(dt, T)]) as ev:
             pt, _ = ev.eval_supplied(0, qe, re_, x0n, w, v)
         want = oracle.eval_supplied(dt, T, qe, re_, x0n, w, v)
-        exact = em.run(oracle, "reference", dt, T, qe, re_, x0n, w, v, em.LD)
+        exact = em.run(oracle, "device", dt, T, qe, re_, x0n, w, v, em.LD)   # P = R K in long double: no cancellation, the most accurate value at hand
         vs_oracle, vs_exact, oracle_vs_exact = rel_err(pt[0], want), em.rel(pt[0], exact), em.rel(want, exact)
         print(f"envelope {name}: cuda-vs-oracle {vs_oracle:.1e}, cuda-vs-long-double {vs_exact:.1e}, oracle-vs-long-double {oracle_vs_exact:.1e}")
         assert vs_exact < 1e-10, (name, vs_exact)                  # the CUDA path itself is at rounding level everywhere
@@ -333,6 +333,30 @@ def test_graph_replay_gives_the_same_bits_as_call_by_call_enqueueing(kfbo):
             a.eval([q], [r])
         total, n = a.kernel_ms_total()
         assert n == len(cands) and 0 < total < 50 * n
+
+
+def test_time_sliced_persistent_rollout_gives_the_same_bits(kfbo, oracle):
+    """rollout_philox_sliced (KFBO_OPT_SLICED_ROLLOUT): 4 CTAs per SM stay resident and draw (slice, tile) items, a trajectory's
+    state passes between the slices of its tile through global memory.  Same arithmetic in the same order as the plain
+    kernel: the cost sums are the same bits -- for step counts that are / are not multiples of the slice length and of 4,
+    more and fewer tiles than resident CTAs, repeated launches (the control block is re-zeroed by the kernel), and it
+    still matches the oracle draw for draw."""
+    from kf_bayesopt_b200 import _lib
+    for B, times in [(70000, [(0.1, 1000), (0.5, 1000)]), (4099, [(0.1, 259), (0.5, 1024)]), (130000, [(0.1, 333)]), (300, [(0.1, 201), (1.0, 201)])]:
+        rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
+        with kfbo.CostEvaluator(rv, times, seed=17) as a, kfbo.CostEvaluator(rv, times, seed=17) as b:
+            a.set_option(_lib.OPT_SLICED_ROLLOUT, _lib.SLICED_ON)
+            b.set_option(_lib.OPT_SLICED_ROLLOUT, _lib.SLICED_OFF)
+            for q, r in [(1.0, 0.1), (0.4, 0.3), (1.0, 0.1)]:
+                ra, rb = a.eval([q], [r]), b.eval([q], [r])
+                assert np.array_equal(a.last_sums(1), b.last_sums(1)), (B, times, q)
+                assert np.array_equal(ra.cost, rb.cost) and ra.index_max == rb.index_max
+            if B == 300:
+                a.set_eval_counter(0)
+                a.eval([0.7], [0.2])
+                for k, (dt, T) in enumerate(times):
+                    want = oracle.eval_philox(17, k, dt, T, Q_TRUTH, R_TRUTH, 0.7, 0.2, 0, B).sum(axis=1)
+                    assert rel_err(a.last_sums(1)[0, k], want) < RTOL
 
 
 def test_eval_single_candidate_equals_batch_of_one(kfbo):

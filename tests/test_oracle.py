@@ -224,10 +224,9 @@ def test_envelope_reference_formulas_lose_accuracy_as_r_est_goes_to_zero(oracle)
     for name, dt, T, qt, rt, qe, re_, inside in em.CASES:
         x0n, w, v = em.noise(oracle, rng, dt, T, B, qt, rt)
         want = oracle.eval_supplied(dt, T, qe, re_, x0n, w, v)
-        # the numpy restatement in float64 IS the oracle, bit for bit -- so its long-double run is "the reference's
-        # formulas without rounding error"
+        # the numpy restatement in float64 IS the oracle, bit for bit: the model of the two formulations is faithful
         assert np.array_equal(em.run(oracle, "reference", dt, T, qe, re_, x0n, w, v), want), name
-        exact = em.run(oracle, "reference", dt, T, qe, re_, x0n, w, v, em.LD)
+        exact = em.run(oracle, "device", dt, T, qe, re_, x0n, w, v, em.LD)   # P = R K in long double: no cancellation, the most accurate value at hand
         dev64 = em.run(oracle, "device", dt, T, qe, re_, x0n, w, v)
         worst[name] = (em.rel(want, exact), em.rel(dev64, exact), em.rel(dev64, want))
         # the device's formulation (P = R K: no 1 - k0 cancellation) stays at rounding level everywhere ...
