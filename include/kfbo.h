@@ -285,6 +285,8 @@ int32_t kfbo_group_size(const kfbo_group *g);
 kfbo_handle *kfbo_group_handle(kfbo_group *g, int32_t i);    /* the handle of device i (owned by the group) */
 int kfbo_group_eval(kfbo_group *g, const double *pn, int32_t npn, const double *on, int32_t non, kfbo_result *out);
 int kfbo_group_eval_batch(kfbo_group *g, int32_t n_candidates, const double *q_est, const double *r_est, kfbo_result *out);
+int kfbo_group_eval_batch_costs(kfbo_group *g, int32_t n_candidates, const double *q_est, const double *r_est,
+                                double *cost, double *max_cost, int32_t *index_max);   /* kfbo_eval_batch_costs on a group */
 int kfbo_group_last_sums(const kfbo_group *g, double *sums, int32_t n_candidates);
 int kfbo_group_last_kernel_ms(const kfbo_group *g, double *ms_max /* slowest device */, int32_t *launches /* all devices */);
 int kfbo_group_set_option(kfbo_group *g, int32_t option, int64_t value);

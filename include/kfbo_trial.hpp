@@ -244,6 +244,18 @@ public:
                  : kfbo_eval_batch(h_, (int32_t)q_est.size(), q_est.data(), r_est.data(), out.data()));
         return out;
     }
+    // The same batch with the cost assembly on the device and a compact answer (kfbo_eval_batch_costs): what a cost-surface
+    // sweep wants -- 16 bytes per candidate in, 8 (D + 1) + 4 out, no per-candidate host work.
+    struct BatchCosts { std::vector<double> cost /*[C][D]*/, max_cost /*[C]*/; std::vector<int32_t> index_max /*[C]*/; };
+    BatchCosts EvalBatchCosts(const std::vector<double> &q_est, const std::vector<double> &r_est)
+    {
+        if (q_est.size() != r_est.size() || q_est.empty()) throw Error(KFBO_EINVAL, "EvalBatchCosts: q_est and r_est must have equal, non-zero length");
+        const size_t C = q_est.size();
+        BatchCosts b{std::vector<double>(C * p_.n_sample_times), std::vector<double>(C), std::vector<int32_t>(C)};
+        Check(g_ ? kfbo_group_eval_batch_costs(g_, (int32_t)C, q_est.data(), r_est.data(), b.cost.data(), b.max_cost.data(), b.index_max.data())
+                 : kfbo_eval_batch_costs(h_, (int32_t)C, q_est.data(), r_est.data(), b.cost.data(), b.max_cost.data(), b.index_max.data()));
+        return b;
+    }
     // sums[n_candidates][D][4] of the last evaluation
     std::vector<double> LastSums(int n_candidates = 1) const
     {

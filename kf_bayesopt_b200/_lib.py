@@ -114,6 +114,7 @@ SIGNATURES = {
     "kfbo_group_handle": (_vp, [_vp, C.c_int32]),
     "kfbo_group_eval": (C.c_int, [_vp, _dp, C.c_int32, _dp, C.c_int32, C.POINTER(KfboResult)]),
     "kfbo_group_eval_batch": (C.c_int, [_vp, C.c_int32, _dp, _dp, C.POINTER(KfboResult)]),
+    "kfbo_group_eval_batch_costs": (C.c_int, [_vp, C.c_int32, _dp, _dp, _dp, _dp, C.POINTER(C.c_int32)]),
     "kfbo_group_last_sums": (C.c_int, [_vp, _dp, C.c_int32]),
     "kfbo_group_last_kernel_ms": (C.c_int, [_vp, _dp, C.POINTER(C.c_int32)]),
     "kfbo_group_set_option": (C.c_int, [_vp, C.c_int32, C.c_int64]),

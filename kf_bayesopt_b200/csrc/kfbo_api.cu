@@ -1075,7 +1075,9 @@ static int eval_collect(kfbo_handle *h, int32_t C, kfbo_result *out, double *cos
     const int D = h->D;
     const size_t nsums = (size_t)C * D * 4;
     h->last_d2h = 0;
-    if (h->compact) {
+    if (h->compact && !cost) {
+        // a device of a group that is not the collecting one: nothing to bring over
+    } else if (h->compact) {
         // trial_node.cpp:70-119 for every candidate on the device, then C x (D + 1) doubles + C ints instead of the sums
         KFBO_CUDA(h, kfbo::launch_assemble_costs(h->result_src, C, &h->p, h->d_compact, h->stream));
         ++h->last_launches;
@@ -1109,7 +1111,7 @@ static int eval_collect(kfbo_handle *h, int32_t C, kfbo_result *out, double *cos
     }
     h->timing_pending = true;            // read back on query (kfbo_last_kernel_ms, kfbo_last_host_us) or, accumulating, at the next launch
     h->last_ncand = (out && !h->compact) ? C : 0;
-    if (h->compact) {
+    if (h->compact && cost) {
         const double *hc = static_cast<const double *>(h->h_compact), *hm = hc + (size_t)C * D;
         const int32_t *hi = reinterpret_cast<const int32_t *>(hm + C);
         std::memcpy(cost, hc, (size_t)C * D * sizeof(double));
@@ -1561,15 +1563,17 @@ const char *kfbo_group_last_error(const kfbo_group *g) { return g ? g->err.c_str
 int32_t kfbo_group_size(const kfbo_group *g) { return g ? (int32_t)g->hs.size() : 0; }
 kfbo_handle *kfbo_group_handle(kfbo_group *g, int32_t i) { return (g && i >= 0 && i < (int32_t)g->hs.size()) ? g->hs[i] : nullptr; }
 
-int kfbo_group_eval_batch(kfbo_group *g, int32_t C, const double *q_est, const double *r_est, kfbo_result *out)
+static int group_eval_impl(kfbo_group *g, int32_t C, const double *q_est, const double *r_est, kfbo_result *out, double *cost, double *max_cost,
+                           int32_t *index_max)
 {
+    const bool compact = cost != nullptr;
     if (!g || g->hs.empty()) return KFBO_EINVAL;
     if (g->poisoned)
         return group_fail(g, KFBO_ESTATE, "an earlier evaluation of this device group failed part-way (" + g->poison_why +
                                           "): its devices are out of step -- destroy the group and create a new one");
     DeviceGuard caller(g->hs[0]->device);    // whatever device the phases below leave current, the caller gets its own back
     auto check = [g](kfbo_handle *h, int rc) { if (rc) g->err = h->err; return rc; };
-    int rc = check(g->hs[0], eval_check(g->hs[0], C, q_est, r_est, out));
+    int rc = check(g->hs[0], eval_check(g->hs[0], C, q_est, r_est, compact ? (const void *)cost : (const void *)out));
     if (rc) return rc;                       // nothing was launched anywhere: the group stays usable
     // From here on a failure on one device leaves the others mid-evaluation (launched, possibly spinning on the failed
     // device's flag until the exchange times out): every device is drained and the group refuses further evaluations --
@@ -1582,7 +1586,7 @@ int kfbo_group_eval_batch(kfbo_group *g, int32_t C, const double *q_est, const d
     const uint8_t *bad = g->hs[0]->cand_bad.data();
     for (kfbo_handle *h : g->hs) {
         h->n_bad = g->hs[0]->n_bad;
-        if ((rc = check(h, eval_launch(h, C, q_est, r_est, bad)))) return abort_all(rc);
+        if ((rc = check(h, eval_launch(h, C, q_est, r_est, bad, compact)))) return abort_all(rc);
     }
     if (g->hs.size() > 1 && g->hs[0]->reduce_path >= 2) {   // the sums met in peer memory (every device took the same path)
         for (kfbo_handle *h : g->hs)
@@ -1605,10 +1609,22 @@ int kfbo_group_eval_batch(kfbo_group *g, int32_t C, const double *q_est, const d
     // will); the first failure is the one reported
     int first = KFBO_OK;
     for (size_t i = 0; i < g->hs.size(); ++i) {
-        const int r1 = eval_collect(g->hs[i], C, i == 0 ? out : nullptr);
+        const int r1 = i == 0 ? eval_collect(g->hs[i], C, out, cost, max_cost, index_max) : eval_collect(g->hs[i], C, nullptr);
         if (r1 && !first) first = check(g->hs[i], r1);
     }
     return first ? abort_all(first) : KFBO_OK;
+}
+
+int kfbo_group_eval_batch(kfbo_group *g, int32_t C, const double *q_est, const double *r_est, kfbo_result *out)
+{
+    if (!out) return group_fail(g, KFBO_EINVAL, "kfbo_group_eval_batch: NULL argument");
+    return group_eval_impl(g, C, q_est, r_est, out, nullptr, nullptr, nullptr);
+}
+
+int kfbo_group_eval_batch_costs(kfbo_group *g, int32_t C, const double *q_est, const double *r_est, double *cost, double *max_cost, int32_t *index_max)
+{
+    if (!cost || !max_cost || !index_max) return group_fail(g, KFBO_EINVAL, "kfbo_group_eval_batch_costs: NULL argument");
+    return group_eval_impl(g, C, q_est, r_est, nullptr, cost, max_cost, index_max);
 }
 
 int kfbo_group_eval(kfbo_group *g, const double *pn, int32_t npn, const double *on, int32_t non, kfbo_result *out)

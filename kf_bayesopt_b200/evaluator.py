@@ -424,6 +424,16 @@ class CostEvaluatorGroup:
         self._check(self._lib.kfbo_group_eval_batch(self._g, q.size, _ptr(q), _ptr(r), res.ctypes.data_as(C.POINTER(KfboResult))))
         return res
 
+    def eval_batch_costs(self, q_est, r_est, with_index: bool = False):
+        """(cost[C][D], max_cost[C][, index_max[C]]), assembled on the collecting device (kfbo_group_eval_batch_costs)."""
+        q, r = _f64(q_est), _f64(r_est)
+        if q.shape != r.shape or q.ndim != 1:
+            raise ValueError("q_est and r_est must be 1-D arrays of equal length")
+        cost, mx, idx = np.empty((q.size, self.D)), np.empty(q.size), np.empty(q.size, dtype=np.int32)
+        self._check(self._lib.kfbo_group_eval_batch_costs(self._g, q.size, _ptr(q), _ptr(r), _ptr(cost), _ptr(mx),
+                                                          idx.ctypes.data_as(C.POINTER(C.c_int32))))
+        return (cost, mx, idx) if with_index else (cost, mx)
+
     def last_sums(self, n_candidates: int = 1) -> np.ndarray:
         out = np.empty((n_candidates, self.D, 4))
         self._check(self._lib.kfbo_group_last_sums(self._g, _ptr(out), n_candidates))

@@ -50,7 +50,7 @@ int main(int nargs, char *args[])
         for (int i = 0; i < grid; ++i)
             for (int j = 0; j < grid; ++j) { q.push_back(axis(0, i)); r.push_back(axis(1, j)); }
         kfbo::Evaluator ev(kfbo::MakeParams(rv, kfbo::SampleTimesFrom(rv, sec), rv.cost_choice_, seed, grid * grid, device), gpus, KFBO_SHARD_CANDIDATES);
-        const std::vector<kfbo_result> res = ev.EvalBatch(q, r);
+        const kfbo::Evaluator::BatchCosts res = ev.EvalBatchCosts(q, r);     // costs assembled on the device
         const int D = ev.params().n_sample_times;
         std::ofstream f(out_path);
         if (!f) throw kfbo::Error(KFBO_EINVAL, "cannot write " + out_path);
@@ -59,16 +59,16 @@ int main(int nargs, char *args[])
         for (int k = 0; k < D; ++k) f << ",cost_dt" << ev.params().dt[k];
         f << ",max_cost,index_max\n";
         size_t best = 0;
-        for (size_t c = 0; c < res.size(); ++c) {
+        for (size_t c = 0; c < q.size(); ++c) {
             f << q[c] << "," << r[c];
-            for (int k = 0; k < D; ++k) f << "," << res[c].cost[k];
-            f << "," << res[c].max_cost << "," << res[c].index_max << "\n";
-            if (res[c].max_cost < res[best].max_cost) best = c;
+            for (int k = 0; k < D; ++k) f << "," << res.cost[c * D + k];
+            f << "," << res.max_cost[c] << "," << res.index_max[c] << "\n";
+            if (res.max_cost[c] < res.max_cost[best]) best = c;
         }
         int launches = 0;
         const double ms = ev.LastKernelMs(&launches);
         std::cout << grid * grid << " candidates x " << kfbo_effective_trials(&ev.params()) << " trials x " << D << " sample times: "
-                  << ms << " ms in " << launches << " launch(es); minimum " << rv.cost_choice_ << " " << res[best].max_cost
+                  << ms << " ms in " << launches << " launch(es); minimum " << rv.cost_choice_ << " " << res.max_cost[best]
                   << " at pnoise " << q[best] << ", onoise " << r[best] << "; written to " << out_path << std::endl;
     } catch (const std::exception &e) {
         std::cerr << e.what() << std::endl;

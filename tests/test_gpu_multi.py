@@ -112,3 +112,34 @@ def test_cpp_node_drives_several_gpus_from_one_process(kfbo, tmp_path):
         outs.append(float(next(l for l in out.stdout.splitlines() if l.startswith("cost JNEES")).split()[-1]))
     assert outs[0] == pytest.approx(1.613, abs=0.01)
     assert outs[1] == pytest.approx(outs[0], rel=1e-5)                  # same trials and streams; printed with 6 digits
+
+
+def test_the_callers_current_cuda_device_is_preserved(kfbo):
+    """The library sits next to other CUDA users of the calling thread (torch): a handle / a group on another device must
+    leave the thread's current device where it was, on every entry point."""
+    import numpy as np
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    torch.cuda.set_device(1)
+    x = torch.ones(8, device="cuda")                                   # torch's work lives on device 1
+    rv = kfbo.ReadParaVehicle(nsimruns_=512, cpu_core_number_=1)
+    with kfbo.CostEvaluator(rv, [(0.1, 201), (0.5, 211)], device=0, max_candidates=3) as ev:
+        assert torch.cuda.current_device() == 1
+        ev.eval([1.0], [0.1])
+        assert torch.cuda.current_device() == 1
+        ev.eval_batch_raw([0.5, 1.0, 2.0], [0.1, 0.1, 0.2])
+        ev.eval_batch_costs([0.5, 1.0, 2.0], [0.1, 0.1, 0.2])
+        ev.eval_philox_trials(0, 1.0, 0.1, 0, 0, 64)
+        ev.trace_trial(0, 1.0, 0.1, 0, 0)
+        ev.last_kernel_ms()
+        assert torch.cuda.current_device() == 1
+    assert torch.cuda.current_device() == 1
+    with kfbo.CostEvaluatorGroup(rv, [(0.1, 201)], n_gpus=2) as gr:
+        gr.eval([1.0], [0.1])
+        assert torch.cuda.current_device() == 1
+    kfbo.measure_fp64_peak(0, 5.0)
+    assert torch.cuda.current_device() == 1
+    assert float((x + 1).sum().item()) == 16.0 and x.device.index == 1
+    torch.cuda.set_device(0)
