@@ -28,8 +28,11 @@ def _noise(rng, oracle, N, dt, T, B):
 @pytest.mark.parametrize("N", [3, 4])
 def test_supplied_noise_matches_the_oracle(kfbo, oracle, N):
     rng = np.random.default_rng(100 + N)
-    # whole and ragged CTAs (32 trajectories each), one trajectory, the minimum and maximum step counts
-    for B, T, dt in [(200, 201, 0.1), (33, 211, 0.5), (1, 2, 0.1), (31, 3, 1.0), (64, 2000, 0.1), (257, 64, 0.25)]:
+    # whole and ragged CTAs (32 trajectories each), one trajectory, the minimum and maximum step counts.  The horizon T dt
+    # is kept where the problem is well conditioned: a chain of N integrators driven by white noise wanders like t^(N-1/2),
+    # and NEES is formed from e = x - xhat -- beyond |x| / |e| ~ 1e6 (N = 4: T dt > ~150) ANY two FP64 evaluations of
+    # these formulas differ by more than 1e-9 (for N = 2 the same effect is 2e-12 at T dt = 2000)
+    for B, T, dt in [(200, 201, 0.1), (33, 211, 0.5), (1, 2, 0.1), (31, 3, 1.0), (64, 2000, 0.1 if N == 3 else 0.05), (257, 64, 0.25)]:
         rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1, state_dof_=N)
         x0n, w, v = _noise(rng, oracle, N, dt, T, B)
         q, r = np.array([1.0, 0.3, 4.0]), np.array([0.1, 0.5, 0.02])
@@ -45,7 +48,7 @@ def test_supplied_noise_matches_the_oracle(kfbo, oracle, N):
 def test_philox_trials_match_the_oracle_draw_for_draw(kfbo, oracle, N):
     seed = 0x0123456789ABCDEF
     rv = kfbo.ReadParaVehicle(nsimruns_=100, cpu_core_number_=1, state_dof_=N)
-    for times in (TIMES, [(0.1, 2), (0.5, 3)], [(0.1, 7), (1.0, 1999)]):       # even and odd step counts (the noise comes in step pairs)
+    for times in (TIMES, [(0.1, 2), (0.5, 3)], [(0.1, 7), (0.05, 1999)]):      # even and odd step counts (the noise comes in step pairs)
         with kfbo.CostEvaluator(rv, times, seed=seed, state_dim=N) as ev:
             for k, (dt, T) in enumerate(times):
                 for qe, re, stream, trial0, n in [(1.0, 0.1, 0, 0, 100), (0.3, 0.7, (1 << 40) + 77, 0xFFFFFF00, 37)]:
