@@ -1645,7 +1645,7 @@ int kfbo_group_last_kernel_ms(const kfbo_group *g, double *ms_max, int32_t *laun
     if (!g || g->hs.empty()) return KFBO_EINVAL;
     double mx = 0.0;
     int32_t n = 0;
-    for (const kfbo_handle *h : g->hs) { mx = std::max(mx, h->last_ms); n += h->last_launches; }
+    for (kfbo_handle *h : g->hs) { resolve_timing(h); mx = std::max(mx, h->last_ms); n += h->last_launches; }
     if (ms_max) *ms_max = mx;
     if (launches) *launches = n;
     return KFBO_OK;
