@@ -597,7 +597,7 @@ def main():
         init_comm(ev, shard, peer=(args.reduce == "auto"))
         ev.set_option(L.OPT_PEER_FUSE, {"never": L.PEER_FUSE_NEVER, "auto": L.PEER_FUSE_AUTO, "always": L.PEER_FUSE_ALWAYS}[args.peer_fuse])
     # tuning experiments only (tools/multi_round.sh): switch one of the launch-path features off
-    for env, opt in (("KFBO_BENCH_SLICED", L.OPT_SLICED_ROLLOUT), ("KFBO_BENCH_GRAPH", L.OPT_CUDA_GRAPH), ("KFBO_BENCH_POLL", L.OPT_HOST_POLL)):
+    for env, opt in (("KFBO_BENCH_GRAPH", L.OPT_CUDA_GRAPH), ("KFBO_BENCH_POLL", L.OPT_HOST_POLL)):
         if env in os.environ:
             ev.set_option(opt, int(os.environ[env]))
     steps_per_eval = float(trials) * n_cand * sum(T for _, T in sample_times)

@@ -212,7 +212,6 @@ enum { KFBO_OPT_SUPPLIED_KERNEL = 1, KFBO_OPT_BULK_SMEM_PAD = 2 /* extra dynamic
                                         is replayed as ONE CUDA graph launch; 0: enqueued call by call */,
        KFBO_OPT_HOST_POLL = 9 /* 1 (default): where the kernel stores the total into mapped host memory (multi-GPU, trials
                                         sharded) the host polls that memory for it; 0: cudaStreamSynchronize */,
-       KFBO_OPT_SLICED_ROLLOUT = 10 /* KFBO_SLICED_* below */,
        KFBO_OPT_RESERVE_SUPPLIED_TRIALS = 7 /* pre-size the scratch of the parity entry points (kfbo_eval_supplied,
                                         kfbo_eval_philox_trials, kfbo_trace_trial) for this many trials x max_candidates
                                         candidates: after it they allocate nothing, like kfbo_eval* */ };
@@ -232,12 +231,6 @@ enum { KFBO_SUPPLIED_AUTO = 0, KFBO_SUPPLIED_LDG = 1, KFBO_SUPPLIED_BULK = 2 };
  *   +2.0 % kernel time for one candidate / a batch, against 2-3 us for the second launch; profiles/NOTES_r1.md) -- so
  *   it stays an option, and the single-GPU kernel is the same machine code either way. */
 enum { KFBO_REDUCE_AUTO = 0, KFBO_REDUCE_NCCL = 1 };
-/* KFBO_OPT_SLICED_ROLLOUT: a single-candidate evaluation whose rollout is more than one and at most a dozen waves of CTAs
- * long (one GPU's share of a many-GPU evaluation) can run as a PERSISTENT, TIME-SLICED kernel -- 4 CTAs per SM stay
- * resident and draw (slice, tile) items from a counter, a trajectory's state passes between the slices of its tile
- * through global memory -- so that the partly filled last wave is a quarter of a trajectory long instead of a whole one.
- * Same arithmetic in the same order: the results are the same bits.  AUTO (default) decides by the launch's shape. */
-enum { KFBO_SLICED_OFF = 0, KFBO_SLICED_AUTO = 1, KFBO_SLICED_ON = 2 };
 enum { KFBO_PEER_FUSE_NEVER = 0, KFBO_PEER_FUSE_AUTO = 1, KFBO_PEER_FUSE_ALWAYS = 2 };
 int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value);
 

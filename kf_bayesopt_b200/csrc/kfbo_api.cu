@@ -165,21 +165,13 @@ struct kfbo_handle {
     cudaGraphNode_t gnode = nullptr;           // the rollout kernel node
     kfbo::PhiloxLaunchRecord grec;
     struct GraphSig {
-        cudaStream_t stream = nullptr; const void *sums = nullptr; int ncases = -1; uint32_t ntrials = 0, t0 = 0; bool peer = false, zero_copy = false, sliced = false;
+        cudaStream_t stream = nullptr; const void *sums = nullptr; int ncases = -1; uint32_t ntrials = 0, t0 = 0; bool peer = false, zero_copy = false;
         bool operator==(const GraphSig &o) const
         {
             return stream == o.stream && sums == o.sums && ncases == o.ncases && ntrials == o.ntrials && t0 == o.t0 && peer == o.peer &&
-                   zero_copy == o.zero_copy && sliced == o.sliced;
+                   zero_copy == o.zero_copy;
         }
     } gsig;
-    // persistent time-sliced rollout for single-candidate evaluations that are a few waves long (kfbo_kernels.cu: rollout_philox_sliced)
-    int use_sliced = KFBO_SLICED_AUTO;
-    int sm_count = 0;
-    kfbo::SliceCtl *d_slice_ctl = nullptr;
-    unsigned *d_slice_progress = nullptr;
-    double *d_slice_state = nullptr;
-    size_t slice_tiles = 0;                    // tiles the buffers above are sized for
-    int slice_groups = 0;
     // the host polls this word of mapped pinned memory for the exchange kernel's "total stored" instead of synchronising the stream
     unsigned *h_flag = nullptr, *h_flag_dev = nullptr;
     uint32_t flag_expect = 0;
@@ -508,9 +500,6 @@ void kfbo_destroy(kfbo_handle *h)
     if (h->h_aug_cases) cudaFreeHost(h->h_aug_cases);
     if (h->d_compact) cudaFree(h->d_compact);
     if (h->h_compact) cudaFreeHost(h->h_compact);
-    if (h->d_slice_ctl) cudaFree(h->d_slice_ctl);
-    if (h->d_slice_progress) cudaFree(h->d_slice_progress);
-    if (h->d_slice_state) cudaFree(h->d_slice_state);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->d_partials) cudaFree(h->d_partials);
@@ -632,12 +621,7 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
     if (cu(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->h_sums_dev), h->h_sums, 0), "cudaHostGetDevicePointer(sums)")) return bail(KFBO_ECUDA);
     if (cu(cudaMallocHost(&h->h_flag, 64), "cudaMallocHost(flag)") ||
         cu(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->h_flag_dev), h->h_flag, 0), "cudaHostGetDevicePointer(flag)")) return bail(KFBO_ECUDA);
-    *h->h_flag = 0;
-    {
-        cudaDeviceProp prop;
-        if (cu(cudaGetDeviceProperties(&prop, h->device), "cudaGetDeviceProperties")) return bail(KFBO_ECUDA);
-        h->sm_count = prop.multiProcessorCount;
-    }
+    std::memset(h->h_flag, 0, 64);
     h->d_hdr = h->d_case_buf + cand_bytes;
     h->h_hdr = h->h_case_buf + cand_bytes;
     std::memset(h->h_hdr, 0, kfbo::kPeerCtxBytes);
@@ -694,10 +678,6 @@ int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value)
     case KFBO_OPT_CUDA_GRAPH:
         h->use_graph = value != 0;
         if (!h->use_graph && h->gexec) { KFBO_ON_DEVICE(h); cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
-        return KFBO_OK;
-    case KFBO_OPT_SLICED_ROLLOUT:
-        if (value < KFBO_SLICED_OFF || value > KFBO_SLICED_ON) return fail(h, KFBO_EINVAL, "kfbo_set_option: sliced rollout %lld", (long long)value);
-        h->use_sliced = (int)value;
         return KFBO_OK;
     case KFBO_OPT_HOST_POLL:
         h->use_poll = value != 0;
@@ -792,31 +772,6 @@ static void resolve_timing(kfbo_handle *h)
     cudaGetLastError();
 }
 
-// Buffers of the time-sliced rollout for `tiles` tiles per sample time (allocated on the first evaluation that uses it:
-// 88 bytes per trajectory).  Returns false (and switches the feature off) if the device has no room.
-static bool ensure_slice_buffers(kfbo_handle *h, size_t tiles)
-{
-    if (h->d_slice_ctl && h->slice_tiles >= tiles) return true;
-    if (h->d_slice_ctl) { cudaFree(h->d_slice_ctl); cudaFree(h->d_slice_progress); cudaFree(h->d_slice_state); h->d_slice_ctl = nullptr; }
-    const size_t ld = tiles * kfbo::kThreads;
-    kfbo::SliceCtl c{};
-    h->slice_groups = kfbo::sliced_rollout_groups(h->max_T);
-    if (cudaMalloc(&h->d_slice_ctl, sizeof c) != cudaSuccess || cudaMalloc(&h->d_slice_progress, (size_t)h->D * tiles * sizeof(unsigned)) != cudaSuccess ||
-        cudaMalloc(&h->d_slice_state, (size_t)h->D * kfbo::kSliceStateDoubles * ld * sizeof(double)) != cudaSuccess) {
-        cudaGetLastError();
-        if (h->d_slice_ctl) cudaFree(h->d_slice_ctl);
-        if (h->d_slice_progress) cudaFree(h->d_slice_progress);
-        h->d_slice_ctl = nullptr; h->d_slice_progress = nullptr; h->d_slice_state = nullptr;
-        h->use_sliced = KFBO_SLICED_OFF;
-        return false;
-    }
-    c.slice_groups = h->slice_groups; c.progress = h->d_slice_progress; c.state = h->d_slice_state; c.state_ld = ld;
-    cudaMemset(h->d_slice_progress, 0, (size_t)h->D * tiles * sizeof(unsigned));
-    cudaMemcpy(h->d_slice_ctl, &c, sizeof c, cudaMemcpyHostToDevice);
-    h->slice_tiles = tiles;
-    return true;
-}
-
 static cudaError_t record_event(kfbo_handle *h, cudaEvent_t ev)
 {
     // inside a stream capture an event that is to be read with cudaEventElapsedTime must be recorded as an "external" node
@@ -905,18 +860,16 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
         if (gather) h->result_src = reinterpret_cast<const double *>(h->d_xchg + kXchgFlagBytes) + (size_t)(epoch & 1u) * slabs * h->xchg_cap;
     }
     if (!use_peer) h->flag_armed = false;
-    // a single-candidate evaluation that is a few waves of CTAs long runs as the persistent time-sliced kernel
-    const bool sliced = h->use_sliced != KFBO_SLICED_OFF && C == 1 && !aug && !fused && has_work && ncases == D &&
-                        (h->use_sliced == KFBO_SLICED_ON || kfbo::sliced_rollout_pays(tiles, D, h->max_T, h->min_T, h->sm_count)) &&
-                        h->min_T >= 32 && ensure_slice_buffers(h, (size_t)tiles);
     h->tp[1] = clk::now();
     // ---- the single-candidate evaluation as ONE graph launch (see kfbo_handle::gexec)
     h->graph_used = false;
-    const bool graphable = h->use_graph && C == 1 && !aug && has_work && ncases <= step && !fused && (!h->comm || use_peer);
+    // Measured (profiles/NOTES_r2.md): where the evaluation is a copy and ONE kernel (a single rank) the replay costs more host
+    // time than the two calls it replaces (10.8 against 8.5 us); with the exchange kernel and its event behind the rollout it
+    // is ahead (13.4 against 16.4 us) -- so: multi-GPU evaluations whose sums meet over peer memory.
+    const bool graphable = h->use_graph && C == 1 && !aug && has_work && ncases <= step && !fused && use_peer;
     if (graphable) {
         kfbo_handle::GraphSig sig;
         sig.stream = h->stream; sig.sums = rollout_sums; sig.ncases = ncases; sig.ntrials = ntrials; sig.t0 = (uint32_t)t0; sig.peer = use_peer; sig.zero_copy = zero_copy;
-        sig.sliced = sliced;
         if (h->gexec && sig == h->gsig) {
             h->grec.st = h->st;
             h->grec.st.k0 = 0; h->grec.st.nk = D;
@@ -1004,8 +957,7 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
             } else {
                 KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, st, h->d_gu, h->d_logtab, h->min_T, h->p.seed, (uint32_t)t0, ntrials,
                                                          nullptr, 0, h->d_partials, h->d_tickets, rollout_sums, h->stream,
-                                                         device_build ? nullptr : h->h_cases + first, fused, h->capturing ? &h->grec : nullptr,
-                                                         sliced ? h->d_slice_ctl : nullptr, h->sm_count));
+                                                         device_build ? nullptr : h->h_cases + first, fused, h->capturing ? &h->grec : nullptr));
                 ++h->last_launches;
             }
         }

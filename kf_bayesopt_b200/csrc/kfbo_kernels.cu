@@ -342,167 +342,6 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
 }
 
 // -----------------------------------------------------------------------------------------
-// The same rollout, PERSISTENT and TIME-SLICED (one candidate, i.e. the "noise" -> "cost" evaluation, when it is several
-// waves of CTAs long).  rollout_philox hands the block scheduler one CTA per 128-trajectory tile; all CTAs take the same
-// time, so the launch runs in waves of 148 x 4 CTAs and the last, partly filled wave runs at half the residency the loop
-// needs to saturate the FP64 pipe -- 3.4 % of the whole evaluation when a GPU's share is 3.46 waves (8 GPUs, cfg3).
-// Here 148 x 4 CTAs stay resident (noise tables loaded once per CTA instead of once per tile) and draw (slice, tile)
-// items from a counter, slice-major: a tile's T steps are cut into slices of `slice_groups` step groups, a trajectory's
-// state (11 doubles) passes from one slice to the next through global memory, and a per-tile progress word (release /
-// acquire) orders them.  The unit of scheduling is a quarter or less of a trajectory, so the partly filled tail is that
-// much shorter.  Items of slice q are handed out only after all items of slice q-1, i.e. at least `tiles` items later:
-// the predecessor is running or done whenever its successor starts, the wait is short and cannot deadlock.
-// grid = (CTAs per sample time, 1, sample times): blockIdx.z still selects the case, so its constants stay uniform.
-// -----------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__global__ void __launch_bounds__(kThreads, KFBO_PHILOX_MIN_BLOCKS)
-rollout_philox_sliced(const Case *__restrict__ cases, const __grid_constant__ SampleTimeConsts st,
-                      const double2 *__restrict__ gu_tables, const math::LogTables *__restrict__ logtab,
-                      const __grid_constant__ PhiloxKeys key, uint32_t trial0, uint32_t ntrials,
-                      int tiles, double *__restrict__ per_trial, size_t per_trial_ld, double *__restrict__ partials,
-                      unsigned *__restrict__ tickets, double *__restrict__ sums, SliceCtl *__restrict__ ctl)
-{
-    extern __shared__ __align__(16) unsigned char s_tables_raw[];
-    math::LogTables &s_log = *reinterpret_cast<math::LogTables *>(s_tables_raw);
-    __shared__ double s_red[kThreads][4];
-    __shared__ unsigned s_item;
-    const int case_idx = blockIdx.z;          // one candidate: the cases are its sample times
-    Case m = cases[case_idx];
-    const int T = m.T;
-    const unsigned kk = st.k0 + blockIdx.z;
-    m.q00 = pick4(st.q00, kk); m.q01 = pick4(st.q01, kk); m.q11 = pick4(st.q11, kk); m.r_est = pick4(st.r_est, kk);
-    const double f = pick4(st.f, kk), l00 = pick4(st.l00, kk), l10 = pick4(st.l10, kk), l11 = pick4(st.l11, kk),
-                 sr = pick4(st.sr, kk);
-    const double2 *__restrict__ gu = gu_tables + (size_t)kk * kMaxSteps;
-    load_noise_tables(&s_log, logtab);
-    // Everything the step loop does not need is kept OUT of registers across it (the loop sits at the 128-register cap and
-    // every register it loses costs re-computed Philox products): the item lives in shared memory and is decoded again
-    // behind the loop, the control block's fields are re-read there.
-    volatile unsigned *const v_item = &s_item;
-    for (;;) {
-        __syncthreads();                       // tables loaded (first pass); s_item and s_red free again (later passes)
-        if (threadIdx.x == 0) s_item = atomicAdd(&ctl->next[blockIdx.z], 1u);
-        __syncthreads();
-        Traj t;
-        uint32_t trial;
-        int g0, g1;
-        {
-            const int nfull = T >> 2, sg = ctl->slice_groups;
-            const int nslices = nfull > 0 ? (nfull + sg - 1) / sg : 1;
-            const unsigned item = *v_item;
-            if (item >= (unsigned)nslices * (unsigned)tiles) break;
-            const int q = (int)(item / (unsigned)tiles), tile = (int)(item - (unsigned)q * (unsigned)tiles);
-            const uint32_t local = (uint32_t)tile * kThreads + threadIdx.x;
-            trial = trial0 + local;
-            if (q == 0) {
-                double a, b;
-                const uint4 w = philox_at(trial, m.stream, m.stream_x, 0u, 0u, key);
-                math::normal_pair(w.x, w.y, s_log, a, b);
-                traj_init<false>(t, a, b);
-            } else {
-                if (threadIdx.x == 0)
-                    while (ld_acquire_gpu(ctl->progress + (size_t)blockIdx.z * tiles + tile) < (unsigned)q) __nanosleep(100);
-                __syncthreads();
-                const size_t sld = ctl->state_ld;
-                const double *sp = ctl->state + (size_t)blockIdx.z * kSliceStateDoubles * sld + local;
-                t.x0 = __ldcg(sp); t.x1 = __ldcg(sp + sld); t.xh0 = __ldcg(sp + 2 * sld); t.xh1 = __ldcg(sp + 3 * sld);
-                t.p00 = __ldcg(sp + 4 * sld); t.p01 = __ldcg(sp + 5 * sld); t.p11 = __ldcg(sp + 6 * sld);
-                t.sdn = __ldcg(sp + 7 * sld); t.sqn = __ldcg(sp + 8 * sld); t.sdi = __ldcg(sp + 9 * sld); t.sqi = __ldcg(sp + 10 * sld);
-                t.kn = kShiftNees; t.ki = kShiftNis;
-            }
-            g0 = q * sg;
-            g1 = (g0 + sg < nfull) ? g0 + sg : nfull;
-        }
-        GroupWords r = philox_group(trial, m.stream, m.stream_x, (uint32_t)g0, key);
-        for (int g = g0; g < g1; ++g) {        // the loop of rollout_philox, word for word
-            const GroupWords nx = philox_group(trial, m.stream, m.stream_x, (uint32_t)g + 1u, key);
-            const double2 *gs = gu + 4 * g;
-            const double2 s0 = __ldg(gs), s1 = __ldg(gs + 1), s2 = __ldg(gs + 2), s3 = __ldg(gs + 3);
-            double p0a, p0b, p1a, p1b, p2a, p2b, p3a, p3b, o0, o1, o2, o3;
-            math::normal_pair(r.c.x, r.c.y, s_log, o0, o1);
-            math::normal_pair(r.a.x, r.a.y, s_log, p0a, p0b);
-            math::normal_pair(r.a.z, r.a.w, s_log, p1a, p1b);
-            filter_step<false, true, false>(t, m, f, s0, StepNoise{p0a, p0b, o0}, l00, l10, l11, sr);
-            math::normal_pair(r.c.z, r.c.w, s_log, o2, o3);
-            math::normal_pair(r.b.x, r.b.y, s_log, p2a, p2b);
-            filter_step<false, true, false>(t, m, f, s1, StepNoise{p1a, p1b, o1}, l00, l10, l11, sr);
-            math::normal_pair(r.b.z, r.b.w, s_log, p3a, p3b);
-            filter_step<false, true, false>(t, m, f, s2, StepNoise{p2a, p2b, o2}, l00, l10, l11, sr);
-            filter_step<false, true, false>(t, m, f, s3, StepNoise{p3a, p3b, o3}, l00, l10, l11, sr);
-            r = nx;
-        }
-        // behind the loop: decode the item again
-        const int nfull = T >> 2, sg = ctl->slice_groups;
-        const int nslices = nfull > 0 ? (nfull + sg - 1) / sg : 1;
-        const unsigned item = *v_item;
-        const int q = (int)(item / (unsigned)tiles), tile = (int)(item - (unsigned)q * (unsigned)tiles);
-        const uint32_t local = (uint32_t)tile * kThreads + threadIdx.x;
-        if (q + 1 < nslices) {                 // hand the trajectories to whoever draws the tile's next slice
-            const size_t sld = ctl->state_ld;
-            double *sp = ctl->state + (size_t)blockIdx.z * kSliceStateDoubles * sld + local;
-            __stcg(sp, t.x0); __stcg(sp + sld, t.x1); __stcg(sp + 2 * sld, t.xh0); __stcg(sp + 3 * sld, t.xh1);
-            __stcg(sp + 4 * sld, t.p00); __stcg(sp + 5 * sld, t.p01); __stcg(sp + 6 * sld, t.p11);
-            __stcg(sp + 7 * sld, t.sdn); __stcg(sp + 8 * sld, t.sqn); __stcg(sp + 9 * sld, t.sdi); __stcg(sp + 10 * sld, t.sqi);
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) st_release_gpu(ctl->progress + (size_t)blockIdx.z * tiles + tile, (unsigned)q + 1u);
-            continue;
-        }
-        // the tile's last slice: the T mod 4 steps that are left, then the per-trial results and the reduction
-        const int rem = T & 3, sT = 4 * nfull;
-        if (rem > 0) {
-            double pa, pb, o0, o1;
-            math::normal_pair(r.c.x, r.c.y, s_log, o0, o1);
-            math::normal_pair(r.a.x, r.a.y, s_log, pa, pb);
-            filter_step<false, true, false>(t, m, f, __ldg(gu + sT), StepNoise{pa, pb, o0}, l00, l10, l11, sr);
-            if (rem > 1) {
-                math::normal_pair(r.a.z, r.a.w, s_log, pa, pb);
-                filter_step<false, true, false>(t, m, f, __ldg(gu + sT + 1), StepNoise{pa, pb, o1}, l00, l10, l11, sr);
-            }
-            if (rem > 2) {
-                math::normal_pair(r.c.z, r.c.w, s_log, o0, o1);
-                math::normal_pair(r.b.x, r.b.y, s_log, pa, pb);
-                filter_step<false, true, false>(t, m, f, __ldg(gu + sT + 2), StepNoise{pa, pb, o0}, l00, l10, l11, sr);
-            }
-        }
-        double out[4] = {0.0, 0.0, 0.0, 0.0}, o[4];
-        traj_finish(t, T, o);
-        if (local < ntrials) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) out[k] = o[k];
-            if (per_trial != nullptr) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) per_trial[((size_t)m.out_slot * 4 + k) * per_trial_ld + local] = o[k];
-            }
-        }
-        block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, s_red);
-    }
-    // the last CTA out re-zeroes the control block: the next launch starts from a clean one without a host-side memset
-    __shared__ bool s_last_out;
-    if (threadIdx.x == 0) {
-        const unsigned n = atomicAdd(&ctl->exited, 1u);
-        s_last_out = (n == gridDim.x * gridDim.z - 1u);
-    }
-    __syncthreads();
-    if (s_last_out) {
-        __threadfence();
-        for (unsigned i = threadIdx.x; i < (unsigned)tiles * gridDim.z; i += kThreads) ctl->progress[i] = 0u;
-        if (threadIdx.x < 4) ctl->next[threadIdx.x] = 0u;
-        if (threadIdx.x == 0) ctl->exited = 0u;
-    }
-}
-
-// -----------------------------------------------------------------------------------------
 // Supplied-noise rollout: x0noise[2][B], w[T][2][B], v[T][B]; trial index fastest, so a warp
 // reads 32 consecutive doubles (256 B) per load.  Loads are software-pipelined kPrefetch
 // steps ahead through registers (3*kPrefetch independent 8-byte loads in flight per thread).
@@ -904,8 +743,7 @@ PhiloxKeys expand_philox_key(uint64_t seed)
 cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, int min_T,
                                   uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
                                   size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
-                                  cudaStream_t stream, const Case *h_cases, bool with_peer, PhiloxLaunchRecord *rec,
-                                  const SliceCtl *d_slice_ctl, int sm_count)
+                                  cudaStream_t stream, const Case *h_cases, bool with_peer, PhiloxLaunchRecord *rec)
 {
     if (ncases <= 0 || ntrials == 0) return cudaSuccess;
     const int tiles = rollout_tiles(ntrials);
@@ -927,37 +765,10 @@ cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleT
     PhiloxLaunchRecord local;
     PhiloxLaunchRecord &r = rec ? *rec : local;
     r.func = reinterpret_cast<const void *>(kernel); r.grid = grid; r.block = kThreads; r.smem = smem;
-    r.slice_ctl = nullptr;
-    if (d_slice_ctl != nullptr && uniform_est && !shift_first && !with_peer && d_per_trial == nullptr) {
-        // persistent, time-sliced: 4 CTAs per SM in all, split evenly over the sample times, never more than there are tiles
-        const cudaError_t a2 = ensure_dynamic_smem(reinterpret_cast<const void *>(rollout_philox_sliced), 14, smem);
-        if (a2 != cudaSuccess) return a2;
-        const int per_k = std::max(1, std::min(tiles, sm_count * KFBO_PHILOX_MIN_BLOCKS / st.nk));
-        r.func = reinterpret_cast<const void *>(rollout_philox_sliced);
-        r.grid = dim3((unsigned)per_k, 1u, (unsigned)st.nk);
-        r.slice_ctl = d_slice_ctl;
-    }
     r.cases = d_cases; r.st = stc; r.gu = d_gu; r.logtab = d_logtab; r.key = expand_philox_key(seed); r.trial0 = trial0; r.ntrials = ntrials;
     r.tiles = tiles; r.per_trial = d_per_trial; r.per_trial_ld = per_trial_ld; r.partials = d_partials; r.tickets = d_tickets; r.sums = d_sums;
     r.bind();
     return cudaLaunchKernel(r.func, r.grid, dim3(r.block), r.argv, r.smem, stream);
-}
-
-// Slices of about a quarter of a trajectory, at least 16 step groups each: short enough for the tail to shrink, long enough
-// for the state hand-over (176 bytes per trajectory and slice boundary) not to matter.
-int sliced_rollout_groups(int T)
-{
-    const int nfull = T >> 2;
-    return std::max(16, (nfull + 3) / 4);
-}
-
-// Worth it when the launch is more than one wave and less than a dozen (beyond that the partly filled last wave is
-// below 1 % of the launch anyway and the plain kernel's simpler code wins) and the trials are long enough to cut.
-bool sliced_rollout_pays(int tiles, int nk, int T, int min_T, int sm_count)
-{
-    const int slots = sm_count * KFBO_PHILOX_MIN_BLOCKS;
-    const long ctas = (long)tiles * nk;
-    return sm_count > 0 && min_T >= kMinStepsConstShift && T >= 256 && ctas > slots && ctas <= 12L * slots;
 }
 
 void set_uniform_estimator(SampleTimeConsts *st, const Case *h_cases)

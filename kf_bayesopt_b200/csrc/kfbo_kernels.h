@@ -105,35 +105,19 @@ struct PhiloxLaunchRecord {
     // the argument list of rollout_philox, in order
     const Case *cases; SampleTimeConsts st; const double2 *gu; const void *logtab; PhiloxKeys key; uint32_t trial0, ntrials; int tiles;
     double *per_trial; size_t per_trial_ld; double *partials; unsigned *tickets; double *sums;
-    const void *slice_ctl;        // rollout_philox_sliced only: its 14th argument
-    void *argv[14];
+    void *argv[13];
     void bind()
     {
-        void *a[14] = {&cases, &st, &gu, &logtab, &key, &trial0, &ntrials, &tiles, &per_trial, &per_trial_ld, &partials, &tickets, &sums, &slice_ctl};
-        for (int i = 0; i < 14; ++i) argv[i] = a[i];
+        void *a[13] = {&cases, &st, &gu, &logtab, &key, &trial0, &ntrials, &tiles, &per_trial, &per_trial_ld, &partials, &tickets, &sums};
+        for (int i = 0; i < 13; ++i) argv[i] = a[i];
     }
 };
-
-// Time-sliced persistent form of the single-candidate Philox rollout (rollout_philox_sliced, kfbo_kernels.cu): its control block.
-struct SliceCtl {
-    unsigned next[4];             // per sample time: the next (slice, tile) item to hand out
-    unsigned exited;              // CTAs that have left the kernel (the last one re-zeroes everything for the next launch)
-    int32_t slice_groups;         // step groups (4 steps each) per slice
-    unsigned *progress;           // [sample time][tile]: slices of that tile completed
-    double *state;                // [sample time][kSliceStateDoubles][tiles * kThreads]: trajectory state between slices
-    size_t state_ld;              // tiles * kThreads
-};
-constexpr int kSliceStateDoubles = 11;   // x(2), xhat(2), P(3), the four shifted sums
-// with a SliceCtl (device pointer; *h_ctl its host copy, for the geometry) the launch is the persistent time-sliced kernel
-bool sliced_rollout_pays(int tiles, int nk, int T, int min_T, int sm_count);
-int sliced_rollout_groups(int T);
 // The by-value estimator constants of a single-candidate launch (SampleTimeConsts::q00 ...), refreshed from its cases.
 void set_uniform_estimator(SampleTimeConsts *st, const Case *h_cases);
 cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, int min_T,
                                   uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
                                   size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
-                                  cudaStream_t stream, const Case *h_cases = nullptr, bool with_peer = false, PhiloxLaunchRecord *rec = nullptr,
-                                  const SliceCtl *d_slice_ctl = nullptr, int sm_count = 0);
+                                  cudaStream_t stream, const Case *h_cases = nullptr, bool with_peer = false, PhiloxLaunchRecord *rec = nullptr);
 
 cudaError_t launch_rollout_supplied(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, int max_T, const double *d_x0noise,
                                     const double *d_w, const double *d_v, size_t B, double *d_per_trial,

@@ -306,7 +306,9 @@ def test_device_side_cost_assembly_matches_the_host(kfbo):
 
 
 def test_graph_replay_gives_the_same_bits_as_call_by_call_enqueueing(kfbo):
-    """A single-candidate evaluation is replayed from a CUDA graph (constants copy + rollout + timing events in one launch;
+    """(On one GPU the library enqueues call by call whatever the option says -- the replay only pays with the exchange kernel
+    behind the rollout, tools/multi_gpu_check.py covers that -- so here this checks the option plumbing and the lazily read times.)
+    A single-candidate evaluation is replayed from a CUDA graph (constants copy + rollout + timing events in one launch;
     only the by-value estimator constants of the kernel node change between replays).  Same kernels, same arguments:
     the results are the same bits as with KFBO_OPT_CUDA_GRAPH = 0 -- across changing candidates, a batch in between,
     a change of the CUDA stream (the graph is rebuilt) and the lazily read kernel time."""
@@ -333,30 +335,6 @@ def test_graph_replay_gives_the_same_bits_as_call_by_call_enqueueing(kfbo):
             a.eval([q], [r])
         total, n = a.kernel_ms_total()
         assert n == len(cands) and 0 < total < 50 * n
-
-
-def test_time_sliced_persistent_rollout_gives_the_same_bits(kfbo, oracle):
-    """rollout_philox_sliced (KFBO_OPT_SLICED_ROLLOUT): 4 CTAs per SM stay resident and draw (slice, tile) items, a trajectory's
-    state passes between the slices of its tile through global memory.  Same arithmetic in the same order as the plain
-    kernel: the cost sums are the same bits -- for step counts that are / are not multiples of the slice length and of 4,
-    more and fewer tiles than resident CTAs, repeated launches (the control block is re-zeroed by the kernel), and it
-    still matches the oracle draw for draw."""
-    from kf_bayesopt_b200 import _lib
-    for B, times in [(70000, [(0.1, 1000), (0.5, 1000)]), (4099, [(0.1, 259), (0.5, 1024)]), (130000, [(0.1, 333)]), (300, [(0.1, 201), (1.0, 201)])]:
-        rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
-        with kfbo.CostEvaluator(rv, times, seed=17) as a, kfbo.CostEvaluator(rv, times, seed=17) as b:
-            a.set_option(_lib.OPT_SLICED_ROLLOUT, _lib.SLICED_ON)
-            b.set_option(_lib.OPT_SLICED_ROLLOUT, _lib.SLICED_OFF)
-            for q, r in [(1.0, 0.1), (0.4, 0.3), (1.0, 0.1)]:
-                ra, rb = a.eval([q], [r]), b.eval([q], [r])
-                assert np.array_equal(a.last_sums(1), b.last_sums(1)), (B, times, q)
-                assert np.array_equal(ra.cost, rb.cost) and ra.index_max == rb.index_max
-            if B == 300:
-                a.set_eval_counter(0)
-                a.eval([0.7], [0.2])
-                for k, (dt, T) in enumerate(times):
-                    want = oracle.eval_philox(17, k, dt, T, Q_TRUTH, R_TRUTH, 0.7, 0.2, 0, B).sum(axis=1)
-                    assert rel_err(a.last_sums(1)[0, k], want) < RTOL
 
 
 def test_eval_single_candidate_equals_batch_of_one(kfbo):

@@ -70,11 +70,22 @@ for mode in (kf.SHARD_TRIALS, kf.SHARD_CANDIDATES):
             ev.set_option(_lib.OPT_PEER_FUSE, _lib.PEER_FUSE_AUTO)
             ev.set_eval_counter(100)
             run_peer = [ev.eval([0.5 + 0.01 * i], [0.1]).cost.copy() for i in range(40)]
+            # the launch-path features one at a time -- graph replay off, host polling off: neither touches the arithmetic,
+            # so the same streams give the same bits
+            for opt, val in ((_lib.OPT_CUDA_GRAPH, 0), (_lib.OPT_HOST_POLL, 0)):
+                ev.set_option(opt, val)
+                ev.set_eval_counter(100)
+                again = [ev.eval([0.5 + 0.01 * i], [0.1]).cost.copy() for i in range(12)]
+                assert all(np.array_equal(a, b) for a, b in zip(again, run_peer)), (opt, val)
+            ev.set_option(_lib.OPT_CUDA_GRAPH, 1)
+            ev.set_option(_lib.OPT_HOST_POLL, 1)
+            ev.set_eval_counter(140)
             # fewer candidates than ranks: ranks without a candidate (or with one) still take part in the exchange
             few_peer = ev.eval_batch_raw(q[:1], r[:1])["cost"].copy()
             ev.set_option(_lib.OPT_REDUCE, _lib.REDUCE_NCCL)
             ev.set_eval_counter(100)
             run_nccl = [ev.eval([0.5 + 0.01 * i], [0.1]).cost.copy() for i in range(40)]
+            ev.set_eval_counter(140)
             few_nccl = ev.eval_batch_raw(q[:1], r[:1])["cost"].copy()
             np.testing.assert_allclose(np.stack(run_peer), np.stack(run_nccl), rtol=1e-10, atol=1e-13)
             np.testing.assert_allclose(few_peer, few_nccl, rtol=1e-10, atol=1e-13)

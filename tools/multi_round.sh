@@ -1,7 +1,6 @@
 #!/bin/bash
 # Multi-GPU visit (round 2): the multi-GPU tests, tools/multi_gpu_check.py, the driver's bench command at N (its line carries
-# parity_n, the cfg4 leg and the NCCL-path timing), and the same with the persistent time-sliced rollout / graph / polling
-# switched off one at a time.     Usage (through gpurun --gpus N): bash tools/multi_round.sh <N> <tag>
+# parity_n, the cfg4 leg and the NCCL-path timing), and the same with graph replay / host polling switched off one at a time.     Usage (through gpurun --gpus N): bash tools/multi_round.sh <N> <tag>
 set -u
 N=${1:-2}; TAG=${2:-r2}
 OUT=gpurun_out
@@ -19,7 +18,7 @@ except Exception as e:
     print("no line:", e, open(sys.argv[1]).read()[-2000:])
 PY
 P=29670
-for V in "sliced_off KFBO_BENCH_SLICED=0" "graph_off KFBO_BENCH_GRAPH=0" "poll_off KFBO_BENCH_POLL=0"; do
+for V in "graph_off KFBO_BENCH_GRAPH=0" "poll_off KFBO_BENCH_POLL=0"; do
   set -- $V; P=$((P+1))
   env $2 timeout 300 $TR --master-port $P bench.py --gpus $N --steps 20 --warmup 3 --no-extra --no-supplied --no-cpu-baseline > $OUT/bench_n${N}_${1}_$TAG.json 2> $OUT/bench_n${N}_${1}_$TAG.err
   echo "bench n$N $1 rc=$?"; python - $OUT/bench_n${N}_${1}_$TAG.json <<'PY'
