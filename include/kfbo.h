@@ -212,6 +212,10 @@ enum { KFBO_OPT_SUPPLIED_KERNEL = 1, KFBO_OPT_BULK_SMEM_PAD = 2 /* extra dynamic
                                         is replayed as ONE CUDA graph launch; 0: enqueued call by call */,
        KFBO_OPT_HOST_POLL = 9 /* 1 (default): where the kernel stores the total into mapped host memory (multi-GPU, trials
                                         sharded) the host polls that memory for it; 0: cudaStreamSynchronize */,
+       KFBO_OPT_SMALL_LAUNCH = 10 /* 1 (default): an on-device-noise launch of at most 2 CTAs per SM -- the reference's default
+                                        200 x 201 x 2 workload is 14 -- runs as the LATENCY form of the rollout: 32 trajectories
+                                        per CTA, one warp runs the filter recursion, three make its noise a step group
+                                        ahead.  Same streams, same arithmetic, same order of the sums: same bits. 0: never */,
        KFBO_OPT_RESERVE_SUPPLIED_TRIALS = 7 /* pre-size the scratch of the parity entry points (kfbo_eval_supplied,
                                         kfbo_eval_philox_trials, kfbo_trace_trial) for this many trials x max_candidates
                                         candidates: after it they allocate nothing, like kfbo_eval* */ };

@@ -24,6 +24,7 @@ OPT_PEER_TIMEOUT_MS = 6
 OPT_RESERVE_SUPPLIED_TRIALS = 7
 OPT_CUDA_GRAPH = 8
 OPT_HOST_POLL = 9
+OPT_SMALL_LAUNCH = 10
 STREAM_BITS = 62
 TRIAL_STREAM_BASE = 1 << 61
 REDUCE_AUTO, REDUCE_NCCL = 0, 1

@@ -172,6 +172,8 @@ struct kfbo_handle {
                    zero_copy == o.zero_copy;
         }
     } gsig;
+    int sm_count = 0;                          // a launch of at most 2 CTAs per SM runs as the latency form of the rollout (rollout_philox_small)
+    bool use_small = true;
     // the host polls this word of mapped pinned memory for the exchange kernel's "total stored" instead of synchronising the stream
     unsigned *h_flag = nullptr, *h_flag_dev = nullptr;
     uint32_t flag_expect = 0;
@@ -622,6 +624,7 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
     if (cu(cudaMallocHost(&h->h_flag, 64), "cudaMallocHost(flag)") ||
         cu(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->h_flag_dev), h->h_flag, 0), "cudaHostGetDevicePointer(flag)")) return bail(KFBO_ECUDA);
     std::memset(h->h_flag, 0, 64);
+    if (cu(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device), "cudaDeviceGetAttribute")) return bail(KFBO_ECUDA);
     h->d_hdr = h->d_case_buf + cand_bytes;
     h->h_hdr = h->h_case_buf + cand_bytes;
     std::memset(h->h_hdr, 0, kfbo::kPeerCtxBytes);
@@ -667,7 +670,7 @@ int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value)
         const size_t B = (size_t)value, T = (size_t)h->max_T, C = (size_t)h->p.max_candidates, NS = (size_t)h->N;
         int rc;
         if ((rc = ensure_scratch(h, 0, NS * B)) || (rc = ensure_scratch(h, 1, NS * T * B)) || (rc = ensure_scratch(h, 2, T * B)) ||
-            (rc = ensure_scratch(h, 3, supplied_scratch3_doubles((int)C, h->N > 2 ? kfbo::aug_tiles(B) : kfbo::rollout_tiles(B)))) ||
+            (rc = ensure_scratch(h, 3, supplied_scratch3_doubles((int)C, h->N > 2 ? kfbo::aug_tiles(B) : kfbo::small_tiles(B)))) ||
             (rc = ensure_scratch(h, 4, std::max(C * 4 * B, (size_t)KFBO_TRACE_COLUMNS * T))))
             return rc;
         h->sup_cases.resize(C);
@@ -678,6 +681,9 @@ int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value)
     case KFBO_OPT_CUDA_GRAPH:
         h->use_graph = value != 0;
         if (!h->use_graph && h->gexec) { KFBO_ON_DEVICE(h); cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+        return KFBO_OK;
+    case KFBO_OPT_SMALL_LAUNCH:
+        h->use_small = value != 0;
         return KFBO_OK;
     case KFBO_OPT_HOST_POLL:
         h->use_poll = value != 0;
@@ -944,6 +950,9 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
         h->last_h2d = (int64_t)bytes;
     }
     h->last_launches = (device_build && ncand > 0) ? 1 : 0;
+    // the latency form of the rollout for launches that cannot fill the GPU: its 32-trajectory tiles need four times the partials
+    const int small_max = (h->use_small && !aug && ncases <= step && (size_t)ncases * kfbo::small_tiles(ntrials) * 4 <= h->partials_cap)
+                              ? 2 * h->sm_count : 0;
     KFBO_CUDA(h, record_event(h, h->ev0));
     if (has_work) {
         for (int first = 0; first < ncases; first += step) {
@@ -957,7 +966,7 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
             } else {
                 KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, st, h->d_gu, h->d_logtab, h->min_T, h->p.seed, (uint32_t)t0, ntrials,
                                                          nullptr, 0, h->d_partials, h->d_tickets, rollout_sums, h->stream,
-                                                         device_build ? nullptr : h->h_cases + first, fused, h->capturing ? &h->grec : nullptr));
+                                                         device_build ? nullptr : h->h_cases + first, fused, h->capturing ? &h->grec : nullptr, small_max));
                 ++h->last_launches;
             }
         }
@@ -1271,7 +1280,7 @@ int kfbo_eval_philox_trials(kfbo_handle *h, int32_t k, double q_est, double r_es
     kfbo::AugCase ca;
     rc = aug ? build_aug_case(h, k, q_est, r_est, stream, 0, &ca) : build_case(h, k, q_est, r_est, stream, 0, &c);
     if (rc) return rc;
-    const int tiles = aug ? kfbo::aug_tiles((size_t)ntrials) : kfbo::rollout_tiles((size_t)ntrials);
+    const int tiles = aug ? kfbo::aug_tiles((size_t)ntrials) : kfbo::small_tiles((size_t)ntrials);   // room for the smaller tiles of the latency form
     if ((rc = ensure_scratch(h, 3, supplied_scratch3_doubles(1, tiles)))) return rc;
     if ((rc = ensure_scratch(h, 4, 4 * (size_t)ntrials))) return rc;
     double *d_partials = h->d_scratch[3];
@@ -1289,7 +1298,8 @@ int kfbo_eval_philox_trials(kfbo_handle *h, int32_t k, double q_est, double r_es
         kfbo::SampleTimeConsts st = h->st;
         st.k0 = k; st.nk = 1;
         KFBO_CUDA(h, kfbo::launch_rollout_philox(static_cast<const Case *>(d_case), 1, st, h->d_gu, h->d_logtab, h->min_T, h->p.seed, trial0, (uint32_t)ntrials,
-                                                 h->d_scratch[4], (size_t)ntrials, d_partials, d_ticket, d_sums, h->stream));
+                                                 h->d_scratch[4], (size_t)ntrials, d_partials, d_ticket, d_sums, h->stream, nullptr, false, nullptr,
+                                                 h->use_small ? 2 * h->sm_count : 0));
     }
     KFBO_CUDA(h, cudaMemcpyAsync(per_trial, h->d_scratch[4], 4 * (size_t)ntrials * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     KFBO_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -117,7 +117,11 @@ void set_uniform_estimator(SampleTimeConsts *st, const Case *h_cases);
 cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, const void *d_logtab, int min_T,
                                   uint64_t seed, uint32_t trial0, uint32_t ntrials, double *d_per_trial,
                                   size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums,
-                                  cudaStream_t stream, const Case *h_cases = nullptr, bool with_peer = false, PhiloxLaunchRecord *rec = nullptr);
+                                  cudaStream_t stream, const Case *h_cases = nullptr, bool with_peer = false, PhiloxLaunchRecord *rec = nullptr,
+                                  int small_max_ctas = 0);
+// small_max_ctas > 0: a launch of at most that many 32-trajectory CTAs runs as the latency form of the kernel
+// (rollout_philox_small; same bits); d_partials must then hold [ncases][small_tiles(ntrials)][4].
+int small_tiles(size_t ntrials);
 
 cudaError_t launch_rollout_supplied(const Case *d_cases, int ncases, const SampleTimeConsts &st, const double2 *d_gu, int max_T, const double *d_x0noise,
                                     const double *d_w, const double *d_v, size_t B, double *d_per_trial,

@@ -337,6 +337,31 @@ def test_graph_replay_gives_the_same_bits_as_call_by_call_enqueueing(kfbo):
         assert n == len(cands) and 0 < total < 50 * n
 
 
+def test_latency_form_of_the_rollout_gives_the_same_bits(kfbo, oracle):
+    """rollout_philox_small (KFBO_OPT_SMALL_LAUNCH; launches of at most 2 CTAs per SM, e.g. the reference's default 200 x 201 x 2
+    workload): 32 trajectories per CTA, one warp runs the filter, three make its noise a step group ahead.  Same streams, same
+    filter_step, partial sums combined four at a time like the warps of a rollout_philox CTA: the sums are THE SAME BITS as the
+    throughput kernel's -- whole and ragged tiles, one trajectory, every T mod 4, both variance-shift policies, batches --
+    and the per-trial outputs still match the oracle draw for draw."""
+    from kf_bayesopt_b200 import _lib
+    shapes = [(200, [(0.1, 201), (1.0, 201)]), (31, [(0.1, 2), (0.5, 3)]), (33, [(0.1, 7), (0.5, 31)]), (1, [(0.1, 32), (0.5, 33)]),
+              (300, [(0.1, 2000)]), (129, [(0.1, 201), (0.5, 211), (1.0, 64), (0.25, 5)])]
+    for B, times in shapes:
+        rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1)
+        with kfbo.CostEvaluator(rv, times, seed=23, max_candidates=3) as a, kfbo.CostEvaluator(rv, times, seed=23, max_candidates=3) as b:
+            b.set_option(_lib.OPT_SMALL_LAUNCH, 0)
+            for q, r in [(1.0, 0.1), (0.4, 0.3)]:
+                ra, rb = a.eval([q], [r]), b.eval([q], [r])
+                assert np.array_equal(a.last_sums(1), b.last_sums(1)), (B, times, q)
+                assert np.array_equal(ra.cost, rb.cost) and ra.index_max == rb.index_max
+            ba, bb = a.eval_batch_raw([0.5, 1.0, 2.0], [0.1, 0.2, 0.05]), b.eval_batch_raw([0.5, 1.0, 2.0], [0.1, 0.2, 0.05])
+            assert np.array_equal(a.last_sums(3), b.last_sums(3)) and np.array_equal(ba["cost"], bb["cost"])
+            for k, (dt, T) in enumerate(times):
+                pa, pb = a.eval_philox_trials(k, 0.7, 0.2, 5, 3, B), b.eval_philox_trials(k, 0.7, 0.2, 5, 3, B)
+                assert np.array_equal(pa, pb), (B, k)
+                assert rel_err(pa, oracle.eval_philox(23, 5, dt, T, Q_TRUTH, R_TRUTH, 0.7, 0.2, 3, B)) < RTOL
+
+
 def test_eval_single_candidate_equals_batch_of_one(kfbo):
     rv = kfbo.ReadParaVehicle()                                   # yaml defaults: B=200, 10 "cores"
     with kfbo.CostEvaluator(rv, seed=11) as a, kfbo.CostEvaluator(rv, seed=11, max_candidates=1) as b:
