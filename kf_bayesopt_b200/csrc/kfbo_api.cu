@@ -606,6 +606,10 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
     size_t part = (size_t)h->cases_cap * tiles * 4;
     const size_t budget = kPartialsBudgetBytes / sizeof(double);
     if (part > budget) part = std::max(budget, (size_t)tiles * 4 * h->D);   // at least one whole candidate per launch
+    {   // the latency form of the rollout (at most 2 CTAs of 32 trajectories per SM) keeps one partial per CTA
+        if (cu(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device), "cudaDeviceGetAttribute")) return bail(KFBO_ECUDA);
+        part = std::max(part, (size_t)2 * h->sm_count * 4);
+    }
     h->partials_cap = part;
     const size_t cand_bytes = (size_t)p->max_candidates * sizeof(double2);
     const size_t case_bytes = cand_bytes + kfbo::kPeerCtxBytes + h->cases_cap * sizeof(Case);
@@ -624,7 +628,6 @@ int kfbo_create(const kfbo_params *p, kfbo_handle **out)
     if (cu(cudaMallocHost(&h->h_flag, 64), "cudaMallocHost(flag)") ||
         cu(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->h_flag_dev), h->h_flag, 0), "cudaHostGetDevicePointer(flag)")) return bail(KFBO_ECUDA);
     std::memset(h->h_flag, 0, 64);
-    if (cu(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device), "cudaDeviceGetAttribute")) return bail(KFBO_ECUDA);
     h->d_hdr = h->d_case_buf + cand_bytes;
     h->h_hdr = h->h_case_buf + cand_bytes;
     std::memset(h->h_hdr, 0, kfbo::kPeerCtxBytes);

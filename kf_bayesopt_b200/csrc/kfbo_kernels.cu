@@ -854,17 +854,33 @@ __global__ void __launch_bounds__(256) dfma_chain(double *out, int iters, double
 // ------------------------------- launchers (host) -------------------------------------------
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel) instead of once per launch (1-2 us each).
 // The attribute lives in the device's context; a race between two threads sets it twice to the same value.
-static cudaError_t ensure_dynamic_smem(const void *kernel, int slot, size_t smem)
+static cudaError_t ensure_dynamic_smem(const void *kernel, int /*slot: unused, the table is keyed by the kernel itself*/, size_t smem)
 {
-    constexpr int kDevs = 64, kSlots = 16;
-    static std::atomic<size_t> have[kDevs][kSlots];
+    // a small open-addressed table keyed by (device, kernel): lock-free reads, entries only ever grow
+    constexpr int kEntries = 256;
+    struct Entry { std::atomic<const void *> key{nullptr}; std::atomic<int> dev{-1}; std::atomic<size_t> have{0}; };
+    static Entry table[kEntries];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    const bool cached = dev < kDevs && slot < kSlots;
-    if (cached && have[dev][slot].load(std::memory_order_acquire) >= smem) return cudaSuccess;
+    size_t i = ((reinterpret_cast<uintptr_t>(kernel) >> 4) * 31u + (unsigned)dev) % kEntries;
+    Entry *slot = nullptr;
+    for (int probe = 0; probe < kEntries; ++probe, i = (i + 1) % kEntries) {
+        const void *k = table[i].key.load(std::memory_order_acquire);
+        if (k == kernel && table[i].dev.load(std::memory_order_acquire) == dev) { slot = &table[i]; break; }
+        if (k == nullptr) {
+            const void *expected = nullptr;
+            if (table[i].key.compare_exchange_strong(expected, kernel, std::memory_order_acq_rel)) {
+                table[i].dev.store(dev, std::memory_order_release);
+                slot = &table[i];
+                break;
+            }
+            if (expected == kernel && table[i].dev.load(std::memory_order_acquire) == dev) { slot = &table[i]; break; }
+        }
+    }
+    if (slot && slot->have.load(std::memory_order_acquire) >= smem) return cudaSuccess;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess && cached) have[dev][slot].store(smem, std::memory_order_release);
+    if (e == cudaSuccess && slot) slot->have.store(smem, std::memory_order_release);
     return e;
 }
 
@@ -911,7 +927,7 @@ cudaError_t launch_rollout_philox(const Case *d_cases, int ncases, const SampleT
     if (!with_peer && small_max_ctas > 0 && (long)tiles32 * ncases <= (long)small_max_ctas) {
         auto *small = uniform_est ? (shift_first ? rollout_philox_small<true, true> : rollout_philox_small<true, false>)
                                   : (shift_first ? rollout_philox_small<false, true> : rollout_philox_small<false, false>);
-        const cudaError_t a2 = ensure_dynamic_smem(reinterpret_cast<const void *>(small), 12 + (uniform_est ? 2 : 0) + (shift_first ? 1 : 0), smem);
+        const cudaError_t a2 = ensure_dynamic_smem(reinterpret_cast<const void *>(small), 16 + (uniform_est ? 2 : 0) + (shift_first ? 1 : 0), smem);
         if (a2 != cudaSuccess) return a2;
         r.func = reinterpret_cast<const void *>(small);
         r.grid = dim3((unsigned)tiles32, (unsigned)(ncases / st.nk), (unsigned)st.nk);
