@@ -342,145 +342,6 @@ rollout_philox(const Case *__restrict__ cases, const __grid_constant__ SampleTim
 }
 
 // -----------------------------------------------------------------------------------------
-// The same rollout for SMALL launches -- the reference's own default workload is 200 trials x 201 steps x 2 sample times
-// (config/vehicleParams.yaml:9-16): 4 CTAs of rollout_philox, one warp per scheduler, and the evaluation takes as long as
-// ONE warp needs for T strictly sequential steps with the noise generator and the filter interleaved in its instruction
-// stream (~410 cycles per step: 47 us of the 63 us call).  When the launch cannot fill the GPU anyway, latency is what
-// counts, and the two halves of a step are independent until the noise is consumed: here a CTA is 32 trajectories,
-// warp 0 runs the filter recursion (the consumer; its loop-carried chain is the covariance recursion, ~110 cycles per
-// step) and warps 1-3 -- on the other three schedulers of the SM -- each make one of the three Philox calls of a step
-// group and its two Box-Muller pairs (the producers), one group ahead, through a double buffer in shared memory.
-// One __syncthreads per group of four steps orders the two sides; no spinning anywhere.
-//   SAME noise streams, SAME filter_step, and the per-CTA partial sums are combined four at a time exactly as the four
-//   warps of a rollout_philox CTA combine theirs: the cost sums are THE SAME BITS as rollout_philox's, so which kernel
-//   runs is invisible (single evaluation == candidate of a batch, one GPU == several).
-// tiles = ceil(ntrials / 32); partials hold [cases][tiles][4].
-// -----------------------------------------------------------------------------------------
-constexpr int kSmallTile = 32;
-
-template <bool kUniformEst, bool kShiftFirst>
-__global__ void __launch_bounds__(kThreads)
-rollout_philox_small(const Case *__restrict__ cases, const __grid_constant__ SampleTimeConsts st,
-                     const double2 *__restrict__ gu_tables, const math::LogTables *__restrict__ logtab,
-                     const __grid_constant__ PhiloxKeys key, uint32_t trial0, uint32_t ntrials,
-                     int tiles, double *__restrict__ per_trial, size_t per_trial_ld, double *__restrict__ partials,
-                     unsigned *__restrict__ tickets, double *__restrict__ sums)
-{
-    extern __shared__ __align__(16) unsigned char s_tables_raw[];
-    math::LogTables &s_log = *reinterpret_cast<math::LogTables *>(s_tables_raw);
-    __shared__ double s_ring[2][12][kSmallTile];      // [buffer][normal of the group][lane]: A -> 0..3, B -> 4..7, C -> 8..11
-    __shared__ bool s_last;
-    const int case_idx = blockIdx.y * gridDim.z + blockIdx.z, tile = blockIdx.x;
-    Case m = cases[case_idx];
-    const int T = m.T;
-    const unsigned kk = st.k0 + blockIdx.z;
-    if (kUniformEst) {
-        m.q00 = pick4(st.q00, kk); m.q01 = pick4(st.q01, kk); m.q11 = pick4(st.q11, kk); m.r_est = pick4(st.r_est, kk);
-    }
-    const double f = pick4(st.f, kk), l00 = pick4(st.l00, kk), l10 = pick4(st.l10, kk), l11 = pick4(st.l11, kk),
-                 sr = pick4(st.sr, kk);
-    const double2 *__restrict__ gu = gu_tables + (size_t)kk * kMaxSteps;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t local = (uint32_t)tile * kSmallTile + lane;
-    const uint32_t trial = trial0 + local;
-    load_noise_tables(&s_log, logtab);
-    __syncthreads();
-    const int ngroups = (T + 3) >> 2;
-    // producer `warp` makes call `warp - 1` of group g (counter block g + 1) and its two normal pairs
-    auto produce = [&](int g) {
-        const uint4 w = philox_at(trial, m.stream, m.stream_x, (uint32_t)g + 1u, (uint32_t)warp - 1u, key);
-        double a, b, c, d;
-        math::normal_pair(w.x, w.y, s_log, a, b);
-        math::normal_pair(w.z, w.w, s_log, c, d);
-        double (*dst)[kSmallTile] = &s_ring[g & 1][4 * (warp - 1)];
-        dst[0][lane] = a; dst[1][lane] = b; dst[2][lane] = c; dst[3][lane] = d;
-    };
-    Traj t;
-    if (warp == 0) {
-        double a, b;
-        const uint4 w = philox_at(trial, m.stream, m.stream_x, 0u, 0u, key);
-        math::normal_pair(w.x, w.y, s_log, a, b);
-        traj_init<kShiftFirst>(t, a, b);
-    } else {
-        produce(0);
-    }
-    __syncthreads();
-    for (int g = 0; g < ngroups; ++g) {
-        if (warp == 0) {
-            const double (*n)[kSmallTile] = s_ring[g & 1];
-            const int s0 = 4 * g;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (s0 + j < T)      // uniform: only the last group can be partial
-                    filter_step<false, true, kShiftFirst>(t, m, f, __ldg(gu + s0 + j), StepNoise{n[2 * j][lane], n[2 * j + 1][lane], n[8 + j][lane]},
-                                                          l00, l10, l11, sr, nullptr, s0 + j == 0);
-            }
-        } else if (g + 1 < ngroups) {
-            produce(g + 1);
-        }
-        __syncthreads();
-    }
-    // ---- results of the tile's trajectories (warp 0), then the reduction: warp sum -> partial of this 32-trajectory tile
-    double r4[4] = {0.0, 0.0, 0.0, 0.0};
-    if (warp == 0) {
-        double o[4], out[4] = {0.0, 0.0, 0.0, 0.0};
-        traj_finish(t, T, o);
-        if (local < ntrials) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) out[k] = o[k];
-            if (per_trial != nullptr) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) per_trial[((size_t)m.out_slot * 4 + k) * per_trial_ld + local] = o[k];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) r4[k] = warp_sum(out[k]);
-        if (lane < 4) {
-            partials[((size_t)case_idx * tiles + tile) * 4 + lane] = lane == 0 ? r4[0] : lane == 1 ? r4[1] : lane == 2 ? r4[2] : r4[3];
-            __threadfence();
-        }
-        __syncwarp();
-        if (lane == 0) {
-            const unsigned tk = atomicAdd(&tickets[case_idx], 1u);
-            s_last = (tk == (unsigned)tiles - 1u);
-        }
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    // The last CTA of the case: the 32-trajectory partials four at a time, in order, from 0.0 -- what the four warps of a
-    // rollout_philox CTA add up to for their 128-trajectory tile -- then that kernel's fixed-order sum over the tiles.
-    double (*s_red)[4] = reinterpret_cast<double (*)[4]>(s_tables_raw);     // the tables are no longer needed
-    const int tiles128 = (tiles + 3) >> 2;
-    double a[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int tt = threadIdx.x; tt < tiles128; tt += kThreads) {
-        double p[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int w = 0; w < 4; ++w) {
-            const int t32 = 4 * tt + w;
-            if (t32 < tiles) {
-                const double *src = partials + ((size_t)case_idx * tiles + t32) * 4;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) p[k] += __ldcg(src + k);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) a[k] += p[k];
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) s_red[threadIdx.x][k] = a[k];
-    __syncthreads();
-    for (int o = kThreads / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) s_red[threadIdx.x][k] += s_red[threadIdx.x + o][k];
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x < 4) sums[(size_t)m.out_slot * 4 + threadIdx.x] = s_red[0][threadIdx.x];
-    if (threadIdx.x == 0) tickets[case_idx] = 0u;  // ready for the next launch
-}
-
-// -----------------------------------------------------------------------------------------
 // Supplied-noise rollout: x0noise[2][B], w[T][2][B], v[T][B]; trial index fastest, so a warp
 // reads 32 consecutive doubles (256 B) per load.  Loads are software-pipelined kPrefetch
 // steps ahead through registers (3*kPrefetch independent 8-byte loads in flight per thread).
@@ -709,6 +570,173 @@ rollout_supplied_bulk(const Case *__restrict__ cases, const __grid_constant__ Sa
     static_assert(sizeof(BulkStage) * kBulkStages >= sizeof(double) * 4 * kThreads, "ring too small for the reduction scratch");
     __syncthreads();
     block_reduce_and_publish(out, case_idx, tile, tiles, m.out_slot, partials, tickets, sums, reinterpret_cast<double (*)[4]>(s_raw));
+}
+
+// -----------------------------------------------------------------------------------------
+// The same rollout for SMALL launches -- the reference's own default workload is 200 trials x 201 steps x 2 sample times
+// (config/vehicleParams.yaml:9-16): 4 CTAs of rollout_philox, one warp per scheduler, and the evaluation takes as long as
+// ONE warp needs for T strictly sequential steps with the noise generator and the filter interleaved in its instruction
+// stream (~410 cycles per step: 47 us of the 63 us call).  When the launch cannot fill the GPU anyway, latency is what
+// counts, and the two halves of a step are independent until the noise is consumed: here a CTA is 32 trajectories,
+// warp 0 runs the filter recursion (the consumer; its loop-carried chain is the covariance recursion, ~110 cycles per
+// step) and warps 1-3 -- on the other three schedulers of the SM -- each make one of the three Philox calls of a step
+// group and its two Box-Muller pairs (the producers), one group ahead, through a double buffer in shared memory.
+// One __syncthreads per group of four steps orders the two sides; no spinning anywhere.
+//   SAME noise streams, SAME filter_step, and the per-CTA partial sums are combined four at a time exactly as the four
+//   warps of a rollout_philox CTA combine theirs: the cost sums are THE SAME BITS as rollout_philox's, so which kernel
+//   runs is invisible (single evaluation == candidate of a batch, one GPU == several).
+// tiles = ceil(ntrials / 32); partials hold [cases][tiles][4].
+// -----------------------------------------------------------------------------------------
+constexpr int kSmallTile = 32;
+
+template <bool kUniformEst, bool kShiftFirst>
+__global__ void __launch_bounds__(kThreads)
+rollout_philox_small(const Case *__restrict__ cases, const __grid_constant__ SampleTimeConsts st,
+                     const double2 *__restrict__ gu_tables, const math::LogTables *__restrict__ logtab,
+                     const __grid_constant__ PhiloxKeys key, uint32_t trial0, uint32_t ntrials,
+                     int tiles, double *__restrict__ per_trial, size_t per_trial_ld, double *__restrict__ partials,
+                     unsigned *__restrict__ tickets, double *__restrict__ sums)
+{
+    extern __shared__ __align__(16) unsigned char s_tables_raw[];
+    math::LogTables &s_log = *reinterpret_cast<math::LogTables *>(s_tables_raw);
+    __shared__ double s_ring[2][12][kSmallTile];      // [buffer][normal of the group][lane]: A -> 0..3, B -> 4..7, C -> 8..11
+    __shared__ bool s_last;
+    const int case_idx = blockIdx.y * gridDim.z + blockIdx.z, tile = blockIdx.x;
+    Case m = cases[case_idx];
+    const int T = m.T;
+    const unsigned kk = st.k0 + blockIdx.z;
+    if (kUniformEst) {
+        m.q00 = pick4(st.q00, kk); m.q01 = pick4(st.q01, kk); m.q11 = pick4(st.q11, kk); m.r_est = pick4(st.r_est, kk);
+    }
+    const double f = pick4(st.f, kk), l00 = pick4(st.l00, kk), l10 = pick4(st.l10, kk), l11 = pick4(st.l11, kk),
+                 sr = pick4(st.sr, kk);
+    const double2 *__restrict__ gu = gu_tables + (size_t)kk * kMaxSteps;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t local = (uint32_t)tile * kSmallTile + lane;
+    const uint32_t trial = trial0 + local;
+    // the noise tables by ONE bulk copy (48.4 KB, 16-byte multiple) instead of 24 rounds of per-thread loads: the launch's fixed
+    // cost is what a small evaluation mostly consists of
+    __shared__ __align__(8) uint64_t s_tab_bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_tab_bar, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+        mbar_arrive_expect_tx(&s_tab_bar, (uint32_t)sizeof(math::LogTables));
+        bulk_g2s(&s_log, logtab, (uint32_t)sizeof(math::LogTables), &s_tab_bar, policy);
+    }
+    __syncthreads();                         // the barrier's initialisation is visible to everyone who waits on it
+    const int ngroups = (T + 3) >> 2, nfull = T >> 2;
+    // the consumer's control inputs g*u of a group, fetched one group ahead (an L2 round trip must not sit in its step chain)
+    double2 gn0 = make_double2(0.0, 0.0), gn1 = gn0, gn2 = gn0, gn3 = gn0;
+    if (warp == 0) { gn0 = __ldg(gu); gn1 = __ldg(gu + 1); gn2 = __ldg(gu + 2); gn3 = __ldg(gu + 3); }
+    mbar_wait(&s_tab_bar, 0u);
+    // producer `warp` makes call `warp - 1` of group g (counter block g + 1) and its two normal pairs
+    auto produce = [&](int g) {
+        const uint4 w = philox_at(trial, m.stream, m.stream_x, (uint32_t)g + 1u, (uint32_t)warp - 1u, key);
+        double a, b, c, d;
+        math::normal_pair(w.x, w.y, s_log, a, b);
+        math::normal_pair(w.z, w.w, s_log, c, d);
+        double (*dst)[kSmallTile] = &s_ring[g & 1][4 * (warp - 1)];
+        dst[0][lane] = a; dst[1][lane] = b; dst[2][lane] = c; dst[3][lane] = d;
+    };
+    Traj t;
+    if (warp == 0) {
+        double a, b;
+        const uint4 w = philox_at(trial, m.stream, m.stream_x, 0u, 0u, key);
+        math::normal_pair(w.x, w.y, s_log, a, b);
+        traj_init<kShiftFirst>(t, a, b);
+    } else {
+        produce(0);
+    }
+    __syncthreads();
+    for (int g = 0; g < ngroups; ++g) {
+        if (warp == 0) {
+            const double (*n)[kSmallTile] = s_ring[g & 1];
+            // everything the group's four steps read, up front: the normals of the group (whole groups are always made)
+            // and, for the group after, g*u
+            const double2 g0 = gn0, g1 = gn1, g2 = gn2, g3 = gn3;
+            const double a0 = n[0][lane], b0 = n[1][lane], a1 = n[2][lane], b1 = n[3][lane], a2 = n[4][lane], b2 = n[5][lane],
+                         a3 = n[6][lane], b3 = n[7][lane], o0 = n[8][lane], o1 = n[9][lane], o2 = n[10][lane], o3 = n[11][lane];
+            if (g + 1 < ngroups) {           // the table has kMaxSteps entries and 4 (g + 1) + 3 < 4 ngroups <= kMaxSteps + 3 ...
+                const double2 *nx = gu + 4 * (g + 1);
+                const int left = kMaxSteps - 4 * (g + 1);          // ... so only the very last group of T = kMaxSteps - 1..3 could run over
+                gn0 = __ldg(nx); gn1 = __ldg(nx + (left > 1 ? 1 : 0)); gn2 = __ldg(nx + (left > 2 ? 2 : 0)); gn3 = __ldg(nx + (left > 3 ? 3 : 0));
+            }
+            if (g < nfull) {
+                filter_step<false, true, kShiftFirst>(t, m, f, g0, StepNoise{a0, b0, o0}, l00, l10, l11, sr, nullptr, g == 0);
+                filter_step<false, true, kShiftFirst>(t, m, f, g1, StepNoise{a1, b1, o1}, l00, l10, l11, sr);
+                filter_step<false, true, kShiftFirst>(t, m, f, g2, StepNoise{a2, b2, o2}, l00, l10, l11, sr);
+                filter_step<false, true, kShiftFirst>(t, m, f, g3, StepNoise{a3, b3, o3}, l00, l10, l11, sr);
+            } else {                         // the partial last group: T mod 4 steps
+                const int rem = T & 3;
+                filter_step<false, true, kShiftFirst>(t, m, f, g0, StepNoise{a0, b0, o0}, l00, l10, l11, sr, nullptr, g == 0);
+                if (rem > 1) filter_step<false, true, kShiftFirst>(t, m, f, g1, StepNoise{a1, b1, o1}, l00, l10, l11, sr);
+                if (rem > 2) filter_step<false, true, kShiftFirst>(t, m, f, g2, StepNoise{a2, b2, o2}, l00, l10, l11, sr);
+            }
+        } else if (g + 1 < ngroups) {
+            produce(g + 1);
+        }
+        __syncthreads();
+    }
+    // ---- results of the tile's trajectories (warp 0), then the reduction: warp sum -> partial of this 32-trajectory tile
+    double r4[4] = {0.0, 0.0, 0.0, 0.0};
+    if (warp == 0) {
+        double o[4], out[4] = {0.0, 0.0, 0.0, 0.0};
+        traj_finish(t, T, o);
+        if (local < ntrials) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out[k] = o[k];
+            if (per_trial != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) per_trial[((size_t)m.out_slot * 4 + k) * per_trial_ld + local] = o[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r4[k] = warp_sum(out[k]);
+        if (lane < 4) {
+            partials[((size_t)case_idx * tiles + tile) * 4 + lane] = lane == 0 ? r4[0] : lane == 1 ? r4[1] : lane == 2 ? r4[2] : r4[3];
+            __threadfence();
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned tk = atomicAdd(&tickets[case_idx], 1u);
+            s_last = (tk == (unsigned)tiles - 1u);
+        }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // The last CTA of the case: the 32-trajectory partials four at a time, in order, from 0.0 -- what the four warps of a
+    // rollout_philox CTA add up to for their 128-trajectory tile -- then that kernel's fixed-order sum over the tiles.
+    double (*s_red)[4] = reinterpret_cast<double (*)[4]>(s_tables_raw);     // the tables are no longer needed
+    const int tiles128 = (tiles + 3) >> 2;
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int tt = threadIdx.x; tt < tiles128; tt += kThreads) {
+        double p[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int w = 0; w < 4; ++w) {
+            const int t32 = 4 * tt + w;
+            if (t32 < tiles) {
+                const double *src = partials + ((size_t)case_idx * tiles + t32) * 4;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) p[k] += __ldcg(src + k);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] += p[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_red[threadIdx.x][k] = a[k];
+    __syncthreads();
+    for (int o = kThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s_red[threadIdx.x][k] += s_red[threadIdx.x + o][k];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) sums[(size_t)m.out_slot * 4 + threadIdx.x] = s_red[0][threadIdx.x];
+    if (threadIdx.x == 0) tickets[case_idx] = 0u;  // ready for the next launch
 }
 
 // -----------------------------------------------------------------------------------------
