@@ -122,6 +122,15 @@ __device__ __forceinline__ uint4 philox_at(uint32_t trial, uint32_t stream, uint
 __device__ __forceinline__ GroupWords philox_group(uint32_t trial, uint32_t stream, uint32_t stream_x, uint32_t group, const PhiloxKeys &key, uint32_t zero = 0u)
 {
     GroupWords w;
+#if defined(KFBO_ABLATE_PHILOX)   // timing experiment only (the results are WRONG): twelve cheap words instead of three Philox calls
+    {
+        const uint32_t s = (trial ^ stream) + (group + 1u) * 0x9E3779B9u;
+        w.a = make_uint4(s * 0xD2511F53u, (s + 1u) * 0xCD9E8D57u, (s + 2u) * 0xD2511F53u, (s + 3u) * 0xCD9E8D57u);
+        w.b = make_uint4((s + 4u) * 0xD2511F53u, (s + 5u) * 0xCD9E8D57u, (s + 6u) * 0xD2511F53u, (s + 7u) * 0xCD9E8D57u);
+        w.c = make_uint4((s + 8u) * 0xD2511F53u, (s + 9u) * 0xCD9E8D57u, (s + 10u) * 0xD2511F53u, (s + 11u) * 0xCD9E8D57u);
+        return w;
+    }
+#endif
     w.a = philox_at(trial, stream, stream_x, group + 1u, 0u, key, zero);
     w.b = philox_at(trial, stream, stream_x, group + 1u, 1u, key, zero);
     w.c = philox_at(trial, stream, stream_x, group + 1u, 2u, key, zero);

@@ -277,6 +277,12 @@ KFBO_HD void rad_direction(double rad, uint32_t dir, const LogTables &tab, doubl
 //     3e-15 per draw, is less than one draw in 10^14.
 KFBO_HD void normal_pair(uint32_t w0, uint32_t w1, const LogTables &tab, double &na, double &nb)
 {
+#if defined(KFBO_ABLATE_NORMAL)   // timing experiment only (the results are WRONG): two uniforms on [-1/2, 1/2), no table, no log / sqrt
+    na = make_double(0x3FF00000u | (w0 >> 12), w1) - 1.5;
+    nb = make_double(0x3FF00000u | (w1 >> 12), w0) - 1.5;
+    (void)tab;
+    return;
+#endif
     // y1 = 1 + (m + 1/2) 2^-44 in [1, 2): mantissa = w0 : w1[31:20] : 1000 0000b
     const double y1 = make_double(0x3FF00000u | (w0 >> 12), (funnel_l(w1, w0, 20) & 0xFFFFFF00u) | 0x80u);
     const double u1 = 2.0 - y1;

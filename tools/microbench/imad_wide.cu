@@ -8,23 +8,30 @@ __global__ void __launch_bounds__(256) k(double *out, int iters, double a, doubl
 {
     double x[8];
     uint32_t y[8], z[8];
+    double w[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { x[j] = threadIdx.x + j; y[j] = threadIdx.x * 7 + j; z[j] = y[j] ^ 0x55555555u; }
+    for (int j = 0; j < 8; ++j) { x[j] = threadIdx.x + j; y[j] = threadIdx.x * 7 + j; z[j] = y[j] ^ 0x55555555u; w[j] = __hiloint2double(0x45300000, (int)y[j]); }
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int u = 0; u < 8; ++u)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                if (MODE == 0 || MODE == 2 || MODE == 4 || MODE == 6) x[j] = fma(x[j], a, b);
+                if (MODE == 0 || MODE == 2 || MODE == 4 || MODE == 6 || MODE == 8) x[j] = fma(x[j], a, b);
                 if (MODE == 1 || MODE == 2) { const uint64_t p = (uint64_t)y[j] * m; y[j] = (uint32_t)p; z[j] ^= (uint32_t)(p >> 32); }   // IMAD.WIDE + LOP3
                 if (MODE == 3 || MODE == 4) { y[j] = __umulhi(y[j], m) ^ z[j]; }                                                            // IMAD.HI + LOP3
+                if (MODE == 7 || MODE == 8) {   // the upper half by a round-down DFMA on (0x45300000 : y), the lower by IMAD, + LOP3
+                    const double t = __fma_rd(w[j], (double)0xD2511F53u * 0x1p-32, 0x1p84 - (double)0xD2511F53u * 0x1p52);
+                    const uint32_t lo = (uint32_t)__double2loint(w[j]) * m;
+                    w[j] = __hiloint2double(__double2hiint(t), __double2loint(t) ^ (int)z[j]);
+                    z[j] = lo;
+                }
                 if (MODE == 5 || MODE == 6) { y[j] = (y[j] & 0xffffu) * (m & 0xffffu) + z[j]; }                                            // LOP3 + IMAD (16x16)
             }
     }
     double s = 0;
     uint32_t t = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s += x[j]; t += y[j] + z[j]; }
+    for (int j = 0; j < 8; ++j) { s += x[j]; t += y[j] + z[j] + (uint32_t)__double2loint(w[j]); }
     if (s == 123.456 || t == 0xdeadbeef) out[0] = s + t;
 }
 
@@ -59,5 +66,7 @@ int main()
     run<4>(d, "8 DFMA + 8 (IMAD.HI + LOP3)");
     run<5>(d, "8 (LOP3 + IMAD 16x16)");
     run<6>(d, "8 DFMA + 8 (LOP3 + IMAD 16x16)");
+    run<7>(d, "8 (DFMA.RM + IMAD + LOP3)");
+    run<8>(d, "8 DFMA + 8 (DFMA.RM + IMAD + LOP3)");
     return 0;
 }
