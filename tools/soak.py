@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Soak run of the evaluator's launch paths (graph replay, polled completion flag, both generations of the peer-memory
+exchange, candidate batches in between): tens of thousands of back-to-back `noise` -> `cost` calls with changing candidates.
+    python tools/soak.py [seconds]                                   one GPU
+    python -m torch.distributed.run --nproc-per-node N ... tools/soak.py [seconds]     N ranks, trials sharded
+Checks, while running: no error code, every cost finite; every 2000 evaluations the first 64 candidates are evaluated
+again on the same Philox streams (set_eval_counter) and must give the same bits; at N > 1 every rank must have seen the
+same bits of every cost (a running hash, compared at the end); free device memory is the same before and after.
+Prints 'soak ok ...' on rank 0."""
+import hashlib
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import kf_bayesopt_b200 as kf
+from kf_bayesopt_b200.dist import init_comm
+
+seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 10.0
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+times = [(0.1, 201), (1.0, 201)]                   # the reference's default workload (vehicleParams.yaml, trial_node.cpp:105-114)
+rv = kf.ReadParaVehicle(nsimruns_=200, cpu_core_number_=1)
+rng = np.random.default_rng(2026)                  # same candidates on every rank
+C = 24
+h = hashlib.sha256()
+with kf.CostEvaluator(rv, times, seed=99, max_candidates=C, device=local) as ev:
+    peer = init_comm(ev, kf.SHARD_TRIALS) if world > 1 else False
+    ev.eval([1.0], [0.1])
+    ev.set_eval_counter(0)
+    ev.eval_batch_costs(np.full(C, 1.0), np.full(C, 0.1))      # both kernels' code is resident before free memory is read
+    torch.zeros(1, device="cuda")                               # torch's caching allocator takes its first 2 MiB segment now, not inside the loop
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    first = []
+    n, n_batch, n_replayed, t0 = 0, 0, 0, time.perf_counter()
+    # every rank runs the same number of evaluations: the stop decision is rank 0's, shared every 2000 evaluations
+    go = True
+    while go:
+        for i in range(2000):
+            q, r = float(np.exp(rng.uniform(np.log(0.1), np.log(5.0)))), float(np.exp(rng.uniform(np.log(0.01), np.log(1.0))))
+            res = ev.eval([q], [r])
+            c = np.asarray(res.cost, dtype=np.float64)
+            assert np.all(np.isfinite(c)), (n, q, r, c)
+            h.update(c.tobytes())
+            if n < 64:
+                first.append((q, r, c.copy()))
+            n += 1
+            if i % 500 == 499:                      # a candidate batch in between (another kernel, another result path)
+                qq, rr = np.exp(rng.uniform(np.log(0.1), np.log(5.0), C)), np.exp(rng.uniform(np.log(0.01), np.log(1.0), C))
+                cost = ev.eval_batch_costs(qq, rr)
+                cost = cost[0] if isinstance(cost, tuple) else cost
+                assert np.all(np.isfinite(cost)), (n, cost)
+                h.update(np.ascontiguousarray(cost, dtype=np.float64).tobytes())
+                n_batch += 1
+        # the first 64 evaluations again, on the same streams: same bits
+        keep = n + n_batch
+        ev.set_eval_counter(1)                      # the warm-up evaluation was number 0
+        for q, r, c in first:
+            again = np.asarray(ev.eval([q], [r]).cost, dtype=np.float64)
+            assert np.array_equal(again, c), (n, q, r, again, c)
+            n_replayed += 1
+        ev.set_eval_counter(keep + 1)
+        stop = torch.tensor([1 if time.perf_counter() - t0 > seconds else 0], device="cuda")
+        if world > 1:
+            dist.broadcast(stop, src=0)
+        go = not bool(stop.item())
+    wall = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    path = ev.last_reduce_path() if world > 1 else "single GPU"
+digest = h.hexdigest()
+same = True
+if world > 1:
+    box = [None] * world
+    dist.all_gather_object(box, digest)
+    same = all(d == box[0] for d in box)
+assert same, "the ranks did not see the same cost bits"
+assert free1 == free0, (free0, free1)
+if rank == 0:
+    print(f"soak ok: {world} rank(s), {n} evaluations + {n_batch} batches of {C} + {n_replayed} replays in {wall:.1f} s "
+          f"({wall / (n + n_replayed) * 1e6:.1f} us per call incl. Python), costs identical on all ranks ({digest[:16]}), "
+          f"free memory delta {free1 - free0} B, sums met by: {path}", flush=True)
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
