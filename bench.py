@@ -437,31 +437,47 @@ def dense_flops_per_step(N: int) -> int:
     return sim + kf_ + met
 
 
+# FP64 instructions the state-augmented kernels EXECUTE per filter-step, noise included (SASS of the step loops,
+# profiles/sass_loops_r2q.txt: per thread and step pair / per lane and step pair x 4 lanes), beside the dense reference-style count
+AUG_FP64_INSTRUCTIONS = {"thread": {3: 144, 4: 234}, "lanes": {3: 347, 4: 450}}
+
+
 def leg_augmented(kf, torch, stream, device, fp64_peak):
-    """SURVEY.md 8 row f4, north_star's "state-augmented variants": the same evaluation on a chain of N = 3 / 4 integrators,
-    one covariance row per lane of a 4-lane group (kfbo_aug.cuh).  The reference has no such variant; reported on its own,
-    with its own flop count, never against the N = 2 figures."""
+    """SURVEY.md 8 row f4, north_star's "state-augmented variants": the same evaluation on a chain of N = 3 / 4 integrators
+    (kfbo_aug.cuh) -- one trajectory per thread (the default) and, beside it, one covariance row per lane of a 4-lane group.
+    The reference has no such variant; reported on its own, with its own flop count, never against the N = 2 figures."""
     import numpy as np
     from oracle import oracle as o
+    from kf_bayesopt_b200 import _lib as L
     out = {}
     trials, T, times = 1 << 18, 1000, [(0.1, 1000), (0.5, 1000)]
+    steps = float(trials) * T * len(times)
     for N in (3, 4):
         rv = kf.ReadParaVehicle(nsimruns_=trials, cpu_core_number_=1, pnoise_=[Q_TRUTH], onoise_=[R_TRUTH], state_dof_=N)
-        with kf.CostEvaluator(rv, times, seed=0x4B46424F00002026, device=device, state_dim=N) as ev:
-            ev.set_cuda_stream(stream.cuda_stream)
-            ms, kms, launches, res = timed_evals(torch, stream, ev, lambda: ev.eval(*CANDIDATE), 5, 3)
-            small = ev.eval_philox_trials(0, 0.7, 0.2, 5, 0, 64)
-        steps = float(trials) * T * len(times)
         flops = dense_flops_per_step(N)
         want = o.aug_eval_philox(N, 0x4B46424F00002026, 5, 0.1, T, Q_TRUTH, R_TRUTH, 0.7, 0.2, 0, 64)
-        ach = flops * steps / (kms * 1e-3) / 1e12
+        legs = {}
+        with kf.CostEvaluator(rv, times, seed=0x4B46424F00002026, device=device, state_dim=N) as ev:
+            ev.set_cuda_stream(stream.cuda_stream)
+            for name, layout, kernel in (("thread", L.AUG_LAYOUT_THREAD, f"rollout_aug_thread<{N}>"), ("lanes", L.AUG_LAYOUT_LANES, f"rollout_aug<{N}>")):
+                ev.set_option(L.OPT_AUG_LAYOUT, layout)
+                ev.set_eval_counter(0)
+                ms, kms, launches, res = timed_evals(torch, stream, ev, lambda: ev.eval(*CANDIDATE), 5, 3)
+                small = ev.eval_philox_trials(0, 0.7, 0.2, 5, 0, 64)
+                ach = flops * steps / (kms * 1e-3) / 1e12
+                legs[name] = {"value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_eval": ms, "kernel_ms": kms, "kernel": kernel,
+                              "achieved_tflops": ach, "frac_of_fp64_peak": ach / fp64_peak if fp64_peak else None,
+                              "fp64_instructions_per_filter_step": AUG_FP64_INSTRUCTIONS[name][N],
+                              "J_NEES": [float(c) for c in res.cost],
+                              "parity_vs_oracle_max_rel": float(np.max(np.abs(small - want) / np.abs(want)))}
         out[f"N{N}"] = {"state_dim": N, "workload": f"{trials} trials x {T} steps x {len(times)} sample times, on-device Philox noise",
-                        "value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_eval": ms, "kernel_ms": kms, "kernel": f"rollout_aug<{N}>",
-                        "flops_per_filter_step": flops, "achieved_tflops": ach, "frac_of_fp64_peak": ach / fp64_peak if fp64_peak else None,
-                        "J_NEES": [float(c) for c in res.cost],
-                        "parity_vs_oracle_max_rel": float(np.max(np.abs(small - want) / np.abs(want)))}
+                        "flops_per_filter_step": flops, **legs["thread"], "layout": "one trajectory per thread (KFBO_AUG_LAYOUT_THREAD, the default)",
+                        "rows_across_lanes": legs["lanes"]}
     out["note"] = ("builder extension named by north_star, not in the reference (system_models.hpp:11-12 fixes N = 2); parity is against "
-                   "oracle/kfbo_oracle_aug.c, which tests/test_oracle_aug.py pins with scipy / closed forms; flop counts by dense_flops_per_step")
+                   "oracle/kfbo_oracle_aug.c, which tests/test_oracle_aug.py pins with scipy / closed forms; flop counts by dense_flops_per_step "
+                   "(the reference-style dense N x N count, mul/add 1, fma 2, structural zeros included: the per-thread kernel executes far fewer "
+                   "instructions than that -- fp64_instructions_per_filter_step -- which is how frac_of_fp64_peak can exceed 1); the two layouts draw "
+                   "the same Philox words and give every trajectory the same bits")
     return out
 
 

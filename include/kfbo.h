@@ -216,6 +216,10 @@ enum { KFBO_OPT_SUPPLIED_KERNEL = 1, KFBO_OPT_BULK_SMEM_PAD = 2 /* extra dynamic
                                         200 x 201 x 2 workload is 14 -- runs as the LATENCY form of the rollout: 32 trajectories
                                         per CTA, one warp runs the filter recursion, three make its noise a step group
                                         ahead.  Same streams, same arithmetic, same order of the sums: same bits. 0: never */,
+       KFBO_OPT_AUG_LAYOUT = 11 /* state_dim 3, 4 with on-device noise: KFBO_AUG_LAYOUT_THREAD (default) one trajectory per
+                                        thread, the whole covariance in its registers; KFBO_AUG_LAYOUT_LANES one covariance
+                                        row per lane of a 4-lane group (the layout that scales beyond N = 4; supplied noise
+                                        always runs it).  Same Philox words, same arithmetic per row: same bits. */,
        KFBO_OPT_RESERVE_SUPPLIED_TRIALS = 7 /* pre-size the scratch of the parity entry points (kfbo_eval_supplied,
                                         kfbo_eval_philox_trials, kfbo_trace_trial) for this many trials x max_candidates
                                         candidates: after it they allocate nothing, like kfbo_eval* */ };
@@ -224,6 +228,7 @@ enum { KFBO_OPT_SUPPLIED_KERNEL = 1, KFBO_OPT_BULK_SMEM_PAD = 2 /* extra dynamic
  * had a "reduced" form -- gain recursion tabulated once per case, error-state trajectories; it was never more than 6 % faster
  * and was removed: DESIGN.md section 4a.  The option number stays reserved.) */
 enum { KFBO_FORM_REFERENCE = 0 };
+enum { KFBO_AUG_LAYOUT_LANES = 0, KFBO_AUG_LAYOUT_THREAD = 1 };
 enum { KFBO_SUPPLIED_AUTO = 0, KFBO_SUPPLIED_LDG = 1, KFBO_SUPPLIED_BULK = 2 };
 /* KFBO_OPT_REDUCE (set it to the same value on every rank):
  *   KFBO_REDUCE_AUTO (default): the peer-memory exchange (below) when the ranks are attached to each other, else NCCL;

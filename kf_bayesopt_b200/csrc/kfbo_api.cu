@@ -74,6 +74,7 @@ constexpr size_t kZeroCopyMaxDoubles = 1024;        // results up to this size a
 constexpr size_t kPeerMaxSummedDoubles = 4096;      // trials sharded: one CTA adds nranks slabs of this many doubles at most
 static_assert(KFBO_MAX_PEERS == kfbo::kMaxPeers, "kfbo.h and kfbo_kernels.h disagree on the peer count");
 static_assert(KFBO_PEER_HANDLE_BYTES == sizeof(cudaIpcMemHandle_t), "cudaIpcMemHandle_t size");
+static_assert(KFBO_AUG_LAYOUT_LANES == kfbo::kAugLayoutLanes && KFBO_AUG_LAYOUT_THREAD == kfbo::kAugLayoutThread, "kfbo.h and kfbo_kernels.h disagree on the layouts");
 static_assert(2 * kfbo::kMaxPeers * sizeof(unsigned) <= kXchgFlagBytes, "flag block");
 
 }  // namespace
@@ -121,6 +122,7 @@ struct kfbo_handle {
     DiscMemo disc_memo[256];
     // the state-augmented variants (kfbo_params.state_dim = 3, 4; kfbo_aug.cuh): their own case / table types
     int N = 2;                                   // state dimension
+    int aug_layout = KFBO_AUG_LAYOUT_THREAD;     // KFBO_OPT_AUG_LAYOUT: which kernel runs an on-device-noise evaluation of N = 3, 4
     kfbo::AugSampleTime h_aug_st[KFBO_MAX_SAMPLE_TIMES]{};
     kfbo::AugSampleTime *d_aug_st = nullptr;     // [D]
     double *d_u = nullptr;                       // [D][kMaxSteps] control table u_[i] per sample time
@@ -691,6 +693,10 @@ int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value)
     case KFBO_OPT_HOST_POLL:
         h->use_poll = value != 0;
         return KFBO_OK;
+    case KFBO_OPT_AUG_LAYOUT:
+        if (value != KFBO_AUG_LAYOUT_LANES && value != KFBO_AUG_LAYOUT_THREAD) return fail(h, KFBO_EINVAL, "kfbo_set_option: aug layout %lld", (long long)value);
+        h->aug_layout = (int)value;
+        return KFBO_OK;
     case KFBO_OPT_PEER_TIMEOUT_MS:
         if (value < 1 || value > 3600000) return fail(h, KFBO_EINVAL, "kfbo_set_option: peer timeout %lld ms", (long long)value);
         h->peer_timeout_ms = value;
@@ -964,8 +970,9 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
             st.k0 = 0; st.nk = D;   // cases are laid out [candidate][sample time]; chunks hold whole candidates
             if (aug) {
                 KFBO_CUDA(h, kfbo::launch_rollout_aug(h->N, false, h->d_aug_cases + first, n, D, 0, h->d_aug_st, h->d_u, h->d_logtab, h->p.seed, (uint32_t)t0,
-                                                      ntrials, nullptr, nullptr, nullptr, 0, nullptr, 0, h->d_partials, h->d_tickets, rollout_sums, h->stream));
-                ++h->last_launches;
+                                                      ntrials, nullptr, nullptr, nullptr, 0, nullptr, 0, h->d_partials, h->d_tickets, rollout_sums, h->stream,
+                                                      h->h_aug_st, h->aug_layout));
+                h->last_launches += h->aug_layout == KFBO_AUG_LAYOUT_THREAD ? D : 1;   // the per-thread layout launches once per sample time
             } else {
                 KFBO_CUDA(h, kfbo::launch_rollout_philox(h->d_cases + first, n, st, h->d_gu, h->d_logtab, h->min_T, h->p.seed, (uint32_t)t0, ntrials,
                                                          nullptr, 0, h->d_partials, h->d_tickets, rollout_sums, h->stream,
@@ -1296,7 +1303,7 @@ int kfbo_eval_philox_trials(kfbo_handle *h, int32_t k, double q_est, double r_es
     if (aug) {
         KFBO_CUDA(h, kfbo::launch_rollout_aug(h->N, false, static_cast<const kfbo::AugCase *>(d_case), 1, 1, k, h->d_aug_st, h->d_u, h->d_logtab, h->p.seed,
                                               trial0, (uint32_t)ntrials, nullptr, nullptr, nullptr, 0, h->d_scratch[4], (size_t)ntrials, d_partials, d_ticket,
-                                              d_sums, h->stream));
+                                              d_sums, h->stream, h->h_aug_st, h->aug_layout));
     } else {
         kfbo::SampleTimeConsts st = h->st;
         st.k0 = k; st.nk = 1;

@@ -212,14 +212,210 @@ rollout_aug(const AugCase *__restrict__ cases, const AugSampleTime *__restrict__
                              kSupplied ? s_red_static : reinterpret_cast<double (*)[4]>(s_tables_raw));
 }
 
+// -----------------------------------------------------------------------------------------
+// The same variants with ONE TRAJECTORY PER THREAD (KFBO_AUG_LAYOUT_THREAD, the default for on-device noise): x, xhat and
+// the whole N x N covariance in the thread's registers, nothing crosses lanes.  It performs lane i's arithmetic of
+// aug_step above for every row i, operation for operation (the products with the structural zeros of Fd and L, which are
+// exact no-ops there, are left out), and draws the same Philox words for the same (trial, lane, step) -- so every
+// trajectory's outputs are the SAME BITS as the rows-across-lanes kernel's (the cost sums add them in another order;
+// test_gpu_aug.py), and the tests' CPU checker pins both.  Why it
+// exists: rows across lanes replicate the scalar part of the step in every lane and pay 45 double shuffles per lane-step;
+// per filter-step this kernel issues a quarter of the instructions (N = 4: 234 FP64 + 2 Philox calls against 4 x 160
+// FP64 + 4 x 132 SHFL).  Why the other one stays: registers -- N (N + 2) doubles of state per thread stop fitting
+// beyond N = 4, the lane layout scales to N = 32 -- and it is the layout BASELINE.json's north_star names.
+// The sample time's constants (Fd, g, L, sqrt R) come by value: one launch per sample time, every use is a
+// constant-bank operand of the FP64 instruction (no register).  The case's Qd sits in shared memory.
+// -----------------------------------------------------------------------------------------
+template <int N>
+struct AugThread {
+    double x[N], xh[N], P[N][N];
+    double kn, ki, sdn, sqn, sdi, sqi;
+};
+
+template <int N, bool kFirst>
+__device__ __forceinline__ void aug_thread_step(const AugSampleTime &st, const double *__restrict__ q /* [N][kAugGroup], shared */,
+                                                const double r_est, AugThread<N> &t, const double u, const double (&nproc)[N],
+                                                const double vobs)
+{
+    // ---- truth and predict: x = Fd x + g u + L n ; xpred = Fd xest + g u ; z = x_0 + sqrt(R) v
+    double xn[N], xp[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double gu = st.g[i] * u;
+        double a = gu, b = gu;
+#pragma unroll
+        for (int j = i; j < N; ++j) {
+            a = fma(st.F[i * kAugGroup + j], t.x[j], a);
+            b = fma(st.F[i * kAugGroup + j], t.xh[j], b);
+        }
+#pragma unroll
+        for (int j = 0; j <= i; ++j) a = fma(st.L[i * kAugGroup + j], nproc[j], a);
+        xn[i] = a; xp[i] = b;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) t.x[i] = xn[i];
+    const double z = fma(st.sr, vobs, t.x[0]);
+    // ---- Ppred = Fd (P Fd^T) + Qd ; Fd(j, k) = Fd(0, k - j)
+    double B[N][N], PP[N][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double b = t.P[i][j];
+#pragma unroll
+            for (int k = j + 1; k < N; ++k) b = fma(t.P[i][k], st.F[k - j], b);
+            B[i][j] = b;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double p = B[i][j] + q[i * kAugGroup + j];
+#pragma unroll
+            for (int d = 1; i + d < N; ++d) p = fma(st.F[i * kAugGroup + i + d], B[i + d][j], p);
+            PP[i][j] = p;
+        }
+    }
+    // ---- gain, update
+    const double s = PP[0][0] + r_est;
+    const double sinv = KFBO_RCP(s);
+    const double nu = z - xp[0];
+    double tj[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) tj[j] = PP[0][j] * sinv;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double c = PP[i][0];
+        t.xh[i] = fma(c * sinv, nu, xp[i]);
+#pragma unroll
+        for (int j = 0; j < N; ++j) t.P[i][j] = (i == 0) ? r_est * tj[j] : fma(-c, tj[j], PP[i][j]);
+    }
+    // ---- NEES by forward elimination of [P | e]
+    double M[N][N], y[N], nees = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        y[i] = t.x[i] - t.xh[i];
+#pragma unroll
+        for (int j = 0; j < N; ++j) M[i][j] = t.P[i][j];
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double rinv = KFBO_RCP(M[k][k]);
+        nees = fma(y[k] * y[k], rinv, nees);
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            const double f = M[i][k] * rinv;
+#pragma unroll
+            for (int j = k + 1; j < N; ++j) M[i][j] = fma(-f, M[k][j], M[i][j]);
+            y[i] = fma(-f, y[k], y[i]);
+        }
+    }
+    const double nu_s = nu * sinv;
+    if (kFirst) { t.kn = nees; t.ki = nu_s * nu; }
+    const double dn = nees - t.kn, di = fma(nu_s, nu, -t.ki);
+    t.sdn += dn; t.sqn = fma(dn, dn, t.sqn);
+    t.sdi += di; t.sqi = fma(di, di, t.sqi);
+}
+
+template <int N>
+__global__ void __launch_bounds__(kThreads, 3)
+rollout_aug_thread(const AugCase *__restrict__ cases, const __grid_constant__ AugSampleTime st, int nk, int k,
+                   const double *__restrict__ u_tab, const math::LogTables *__restrict__ logtab, const __grid_constant__ PhiloxKeys key,
+                   uint32_t trial0, uint32_t ntrials, int tiles, double *__restrict__ per_trial, size_t per_trial_ld,
+                   double *__restrict__ partials, unsigned *__restrict__ tickets, double *__restrict__ sums)
+{
+    static_assert(N >= 2 && N <= kAugGroup, "matrices are stored with a row stride of kAugGroup");
+    extern __shared__ __align__(16) unsigned char s_tables_raw[];
+    __shared__ double s_q[N * kAugGroup];
+    math::LogTables &s_log = *reinterpret_cast<math::LogTables *>(s_tables_raw);
+    const int case_idx = blockIdx.y * nk + k, tile = blockIdx.x;
+    const AugCase &cs = cases[case_idx];
+    const int T = cs.T;
+    const double r_est = cs.r_est;
+    const uint32_t stream = cs.stream, stream_x = cs.stream_x;
+    const int out_slot = cs.out_slot;
+    if (threadIdx.x < N * kAugGroup) s_q[threadIdx.x] = cs.qd[threadIdx.x];
+    load_noise_tables(&s_log, logtab);
+    __syncthreads();
+    const uint32_t local = (uint32_t)tile * kThreads + threadIdx.x;
+    const bool live = local < ntrials;
+    const uint32_t trial = trial0 + (live ? local : ntrials - 1u);   // padding threads repeat the last trajectory
+    AugThread<N> t;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {                                    // x = x0 + N(0, P0), x0 = 0, P0 = I; xhat = 0
+        double a, b;
+        const uint4 r0 = philox_at(trial, stream, stream_x, 0u, (uint32_t)i, key);
+        math::normal_pair(r0.x, r0.y, s_log, a, b);
+        t.x[i] = a; t.xh[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) t.P[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+    t.kn = 0.0; t.ki = 0.0; t.sdn = 0.0; t.sqn = 0.0; t.sdi = 0.0; t.sqi = 0.0;
+    const int npairs = (T + 1) >> 1;
+    for (int p = 0; p < npairs; ++p) {
+        // the step pair 2p, 2p+1: call i's words (x, y) -> row i's process normals of the two steps, call 0's (z, w) -> the observation normals
+        double na[N], nb[N], oa, ob;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const uint4 r = philox_at(trial, stream, stream_x, (uint32_t)p + 1u, (uint32_t)i, key);
+            math::normal_pair(r.x, r.y, s_log, na[i], nb[i]);
+            if (i == 0) math::normal_pair(r.z, r.w, s_log, oa, ob);
+        }
+        const int s = 2 * p;
+        if (p == 0) aug_thread_step<N, true>(st, s_q, r_est, t, __ldg(u_tab + s), na, oa);
+        else        aug_thread_step<N, false>(st, s_q, r_est, t, __ldg(u_tab + s), na, oa);
+        if (s + 1 < T) aug_thread_step<N, false>(st, s_q, r_est, t, __ldg(u_tab + s + 1), nb, ob);
+    }
+    double out[4] = {0.0, 0.0, 0.0, 0.0};
+    {
+        Traj tf;
+        tf.kn = t.kn; tf.ki = t.ki; tf.sdn = t.sdn; tf.sqn = t.sqn; tf.sdi = t.sdi; tf.sqi = t.sqi;
+        double o[4];
+        traj_finish(tf, T, o);
+        if (live) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) out[m] = o[m];
+            if (per_trial != nullptr) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) per_trial[((size_t)out_slot * 4 + m) * per_trial_ld + local] = o[m];
+            }
+        }
+    }
+    __syncthreads();
+    block_reduce_and_publish(out, case_idx, tile, tiles, out_slot, partials, tickets, sums, reinterpret_cast<double (*)[4]>(s_tables_raw));
+}
+
 int aug_tiles(size_t ntrials) { return (int)((ntrials * kAugGroup + kThreads - 1) / kThreads); }
 
 cudaError_t launch_rollout_aug(int N, bool supplied, const AugCase *d_cases, int ncases, int nk, int k0, const AugSampleTime *d_sts,
                                const double *d_u, const void *d_logtab, uint64_t seed, uint32_t trial0, uint32_t ntrials,
                                const double *d_x0noise, const double *d_w, const double *d_v, size_t B, double *d_per_trial,
-                               size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums, cudaStream_t stream)
+                               size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums, cudaStream_t stream,
+                               const AugSampleTime *h_sts, int layout)
 {
     if (ncases <= 0 || ntrials == 0) return cudaSuccess;
+    if (!supplied && layout == kAugLayoutThread && h_sts != nullptr) {
+        // one trajectory per thread: one launch per sample time, its constants by value
+        const int tiles = rollout_tiles(ntrials);
+        const dim3 grid((unsigned)tiles, (unsigned)(ncases / nk), 1u);
+        const size_t smem = sizeof(math::LogTables);
+        auto go = [&](auto *kernel) -> cudaError_t {
+            const cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), 0, smem);
+            if (e != cudaSuccess) return e;
+            for (int k = 0; k < nk; ++k) {
+                kernel<<<grid, kThreads, smem, stream>>>(d_cases, h_sts[k0 + k], nk, k, d_u + (size_t)(k0 + k) * kMaxSteps,
+                                                          static_cast<const math::LogTables *>(d_logtab), expand_philox_key(seed), trial0,
+                                                          ntrials, tiles, d_per_trial, per_trial_ld, d_partials, d_tickets, d_sums);
+                const cudaError_t el = cudaGetLastError();
+                if (el != cudaSuccess) return el;
+            }
+            return cudaSuccess;
+        };
+        if (N == 3) return go(rollout_aug_thread<3>);
+        if (N == 4) return go(rollout_aug_thread<4>);
+        return cudaErrorInvalidValue;
+    }
     const int tiles = aug_tiles(ntrials);
     const dim3 grid((unsigned)tiles, (unsigned)(ncases / nk), (unsigned)nk);
     const size_t smem = supplied ? 0 : sizeof(math::LogTables);

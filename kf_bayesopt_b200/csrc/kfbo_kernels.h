@@ -178,7 +178,10 @@ int aug_tiles(size_t ntrials);        // CTAs per case: 32 trajectories per 128-
 cudaError_t launch_rollout_aug(int N, bool supplied, const AugCase *d_cases, int ncases, int nk, int k0, const AugSampleTime *d_sts,
                                const double *d_u, const void *d_logtab, uint64_t seed, uint32_t trial0, uint32_t ntrials,
                                const double *d_x0noise, const double *d_w, const double *d_v, size_t B, double *d_per_trial,
-                               size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums, cudaStream_t stream);
+                               size_t per_trial_ld, double *d_partials, unsigned *d_tickets, double *d_sums, cudaStream_t stream,
+                               const AugSampleTime *h_sts = nullptr /* host copy of d_sts: the per-thread layout takes a sample time's constants by value */,
+                               int layout = 0);
+constexpr int kAugLayoutLanes = 0, kAugLayoutThread = 1;   // KFBO_AUG_LAYOUT_* of kfbo.h
 
 cudaError_t launch_dfma_chain(double *d_out, int blocks, int iters, bool reg_multiplier, cudaStream_t stream);
 

@@ -1,5 +1,6 @@
 """GPU parity tests of the STATE-AUGMENTED variants (kfbo_params.state_dim = 3, 4; kf_bayesopt_b200/csrc/kfbo_aug.cuh: one
-covariance row per lane of a 4-lane group) against their oracle (oracle/kfbo_oracle_aug.c) through the C ABI.
+trajectory per thread -- the default with on-device noise -- or one covariance row per lane of a 4-lane group,
+KFBO_OPT_AUG_LAYOUT) against their oracle (oracle/kfbo_oracle_aug.c) through the C ABI.
 
 The reference has no such variant (include/system_models.hpp:11-12 fixes N = 2): the oracle states the generalisation
 and tests/test_oracle_aug.py pins it (scipy expm, closed forms, a numpy filter, N = 2 == the main oracle bit for bit).
@@ -44,12 +45,22 @@ def test_supplied_noise_matches_the_oracle(kfbo, oracle, N):
             assert rel_err(sums[c], want.sum(axis=1)) < RTOL, (N, B, T, c)
 
 
+LAYOUTS = ["thread", "lanes"]
+
+
+def _set_layout(kfbo, ev, layout):
+    from kf_bayesopt_b200 import _lib
+    ev.set_option(_lib.OPT_AUG_LAYOUT, {"thread": _lib.AUG_LAYOUT_THREAD, "lanes": _lib.AUG_LAYOUT_LANES}[layout])
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("N", [3, 4])
-def test_philox_trials_match_the_oracle_draw_for_draw(kfbo, oracle, N):
+def test_philox_trials_match_the_oracle_draw_for_draw(kfbo, oracle, N, layout):
     seed = 0x0123456789ABCDEF
     rv = kfbo.ReadParaVehicle(nsimruns_=100, cpu_core_number_=1, state_dof_=N)
     for times in (TIMES, [(0.1, 2), (0.5, 3)], [(0.1, 7), (0.05, 1999)]):      # even and odd step counts (the noise comes in step pairs)
         with kfbo.CostEvaluator(rv, times, seed=seed, state_dim=N) as ev:
+            _set_layout(kfbo, ev, layout)
             for k, (dt, T) in enumerate(times):
                 for qe, re, stream, trial0, n in [(1.0, 0.1, 0, 0, 100), (0.3, 0.7, (1 << 40) + 77, 0xFFFFFF00, 37)]:
                     got = ev.eval_philox_trials(k, qe, re, stream, trial0, n)
@@ -58,12 +69,39 @@ def test_philox_trials_match_the_oracle_draw_for_draw(kfbo, oracle, N):
 
 
 @pytest.mark.parametrize("N", [3, 4])
-def test_batch_costs_match_the_oracle_and_the_selection_is_identical(kfbo, oracle, N):
+def test_the_two_layouts_give_the_same_bits(kfbo, N):
+    # one trajectory per thread performs lane i's arithmetic for every row i, on the same Philox words: the per-trial outputs
+    # are bit-identical; the cost sums add them in another order (32 / 128 trajectories per CTA) and agree to rounding.
+    # Ragged tiles of either kernel, odd and even step counts, the shortest trial (T = 2: one step pair).
+    from kf_bayesopt_b200 import _lib
+    seed = 0xFEEDFACE12345678
+    for B, times in [(1000, TIMES), (33, [(0.1, 7), (1.0, 64)]), (129, [(0.25, 2)])]:
+        rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=1, state_dof_=N)
+        q, r = np.array([1.0, 0.2, 3.0]), np.array([0.1, 0.9, 0.03])
+        got = {}
+        for layout in LAYOUTS:
+            with kfbo.CostEvaluator(rv, times, seed=seed, max_candidates=len(q), state_dim=N) as ev:
+                _set_layout(kfbo, ev, layout)
+                ev.eval_batch(q, r)
+                sums = ev.last_sums(len(q)).copy()
+                pt = [ev.eval_philox_trials(k, 0.7, 0.3, 5 + k, 11, B) for k in range(len(times))]
+                launches = ev.last_kernel_ms()[1]
+            got[layout] = (sums, pt, launches)
+        assert rel_err(got["thread"][0], got["lanes"][0]) < 1e-13, (N, B)
+        for a, b in zip(got["thread"][1], got["lanes"][1]):
+            assert np.array_equal(a, b), (N, B)
+        assert np.all(np.isfinite(got["thread"][0]))
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("N", [3, 4])
+def test_batch_costs_match_the_oracle_and_the_selection_is_identical(kfbo, oracle, N, layout):
     B, cores, seed = 96, 4, 7
     rv = kfbo.ReadParaVehicle(nsimruns_=B, cpu_core_number_=cores, state_dof_=N)
     q, r = np.array([1.0, 0.1, 5.0, 0.5]), np.array([0.1, 0.1, 1.0, 0.01])
     D = len(TIMES)
     with kfbo.CostEvaluator(rv, TIMES, seed=seed, max_candidates=len(q), state_dim=N) as ev:
+        _set_layout(kfbo, ev, layout)
         res = ev.eval_batch(q, r)
         sums = ev.last_sums(len(q))
         ev.set_eval_counter(0)
