@@ -277,6 +277,34 @@ def run_bo_loop(args):
     emit(line)
 
 
+def leg_cfg5(ref_node_ms=None):
+    """BASELINE.json configs[4] as a leg of the default line (N = 1): the 200-evaluation BO loop of kfbo_bo_loop over the
+    noise/cost topic contract, without the reference's sleeps (the measured with-sleeps run and the reference node's own
+    200 callbacks are `--workload cfg5`, profiles/bench_cfg5_r2*.json).  ref_node_ms: the reference node's callback time per
+    message measured by the cfg1 leg of this same run."""
+    exe = os.path.join(ROOT, "kf_bayesopt_b200", "bin", "kfbo_bo_loop")
+    if not os.path.exists(exe):
+        return {"unavailable": "kf_bayesopt_b200/bin/kfbo_bo_loop is not built (make -C kf_bayesopt_b200/host)"}
+    try:
+        out = subprocess.run([exe, "--iterations", "180", "--init", "20", "--quiet"], capture_output=True, text=True, check=True, timeout=120)
+        loop = json.loads(next(l for l in out.stdout.splitlines() if l.startswith("{")))
+    except Exception as e:                                   # a leg, not the headline: report, do not fail the line
+        return {"unavailable": f"kfbo_bo_loop failed: {e}"}
+    n = loop["iterations"]
+    leg = {"workload": "cfg5: Bayesian-optimisation loop, %d cost evaluations (20 initial + 180 iterations) of 200 trials x 201 steps x 2 "
+                       "sample times over the noise/cost topic contract; optimiser = GP/EI stand-in for the absent bayesopt library "
+                       "(settings of bayesParams.yaml)" % n,
+           "iterations": n, "wall_s": loop["wall_s"], "evaluator_s": loop["evaluator_s"],
+           "evaluator_ms_per_iteration": loop["evaluator_ms_per_iteration"], "optimiser_s": loop["optimiser_s"],
+           "wall_s_with_the_reference_sleeps": loop["wall_s"] + 0.5 * n, "best_cost": loop["best_cost"], "best_x": loop["best_x"],
+           "note": "robot1d_bayesopt.cpp:91,96 sleeps 0.5 s per iteration: with them the loop is sleep-bound on either evaluator"}
+    if ref_node_ms:
+        leg["reference_node_ms_per_iteration"] = ref_node_ms
+        leg["evaluator_speedup"] = ref_node_ms / loop["evaluator_ms_per_iteration"]
+        leg["wall_s_with_the_reference_node_estimate"] = loop["optimiser_s"] + ref_node_ms * 1e-3 * n
+    return leg
+
+
 def emit(line: dict) -> None:
     """The ONE JSON line, on the real stdout."""
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
@@ -751,6 +779,8 @@ def main():
         if rank == 0:
             extra.update(leg_default_workload(kf, torch, stream, local_rank, with_cpu=(world == 1 and not args.no_cpu_baseline)))
             extra["state_augmented"] = leg_augmented(kf, torch, stream, local_rank, line_extra.get("roofline", {}).get("peak"))
+            if world == 1:
+                extra["cfg5"] = leg_cfg5(extra.get("cfg1", {}).get("cpu_baseline", {}).get("latency_ms"))
             if world == 1:     # single GPU: the CUDA path against the oracle on a 300-trial slice of the headline workload's streams
                 seed = 0x4B46424F00002026
                 extra["parity_vs_oracle"] = {
