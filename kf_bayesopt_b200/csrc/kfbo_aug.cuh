@@ -226,6 +226,12 @@ rollout_aug(const AugCase *__restrict__ cases, const AugSampleTime *__restrict__
 // The sample time's constants (Fd, g, L, sqrt R) come by value: one launch per sample time, every use is a
 // constant-bank operand of the FP64 instruction (no register).  The case's Qd sits in shared memory.
 // -----------------------------------------------------------------------------------------
+// CTAs per SM the per-thread kernels are compiled for (registers per thread <= 65536 / (128 x this)).  Measured
+// (profiles/variants_aug_r2q.txt): N = 3 fits 126 registers without a spill, 4 CTAs per SM 6.40 ms against 6.63 with 3;
+// N = 4 needs 168 (3 CTAs: 9.86 ms; 2 CTAs with 202 registers and no spill at all: 10.13).
+#ifndef KFBO_AUG_THREAD_MIN_BLOCKS
+#define KFBO_AUG_THREAD_MIN_BLOCKS(N) ((N) == 3 ? 4 : 3)
+#endif
 template <int N>
 struct AugThread {
     double x[N], xh[N], P[N][N];
@@ -319,7 +325,7 @@ __device__ __forceinline__ void aug_thread_step(const AugSampleTime &st, const d
 }
 
 template <int N>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, KFBO_AUG_THREAD_MIN_BLOCKS(N))
 rollout_aug_thread(const AugCase *__restrict__ cases, const __grid_constant__ AugSampleTime st, int nk, int k,
                    const double *__restrict__ u_tab, const math::LogTables *__restrict__ logtab, const __grid_constant__ PhiloxKeys key,
                    uint32_t trial0, uint32_t ntrials, int tiles, double *__restrict__ per_trial, size_t per_trial_ld,
