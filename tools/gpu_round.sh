@@ -17,5 +17,7 @@ ncu --set full --clock-control none --import-source on -k regex:rollout_philox -
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-supplied --no-reduced --no-extra > $OUT/ncu_full_philox_$TAG.log 2>&1; echo "ncu philox rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:rollout_supplied_bulk -s 3 -c 1 -f -o $OUT/prof_supplied_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-reduced --no-extra > $OUT/ncu_full_supplied_$TAG.log 2>&1; echo "ncu supplied rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:rollout_aug_thread -s 20 -c 1 -f -o $OUT/prof_aug_thread_$TAG \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-supplied > $OUT/ncu_full_aug_$TAG.log 2>&1; echo "ncu aug thread (N = 4) rc=$?"
 fi
 ls -la $OUT | tail -12
