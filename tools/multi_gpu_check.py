@@ -89,6 +89,21 @@ for mode in (kf.SHARD_TRIALS, kf.SHARD_CANDIDATES):
             few_nccl = ev.eval_batch_raw(q[:1], r[:1])["cost"].copy()
             np.testing.assert_allclose(np.stack(run_peer), np.stack(run_nccl), rtol=1e-10, atol=1e-13)
             np.testing.assert_allclose(few_peer, few_nccl, rtol=1e-10, atol=1e-13)
+# the state-augmented variants (both layouts) shard the same way: trials-sharded sums == one GPU's to rounding
+aug = {}
+for N in (3, 4):
+    rva = kf.ReadParaVehicle(nsimruns_=1031, cpu_core_number_=1, state_dof_=N)
+    for layout in (_lib.AUG_LAYOUT_THREAD, _lib.AUG_LAYOUT_LANES):
+        with kf.CostEvaluator(rva, times, seed=seed, max_candidates=3, device=local, state_dim=N) as ev:
+            ev.set_option(_lib.OPT_AUG_LAYOUT, layout)
+            init_comm(ev, kf.SHARD_TRIALS)
+            ev.eval_batch(q[:3], r[:3])
+            aug[(N, layout)] = ev.last_sums(3).copy()
+        if rank == 0:
+            with kf.CostEvaluator(rva, times, seed=seed, max_candidates=3, device=local, state_dim=N) as ev1:
+                ev1.set_option(_lib.OPT_AUG_LAYOUT, layout)
+                ev1.eval_batch(q[:3], r[:3])
+                np.testing.assert_allclose(aug[(N, layout)], ev1.last_sums(3), rtol=1e-12, err_msg=f"aug N={N} layout={layout}")
 if rank == 0:
     with kf.CostEvaluator(rv, times, seed=seed, max_candidates=C, device=local) as ev:
         out = ev.eval_batch(q, r)
@@ -101,7 +116,7 @@ if rank == 0:
     assert i_t == idx
     s_c, c_c, i_c, o_c = res[kf.SHARD_CANDIDATES]
     assert np.array_equal(s_c, sums) and np.array_equal(c_c, cost) and i_c == idx and np.array_equal(o_c, one)
-    print(f"multi_gpu_check ok: {world} ranks, trials-sharded max rel diff "
+    print(f"multi_gpu_check ok: {world} ranks (state-augmented N = 3, 4, both layouts, included), trials-sharded max rel diff "
           f"{np.max(np.abs(s_t - sums) / np.abs(sums)):.2e}, candidates-sharded bit-identical; the sums met by: {paths}", flush=True)
 dist.barrier()
 dist.destroy_process_group()

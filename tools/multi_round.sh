@@ -17,6 +17,7 @@ try:
 except Exception as e:
     print("no line:", e, open(sys.argv[1]).read()[-2000:])
 PY
+timeout 300 $TR --master-port 29665 tools/soak.py ${SOAK_SECONDS:-15} 2>&1 | grep -E "soak ok|Error|error|assert" | tee $OUT/soak_n${N}_$TAG.txt; echo "soak n$N rc=${PIPESTATUS[0]}"
 P=29670
 for V in "graph_off KFBO_BENCH_GRAPH=0" "poll_off KFBO_BENCH_POLL=0"; do
   set -- $V; P=$((P+1))
