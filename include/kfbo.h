@@ -220,6 +220,10 @@ enum { KFBO_OPT_SUPPLIED_KERNEL = 1, KFBO_OPT_BULK_SMEM_PAD = 2 /* extra dynamic
                                         thread, the whole covariance in its registers; KFBO_AUG_LAYOUT_LANES one covariance
                                         row per lane of a 4-lane group (the layout that scales beyond N = 4; supplied noise
                                         always runs it).  Same Philox words, same arithmetic per row: same bits. */,
+       KFBO_OPT_GROUP_THREADS = 12 /* kfbo_group_set_option only. 1 (default): a device group runs the launch, the exchange and the
+                                        wait of an evaluation on all its devices at once, one persistent host thread per device
+                                        beyond the first (they spin for 200 us after an evaluation, then sleep); 0: the calling
+                                        thread serves one device after the other */,
        KFBO_OPT_RESERVE_SUPPLIED_TRIALS = 7 /* pre-size the scratch of the parity entry points (kfbo_eval_supplied,
                                         kfbo_eval_philox_trials, kfbo_trace_trial) for this many trials x max_candidates
                                         candidates: after it they allocate nothing, like kfbo_eval* */ };

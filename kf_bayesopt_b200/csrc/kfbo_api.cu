@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <new>
 #include <string>
@@ -738,6 +739,14 @@ static int check_point_candidate(kfbo_handle *h, const char *who, double q, doub
 // An evaluation in three phases, so that a device group (kfbo_group_*) can run each phase on all its devices before
 // the next:  launch (constants, copies, rollout kernels)  ->  reduce (the all-reduce of the cost sums)  ->
 // collect (result copy, wait, cost assembly).  kfbo_eval_batch is the three in a row on one handle.
+// Whether the cost sums of an evaluation with `nsums` doubles will meet over peer memory (else: one ncclAllReduce).  The same
+// answer on every rank / device: it depends on the batch size and on options only.
+static bool sums_meet_in_peer_memory(const kfbo_handle *h, size_t nsums)
+{
+    return h->comm && h->peer_ready && h->reduce_pref != KFBO_REDUCE_NCCL && nsums <= h->xchg_cap &&
+           (h->shard_mode == KFBO_SHARD_CANDIDATES || nsums <= kPeerMaxSummedDoubles);
+}
+
 static int eval_check(kfbo_handle *h, int32_t C, const double *q_est, const double *r_est, const void *out)
 {
     if (h->poisoned)
@@ -832,8 +841,7 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
     const size_t nsums = (size_t)C * D * 4;
     // ---- how the sums of the ranks will meet (the same decision on every rank: it depends on C, D and options only)
     const bool gather = h->shard_mode == KFBO_SHARD_CANDIDATES;
-    const bool use_peer = h->comm && h->peer_ready && h->reduce_pref != KFBO_REDUCE_NCCL && nsums <= h->xchg_cap &&
-                          (gather || nsums <= kPeerMaxSummedDoubles);
+    const bool use_peer = sums_meet_in_peer_memory(h, nsums);
     const uint32_t ntrials = (uint32_t)(t1 - t0);
     const int tiles = aug ? kfbo::aug_tiles(ntrials) : kfbo::rollout_tiles(ntrials);
     int step = cases_per_launch(h, std::max(tiles, 1));
@@ -1445,7 +1453,87 @@ struct kfbo_group {
     std::string err;
     bool poisoned = false;      // an evaluation failed part-way: the devices' counters / exchange generations may disagree
     std::string poison_why;
+    // One persistent host thread per device beyond the first (KFBO_OPT_GROUP_THREADS, default on): the launch, the exchange and
+    // the wait of an evaluation run on all devices at once instead of one device after the other -- a single thread enqueues on 8
+    // devices in ~120 us, which is the start-up skew of the last device and 7 % of a 1.7 ms evaluation.  A worker spins on the task
+    // generation for kGroupSpinUs after its last task (back-to-back evaluations find it awake), then blocks on the condition
+    // variable (an idle node burns no cores).  The caller's thread is device 0's worker.
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<uint32_t> task_gen{0};
+    std::atomic<int> pending{0}, sleepers{0};
+    std::atomic<bool> quit{false};
+    std::function<int(kfbo_handle *)> task;
+    std::vector<int> rcs;
+    bool use_threads = true;
 };
+
+namespace {
+
+constexpr int kGroupSpinUs = 200;
+
+inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    sched_yield();
+#endif
+}
+
+void group_worker(kfbo_group *g, size_t i)
+{
+    using clk = std::chrono::steady_clock;
+    cudaSetDevice(g->hs[i]->device);          // once: every CUDA call of this thread is for this device
+    uint32_t seen = 0;
+    for (;;) {
+        const clk::time_point t0 = clk::now();
+        unsigned spins = 0;
+        while (g->task_gen.load() == seen && !g->quit.load()) {
+            cpu_relax();
+            if ((++spins & 0xFFu) == 0 && clk::now() - t0 > std::chrono::microseconds(kGroupSpinUs)) break;
+        }
+        if (g->task_gen.load() == seen && !g->quit.load()) {
+            std::unique_lock<std::mutex> lk(g->mu);
+            g->sleepers.fetch_add(1);
+            g->cv.wait(lk, [&] { return g->task_gen.load() != seen || g->quit.load(); });
+            g->sleepers.fetch_sub(1);
+        }
+        if (g->quit.load()) return;
+        seen = g->task_gen.load();
+        g->rcs[i] = g->task(g->hs[i]);
+        g->pending.fetch_sub(1);
+    }
+}
+
+// fn on every device of the group at once: devices 1.. on their workers, device 0 on the calling thread.  Returns when all are done.
+void group_run(kfbo_group *g, const std::function<int(kfbo_handle *)> &fn)
+{
+    g->task = fn;
+    g->pending.store((int)g->workers.size());
+    g->task_gen.fetch_add(1);
+    if (g->sleepers.load() > 0) {
+        std::lock_guard<std::mutex> lk(g->mu);
+        g->cv.notify_all();
+    }
+    g->rcs[0] = fn(g->hs[0]);
+    while (g->pending.load() > 0) cpu_relax();
+}
+
+void group_stop_workers(kfbo_group *g)
+{
+    if (g->workers.empty()) return;
+    g->quit.store(true);
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        g->cv.notify_all();
+    }
+    for (std::thread &t : g->workers) t.join();
+    g->workers.clear();
+}
+
+}  // namespace
 
 static int group_fail(kfbo_group *g, int code, const std::string &what)
 {
@@ -1519,6 +1607,12 @@ int kfbo_group_create(const kfbo_params *p, int32_t n_devices, const int32_t *de
                 for (int j = 0; j < n_devices; ++j) g->hs[i]->peer_base[j] = g->hs[j]->d_xchg;
                 g->hs[i]->peer_ready = true;
             }
+        g->rcs.assign((size_t)n_devices, KFBO_OK);
+        try {
+            for (int i = 1; i < n_devices; ++i) g->workers.emplace_back(group_worker, g, (size_t)i);
+        } catch (...) {        // no threads to be had: the group works without them, one device after the other
+            group_stop_workers(g);
+        }
     }
     *out = g;
     return KFBO_OK;
@@ -1527,6 +1621,7 @@ int kfbo_group_create(const kfbo_params *p, int32_t n_devices, const int32_t *de
 void kfbo_group_destroy(kfbo_group *g)
 {
     if (!g) return;
+    group_stop_workers(g);
     for (kfbo_handle *h : g->hs) kfbo_destroy(h);
     delete g;
 }
@@ -1556,10 +1651,26 @@ static int group_eval_impl(kfbo_group *g, int32_t C, const double *q_est, const 
         return code;
     };
     const uint8_t *bad = g->hs[0]->cand_bad.data();
-    for (kfbo_handle *h : g->hs) {
-        h->n_bad = g->hs[0]->n_bad;
-        if ((rc = check(h, eval_launch(h, C, q_est, r_est, bad, compact)))) return abort_all(rc);
+    for (kfbo_handle *h : g->hs) h->n_bad = g->hs[0]->n_bad;
+    // All devices at once (one host thread per device) when the sums will meet in peer memory: launch, exchange kernel and
+    // wait are independent per device there -- the exchange itself synchronises the devices, as between processes.  (The NCCL
+    // fallback keeps the one-thread order below: its grouped call is made from one thread.)
+    bool peer_path = true;
+    for (kfbo_handle *h : g->hs) peer_path = peer_path && sums_meet_in_peer_memory(h, (size_t)C * h->D * 4);
+    if (g->use_threads && !g->workers.empty() && peer_path) {
+        group_run(g, [&](kfbo_handle *h) -> int {
+            int r = eval_launch(h, C, q_est, r_est, bad, compact);
+            if (!r && h->reduce_path < 2) r = fail(h, KFBO_ESTATE, "device group: the devices did not take the peer-memory path together");
+            if (!r) r = eval_reduce(h, C, false);
+            if (r) return r;       // this device is out; the others run into the exchange's timeout and report KFBO_EPEER
+            return h == g->hs[0] ? eval_collect(h, C, out, cost, max_cost, index_max) : eval_collect(h, C, nullptr);
+        });
+        for (size_t i = 0; i < g->hs.size(); ++i)
+            if (g->rcs[i]) return abort_all(check(g->hs[i], g->rcs[i]));
+        return KFBO_OK;
     }
+    for (kfbo_handle *h : g->hs)
+        if ((rc = check(h, eval_launch(h, C, q_est, r_est, bad, compact)))) return abort_all(rc);
     if (g->hs.size() > 1 && g->hs[0]->reduce_path >= 2) {   // the sums met in peer memory (every device took the same path)
         for (kfbo_handle *h : g->hs)
             if ((rc = check(h, eval_reduce(h, C, false)))) return abort_all(rc);
@@ -1626,6 +1737,7 @@ int kfbo_group_last_kernel_ms(const kfbo_group *g, double *ms_max, int32_t *laun
 int kfbo_group_set_option(kfbo_group *g, int32_t option, int64_t value)
 {
     if (!g) return KFBO_EINVAL;
+    if (option == KFBO_OPT_GROUP_THREADS) { g->use_threads = value != 0; return KFBO_OK; }
     for (kfbo_handle *h : g->hs) {
         const int rc = kfbo_set_option(h, option, value);
         if (rc) { g->err = h->err; return rc; }
