@@ -84,6 +84,17 @@ def test_device_group_matches_single_device(kfbo):
             gr.set_eval_counter(50)
             run_b = [gr.eval([0.4 + 0.05 * i], [0.1]).cost.copy() for i in range(12)]
             np.testing.assert_allclose(np.stack(run_a), np.stack(run_b), rtol=1e-10, atol=1e-13)
+            # one host thread per device (the default, above) or the calling thread serving one device after the other: the
+            # same launches in another order on the host -- the same bits
+            gr.set_option(_lib.OPT_REDUCE, _lib.REDUCE_AUTO)
+            gr.set_option(_lib.OPT_GROUP_THREADS, 0)
+            gr.set_eval_counter(0)
+            got_1t = gr.eval_batch_raw(q, r)
+            assert np.array_equal(gr.last_sums(C), sums) and np.array_equal(got_1t["cost"], got["cost"])
+            gr.set_eval_counter(50)
+            run_c = [gr.eval([0.4 + 0.05 * i], [0.1]).cost.copy() for i in range(12)]
+            assert all(np.array_equal(a, c) for a, c in zip(run_a, run_c))
+            gr.set_option(_lib.OPT_GROUP_THREADS, 1)
         if mode == kfbo.SHARD_CANDIDATES:                               # every slot written by one device, the others add 0.0
             assert np.array_equal(sums, want_sums) and np.array_equal(got["cost"], want["cost"])
         else:                                                           # the same trials, summed in another order
