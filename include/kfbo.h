@@ -224,6 +224,11 @@ enum { KFBO_OPT_SUPPLIED_KERNEL = 1, KFBO_OPT_BULK_SMEM_PAD = 2 /* extra dynamic
                                         wait of an evaluation on all its devices at once, one persistent host thread per device
                                         beyond the first (they spin for 200 us after an evaluation, then sleep); 0: the calling
                                         thread serves one device after the other */,
+       KFBO_OPT_INJECT_FAULT = 13 /* fault injection for tests: 1 makes the NEXT evaluation of this handle fail with KFBO_ECUDA before
+                                        anything is launched on its device -- a rank (or, through kfbo_group_handle, a device
+                                        of a group) dropping out of a multi-GPU evaluation.  The others then see KFBO_EPEER
+                                        after KFBO_OPT_PEER_TIMEOUT_MS and every handle involved refuses further evaluations
+                                        with KFBO_ESTATE (tests/test_gpu_multi.py) */,
        KFBO_OPT_RESERVE_SUPPLIED_TRIALS = 7 /* pre-size the scratch of the parity entry points (kfbo_eval_supplied,
                                         kfbo_eval_philox_trials, kfbo_trace_trial) for this many trials x max_candidates
                                         candidates: after it they allocate nothing, like kfbo_eval* */ };

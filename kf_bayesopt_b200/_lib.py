@@ -27,6 +27,7 @@ OPT_HOST_POLL = 9
 OPT_SMALL_LAUNCH = 10
 OPT_AUG_LAYOUT = 11
 OPT_GROUP_THREADS = 12
+OPT_INJECT_FAULT = 13
 AUG_LAYOUT_LANES, AUG_LAYOUT_THREAD = 0, 1
 STREAM_BITS = 62
 TRIAL_STREAM_BASE = 1 << 61

@@ -156,6 +156,7 @@ struct kfbo_handle {
     // evaluation counters and exchange generations may no longer agree, so every later evaluation fails fast
     bool poisoned = false;
     std::string poison_why;
+    bool inject_fault = false;             // KFBO_OPT_INJECT_FAULT (tests): the next launch of this handle fails before anything is enqueued
     std::vector<Case> sup_cases;           // host scratch of the supplied-noise entry points (grow-only)
     std::vector<double> sup_sums;
     int supplied_kernel = kfbo::kSuppliedAuto;
@@ -694,6 +695,9 @@ int kfbo_set_option(kfbo_handle *h, int32_t option, int64_t value)
     case KFBO_OPT_HOST_POLL:
         h->use_poll = value != 0;
         return KFBO_OK;
+    case KFBO_OPT_INJECT_FAULT:
+        h->inject_fault = value != 0;
+        return KFBO_OK;
     case KFBO_OPT_AUG_LAYOUT:
         if (value != KFBO_AUG_LAYOUT_LANES && value != KFBO_AUG_LAYOUT_THREAD) return fail(h, KFBO_EINVAL, "kfbo_set_option: aug layout %lld", (long long)value);
         h->aug_layout = (int)value;
@@ -808,6 +812,10 @@ static int eval_launch(kfbo_handle *h, int32_t C, const double *q_est, const dou
 {
     using clk = std::chrono::steady_clock;
     KFBO_ON_DEVICE(h);
+    if (h->inject_fault) {      // a rank / device that drops out of a multi-GPU evaluation, for the tests of what the others do then
+        h->inject_fault = false;
+        return fail(h, KFBO_ECUDA, "injected fault (KFBO_OPT_INJECT_FAULT): nothing was launched on device %d", h->device);
+    }
     const int D = h->D;
     int64_t c0 = 0, c1 = C, t0 = 0, t1 = h->b_eff;
     if (h->comm) {

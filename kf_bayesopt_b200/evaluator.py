@@ -447,6 +447,15 @@ class CostEvaluatorGroup:
     def set_option(self, option: int, value: int) -> None:
         self._check(self._lib.kfbo_group_set_option(self._g, option, value))
 
+    def set_device_option(self, i: int, option: int, value: int) -> None:
+        """An option of ONE device's handle of the group (kfbo_group_handle + kfbo_set_option) -- the tests' fault injection."""
+        h = self._lib.kfbo_group_handle(self._g, i)
+        if not h:
+            raise ValueError(f"the group has no device {i}")
+        rc = self._lib.kfbo_set_option(h, option, value)
+        if rc:
+            raise KfboError(rc, (self._lib.kfbo_last_error(h) or b"").decode())
+
     def last_reduce_path(self) -> str:
         return _lib.REDUCE_PATHS.get(self._lib.kfbo_last_reduce_path(self._lib.kfbo_group_handle(self._g, 0)), "?")
 

@@ -4,6 +4,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 from conftest import ROOT
@@ -102,6 +103,37 @@ def test_device_group_matches_single_device(kfbo):
             np.testing.assert_allclose(got["cost"], want["cost"], rtol=1e-10, atol=1e-13)
         assert np.array_equal(got["index_max"], want["index_max"])
         np.testing.assert_allclose(one, want_one, rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("threads", [1, 0])
+def test_a_device_dropping_out_fails_the_evaluation_and_poisons_the_group(kfbo, threads):
+    # one device of a group fails before it launches anything (KFBO_OPT_INJECT_FAULT): the evaluation must come back with an
+    # error -- not hang: the other device's exchange gives up after KFBO_OPT_PEER_TIMEOUT_MS --, every device must be drained,
+    # and the group must refuse further evaluations (its devices' counters and exchange generations no longer agree) instead
+    # of returning numbers from mismatched streams.  With one host thread per device and with one thread for all.
+    import time
+    import torch
+    from kf_bayesopt_b200 import _lib
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    rv = kfbo.ReadParaVehicle(nsimruns_=4096, cpu_core_number_=1)
+    with kfbo.CostEvaluatorGroup(rv, [(0.1, 201), (0.5, 211)], n_gpus=2, seed=3) as gr:
+        gr.set_option(_lib.OPT_GROUP_THREADS, threads)
+        gr.set_option(_lib.OPT_PEER_TIMEOUT_MS, 300)
+        good = gr.eval([1.0], [0.1]).cost.copy()
+        assert good.shape == (2,) and all(good > 0)
+        gr.set_device_option(1, _lib.OPT_INJECT_FAULT, 1)
+        t = time.perf_counter()
+        with pytest.raises(kfbo.KfboError) as e1:
+            gr.eval([1.0], [0.1])
+        assert time.perf_counter() - t < 5.0                              # the timeout, not the 10 s default, and no hang
+        assert e1.value.code in (1, 3)                                    # KFBO_ECUDA of the failed device or KFBO_EPEER of the waiting one
+        with pytest.raises(kfbo.KfboError) as e2:
+            gr.eval([1.0], [0.1])
+        assert e2.value.code == -4                                        # KFBO_ESTATE: fails fast from now on
+    # a new group on the same devices works again
+    with kfbo.CostEvaluatorGroup(rv, [(0.1, 201), (0.5, 211)], n_gpus=2, seed=3) as gr:
+        assert np.array_equal(gr.eval([1.0], [0.1]).cost, good)
 
 
 def test_cpp_node_drives_several_gpus_from_one_process(kfbo, tmp_path):

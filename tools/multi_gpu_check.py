@@ -6,7 +6,8 @@
   * the cost sums meet over peer memory (fused into the rollout kernel / as a kernel behind it) or in an
     ncclAllReduce: the three give the same numbers (bit for bit between the two peer-memory forms, and against NCCL
     where the sum has one order: candidates sharded, or two ranks), also over a run of back-to-back evaluations
-    (both generations of the exchange buffers) and for batches with fewer candidates than ranks.
+    (both generations of the exchange buffers) and for batches with fewer candidates than ranks;
+  * a rank that drops out of an evaluation: KFBO_EPEER on the others after the timeout, then KFBO_ESTATE everywhere.
 Prints 'multi_gpu_check ok' on rank 0."""
 import os
 import sys
@@ -104,6 +105,30 @@ for N in (3, 4):
                 ev1.set_option(_lib.OPT_AUG_LAYOUT, layout)
                 ev1.eval_batch(q[:3], r[:3])
                 np.testing.assert_allclose(aug[(N, layout)], ev1.last_sums(3), rtol=1e-12, err_msg=f"aug N={N} layout={layout}")
+# a rank dropping out of an evaluation (fault injected before its launch): it reports its own error, the others KFBO_EPEER
+# after the timeout instead of hanging, and every rank refuses further evaluations on that communicator (KFBO_ESTATE)
+import time
+with kf.CostEvaluator(rv, times, seed=seed, max_candidates=C, device=local) as ev:
+    if init_comm(ev, kf.SHARD_TRIALS):
+        ev.set_option(_lib.OPT_PEER_TIMEOUT_MS, 300)
+        ev.eval([1.0], [0.1])
+        if rank == world - 1:
+            ev.set_option(_lib.OPT_INJECT_FAULT, 1)
+        t = time.perf_counter()
+        try:
+            ev.eval([1.0], [0.1])
+            code = 0
+        except kf.KfboError as e:
+            code = e.code
+        assert time.perf_counter() - t < 5.0, "the exchange did not time out"
+        assert code == (1 if rank == world - 1 else 3), (rank, code)      # KFBO_ECUDA on the rank that failed, KFBO_EPEER on the others
+        try:
+            ev.eval([1.0], [0.1])
+            code = 0
+        except kf.KfboError as e:
+            code = e.code
+        assert code == -4, (rank, code)                                    # KFBO_ESTATE
+    dist.barrier()
 if rank == 0:
     with kf.CostEvaluator(rv, times, seed=seed, max_candidates=C, device=local) as ev:
         out = ev.eval_batch(q, r)
