@@ -28,6 +28,21 @@ def test_library_exports_every_declared_symbol(kfbo):
     assert b"sm_100a" in lib.kfbo_version()
 
 
+def test_python_constants_match_the_header_enums(kfbo):
+    # every KFBO_OPT_* / KFBO_REDUCE_* / KFBO_PEER_FUSE_* / KFBO_AUG_LAYOUT_* / KFBO_SHARD_* value the ctypes layer carries is the header's
+    from kf_bayesopt_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "kfbo.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    header = {m.group(1): int(m.group(2)) for m in re.finditer(r"\bKFBO_([A-Z0-9_]+)\s*=\s*(-?\d+)", src)}
+    checked = 0
+    for name, value in vars(_lib).items():
+        if isinstance(value, int) and not isinstance(value, bool) and name.isupper() and name in header:
+            assert header[name] == value, f"_lib.{name} = {value}, kfbo.h says KFBO_{name} = {header[name]}"
+            checked += 1
+    opts = [n for n in header if n.startswith("OPT_")]
+    assert checked >= 15 and all(hasattr(_lib, n) for n in opts), [n for n in opts if not hasattr(_lib, n)]
+
+
 def test_numpy_result_record_matches_the_struct(kfbo):
     import ctypes
     from kf_bayesopt_b200 import _lib, evaluator
