@@ -453,6 +453,32 @@ def leg_cfg4(kf, torch, dist, stream, device, world, rank, steps=10, warmup=3):
             "host_phases_us": {k: round(v, 1) for k, v in phases.items()}, "gpu_launches_per_sweep": launches / steps}
 
 
+def leg_one_process(kf, world, steps=20, warmup=3):
+    """N > 1, rank 0 only, while the other ranks sit idle on the host: the SAME cfg3 evaluation and cfg4 sweep with ONE process
+    driving all N GPUs (kfbo_group_*: one handle per device, one host thread per device, peer-memory exchange) -- the mode of
+    the reference's node, which is one process.  Wall time per call, host buffers in and out."""
+    import numpy as np
+    out = {"mode": "one process drives all %d GPUs (kfbo_group_*, KFBO_OPT_GROUP_THREADS = 1); the other ranks of this run are idle" % world}
+    qq = np.repeat(np.geomspace(*CFG4_BOUNDS[0], CFG4_GRID), CFG4_GRID)
+    rr = np.tile(np.geomspace(*CFG4_BOUNDS[1], CFG4_GRID), CFG4_GRID)
+    rv3 = kf.ReadParaVehicle(nsimruns_=TRIALS, cpu_core_number_=1, pnoise_=[Q_TRUTH], onoise_=[R_TRUTH])
+    with kf.CostEvaluatorGroup(rv3, SAMPLE_TIMES, n_gpus=world, shard_mode=kf.SHARD_TRIALS, seed=0x4B46424F00002026) as gr:
+        ms = wall_evals(lambda: gr.eval(*CANDIDATE), steps, warmup)
+        res, path = gr.eval(*CANDIDATE), gr.last_reduce_path()
+    steps3 = float(TRIALS) * sum(T for _, T in SAMPLE_TIMES)
+    out["cfg3"] = {"ms_per_eval": ms, "value": steps3 / (ms * 1e-3), "unit": UNIT, "sums_meet_by": path,
+                   "J_NEES": [float(c) for c in res.cost], "api": "CostEvaluatorGroup.eval over the C ABI kfbo_group_eval (wall clock)"}
+    rv4 = kf.ReadParaVehicle(nsimruns_=CFG4_TRIALS, cpu_core_number_=1, pnoise_=[Q_TRUTH], onoise_=[R_TRUTH])
+    with kf.CostEvaluatorGroup(rv4, CFG4_SAMPLE_TIMES, n_gpus=world, shard_mode=kf.SHARD_CANDIDATES, seed=0x4B46424F00002026,
+                               max_candidates=qq.size) as gr:
+        ms4 = wall_evals(lambda: gr.eval_batch_costs(qq, rr), max(steps // 2, 5), warmup)
+        path4 = gr.last_reduce_path()
+    steps4 = float(CFG4_TRIALS) * qq.size * sum(T for _, T in CFG4_SAMPLE_TIMES)
+    out["cfg4"] = {"ms_per_sweep": ms4, "value": steps4 / (ms4 * 1e-3), "unit": UNIT, "sums_meet_by": path4,
+                   "api": "CostEvaluatorGroup.eval_batch_costs over kfbo_group_eval_batch_costs (wall clock)"}
+    return out
+
+
 def dense_flops_per_step(N: int) -> int:
     """The reference-faithful dense flop count of one filter-step for an N-state, 1-observation model -- SURVEY.md 8(d)'s
     convention (every mul / add / sub / div of the N x N and 1 x 1 products counts 1, RNG excluded), which gives 137 for N = 2:
@@ -788,6 +814,35 @@ def main():
                                                                                   seed=seed, device=local_rank), sample_times, 1.0, 0.1, seed),
                     "what": "cost sums of 300 trials x 1000 steps x 2 sample times, CUDA path vs CPU oracle on the same Philox streams", "tolerance": 1e-9}
         line_extra["extra"] = extra
+
+    # ---- N > 1: the single-process mode (the reference's node is one process) on the same GPUs, rank 0 only.  The other
+    # ranks wait on the HOST (a key of the rendezvous store, polled with sleeps -- no collective, no kernel on their GPUs),
+    # for at most two minutes; a failure of this leg is reported in the line and does not fail the run.
+    if world > 1 and not args.no_extra and not cfg4:
+        torch.cuda.synchronize()
+        dist.barrier()
+        store, key = None, "kfbo_one_process_leg_done"
+        try:
+            store = dist.distributed_c10d._get_default_store()
+        except Exception:
+            store = None
+        if store is not None:
+            if rank == 0:
+                try:
+                    line_extra.setdefault("extra", {})["one_process"] = leg_one_process(kf, world)
+                except Exception as e:
+                    line_extra.setdefault("extra", {})["one_process"] = {"unavailable": f"{type(e).__name__}: {e}"}
+                finally:
+                    store.set(key, "1")
+            else:
+                deadline = time.perf_counter() + 120.0
+                while time.perf_counter() < deadline:
+                    try:
+                        if store.check([key]):
+                            break
+                    except Exception:
+                        break
+                    time.sleep(0.02)
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle's threaded path on a bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not cfg4:
