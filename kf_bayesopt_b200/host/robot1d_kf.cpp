@@ -68,6 +68,7 @@ int main(int nargs, char *args[])
                 }
             };
         ros::Subscriber sub = n.subscribe<std_msgs::Float64MultiArray>("noise", 10, cb);           // trial_node.cpp:150
+        (void)sub;              // kept alive until spin() returns
         ros::spin();
 #else
         kfbo::RunTrial rT(rv, sec, n_init, nullptr, verbose, device, seed, max_cand, gpus);

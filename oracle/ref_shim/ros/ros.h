@@ -22,6 +22,12 @@
 
 #include <unistd.h>      // roscpp's headers pull it in; src/test_trial.cpp relies on that for usleep
 
+// roscpp is built on boost: callers that subscribe with a callable spell its type boost::function<void(const M::ConstPtr &)>
+// (kf_bayesopt_b200/host/robot1d_kf.cpp under -DKFBO_WITH_ROS does).  Boost is not installed; the std equivalent stands in.
+namespace boost {
+template <typename Signature> using function = std::function<Signature>;
+}
+
 namespace ros {
 
 struct ShimParam {
@@ -97,6 +103,16 @@ public:
         });
         return Subscriber();
     }
+    // subscribe<M>(topic, queue, boost::function<void(const M::ConstPtr &)>): roscpp's overload for callables
+    template <typename M>
+    Subscriber subscribe(const std::string &topic, unsigned /*queue_size*/, const std::function<void(const std::shared_ptr<const M> &)> &cb)
+    {
+        ShimMaster::get().callbacks[topic].push_back([cb](const std::shared_ptr<void> &m) {
+            const std::shared_ptr<const M> typed = std::static_pointer_cast<const M>(m);
+            cb(typed);
+        });
+        return Subscriber();
+    }
 private:
     static const ShimParam *find(const std::string &name)
     {
@@ -105,6 +121,11 @@ private:
         return it == ps.end() ? nullptr : &it->second;
     }
 };
+
+namespace param {
+// ros::param::get("~name", out): private names are looked up as given ("~vehicle_yaml" is the key the tests set)
+inline bool get(const std::string &name, std::string &out) { return NodeHandle().getParam(name, out); }
+}  // namespace param
 
 inline void init(int &, char **, const std::string &) {}
 inline bool ok() { return true; }
