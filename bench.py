@@ -236,6 +236,7 @@ def run_bo_loop(args):
                     "wall_s_with_reference_sleeps": loop["wall_s"] + 0.5 * n,
                     "api": "kfbo_bo_loop: Robot1D::evaluateSample contract -> topic bus -> kfbo::RunTrial::ProcessNoiseCallback -> C ABI"},
             "gpu_launches": n}
+    line["both_reference_nodes_unmodified"] = reference_nodes_loop()
     if not args.no_cpu_baseline:
         from oracle import oracle as o
         from oracle import ref
@@ -277,6 +278,57 @@ def run_bo_loop(args):
     emit(line)
 
 
+def reference_nodes_loop(n_init=20, n_iterations=180):
+    """The same loop with BOTH of the reference's nodes unmodified in one process (tests/native/boloop: robot1d_bayesopt.cpp and
+    trial_node.cpp built where they lie, one thread each, over the roscpp stand-in; trial_node.cpp on include/compat, so its
+    Trial::Run calls -- CPUcoreNumber = 10 of them per sample time, on std::threads -- are launches on the GPU; the bayesopt LIBRARY
+    is the GP / EI stand-in behind its interface).  The reference's sleeps are scaled to zero."""
+    import ctypes as C
+    import numpy as np
+    lib = os.path.join(ROOT, "tests", "native", "boloop", "_boloop", "libkfbo_boloop.so")
+    if not os.path.exists(lib):
+        return {"unavailable": "tests/native/boloop is not built (needs the reference tree at build time)"}
+    try:
+        l = C.CDLL(lib)
+        dp = C.POINTER(C.c_double)
+        l.kfbo_boloop_param_clear.restype = None
+        l.kfbo_boloop_param_set_int.argtypes = [C.c_char_p, C.c_longlong]
+        l.kfbo_boloop_param_set_double.argtypes = [C.c_char_p, C.c_double]
+        l.kfbo_boloop_param_set_string.argtypes = [C.c_char_p, C.c_char_p]
+        l.kfbo_boloop_param_set_vector.argtypes = [C.c_char_p, dp, C.c_int]
+        l.kfbo_boloop_run.restype = C.c_int
+        l.kfbo_boloop_run.argtypes = [C.c_double, dp, dp, C.c_int, C.POINTER(C.c_int), dp, dp, C.c_char_p, C.c_int]
+        # config/vehicleParams.yaml and config/bayesParams.yaml as `rosparam load` leaves them on the parameter server
+        params = {"CPUcoreNumber": 10, "stateDOF": 2, "observationDOF": 1, "t_start": 0.0, "t_end": 20.1, "dt": 0.1, "xi0": 0.0, "xidot0": 0.0,
+                  "Nsimruns": 200, "pnoise": [Q_TRUTH], "onoise": [R_TRUTH], "optimizationChoice": "all", "costChoice": "JNEES",
+                  "surr_name": "sGaussianProcess", "kernel_name": "kMaternARD3", "crit_name": "cEI", "n_init_samples": n_init,
+                  "n_iterations": n_iterations, "random_seed": 7, "verbose_level": 0, "noise": 1e-8, "force_jump": 10, "epsilon": 0.2,
+                  "lower_bound": [0.1, 0.01], "upper_bound": [5.0, 1.0], "n_iteration_relearn": 10, "n_inner_evaluation": 500}
+        l.kfbo_boloop_param_clear()
+        for k, v in params.items():
+            if isinstance(v, int):
+                l.kfbo_boloop_param_set_int(k.encode(), v)
+            elif isinstance(v, float):
+                l.kfbo_boloop_param_set_double(k.encode(), v)
+            elif isinstance(v, str):
+                l.kfbo_boloop_param_set_string(k.encode(), v.encode())
+            else:
+                a = np.ascontiguousarray(v, dtype=np.float64)
+                l.kfbo_boloop_param_set_vector(k.encode(), a.ctypes.data_as(dp), a.size)
+        cap = n_init + n_iterations + 8
+        noise, costs = np.zeros((cap, 4)), np.full(cap, np.nan)
+        nc, wall, slept, log = C.c_int(0), C.c_double(0), C.c_double(0), C.create_string_buffer(1 << 12)
+        n = l.kfbo_boloop_run(0.0, noise.ctypes.data_as(dp), costs.ctypes.data_as(dp), cap, C.byref(nc), C.byref(wall), C.byref(slept), log, len(log))
+        costs = costs[:nc.value]
+        return {"iterations": int(n), "costs_received": int(nc.value), "wall_s": wall.value, "ms_per_iteration": wall.value / max(n, 1) * 1e3,
+                "best_cost": float(np.nanmin(costs)) if costs.size else None,
+                "what": "robot1d_bayesopt.cpp (optimiser node) and trial_node.cpp (evaluator node, on include/compat: 2 x 10 Trial::Run "
+                        "launches per message) compiled unmodified, one thread each, roscpp stand-in; the reference's 0.5 s of sleeps per "
+                        "iteration scaled to 0; bayesopt library = the GP / EI stand-in"}
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def leg_cfg5(ref_node_ms=None):
     """BASELINE.json configs[4] as a leg of the default line (N = 1): the 200-evaluation BO loop of kfbo_bo_loop over the
     noise/cost topic contract, without the reference's sleeps (the measured with-sleeps run and the reference node's own
@@ -298,6 +350,7 @@ def leg_cfg5(ref_node_ms=None):
            "evaluator_ms_per_iteration": loop["evaluator_ms_per_iteration"], "optimiser_s": loop["optimiser_s"],
            "wall_s_with_the_reference_sleeps": loop["wall_s"] + 0.5 * n, "best_cost": loop["best_cost"], "best_x": loop["best_x"],
            "note": "robot1d_bayesopt.cpp:91,96 sleeps 0.5 s per iteration: with them the loop is sleep-bound on either evaluator"}
+    leg["both_reference_nodes_unmodified"] = reference_nodes_loop()
     if ref_node_ms:
         leg["reference_node_ms_per_iteration"] = ref_node_ms
         leg["evaluator_speedup"] = ref_node_ms / loop["evaluator_ms_per_iteration"]

@@ -8,16 +8,24 @@
 //   * topics: advertise<T>() returns a Publisher whose publish() appends the message to the topic's outbox;
 //     subscribe() registers a member-function callback; ros::spin() delivers every message queued in the
 //     topic's inbox to the callbacks, in order, on the calling thread, and returns (roscpp's spin() returns on
-//     shutdown; here "the inbox is empty" is the shutdown).
+//     shutdown; here "the inbox is empty" is the shutdown);
+//   * BUS MODE (ShimMaster::set_bus(true); tests/native/boloop): two nodes of this process -- one thread each -- talk to each
+//     other: publish() also queues the message for the process' own subscribers, spinOnce() delivers what is pending for the
+//     callbacks THE CALLING THREAD registered (a node's callbacks run on its own thread, as in roscpp), spin() does that until
+//     ros::shutdown().  The master is then shared by two threads: every access goes through its mutex.
 // In- and outboxes hold type-erased shared_ptr<void>; the driver knows the message types of the two topics of
 // the contract ("noise": std_msgs::Float64MultiArray, "cost": std_msgs::Float64).
 #pragma once
 #include <algorithm>   // roscpp's headers pull it in; trial_node.cpp relies on that for max_element
+#include <atomic>
+#include <chrono>
 #include <deque>
 #include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <unistd.h>      // roscpp's headers pull it in; src/test_trial.cpp relies on that for usleep
@@ -38,14 +46,65 @@ struct ShimParam {
     std::vector<double> v;
 };
 
+struct ShimCallback {
+    std::thread::id owner;                                   // the thread (node) that subscribed
+    std::function<void(const std::shared_ptr<void> &)> fn;
+};
+
 struct ShimMaster {
     std::map<std::string, ShimParam> params;
     std::map<std::string, std::deque<std::shared_ptr<void>>> inbox, outbox;
-    std::map<std::string, std::vector<std::function<void(const std::shared_ptr<void> &)>>> callbacks;
+    std::map<std::string, std::vector<ShimCallback>> callbacks;
+    std::mutex mu;
+    bool bus = false;
+    std::atomic<bool> down{false};
     static ShimMaster &get()
     {
         static ShimMaster m;
         return m;
+    }
+    void set_bus(bool on)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        bus = on;
+        down.store(false);
+    }
+    size_t subscribers(const std::string &topic)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        const auto it = callbacks.find(topic);
+        return it == callbacks.end() ? 0 : it->second.size();
+    }
+    // deliver what is queued for the callbacks of `who` (all callbacks: every = true); returns the number of deliveries
+    size_t dispatch(std::thread::id who, bool every)
+    {
+        std::vector<std::pair<std::function<void(const std::shared_ptr<void> &)>, std::shared_ptr<void>>> work;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (auto &kv : callbacks) {
+                std::vector<const ShimCallback *> mine;
+                for (const ShimCallback &cb : kv.second)
+                    if (every || cb.owner == who) mine.push_back(&cb);
+                if (mine.empty()) continue;
+                std::deque<std::shared_ptr<void>> &q = inbox[kv.first];
+                while (!q.empty()) {
+                    for (const ShimCallback *cb : mine) work.emplace_back(cb->fn, q.front());
+                    q.pop_front();
+                }
+            }
+        }
+        for (auto &w : work) w.first(w.second);              // outside the lock: a callback publishes
+        return work.size();
+    }
+    void drop_callbacks(std::thread::id who, bool every)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &kv : callbacks) {
+            std::vector<ShimCallback> keep;
+            for (ShimCallback &cb : kv.second)
+                if (!every && cb.owner != who) keep.push_back(cb);
+            kv.second.swap(keep);
+        }
     }
 };
 
@@ -55,7 +114,11 @@ public:
     explicit Publisher(const std::string &topic) : topic_(topic) {}
     template <typename M> void publish(const M &msg) const
     {
-        ShimMaster::get().outbox[topic_].push_back(std::make_shared<M>(msg));
+        ShimMaster &m = ShimMaster::get();
+        const std::shared_ptr<void> p = std::make_shared<M>(msg);
+        std::lock_guard<std::mutex> lk(m.mu);
+        m.outbox[topic_].push_back(p);
+        if (m.bus) m.inbox[topic_].push_back(p);
     }
 private:
     std::string topic_;
@@ -97,20 +160,24 @@ public:
     template <typename M, typename T>
     Subscriber subscribe(const std::string &topic, unsigned /*queue_size*/, void (T::*fp)(const std::shared_ptr<const M> &), T *obj)
     {
-        ShimMaster::get().callbacks[topic].push_back([fp, obj](const std::shared_ptr<void> &m) {
+        ShimMaster &master = ShimMaster::get();
+        std::lock_guard<std::mutex> lk(master.mu);
+        master.callbacks[topic].push_back(ShimCallback{std::this_thread::get_id(), [fp, obj](const std::shared_ptr<void> &m) {
             const std::shared_ptr<const M> typed = std::static_pointer_cast<const M>(m);
             (obj->*fp)(typed);
-        });
+        }});
         return Subscriber();
     }
     // subscribe<M>(topic, queue, boost::function<void(const M::ConstPtr &)>): roscpp's overload for callables
     template <typename M>
     Subscriber subscribe(const std::string &topic, unsigned /*queue_size*/, const std::function<void(const std::shared_ptr<const M> &)> &cb)
     {
-        ShimMaster::get().callbacks[topic].push_back([cb](const std::shared_ptr<void> &m) {
+        ShimMaster &master = ShimMaster::get();
+        std::lock_guard<std::mutex> lk(master.mu);
+        master.callbacks[topic].push_back(ShimCallback{std::this_thread::get_id(), [cb](const std::shared_ptr<void> &m) {
             const std::shared_ptr<const M> typed = std::static_pointer_cast<const M>(m);
             cb(typed);
-        });
+        }});
         return Subscriber();
     }
 private:
@@ -128,20 +195,25 @@ inline bool get(const std::string &name, std::string &out) { return NodeHandle()
 }  // namespace param
 
 inline void init(int &, char **, const std::string &) {}
-inline bool ok() { return true; }
-inline void shutdown() {}
+inline bool ok() { return !ShimMaster::get().down.load(); }
+inline void shutdown() { ShimMaster::get().down.store(true); }
+inline void spinOnce() { ShimMaster::get().dispatch(std::this_thread::get_id(), false); }
 inline void spin()
 {
     ShimMaster &m = ShimMaster::get();
-    for (auto &kv : m.callbacks) {
-        std::deque<std::shared_ptr<void>> &q = m.inbox[kv.first];
-        while (!q.empty()) {
-            const std::shared_ptr<void> msg = q.front();
-            q.pop_front();
-            for (auto &cb : kv.second) cb(msg);
-        }
+    bool bus;
+    {
+        std::lock_guard<std::mutex> lk(m.mu);
+        bus = m.bus;
     }
-    m.callbacks.clear();      // the node object the callbacks point into dies when its main() returns
+    if (!bus) {
+        while (m.dispatch(std::this_thread::get_id(), true) > 0) {}
+        m.drop_callbacks(std::this_thread::get_id(), true);   // the node object the callbacks point into dies when its main() returns
+        return;
+    }
+    while (ok())
+        if (m.dispatch(std::this_thread::get_id(), false) == 0) std::this_thread::sleep_for(std::chrono::microseconds(20));
+    m.drop_callbacks(std::this_thread::get_id(), false);
 }
 }  // namespace ros
 #define ROS_INFO(...) ((void)0)
