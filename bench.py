@@ -297,7 +297,7 @@ def reference_nodes_loop(n_init=20, n_iterations=180):
         l.kfbo_boloop_param_set_string.argtypes = [C.c_char_p, C.c_char_p]
         l.kfbo_boloop_param_set_vector.argtypes = [C.c_char_p, dp, C.c_int]
         l.kfbo_boloop_run.restype = C.c_int
-        l.kfbo_boloop_run.argtypes = [C.c_double, dp, dp, C.c_int, C.POINTER(C.c_int), dp, dp, C.c_char_p, C.c_int]
+        l.kfbo_boloop_run.argtypes = [C.c_int, C.c_char_p, C.c_double, dp, dp, C.c_int, C.POINTER(C.c_int), dp, dp, C.c_char_p, C.c_int]
         # config/vehicleParams.yaml and config/bayesParams.yaml as `rosparam load` leaves them on the parameter server
         params = {"CPUcoreNumber": 10, "stateDOF": 2, "observationDOF": 1, "t_start": 0.0, "t_end": 20.1, "dt": 0.1, "xi0": 0.0, "xidot0": 0.0,
                   "Nsimruns": 200, "pnoise": [Q_TRUTH], "onoise": [R_TRUTH], "optimizationChoice": "all", "costChoice": "JNEES",
@@ -318,7 +318,7 @@ def reference_nodes_loop(n_init=20, n_iterations=180):
         cap = n_init + n_iterations + 8
         noise, costs = np.zeros((cap, 4)), np.full(cap, np.nan)
         nc, wall, slept, log = C.c_int(0), C.c_double(0), C.c_double(0), C.create_string_buffer(1 << 12)
-        n = l.kfbo_boloop_run(0.0, noise.ctypes.data_as(dp), costs.ctypes.data_as(dp), cap, C.byref(nc), C.byref(wall), C.byref(slept), log, len(log))
+        n = l.kfbo_boloop_run(0, b"", 0.0, noise.ctypes.data_as(dp), costs.ctypes.data_as(dp), cap, C.byref(nc), C.byref(wall), C.byref(slept), log, len(log))
         costs = costs[:nc.value]
         return {"iterations": int(n), "costs_received": int(nc.value), "wall_s": wall.value, "ms_per_iteration": wall.value / max(n, 1) * 1e3,
                 "best_cost": float(np.nanmin(costs)) if costs.size else None,

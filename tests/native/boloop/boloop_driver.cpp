@@ -1,6 +1,8 @@
 // boloop_driver.cpp -- BASELINE.json configs[4] with BOTH of the reference's nodes unmodified, in one process:
 //   thread A: /root/reference/trial_node.cpp           (the evaluator node "robot_1d_kf") compiled against include/compat, i.e.
 //             its Trial::Run calls are kernel launches on the B200 (as in tests/native/dropin)
+//             -- or (evaluator = 1) THIS repository's ROS node, kf_bayesopt_b200/host/robot1d_kf.cpp under -DKFBO_WITH_ROS: one
+//             fused launch per message; the deployment BASELINE.json configs[4] describes (bayesopt node unchanged, GPU evaluator)
 //   thread B: /root/reference/robot1d_bayesopt.cpp     (the optimiser node "robot1d_bayes": Robot1D::evaluateSample builds the
 //             "noise" message per optimizationChoice, publishes it, waits for "cost") compiled against the stand-in of the
 //             absent bayesopt library (shim/bayesopt/bayesopt.hpp: the GP / EI optimiser of kf_bayesopt_b200/host/gp_ei.hpp)
@@ -15,12 +17,14 @@
 #include <streambuf>
 #include <string>
 #include <thread>
+#include <vector>
 
 #include <ros/ros.h>
 #include <std_msgs/Float64.h>
 #include <std_msgs/Float64MultiArray.h>
 
 int kfbo_boloop_trial_node_main(int nargs, char *args[]);   // trial_node.cpp's main()
+int kfbo_boloop_robot1d_kf_main(int nargs, char *args[]);   // kf_bayesopt_b200/host/robot1d_kf.cpp's main(), -DKFBO_WITH_ROS
 int kfbo_boloop_bayesopt_main(int nargs, char *args[]);     // robot1d_bayesopt.cpp's main()
 
 namespace {
@@ -94,8 +98,10 @@ void kfbo_boloop_param_set_vector(const char *name, const double *v, int n)
 // data[0], data[1]) of the i-th "noise" message, costs[i] the i-th "cost" message; log: the END of what both nodes printed.
 // Returns the number of "noise" messages; *n_costs the number of "cost" messages; *wall_s, *slept_s the loop's wall time and
 // the time spent in the optimiser node's (scaled) sleeps.
-int kfbo_boloop_run(double sleep_scale, double *noise, double *costs, int cap, int *n_costs, double *wall_s, double *slept_s,
-                    char *log, int log_cap)
+// evaluator: 0 = the reference's trial_node.cpp on include/compat, 1 = this repository's robot1d_kf.cpp (its command line after
+// the program name in evaluator_args, space separated; its yaml comes from the ~vehicle_yaml parameter).
+int kfbo_boloop_run(int evaluator_kind, const char *evaluator_args, double sleep_scale, double *noise, double *costs, int cap, int *n_costs,
+                    double *wall_s, double *slept_s, char *log, int log_cap)
 {
     ros::ShimMaster &m = ros::ShimMaster::get();
     {
@@ -107,10 +113,24 @@ int kfbo_boloop_run(double sleep_scale, double *noise, double *costs, int cap, i
     g_slept_s = 0.0;
     LockedSink sink;
     std::streambuf *old = std::cout.rdbuf(&sink);
-    char a0[] = "robot1d_kf", b0[] = "robot1d_bayesopt";
-    char *args_a[] = {a0, nullptr}, *args_b[] = {b0, nullptr};
+    char b0[] = "robot1d_bayesopt";
+    char *args_b[] = {b0, nullptr};
+    std::vector<std::string> words{"robot1d_kf"};
+    for (const char *p = evaluator_args ? evaluator_args : ""; *p;) {
+        while (*p == ' ') ++p;
+        const char *e = p;
+        while (*e && *e != ' ') ++e;
+        if (e > p) words.emplace_back(p, e);
+        p = e;
+    }
+    std::vector<char *> args_a;
+    for (std::string &w : words) args_a.push_back(&w[0]);
+    args_a.push_back(nullptr);
     std::thread evaluator([&] {
-        try { kfbo_boloop_trial_node_main(1, args_a); } catch (const std::exception &e) { std::cerr << "evaluator node: " << e.what() << std::endl; }
+        try {
+            if (evaluator_kind == 1) kfbo_boloop_robot1d_kf_main((int)words.size(), args_a.data());
+            else kfbo_boloop_trial_node_main(1, args_a.data());
+        } catch (const std::exception &e) { std::cerr << "evaluator node: " << e.what() << std::endl; }
     });
     for (int i = 0; i < 30000 && m.subscribers("noise") == 0; ++i) std::this_thread::sleep_for(std::chrono::milliseconds(1));
     const auto t0 = std::chrono::steady_clock::now();

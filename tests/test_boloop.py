@@ -32,7 +32,7 @@ def boloop(kfbo):
     l.kfbo_boloop_param_set_string.argtypes = [C.c_char_p, C.c_char_p]
     l.kfbo_boloop_param_set_vector.argtypes = [C.c_char_p, _dp, C.c_int]
     l.kfbo_boloop_run.restype = C.c_int
-    l.kfbo_boloop_run.argtypes = [C.c_double, _dp, _dp, C.c_int, C.POINTER(C.c_int), _dp, _dp, C.c_char_p, C.c_int]
+    l.kfbo_boloop_run.argtypes = [C.c_int, C.c_char_p, C.c_double, _dp, _dp, C.c_int, C.POINTER(C.c_int), _dp, _dp, C.c_char_p, C.c_int]
     return l
 
 
@@ -54,10 +54,11 @@ def set_params(l, **over):
     return params
 
 
-def run(l, sleep_scale=0.0, cap=512):
+def run(l, sleep_scale=0.0, cap=512, evaluator=0, evaluator_args=""):
+    """evaluator 0: the reference's trial_node.cpp (on include/compat); 1: this repository's robot1d_kf.cpp (-DKFBO_WITH_ROS)."""
     noise, costs = np.zeros((cap, 4)), np.full(cap, np.nan)
     nc, wall, slept, log = C.c_int(0), C.c_double(0), C.c_double(0), C.create_string_buffer(1 << 15)
-    n = l.kfbo_boloop_run(sleep_scale, noise.ctypes.data_as(_dp), costs.ctypes.data_as(_dp), cap, C.byref(nc), C.byref(wall),
+    n = l.kfbo_boloop_run(evaluator, evaluator_args.encode(), sleep_scale, noise.ctypes.data_as(_dp), costs.ctypes.data_as(_dp), cap, C.byref(nc), C.byref(wall),
                           C.byref(slept), log, len(log))
     return noise[:n].copy(), costs[:nc.value].copy(), wall.value, slept.value, log.value.decode(errors="replace")
 
@@ -106,3 +107,19 @@ def test_the_reference_sleeps_half_a_second_per_iteration(boloop):
     set_params(boloop, n_init_samples=2, n_iterations=2, random_seed=1, verbose_level=0)
     noise, costs, wall, slept, _ = run(boloop, sleep_scale=1.0)
     assert len(costs) == 4 and slept == pytest.approx(4 * 0.5, abs=1e-9) and wall >= 2.0
+
+
+@pytest.mark.gpu
+def test_reference_optimiser_node_drives_this_repositorys_ros_node(boloop, tmp_path, kfbo):
+    # the deployment configs[4] describes: the bayesopt node unchanged, the evaluator node replaced by kfbo_robot1d_kf (ROS glue,
+    # one fused launch per message).  Every cost it publishes is what the Python RunTrial gives for the same message and seed.
+    vy = tmp_path / "vehicleParams.yaml"
+    vy.write_text(VEHICLE_YAML)
+    seed = 99
+    p = set_params(boloop, n_init_samples=8, n_iterations=12, random_seed=5, verbose_level=0, **{"~vehicle_yaml": str(vy)})
+    noise, costs, wall, slept, log = run(boloop, evaluator=1, evaluator_args=f"--seed {seed} --quiet")
+    assert len(noise) == 20 == len(costs) and np.all(np.isfinite(costs))
+    rt = kfbo.RunTrial(kfbo.ReadParaVehicle.from_yaml(str(vy)), seed=seed)
+    for (_, _, q, r), c in zip(noise, costs):
+        assert rt.ProcessNoiseCallback(kfbo.Float64MultiArray.noise([q], [r])).data == c     # same streams: the same bits
+    assert re.search(r"final optimization result ([0-9.e+-]+),([0-9.e+-]+),", log)
