@@ -1,5 +1,5 @@
 // boost/numeric/ublas/vector.hpp -- stand-in (Boost is not installed): what the reference's robot1d_bayesopt.cpp uses of
-// ublas::vector<double> -- size constructor, operator()(i), size(), begin() / end().  Test infrastructure (../../../../README in Makefile).
+// ublas::vector<double> -- size constructor, operator()(i), size(), begin() / end().  Test infrastructure (tests/native/boloop/Makefile).
 #pragma once
 #include <cstddef>
 #include <vector>
