@@ -86,6 +86,15 @@ def test_host_layer_cpu_checks(tmp_path, yamls, kfbo):
         assert f"ok {name}" in out.stdout
 
 
+def test_ros_stand_in_bus_mode_ping_pong(tmp_path):
+    # the two-node loop of tests/native/boloop rests on it: two threads, publish -> the other node's callback -> answer
+    exe = tmp_path / "ros_bus_check"
+    subprocess.check_call(["g++", "-O2", "-std=c++14", "-pthread", "-I", os.path.join(ROOT, "oracle", "ref_shim"),
+                           os.path.join(ROOT, "tests", "native", "ros_bus_check.cpp"), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ok ros_bus" in out.stdout, out.stdout + out.stderr
+
+
 def test_python_and_cpp_yaml_readers_agree(yamls, kfbo):
     rv = kfbo.ReadParaVehicle.from_yaml(yamls[0])
     assert (rv.cpu_core_number_, rv.nsimruns_, rv.max_iterations_, rv.cost_choice_) == (10, 200, 201, "JNEES")
