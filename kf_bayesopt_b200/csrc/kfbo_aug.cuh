@@ -220,8 +220,8 @@ rollout_aug(const AugCase *__restrict__ cases, const AugSampleTime *__restrict__
 // trajectory's outputs are the SAME BITS as the rows-across-lanes kernel's (the cost sums add them in another order;
 // test_gpu_aug.py), and the tests' CPU checker pins both.  Why it
 // exists: rows across lanes replicate the scalar part of the step in every lane and pay 45 double shuffles per lane-step;
-// per filter-step this kernel issues a quarter of the instructions (N = 4: 234 FP64 + 2 Philox calls against 4 x 160
-// FP64 + 4 x 132 SHFL).  Why the other one stays: registers -- N (N + 2) doubles of state per thread stop fitting
+// per filter-step this kernel issues under a third of the instructions (N = 4: 234 FP64 + 2 Philox calls against 450
+// FP64 + 350 SHFL).  Why the other one stays: registers -- N (N + 2) doubles of state per thread stop fitting
 // beyond N = 4, the lane layout scales to N = 32 -- and it is the layout BASELINE.json's north_star names.
 // The sample time's constants (Fd, g, L, sqrt R) come by value: one launch per sample time, every use is a
 // constant-bank operand of the FP64 instruction (no register).  The case's Qd sits in shared memory.
